@@ -1,0 +1,164 @@
+// adi_api.cu -- context, memory and error plumbing of the C ABI (include/adi_b200.h).
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "adi_ctx.h"
+
+namespace adi {
+
+static thread_local std::string g_err;
+
+void set_error(const std::string &msg) { g_err = msg; }
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return ADI_ECUDA;
+}
+
+void cyl_release(adi_ctx *ctx);  // adi_cyl.cu
+
+int prof_mark(adi_ctx *ctx, int slot, cudaStream_t st)
+{
+    if (!ctx->opt_profile) return ADI_OK;
+    const size_t need = (size_t)(ctx->prof_steps + 1) * 4;
+    while (ctx->prof_ev.size() < need) {
+        cudaEvent_t e;
+        ADI_CUDA(cudaEventCreate(&e));
+        ctx->prof_ev.push_back(e);
+    }
+    ADI_CUDA(cudaEventRecord(ctx->prof_ev[(size_t)ctx->prof_steps * 4 + slot], st));
+    if (slot == 3) ctx->prof_steps++;
+    return ADI_OK;
+}
+
+}  // namespace adi
+
+extern "C" {
+
+const char *adi_last_error(void) { return adi::g_err.c_str(); }
+
+const char *adi_version(void) { return "adi_b200 0.1 (sm_100a)"; }
+
+int adi_ctx_create(int device, adi_ctx **out)
+{
+    if (!out) {
+        adi::set_error("adi_ctx_create: out is NULL");
+        return ADI_EINVAL;
+    }
+    int ndev = 0;
+    ADI_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) {
+        adi::set_error("adi_ctx_create: no such CUDA device");
+        return ADI_EINVAL;
+    }
+    ADI_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ADI_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        adi::set_error("adi_ctx_create: this library is built for sm_100a (B200) only");
+        return ADI_EINVAL;
+    }
+    adi_ctx *c = new (std::nothrow) adi_ctx();
+    if (!c) return ADI_ENOMEM;
+    c->device = device;
+    *out = c;
+    return ADI_OK;
+}
+
+int adi_ctx_destroy(adi_ctx *ctx)
+{
+    if (!ctx) return ADI_OK;
+    cudaSetDevice(ctx->device);
+    for (int a = 0; a < 3; ++a)
+        if (ctx->code_buf[a]) cudaFree(ctx->code_buf[a]);
+    for (int a = 0; a < 2; ++a)
+        if (ctx->stage[a]) cudaFree(ctx->stage[a]);
+    if (ctx->stage_mask) cudaFree(ctx->stage_mask);
+    if (ctx->stage_src) cudaFree(ctx->stage_src);
+    adi::cyl_release(ctx);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    delete ctx;
+    return ADI_OK;
+}
+
+int adi_sync(adi_ctx *ctx, void *stream)
+{
+    if (!ctx) return ADI_EINVAL;
+    ADI_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return ADI_OK;
+}
+
+int adi_malloc(adi_ctx *ctx, size_t bytes, void **d_ptr)
+{
+    if (!ctx || !d_ptr) return ADI_EINVAL;
+    ADI_CUDA(cudaSetDevice(ctx->device));
+    ADI_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 1));
+    return ADI_OK;
+}
+
+int adi_free(adi_ctx *ctx, void *d_ptr)
+{
+    if (!ctx) return ADI_EINVAL;
+    ADI_CUDA(cudaFree(d_ptr));
+    return ADI_OK;
+}
+
+int adi_h2d(adi_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream)
+{
+    if (!ctx) return ADI_EINVAL;
+    ADI_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return ADI_OK;
+}
+
+int adi_d2h(adi_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream)
+{
+    if (!ctx) return ADI_EINVAL;
+    ADI_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    ADI_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return ADI_OK;
+}
+
+int adi_set_option(adi_ctx *ctx, const char *name, long value)
+{
+    if (!ctx || !name) return ADI_EINVAL;
+    if (!strcmp(name, "kt")) ctx->opt_kt = value;
+    else if (!strcmp(name, "lt")) ctx->opt_lt = value;
+    else if (!strcmp(name, "m")) ctx->opt_m = value;
+    else if (!strcmp(name, "sync_check")) ctx->opt_sync_check = value;
+    else if (!strcmp(name, "profile")) ctx->opt_profile = value;
+    else {
+        adi::set_error(std::string("adi_set_option: unknown option ") + name);
+        return ADI_EINVAL;
+    }
+    return ADI_OK;
+}
+
+long adi_launch_count(adi_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+int adi_profile_reset(adi_ctx *ctx)
+{
+    if (!ctx) return ADI_EINVAL;
+    ctx->prof_steps = 0;
+    return ADI_OK;
+}
+
+int adi_profile_read(adi_ctx *ctx, double ms[3], long *nsteps)
+{
+    if (!ctx || !ms) return ADI_EINVAL;
+    ms[0] = ms[1] = ms[2] = 0.0;
+    for (long s = 0; s < ctx->prof_steps; ++s) {
+        cudaEvent_t *e = &ctx->prof_ev[(size_t)s * 4];
+        ADI_CUDA(cudaEventSynchronize(e[3]));
+        for (int k = 0; k < 3; ++k) {
+            float t = 0.f;
+            ADI_CUDA(cudaEventElapsedTime(&t, e[k], e[k + 1]));
+            ms[k] += (double)t;
+        }
+    }
+    if (nsteps) *nsteps = ctx->prof_steps;
+    return ADI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+// adi_cart.cu -- Cartesian entry points of the C ABI: operand binding, variant
+// selection and launch of the kernels in adi_cart.cuh.
+#include <algorithm>
+#include <cstdio>
+
+#include "adi_cart.cuh"
+#include "adi_ctx.h"
+
+using namespace adi;
+
+namespace {
+
+constexpr int kM = 16;          // cells per thread-chunk
+constexpr int kMaxThreads = 512;
+
+int check_cart(adi_ctx *ctx, const char *who)
+{
+    if (!ctx) {
+        set_error(std::string(who) + ": ctx is NULL");
+        return ADI_EINVAL;
+    }
+    if (!ctx->cart_bound) {
+        set_error(std::string(who) + ": adi_cart_bind has not been called");
+        return ADI_ESTATE;
+    }
+    return ADI_OK;
+}
+
+int ensure_code(adi_ctx *ctx, cudaStream_t st)
+{
+    if (!ctx->code_dirty) return ADI_OK;
+    if (!ctx->d_mask) {
+        set_error("adi_cart_step: no mask bound (adi_cart_set_mask)");
+        return ADI_ESTATE;
+    }
+    const size_t n = (size_t)ctx->nx * ctx->ny * ctx->nz;
+    // one code array when the three packs share their Dirichlet mask, else one per axis
+    const bool shared = ctx->pack[0].dirm == ctx->pack[1].dirm && ctx->pack[1].dirm == ctx->pack[2].dirm;
+    const int ncodes = shared ? 1 : 3;
+    if (ctx->code_cells != n) {
+        for (int a = 0; a < 3; ++a)
+            if (ctx->code_buf[a]) { cudaFree(ctx->code_buf[a]); ctx->code_buf[a] = nullptr; }
+        ctx->code_cells = n;
+    }
+    for (int a = 0; a < ncodes; ++a)
+        if (!ctx->code_buf[a]) ADI_CUDA(cudaMalloc(&ctx->code_buf[a], n ? n : 1));
+    if (n) {
+        const int threads = 256;
+        const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, 148 * 64);
+        for (int a = 0; a < ncodes; ++a) {
+            k_build_code<<<blocks, threads, 0, st>>>(ctx->d_mask, ctx->pack[a].dirm, ctx->code_buf[a],
+                                                     ctx->nx, ctx->ny, ctx->nz);
+            ctx->launches++;
+        }
+        ADI_CUDA(cudaGetLastError());
+    }
+    for (int a = 0; a < 3; ++a) ctx->code[a] = ctx->code_buf[shared ? 0 : a];
+    ctx->code_dirty = false;
+    return ADI_OK;
+}
+
+template <typename K>
+int launch(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const SweepArgs &a, adi_ctx *ctx)
+{
+    if (smem > 48 * 1024)
+        ADI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, block, smem, st>>>(a);
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
+    return ADI_OK;
+}
+
+template <int AXIS>
+int launch_strided(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, bool expl, cudaStream_t st)
+{
+    const int n = AXIS == 0 ? a.nx : a.ny;
+    const int other = AXIS == 0 ? a.ny : a.nx;
+    const int P = (n + kM - 1) / kM;
+    int KT = 32;
+    while (KT > 4 && KT * P > 256) KT >>= 1;
+    if (ctx->opt_kt > 0) KT = (int)ctx->opt_kt;
+    if (KT * P > kMaxThreads || P > kMaxThreads) {
+        set_error("adi_cart_step: line too long for the register-resident sweep (n > 2048)");
+        return ADI_EINVAL;
+    }
+    dim3 block(KT, P), grid((a.nz + KT - 1) / KT, other);
+    const size_t smem = (size_t)6 * KT * P * sizeof(double);
+#define ADI_GO(CM, EX, XP) return launch(k_sweep_strided<AXIS, kM, CM, EX, XP>, grid, block, smem, st, a, ctx)
+    if (AXIS == 0 && expl) {
+        if (dense) { if (extra) ADI_GO(2, true, (AXIS == 0)); else ADI_GO(2, false, (AXIS == 0)); }
+        else       { if (extra) ADI_GO(1, true, (AXIS == 0)); else ADI_GO(1, false, (AXIS == 0)); }
+    } else {
+        if (dense) { if (extra) ADI_GO(2, true, false); else ADI_GO(2, false, false); }
+        else       { if (extra) ADI_GO(1, true, false); else ADI_GO(1, false, false); }
+    }
+#undef ADI_GO
+}
+
+int launch_z(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, cudaStream_t st)
+{
+    const int P = (a.nz + kM - 1) / kM;
+    if (P > kMaxThreads) {
+        set_error("adi_cart_step: z line too long for the register-resident sweep");
+        return ADI_EINVAL;
+    }
+    int LT = std::max(1, 256 / P);
+    if (ctx->opt_lt > 0) LT = (int)ctx->opt_lt;
+    LT = std::min(LT, kMaxThreads / P);
+    const size_t nlines = (size_t)a.nx * a.ny;
+    dim3 block(P, LT), grid((unsigned)((nlines + LT - 1) / LT));
+    const size_t LS = (size_t)P * zpad<kM>();
+    const size_t smem = ((dense ? 2 : 1) * LT * LS + 6 * (size_t)P * LT) * sizeof(double) + (size_t)LT * P * kM;
+    if (smem > 227 * 1024) {
+        set_error("adi_cart_step: z tile does not fit shared memory");
+        return ADI_EINVAL;
+    }
+    if (dense) {
+        if (extra) return launch(k_sweep_z<kM, 2, true>, grid, block, smem, st, a, ctx);
+        return launch(k_sweep_z<kM, 2, false>, grid, block, smem, st, a, ctx);
+    }
+    if (extra) return launch(k_sweep_z<kM, 1, true>, grid, block, smem, st, a, ctx);
+    return launch(k_sweep_z<kM, 1, false>, grid, block, smem, st, a, ctx);
+}
+
+int ensure_stage(adi_ctx *ctx, size_t cells)
+{
+    if (ctx->stage_cells >= cells && ctx->stage[0]) return ADI_OK;
+    for (int a = 0; a < 2; ++a) {
+        if (ctx->stage[a]) cudaFree(ctx->stage[a]);
+        ctx->stage[a] = nullptr;
+        ADI_CUDA(cudaMalloc(&ctx->stage[a], std::max<size_t>(cells, 1) * sizeof(double)));
+    }
+    ctx->stage_cells = cells;
+    return ADI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int adi_cart_bind(adi_ctx *ctx, int nx, int ny, int nz, double dx)
+{
+    if (!ctx) return ADI_EINVAL;
+    if (nx < 0 || ny < 0 || nz < 0 || !(dx > 0.0)) {
+        set_error("adi_cart_bind: bad grid");
+        return ADI_EINVAL;
+    }
+    ADI_CUDA(cudaSetDevice(ctx->device));
+    ctx->nx = nx; ctx->ny = ny; ctx->nz = nz; ctx->dx = dx;
+    ctx->cart_bound = true;
+    ctx->d_mask = nullptr;
+    for (int a = 0; a < 3; ++a) ctx->pack[a] = Pack();
+    ctx->scalar_robin = false;
+    ctx->code_dirty = true;
+    return ADI_OK;
+}
+
+int adi_cart_set_mask(adi_ctx *ctx, const uint8_t *d_mask)
+{
+    int rc = check_cart(ctx, "adi_cart_set_mask");
+    if (rc) return rc;
+    ctx->d_mask = d_mask;
+    ctx->code_dirty = true;
+    return ADI_OK;
+}
+
+int adi_cart_set_pack(adi_ctx *ctx, int axis, const double *d_coeff, const uint8_t *d_dir_mask,
+                      const double *d_dir_val, const double *d_qflux)
+{
+    int rc = check_cart(ctx, "adi_cart_set_pack");
+    if (rc) return rc;
+    if (axis < 0 || axis > 2) {
+        set_error("adi_cart_set_pack: axis must be 0, 1 or 2");
+        return ADI_EINVAL;
+    }
+    if (d_dir_mask && !d_dir_val) {
+        set_error("adi_cart_set_pack: dir_mask given without dir_val");
+        return ADI_EINVAL;
+    }
+    Pack &p = ctx->pack[axis];
+    if (p.dirm || d_dir_mask) ctx->code_dirty = true;  // Dirichlet bit lives in the code
+    p.coeff = d_coeff; p.dirm = d_dir_mask; p.dirv = d_dir_mask ? d_dir_val : nullptr; p.q = d_qflux;
+    ctx->scalar_robin = false;
+    return ADI_OK;
+}
+
+int adi_cart_set_robin_scalar(adi_ctx *ctx, const double face_coeff[6])
+{
+    int rc = check_cart(ctx, "adi_cart_set_robin_scalar");
+    if (rc) return rc;
+    if (!face_coeff) return ADI_EINVAL;
+    for (int f = 0; f < 6; ++f) ctx->face_coeff[f] = face_coeff[f];
+    for (int a = 0; a < 3; ++a) ctx->pack[a].coeff = nullptr;
+    ctx->scalar_robin = true;
+    return ADI_OK;
+}
+
+int adi_cart_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, double theta,
+                  double kappa, double Tinf, void *stream)
+{
+    int rc = check_cart(ctx, "adi_cart_step");
+    if (rc) return rc;
+    if (!d_Tin || !d_Tout || d_Tin == d_Tout) {
+        set_error("adi_cart_step: Tin/Tout must be distinct device arrays");
+        return ADI_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ncell = (size_t)ctx->nx * ctx->ny * ctx->nz;
+    if (ncell == 0) return ADI_OK;
+    rc = ensure_code(ctx, st);
+    if (rc) return rc;
+
+    // adi3d_numba_coeff.py:291-292,298 -- scalars in the reference's evaluation order
+    const double dx = ctx->dx;
+    const double gam = kappa * dt / (dx * dx);
+    SweepArgs a;
+    a.nx = ctx->nx; a.ny = ctx->ny; a.nz = ctx->nz;
+    a.k.g = theta * gam;
+    a.k.dt = dt;
+    a.k.Tinf = Tinf;
+    a.k.beta = dt * kappa * (1.0 - theta);
+    a.k.invdx2 = 1.0 / (dx * dx);
+    const bool expl = a.k.beta != 0.0;
+
+    rc = prof_mark(ctx, 0, st);
+    if (rc) return rc;
+    for (int axis = 0; axis < 3; ++axis) {
+        const Pack &p = ctx->pack[axis];
+        a.in = axis == 0 ? d_Tin : d_Tout;  // y and z sweeps run in place on Tout
+        a.out = d_Tout;
+        a.code = ctx->code[axis];
+        a.coeff = p.coeff;
+        a.q = p.q;
+        a.dirv = p.dirv;
+        a.k.h_lo = ctx->scalar_robin ? ctx->face_coeff[2 * axis] : 0.0;
+        a.k.h_hi = ctx->scalar_robin ? ctx->face_coeff[2 * axis + 1] : 0.0;
+        const bool dense = p.coeff != nullptr;
+        const bool extra = p.q != nullptr || p.dirm != nullptr;
+        if (axis == 0) rc = launch_strided<0>(ctx, a, dense, extra, expl, st);
+        else if (axis == 1) rc = launch_strided<1>(ctx, a, dense, extra, false, st);
+        else rc = launch_z(ctx, a, dense, extra, st);
+        if (rc) return rc;
+        rc = prof_mark(ctx, axis + 1, st);
+        if (rc) return rc;
+    }
+    if (ctx->opt_sync_check) ADI_CUDA(cudaStreamSynchronize(st));
+    return ADI_OK;
+}
+
+int adi_cart_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int nsteps, double dt,
+                       double theta, double kappa, double Tinf, void *stream)
+{
+    int rc = check_cart(ctx, "adi_cart_step_host");
+    if (rc) return rc;
+    if (!h_Tin || !h_Tout || nsteps < 1) {
+        set_error("adi_cart_step_host: bad arguments");
+        return ADI_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ncell = (size_t)ctx->nx * ctx->ny * ctx->nz;
+    rc = ensure_stage(ctx, ncell);
+    if (rc) return rc;
+    ADI_CUDA(cudaMemcpyAsync(ctx->stage[0], h_Tin, ncell * sizeof(double), cudaMemcpyHostToDevice, st));
+    int cur = 0;
+    for (int s = 0; s < nsteps; ++s) {
+        rc = adi_cart_step(ctx, ctx->stage[cur], ctx->stage[cur ^ 1], dt, theta, kappa, Tinf, stream);
+        if (rc) return rc;
+        cur ^= 1;
+    }
+    ADI_CUDA(cudaMemcpyAsync(h_Tout, ctx->stage[cur], ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
+    ADI_CUDA(cudaStreamSynchronize(st));
+    return ADI_OK;
+}
+
+int adi_cart_build_packs(adi_ctx *ctx, double rho, double cp, const int h_kind[6],
+                         const double h_scalar[6], const double *const d_h_field[6],
+                         const int q_kind[6], const double q_scalar[6],
+                         const double *const d_q_field[6], double *d_coeff_x, double *d_coeff_y,
+                         double *d_coeff_z, double *d_q_x, double *d_q_y, double *d_q_z,
+                         void *stream)
+{
+    int rc = check_cart(ctx, "adi_cart_build_packs");
+    if (rc) return rc;
+    if (!ctx->d_mask) {
+        set_error("adi_cart_build_packs: no mask bound");
+        return ADI_ESTATE;
+    }
+    PackArgs a;
+    a.mask = ctx->d_mask;
+    a.nx = ctx->nx; a.ny = ctx->ny; a.nz = ctx->nz;
+    const double dx = ctx->dx;
+    a.A = dx * dx;
+    const double V = dx * dx * dx;  // dx**3 (adi3d_numba_coeff.py:70)
+    a.Ccell = rho * cp * V;
+    for (int f = 0; f < 6; ++f) {
+        a.h_kind[f] = h_kind ? h_kind[f] : 0;
+        a.h_scalar[f] = h_scalar ? h_scalar[f] : 0.0;
+        a.h_field[f] = d_h_field ? d_h_field[f] : nullptr;
+        a.q_kind[f] = q_kind ? q_kind[f] : 0;
+        a.q_scalar[f] = q_scalar ? q_scalar[f] : 0.0;
+        a.q_field[f] = d_q_field ? d_q_field[f] : nullptr;
+        if ((a.h_kind[f] == 2 && !a.h_field[f]) || (a.q_kind[f] == 2 && !a.q_field[f]) ||
+            a.h_kind[f] < 0 || a.h_kind[f] > 2 || a.q_kind[f] < 0 || a.q_kind[f] > 2) {
+            set_error("adi_cart_build_packs: bad kind / missing field");
+            return ADI_EINVAL;
+        }
+    }
+    a.coeff[0] = d_coeff_x; a.coeff[1] = d_coeff_y; a.coeff[2] = d_coeff_z;
+    a.qout[0] = d_q_x; a.qout[1] = d_q_y; a.qout[2] = d_q_z;
+    const size_t n = (size_t)a.nx * a.ny * a.nz;
+    if (!n) return ADI_OK;
+    const int threads = 256;
+    const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, 148 * 64);
+    k_build_packs<<<blocks, threads, 0, (cudaStream_t)stream>>>(a);
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
+    return ADI_OK;
+}
+
+int adi_cart_exposed_mask(adi_ctx *ctx, int face, uint8_t *d_out, void *stream)
+{
+    int rc = check_cart(ctx, "adi_cart_exposed_mask");
+    if (rc) return rc;
+    if (face < 0 || face > 5) {
+        set_error("bad face");  // ValueError("bad face") adi3d_gpu_coeff.py:47
+        return ADI_EINVAL;
+    }
+    if (!ctx->d_mask || !d_out) {
+        set_error("adi_cart_exposed_mask: no mask bound / no output");
+        return ADI_ESTATE;
+    }
+    const size_t n = (size_t)ctx->nx * ctx->ny * ctx->nz;
+    if (!n) return ADI_OK;
+    const int threads = 256;
+    const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, 148 * 64);
+    k_exposed_mask<<<blocks, threads, 0, (cudaStream_t)stream>>>(ctx->d_mask, d_out, face, ctx->nx,
+                                                                ctx->ny, ctx->nz);
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
+    return ADI_OK;
+}
+
+}  // extern "C"

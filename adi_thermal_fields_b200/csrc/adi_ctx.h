@@ -1,0 +1,69 @@
+// adi_ctx.h -- the opaque context behind include/adi_b200.h (host side).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/adi_b200.h"
+
+namespace adi {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define ADI_CUDA(call)                                            \
+    do {                                                          \
+        cudaError_t _e = (call);                                  \
+        if (_e != cudaSuccess) return adi::cuda_fail(_e, #call);  \
+    } while (0)
+
+struct Pack {
+    const double *coeff = nullptr;
+    const uint8_t *dirm = nullptr;
+    const double *dirv = nullptr;
+    const double *q = nullptr;
+};
+
+struct CylTables;  // adi_cyl.cu
+
+// profile helpers (adi_api.cu): record event #slot (0..3) of the current step
+int prof_mark(adi_ctx *ctx, int slot, cudaStream_t st);
+
+}  // namespace adi
+
+struct adi_ctx {
+    int device = 0;
+    long launches = 0;
+    // options (adi_set_option)
+    long opt_kt = 0, opt_lt = 0, opt_m = 0, opt_sync_check = 0, opt_profile = 0;
+    // per-sweep timing (adi_profile_*): 4 events per step, read lazily
+    std::vector<cudaEvent_t> prof_ev;
+    long prof_steps = 0;
+
+    // ---- Cartesian ----
+    bool cart_bound = false;
+    int nx = 0, ny = 0, nz = 0;
+    double dx = 0.0;
+    const uint8_t *d_mask = nullptr;
+    adi::Pack pack[3];
+    bool scalar_robin = false;
+    double face_coeff[6] = {0, 0, 0, 0, 0, 0};
+    uint8_t *code[3] = {nullptr, nullptr, nullptr};  // code[a] may alias code[0]
+    uint8_t *code_buf[3] = {nullptr, nullptr, nullptr};
+    size_t code_cells = 0;
+    bool code_dirty = true;
+    // host-array convenience path
+    double *stage[2] = {nullptr, nullptr};
+    size_t stage_cells = 0;
+
+    // ---- cylindrical ----
+    bool cyl_bound = false;
+    int nr = 0, nphi = 0, cnz = 0, nz_pitch = 0;
+    double dr = 0.0, dphi = 0.0, dz = 0.0;
+    adi::CylTables *cyl = nullptr;
+    uint8_t *stage_mask = nullptr;
+    double *stage_src = nullptr;
+    size_t stage_aux_cells = 0;
+};

@@ -1,0 +1,157 @@
+// host_emulation.cpp -- runs the per-thread code of adi_core.h (the same source the
+// sm_100a kernels are compiled from) on the CPU, one "thread" after another with the
+// shared-memory exchange replaced by plain arrays.  Built only by tests/ (g++), so that
+// the partitioned solve can be checked against the oracle without a GPU.  Not shipped in
+// libadi_b200.so and never used by the product path.
+#include <stdint.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "adi_core.h"
+
+using namespace adi;
+
+namespace {
+
+constexpr int M = 16;
+
+template <int CMODE, bool EXTRA>
+void sweep_line(double *T, const uint8_t *code, const double *coeff, const double *q,
+                const double *dirv, size_t base, size_t stride, int n, unsigned LO, unsigned HI,
+                const SweepConst &k)
+{
+    const int P = (n + M - 1) / M;
+    std::vector<Chunk<M>> ch(P);
+    std::vector<First> fi(P);
+    std::vector<Red> red(P), nxt(P);
+    for (int p = 0; p < P; ++p) {
+        double Q[M], DV[M];
+        for (int e = 0; e < M; ++e) {
+            const int t = p * M + e;
+            const bool ok = t < n;
+            const size_t idx = base + (size_t)t * stride;
+            ch[p].code[e] = ok ? code[idx] : 0u;
+            ch[p].T[e] = ok ? T[idx] : 0.0;
+            ch[p].Cc[e] = (CMODE == 2 && ok) ? coeff[idx] : 0.0;
+            Q[e] = (q && ok) ? q[idx] : 0.0;
+            DV[e] = (dirv && ok && (ch[p].code[e] & CB_DIR)) ? dirv[idx] : 0.0;
+        }
+        fi[p] = chunk_forward<M, CMODE, EXTRA>(ch[p], Q, DV, LO, HI, k);
+    }
+    for (int p = 0; p < P; ++p) {
+        First nx;
+        nx.Y = nx.V = nx.W = 0.0;
+        if (p + 1 < P) nx = fi[p + 1];
+        red[p] = chunk_reduced_row(ch[p], nx);
+    }
+    for (int s = 1; s < P; s <<= 1) {
+        for (int p = 0; p < P; ++p) {
+            Red lo, hi;
+            lo.A = lo.C = lo.D = 0.0;
+            hi.A = hi.C = hi.D = 0.0;
+            if (p - s >= 0) lo = red[p - s];
+            if (p + s < P) hi = red[p + s];
+            nxt[p] = pcr_step(red[p], lo, hi);
+        }
+        red.swap(nxt);
+    }
+    for (int p = 0; p < P; ++p) {
+        chunk_backward<M>(ch[p], p > 0 ? red[p - 1].D : 0.0, red[p].D);
+        for (int e = 0; e < M; ++e) {
+            const int t = p * M + e;
+            if (t < n) T[base + (size_t)t * stride] = ch[p].T[e];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// code as built by k_build_code (adi_cart.cuh)
+void emu_build_code(const uint8_t *mask, const uint8_t *dirm, uint8_t *code, int nx, int ny, int nz)
+{
+    const size_t snx = (size_t)ny * nz;
+    for (int i = 0; i < nx; ++i)
+        for (int j = 0; j < ny; ++j)
+            for (int k = 0; k < nz; ++k) {
+                const size_t idx = ((size_t)i * ny + j) * nz + k;
+                unsigned c = 0;
+                if (mask[idx]) {
+                    c = CB_SELF;
+                    if (dirm && dirm[idx]) c |= CB_DIR;
+                }
+                if (i > 0 && mask[idx - snx]) c |= CB_XM;
+                if (i + 1 < nx && mask[idx + snx]) c |= CB_XP;
+                if (j > 0 && mask[idx - nz]) c |= CB_YM;
+                if (j + 1 < ny && mask[idx + nz]) c |= CB_YP;
+                if (k > 0 && mask[idx - 1]) c |= CB_ZM;
+                if (k + 1 < nz && mask[idx + 1]) c |= CB_ZP;
+                code[idx] = (uint8_t)c;
+            }
+}
+
+// One full step with the operand conventions of adi_cart_step (adi_b200.h).
+// coeff[a]/q[a]/dirm[a]/dirv[a] may be NULL; face_coeff != NULL selects the scalar Robin mode.
+int emu_cart_step(const double *Tin, double *Tout, const uint8_t *mask, int nx, int ny, int nz,
+                  double dx, double dt, double theta, double kappa, double Tinf,
+                  const double *const coeff[3], const uint8_t *const dirm[3],
+                  const double *const dirv[3], const double *const q[3], const double *face_coeff)
+{
+    const size_t n = (size_t)nx * ny * nz;
+    std::vector<uint8_t> code(n ? n : 1);
+    SweepConst k;
+    const double gam = kappa * dt / (dx * dx);
+    k.g = theta * gam;
+    k.dt = dt;
+    k.Tinf = Tinf;
+    k.beta = dt * kappa * (1.0 - theta);
+    k.invdx2 = 1.0 / (dx * dx);
+    const size_t snx = (size_t)ny * nz;
+    // explicit stage fused in front of the x sweep
+    emu_build_code(mask, dirm[0], code.data(), nx, ny, nz);
+    for (size_t idx = 0; idx < n; ++idx) {
+        const unsigned c = code[idx];
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        if (c & CB_SELF) {
+            if (c & CB_XM) v[0] = Tin[idx - snx];
+            if (c & CB_XP) v[1] = Tin[idx + snx];
+            if (c & CB_YM) v[2] = Tin[idx - nz];
+            if (c & CB_YP) v[3] = Tin[idx + nz];
+            if (c & CB_ZM) v[4] = Tin[idx - 1];
+            if (c & CB_ZP) v[5] = Tin[idx + 1];
+        }
+        Tout[idx] = (k.beta != 0.0) ? explicit_r0(c, Tin[idx], v[0], v[1], v[2], v[3], v[4], v[5], k)
+                                    : Tin[idx];
+    }
+    for (int axis = 0; axis < 3; ++axis) {
+        if (axis > 0) emu_build_code(mask, dirm[axis], code.data(), nx, ny, nz);
+        k.h_lo = face_coeff ? face_coeff[2 * axis] : 0.0;
+        k.h_hi = face_coeff ? face_coeff[2 * axis + 1] : 0.0;
+        const int len = axis == 0 ? nx : (axis == 1 ? ny : nz);
+        const size_t stride = axis == 0 ? snx : (axis == 1 ? (size_t)nz : 1);
+        const unsigned LO = axis == 0 ? CB_XM : (axis == 1 ? CB_YM : CB_ZM);
+        const unsigned HI = axis == 0 ? CB_XP : (axis == 1 ? CB_YP : CB_ZP);
+        const int n1 = axis == 0 ? ny : nx, n2 = axis == 2 ? ny : nz;
+        const bool dense = coeff[axis] != nullptr;
+        const bool extra = q[axis] != nullptr || dirm[axis] != nullptr;
+        for (int u = 0; u < n1; ++u)
+            for (int v = 0; v < n2; ++v) {
+                size_t base;
+                if (axis == 0) base = (size_t)u * nz + v;
+                else if (axis == 1) base = (size_t)u * snx + v;
+                else base = ((size_t)u * ny + v) * nz;
+                if (dense) {
+                    if (extra) sweep_line<2, true>(Tout, code.data(), coeff[axis], q[axis], dirv[axis], base, stride, len, LO, HI, k);
+                    else sweep_line<2, false>(Tout, code.data(), coeff[axis], nullptr, nullptr, base, stride, len, LO, HI, k);
+                } else {
+                    if (extra) sweep_line<1, true>(Tout, code.data(), nullptr, q[axis], dirv[axis], base, stride, len, LO, HI, k);
+                    else sweep_line<1, false>(Tout, code.data(), nullptr, nullptr, nullptr, base, stride, len, LO, HI, k);
+                }
+            }
+    }
+    return 0;
+}
+
+}  // extern "C"

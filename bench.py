@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+# -*- coding: utf-8 -*-
+"""bench.py -- ADI cell-steps/s (fp64) of the B200 engine on BASELINE.json's workload.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+N=1 workload: BASELINE.json configs[1], `single_track_on_plate` at 512^3 -- Cartesian plate
++ track mask, Robin on six faces with per-face variable h (dense coefficient field per axis:
+75 algorithmic bytes per cell-step), theta=0.5, dt=0.02 s.
+A "step" is one full ADI time step (explicit stage + x, y, z implicit sweeps) of the whole grid.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs in HBM,
+CUDA events); `e2e` is the same metric through the host-array C-ABI call
+(adi_cart_step_host: H2D + step + D2H inside the timed region).  `roofline` is for the
+slowest of the three sweep kernels, timed live with CUDA events recorded inside the engine on
+the launching stream.  `cpu_baseline` is the oracle (C restatement of the reference's Numba
+path, oracle/adi_oracle.c) timed on this box's host cores on a bounded sample; the same run
+also checks GPU-vs-oracle parity on that sample.
+
+--impl reference times the CPU restatement alone (the reference is pure Python + Numba and
+does not travel to the GPU box; the oracle is bit-identical to it on the golden vectors).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ADI cell-steps/sec (fp64)"
+UNIT = "cell-steps/s"
+RHO, CP, K = 7800.0, 500.0, 25.0
+DX, DT, THETA, TINF = 1.0e-3, 0.02, 0.5, 20.0
+FACES = ("x-", "x+", "y-", "y+", "z-", "z+")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------
+# workload: single_track_on_plate (single_track_on_plate.py:113-114,159)
+# ------------------------------------------------------------------------------------------
+def plate_track_mask_np(n, ny=None):
+    ny = ny or n
+    m = np.zeros((n, ny, n), dtype=bool)
+    nzp = n - max(1, n // 64)
+    m[:, :, :nzp] = True
+    m[: max(1, n // 32), : ny // 2, nzp:] = True
+    return m
+
+
+def host_inputs(n, ny, seed=0):
+    """Seeded host inputs (sample sub-box for the CPU legs and the parity check)."""
+    rng = np.random.default_rng(seed)
+    mask = plate_track_mask_np(n, ny)
+    T0 = np.full(mask.shape, TINF)
+    T0[mask] = 20.0 + 1380.0 * rng.random(int(mask.sum()))
+    rng2 = np.random.default_rng(1234)
+    h = {f: 10.0 * (0.3 + rng2.random(mask.shape)) for f in FACES}
+    return mask, T0, h
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, smax, reasons, power = [], [], set(), []
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (oracle) -- the only place bench.py touches oracle/
+# ------------------------------------------------------------------------------------------
+def cpu_leg(n, ny_sample, threads, steps=1, check_against=None):
+    from oracle import cart
+    mask, T0, h = host_inputs(n, ny_sample)
+    cart.set_threads(threads)
+    grid = cart.Grid3D(n, ny_sample, n, DX, mask)
+    mat = cart.Material(RHO, CP, K)
+    prm = cart.Params(DT, THETA)
+    packs = cart.precompute_coeff_packs_unified(grid, mat, robin_h=h)
+    work = np.empty(3 * T0.size)
+    T = T0
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        T = cart.adi_step_numba_coeff(T, grid, mat, prm, packs, Tinf=TINF, work=work)
+        times.append(time.perf_counter() - t0)
+    return T, times, (mask, T0, h)
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference path, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import cart
+    n = args.size
+    threads = cart.max_threads()
+    # bounded sample: a y-slab of the workload (x and z lines keep their full length)
+    ny_s = min(n, args.ref_ny)
+    cells = n * ny_s * n
+    _, times, _ = cpu_leg(n, ny_s, threads, steps=args.warmup + args.steps)
+    tt = times[args.warmup:]
+    dt_step = sum(tt) / len(tt)
+    value = cells / dt_step
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args, 1) | {"sample": f"{n}x{ny_s}x{n} y-slab of the workload per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n}x{ny_s}x{n} y-slab, {args.steps} steps, OpenMP over lines "
+                                   f"(the reference itself is serial Numba)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, world):
+    n = args.size
+    return {"workload": f"single_track_on_plate {n}^3 (BASELINE configs[1]): plate+track mask, Robin x6, "
+                        f"per-face variable h (dense coeff per axis), theta={THETA}, dt={DT}",
+            "grid": [n, n, n], "cells": n ** 3, "bytes_per_cell_step": 75,
+            "l2": "fields (1.07 GB each at 512^3) exceed the 126 MB L2; no flush needed",
+            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (weak)"}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from adi_thermal_fields_b200 import _capi, adi3d_gpu_coeff as g, devarray as cp
+
+    n = args.size
+    dev = torch.device("cuda", local)
+    # ---- synthetic inputs, created on the device (outside any timed region) ----
+    mask = torch.zeros((n, n, n), dtype=torch.bool, device=dev)
+    nzp = n - max(1, n // 64)
+    mask[:, :, :nzp] = True
+    mask[: max(1, n // 32), : n // 2, nzp:] = True
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    T0 = torch.full((n, n, n), TINF, dtype=torch.float64, device=dev)
+    T0 = torch.where(mask, 20.0 + 1380.0 * torch.rand((n, n, n), dtype=torch.float64, device=dev, generator=gen), T0)
+    gen2 = torch.Generator(device=dev).manual_seed(1234)
+    grid = g.Grid3D.__new__(g.Grid3D)
+    grid.nx = grid.ny = grid.nz = n
+    grid.dx = DX
+    grid.mask = cp.ndarray(mask)
+    mat = g.Material(RHO, CP, K)
+    prm = g.Params(DT, THETA)
+    h = {}
+    for f in FACES:
+        h[f] = cp.ndarray(10.0 * (0.3 + torch.rand((n, n, n), dtype=torch.float64, device=dev, generator=gen2)))
+    packs = g.precompute_coeff_packs_unified(grid, mat, robin_h=h)
+    del h
+    torch.cuda.synchronize()
+
+    L = _capi.load()
+    eng = g._engine
+    eng.bind(grid); eng.set_mask(grid); eng.set_packs(packs)
+    ctx = eng.context()
+    kappa = K / (RHO * CP)
+    A = T0.clone()
+    B = torch.empty_like(A)
+    stream = torch.cuda.current_stream()
+
+    def step(src, dst):
+        _capi.check(L.adi_cart_step(ctx, src.data_ptr(), dst.data_ptr(), DT, THETA, kappa, TINF,
+                                    stream.cuda_stream), "adi_cart_step")
+
+    for _ in range(args.warmup):
+        step(A, B); A, B = B, A
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: K steps, device-resident ----
+    L.adi_set_option(ctx, b"profile", 1)
+    L.adi_profile_reset(ctx)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.adi_launch_count(ctx)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step(A, B); A, B = B, A
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = L.adi_launch_count(ctx) - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms3 = (C.c_double * 3)()
+    nst = C.c_long()
+    L.adi_profile_read(ctx, ms3, C.byref(nst))
+    L.adi_set_option(ctx, b"profile", 0)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    cells = n ** 3
+    value = world * cells * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host arrays through the C ABI (H2D + step + D2H per step) ----
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    hin = torch.empty((n, n, n), dtype=torch.float64, pin_memory=True)
+    hout = torch.empty((n, n, n), dtype=torch.float64, pin_memory=True)
+    hin.copy_(T0)
+    torch.cuda.synchronize()
+
+    def host_step():
+        _capi.check(L.adi_cart_step_host(ctx, hin.data_ptr(), hout.data_ptr(), 1, DT, THETA, kappa, TINF,
+                                         stream.cuda_stream), "adi_cart_step_host")
+
+    host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_step()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_value = world * cells * e2e_steps / t_e2e
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the slowest sweep kernel (live CUDA events inside the engine) ----
+    peak, peak_src = peaks()
+    per = [ms3[i] / max(1, nst.value) for i in range(3)]
+    names = ["k_sweep_strided<x,explicit fused>", "k_sweep_strided<y>", "k_sweep_z"]
+    dom = int(np.argmax(per))
+    bytes_per_launch = 25.0 * cells  # in 8 + out 8 + mask/code 1 + dense coeff 8
+    achieved = bytes_per_launch / (per[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "sweep_ms": {"x": per[0], "y": per[1], "z": per[2]},
+                "step_achieved_GBs": 75.0 * cells / (ms_per_step * 1e-3) / 1e9,
+                "step_frac": 75.0 * cells / (ms_per_step * 1e-3) / 1e9 / peak}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            roofline["traffic"] = json.load(open(tp)).get(names[dom].split("<")[0])
+        except Exception:
+            pass
+
+    # ---- CPU baseline + parity on a bounded sample (rank 0, N=1 only) ----
+    cpu = None
+    parity = None
+    if world == 1 and not args.no_cpu:
+        from oracle import cart
+        nth = cart.max_threads()
+        ny_s = min(n, args.cpu_ny)
+        Tref, times, (m_s, T0_s, h_s) = cpu_leg(n, ny_s, nth, steps=1)
+        v_all = n * ny_s * n / times[0]
+        ny_1 = max(8, ny_s // 8)
+        _, t1, _ = cpu_leg(n, ny_1, 1, steps=1)
+        v_one = n * ny_1 * n / t1[0]
+        cpu = {"value": v_all, "unit": UNIT, "cores": nth, "kind": "port",
+               "sample": f"one step of a {n}x{ny_s}x{n} y-slab of the workload, OpenMP over lines",
+               "value_1core": v_one,
+               "note": "the reference's Numba path is serial (1 core); value_1core is the like-for-like figure"}
+        # the same sample through the GPU engine
+        gs = g.Grid3D(n, ny_s, n, DX, m_s)
+        ps = g.precompute_coeff_packs_unified(gs, mat, robin_h=h_s)
+        out = g.adi_step_gpu_coeff(cp.asarray(T0_s), gs, mat, prm, ps, Tinf=TINF)
+        Tg = cp.asnumpy(out)
+        num = float(np.sqrt(np.sum((Tg[m_s] - Tref[m_s]) ** 2)))
+        den = float(np.sqrt(np.sum(Tref[m_s] ** 2)))
+        parity = {"rel_l2_vs_oracle": num / den, "void_bit_equal": bool(np.array_equal(Tg[~m_s], T0_s[~m_s])),
+                  "sample": f"{n}x{ny_s}x{n}", "tol": 1e-12}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * cells, "d2h_bytes_per_step": 8 * cells,
+                "steps": e2e_steps, "api": "adi_cart_step_host (pinned host arrays in/out)"},
+        "gpu_launches": int(launches), "parity": parity,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-ny", type=int, default=128, help="y extent of the CPU-baseline sample slab")
+    ap.add_argument("--ref-ny", type=int, default=64, help="y extent of the --impl reference sample slab")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,133 @@
+/*
+ * adi_b200.h -- C ABI of libadi_b200.so, the B200 (sm_100a) ADI heat-step engine.
+ *
+ * The reference (Matemusi/ADI_thermal_fields) has no FFI: its hot path is reached
+ * through Python module functions.  Each entry point below names the reference
+ * interface it stands behind (file:line relative to the reference tree); the
+ * Python glue in adi_thermal_fields_b200/ binds them with ctypes and re-exports
+ * the reference's own names.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ADI_E* code otherwise;
+ *     adi_last_error() returns a thread-local message for the last failure.
+ *   - `d_*` pointers are DEVICE pointers borrowed for the duration of the call
+ *     (or until replaced, for bound operands); `h_*` pointers are host pointers.
+ *   - arrays are C-order: Cartesian (nx,ny,nz) and cylindrical (nr,nphi,nz) have
+ *     z contiguous; fields are IEEE fp64, masks are 1 byte per cell (0 / non-0).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the default stream).
+ *     Calls are asynchronous on that stream unless stated otherwise.
+ *   - no CPU fallback exists anywhere behind this ABI.
+ */
+#ifndef ADI_B200_H
+#define ADI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADI_OK 0
+#define ADI_EINVAL (-1)   /* bad argument / shape / unknown kind (ValueError in the reference) */
+#define ADI_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+#define ADI_ESTATE (-3)   /* call order violated (e.g. step before bind) */
+#define ADI_ENOMEM (-4)
+
+typedef struct adi_ctx adi_ctx;
+
+/* ---- context / memory ------------------------------------------------------------- */
+/* One context per process and GPU (SURVEY 8b "Threading").  Owns scratch buffers. */
+int adi_ctx_create(int device, adi_ctx **out);
+int adi_ctx_destroy(adi_ctx *ctx);
+const char *adi_last_error(void);
+const char *adi_version(void);
+/* cp.cuda.Stream.null.synchronize() (quick_compare_neumann_robin_backend.py:184) */
+int adi_sync(adi_ctx *ctx, void *stream);
+/* Plain device memory for hosts without their own allocator (cp.full / cp.asarray / cp.asnumpy,
+ * quick_compare_neumann_robin_backend.py:140-141,163-164). */
+int adi_malloc(adi_ctx *ctx, size_t bytes, void **d_ptr);
+int adi_free(adi_ctx *ctx, void *d_ptr);
+int adi_h2d(adi_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream);
+int adi_d2h(adi_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream);
+
+/* ---- Cartesian path --------------------------------------------------------------- */
+/* Grid3D(nx,ny,nz,dx,mask)  adi3d_gpu_coeff.py:6-12 / adi3d_numba_coeff.py:14-19 */
+int adi_cart_bind(adi_ctx *ctx, int nx, int ny, int nz, double dx);
+/* grid.mask (re)binding or in-place mutation (quick_compare_layer_birth_robin_v3.py:277,
+ * waam_from_stl_v7_mm.py:494-495).  Borrowed device pointer; must stay valid until replaced.
+ * Marks the per-cell neighbour code dirty (rebuilt lazily by the next step). */
+int adi_cart_set_mask(adi_ctx *ctx, const uint8_t *d_mask);
+/* AxisCoeffPack(coeff, dir_mask, dir_val, qflux)  adi3d_gpu_coeff.py:22-29, for axis 0/1/2.
+ * NULL d_coeff / d_qflux mean all-zero; NULL d_dir_mask means no Dirichlet cell
+ * (d_dir_val is then ignored).  Borrowed device pointers. */
+int adi_cart_set_pack(adi_ctx *ctx, int axis, const double *d_coeff, const uint8_t *d_dir_mask,
+                      const double *d_dir_val, const double *d_qflux);
+/* Scalar Robin on the six faces ('x-','x+','y-','y+','z-','z+'): the coefficient
+ * h*A/Ccell of adi3d_numba_coeff.py:93-99 is derived from the mask inside the sweep instead
+ * of being read from a dense array.  face_coeff[f] = h_f*dx^2/(rho*cp*dx^3) as the reference
+ * evaluates it.  Replaces the `coeff` operand of all three packs until set_pack is called. */
+int adi_cart_set_robin_scalar(adi_ctx *ctx, const double face_coeff[6]);
+/* adi_step_gpu_coeff(Tn, grid, mat, params, packs, Tinf)  adi3d_gpu_coeff.py:213-230
+ * (same mathematics as adi_step_numba_coeff, adi3d_numba_coeff.py:290-302).
+ * d_Tin is not modified; d_Tout must not alias it.  kappa = k/(rho*cp). */
+int adi_cart_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, double theta,
+                  double kappa, double Tinf, void *stream);
+/* The same step for callers holding HOST arrays (the CPU module's calling convention,
+ * adi3d_numba_coeff.py:290): copies h_Tin to the device, steps `nsteps` times, copies the
+ * result back and synchronises.  Used for end-to-end timing. */
+int adi_cart_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int nsteps, double dt,
+                       double theta, double kappa, double Tinf, void *stream);
+/* precompute_coeff_packs_unified  adi3d_gpu_coeff.py:50-110 on the device.
+ * For face f: h_kind[f] 0 = no Robin, 1 = scalar h_scalar[f], 2 = device field d_h_field[f];
+ * likewise q_* for Neumann (q'' > 0 heats the solid).  Writes the six dense outputs
+ * (any of which may be NULL to skip it).  Uses the mask bound with adi_cart_set_mask. */
+int adi_cart_build_packs(adi_ctx *ctx, double rho, double cp, const int h_kind[6],
+                         const double h_scalar[6], const double *const d_h_field[6],
+                         const int q_kind[6], const double q_scalar[6],
+                         const double *const d_q_field[6], double *d_coeff_x, double *d_coeff_y,
+                         double *d_coeff_z, double *d_q_x, double *d_q_y, double *d_q_z,
+                         void *stream);
+/* exposed_mask(mask, face)  adi3d_gpu_coeff.py:31-48; face index 0..5 as above. */
+int adi_cart_exposed_mask(adi_ctx *ctx, int face, uint8_t *d_out, void *stream);
+/* Tuning / introspection: kernel variant selection (0 = default) and launch counter. */
+int adi_set_option(adi_ctx *ctx, const char *name, long value);
+long adi_launch_count(adi_ctx *ctx);
+/* Per-kernel device timing (the `[time]` prints of quick_compare_neumann_robin_backend.py:
+ * 173-186 are the reference's only profiling hook).  After adi_set_option(ctx,"profile",1)
+ * every adi_cart_step / adi_cyl_step records CUDA events around its three sweeps on the
+ * caller's stream; adi_profile_read synchronises, returns the accumulated milliseconds per
+ * sweep (x|r, y|phi, z) and the number of steps since the last adi_profile_reset. */
+int adi_profile_reset(adi_ctx *ctx);
+int adi_profile_read(adi_ctx *ctx, double ms[3], long *nsteps);
+
+/* ---- cylindrical path --------------------------------------------------------------- */
+/* GridCyl(nr,nphi,nz,dr,dphi,dz,R)  adi3d_cyl_phi_v3.py:33-43.  nz_pitch >= nz is the
+ * allocated z extent of the fields (layer births grow nz without reallocating,
+ * quick_compare_layer_birth_robin_cyl_v3.py:195-204). */
+int adi_cyl_bind(adi_ctx *ctx, int nr, int nphi, int nz, int nz_pitch, double dr, double dphi,
+                 double dz);
+#define ADI_Z_NEUMANN0 0
+#define ADI_Z_DIRICHLET 1
+#define ADI_Z_ROBIN 2
+typedef struct adi_cyl_params {
+    double dt;                /* Params.dt            adi3d_cyl_phi_v3.py:52-54 */
+    double rho, cp, k;        /* Material             :45-50 */
+    double h_r, Tinf_r;       /* RobinR               :56-58 */
+    int kind_bot, kind_top;   /* ZBC kinds            :60-68 */
+    double h_bot, h_top, Tinf_bot, Tinf_top, T_bot, T_top;
+    double T_void, T_inner;   /* adi_step_masked clamps, quick_spiral_deposition_gif_v5.py:51-68 */
+} adi_cyl_params;
+/* adi_step(Tn, grid, mat, prm, robin_r, zbc, S)  adi3d_cyl_phi_v3.py:332-350 (scheme "be"),
+ * and, when d_active != NULL, adi_step_masked  quick_spiral_deposition_gif_v5.py:31-70.
+ * d_S may be NULL (no source). */
+int adi_cyl_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_cyl_params *p,
+                 const uint8_t *d_active, const double *d_S, void *stream);
+int adi_cyl_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int nsteps,
+                      const adi_cyl_params *p, const uint8_t *h_active, const double *h_S,
+                      void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADI_B200_H */

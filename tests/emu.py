@@ -1,0 +1,64 @@
+# -*- coding: utf-8 -*-
+"""Builds and binds csrc/host_emulation.cpp (the kernel's per-thread code run on the CPU).
+Test-only helper."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "adi_thermal_fields_b200", "csrc")
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(ROOT, "tests", "_emu.so")
+        srcs = [os.path.join(CSRC, f) for f in ("host_emulation.cpp", "adi_core.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                            "-o", so, srcs[0]], check=True)
+        _LIB = C.CDLL(so)
+    return _LIB
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty)) if a is not None else C.cast(None, C.POINTER(ty))
+
+
+def cart_step(T, mask, dx, dt, theta, kappa, Tinf, coeff=(None,) * 3, dirm=(None,) * 3,
+              dirv=(None,) * 3, q=(None,) * 3, face_coeff=None):
+    L = lib()
+    T = np.ascontiguousarray(T, dtype=np.float64)
+    nx, ny, nz = T.shape
+    out = np.empty_like(T)
+    m8 = np.ascontiguousarray(mask, dtype=np.bool_).view(np.uint8)
+    dp, bp = C.POINTER(C.c_double), C.POINTER(C.c_uint8)
+    keep = []
+
+    def arr3(xs, ty, dtype):
+        ps = []
+        for x in xs:
+            if x is None:
+                ps.append(C.cast(None, C.POINTER(ty)))
+            else:
+                a = np.ascontiguousarray(x, dtype=dtype)
+                if dtype == np.bool_:
+                    a = a.view(np.uint8)
+                keep.append(a)
+                ps.append(_ptr(a, ty))
+        return (C.POINTER(ty) * 3)(*ps)
+
+    fc = None
+    if face_coeff is not None:
+        fc = np.ascontiguousarray(face_coeff, dtype=np.float64)
+    L.emu_cart_step.argtypes = [dp, dp, bp, C.c_int, C.c_int, C.c_int] + [C.c_double] * 5 + \
+        [C.POINTER(dp), C.POINTER(bp), C.POINTER(dp), C.POINTER(dp), dp]
+    rc = L.emu_cart_step(_ptr(T, C.c_double), _ptr(out, C.c_double), _ptr(m8, C.c_uint8), nx, ny, nz,
+                         dx, dt, theta, kappa, Tinf, arr3(coeff, C.c_double, np.float64),
+                         arr3(dirm, C.c_uint8, np.bool_), arr3(dirv, C.c_double, np.float64),
+                         arr3(q, C.c_double, np.float64), _ptr(fc, C.c_double))
+    assert rc == 0
+    return out

@@ -1,0 +1,256 @@
+# -*- coding: utf-8 -*-
+"""GPU parity of the Cartesian ADI step (sm_100a kernels through the C ABI / the
+reference's adi3d_gpu_coeff interface) against golden vectors of the unmodified reference.
+
+Bar (north_star): relative L2 <= 1e-12 per step on active cells; cells outside the mask
+bit-identical to the input (adi3d_gpu_coeff.py:229).  Nothing here reads /root/reference."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def g():
+    from adi_thermal_fields_b200 import adi3d_gpu_coeff as mod
+    return mod
+
+
+@pytest.fixture(scope="module")
+def cp():
+    from adi_thermal_fields_b200 import devarray
+    return devarray
+
+
+def _run(g, cp, c, host_bcs=True):
+    nx, ny, nz = c["shape"]
+    grid = g.Grid3D(nx, ny, nz, c["dx"], c["mask"])
+    mat = g.Material(c["rho"], c["cp"], c["k"])
+    prm = g.Params(c["dt"], c["theta"])
+    packs = g.precompute_coeff_packs_unified(grid, mat, robin_Tinf=c["Tinf"], **c["bcs"])
+    T = cp.asarray(c["T0"])
+    trace = []
+    for _ in range(c["nsteps"]):
+        T = g.adi_step_gpu_coeff(T, grid, mat, prm, packs, Tinf=c["Tinf"])
+        trace.append(cp.asnumpy(T[nx // 2, ny // 2, :]))
+    return cp.asnumpy(T), np.array(trace), packs
+
+
+@pytest.mark.parametrize("name", sorted(cases.CART_CASES))
+def test_step_matches_reference(name, g, cp, golden_dir):
+    c = cases.build_cart_case(name)
+    gold = np.load(os.path.join(golden_dir, f"cart_{name}.npz"))
+    T, trace, _ = _run(g, cp, c)
+    m = c["mask"]
+    assert cases.rel_l2(T, gold["T_out"], m) <= TOL
+    assert np.array_equal(T[~m], c["T0"][~m], equal_nan=True)
+    if m[c["shape"][0] // 2, c["shape"][1] // 2].any():
+        assert cases.rel_l2(trace, gold["trace"], np.isfinite(gold["trace"])) <= TOL
+
+
+@pytest.mark.parametrize("name", ["holes_combined", "track_mixed", "random_neumann_fields"])
+def test_device_pack_builder_bit_exact(name, g, cp, golden_dir):
+    """precompute_coeff_packs_unified on the device (kernel k_build_packs) vs the reference."""
+    c = cases.build_cart_case(name)
+    gold = np.load(os.path.join(golden_dir, f"packs_{name}.npz"))
+    _, _, packs = _run(g, cp, c)
+    for a, ax in enumerate("xyz"):
+        assert np.array_equal(cp.asnumpy(packs[a].coeff), gold[f"coeff_{ax}"])
+        assert np.array_equal(cp.asnumpy(packs[a].qflux), gold[f"q_{ax}"])
+    assert np.array_equal(cp.asnumpy(packs[0].dir_mask), gold["dir_mask"])
+    assert np.array_equal(cp.asnumpy(packs[0].dir_val), gold["dir_val"])
+
+
+@pytest.mark.parametrize("face", ["x-", "x+", "y-", "y+", "z-", "z+"])
+def test_exposed_mask(face, g, cp):
+    from oracle import cart
+    m = cases.make_mask("thin", cases.SHAPE_A, 3) | cases.make_mask("cyl_holes", cases.SHAPE_A, 5)
+    assert np.array_equal(cp.asnumpy(g.exposed_mask(m, face)), cart.exposed_mask(m, face))
+
+
+def test_exposed_mask_bad_face(g):
+    with pytest.raises(ValueError):
+        g.exposed_mask(np.ones((3, 3, 3), bool), "w+")
+
+
+@pytest.mark.parametrize("name", ["full_robin6", "cyl_robin6", "track_robin6", "B_full_robin6"])
+def test_scalar_robin_lazy_packs(name, g, cp, golden_dir):
+    """Scalar Robin packs stay symbolic (no dense coeff array) and still match; reading
+    pack.coeff afterwards materialises the reference's dense array."""
+    from oracle import cart
+    c = cases.build_cart_case(name)
+    gold = np.load(os.path.join(golden_dir, f"cart_{name}.npz"))
+    T, _, packs = _run(g, cp, c)
+    assert all(p._coeff is None for p in packs)
+    assert cases.rel_l2(T, gold["T_out"], c["mask"]) <= TOL
+    nx, ny, nz = c["shape"]
+    ref = cart.precompute_coeff_packs_unified(cart.Grid3D(nx, ny, nz, c["dx"], c["mask"]),
+                                              cart.Material(c["rho"], c["cp"], c["k"]), **c["bcs"])
+    for a in range(3):
+        assert np.array_equal(cp.asnumpy(packs[a].coeff), ref[a].coeff)
+        assert not cp.asnumpy(packs[a].qflux).any()
+
+
+def test_user_built_packs_and_oracle(g, cp):
+    """AxisCoeffPack objects built by the caller from host arrays (different Dirichlet masks
+    per axis), checked against the oracle on the same inputs."""
+    from oracle import cart
+    shape = (21, 18, 35)
+    mask = cases.make_mask("random", shape, 9) | cases.make_mask("cyl", shape, 9)
+    T0 = 20.0 + 500.0 * cases.splitmix_uniform(901, shape)
+    kappa = cases.K / (cases.RHO * cases.CP)
+    dt = 1.7 * cases.DX ** 2 / kappa
+    hp, dp_ = [], []
+    for a in range(3):
+        coeff = 2.0 * cases.splitmix_uniform(910 + a, shape)
+        dm = cases.splitmix_uniform(920 + a, shape) < 0.05
+        dv = 100.0 * cases.splitmix_uniform(930 + a, shape)
+        q = 50.0 * (cases.splitmix_uniform(940 + a, shape) - 0.5)
+        hp.append(cart.AxisCoeffPack(coeff, dm, dv, q))
+        dp_.append(g.AxisCoeffPack(coeff, dm, dv, q))
+    nx, ny, nz = shape
+    ref = cart.adi_step_numba_coeff(T0, cart.Grid3D(nx, ny, nz, cases.DX, mask),
+                                    cart.Material(cases.RHO, cases.CP, cases.K), cart.Params(dt, 0.5),
+                                    hp, Tinf=15.0)
+    out = g.adi_step_gpu_coeff(cp.asarray(T0), g.Grid3D(nx, ny, nz, cases.DX, mask),
+                               g.Material(cases.RHO, cases.CP, cases.K), g.Params(dt, 0.5), dp_, Tinf=15.0)
+    assert cases.rel_l2(cp.asnumpy(out), ref, mask) <= TOL
+
+
+def test_host_array_entry_point(g, golden_dir):
+    """adi_cart_step_host: NumPy in, NumPy out (H2D + steps + D2H inside the C ABI)."""
+    c = cases.build_cart_case("cyl_backend_10steps")
+    gold = np.load(os.path.join(golden_dir, "cart_cyl_backend_10steps.npz"))
+    nx, ny, nz = c["shape"]
+    grid = g.Grid3D(nx, ny, nz, c["dx"], c["mask"])
+    mat = g.Material(c["rho"], c["cp"], c["k"])
+    packs = g.precompute_coeff_packs_unified(grid, mat, **c["bcs"])
+    T = g.adi_step_host(c["T0"], grid, mat, g.Params(c["dt"], c["theta"]), packs, Tinf=c["Tinf"],
+                        nsteps=c["nsteps"])
+    assert isinstance(T, np.ndarray)
+    assert cases.rel_l2(T, gold["T_out"], c["mask"]) <= TOL
+
+
+def test_input_not_modified_and_new_array(g, cp):
+    c = cases.build_cart_case("cyl_robin6")
+    nx, ny, nz = c["shape"]
+    grid = g.Grid3D(nx, ny, nz, c["dx"], c["mask"])
+    mat = g.Material(c["rho"], c["cp"], c["k"])
+    packs = g.precompute_coeff_packs_unified(grid, mat, **c["bcs"])
+    T = cp.asarray(c["T0"])
+    out = g.adi_step_gpu_coeff(T, grid, mat, g.Params(c["dt"], 0.5), packs, Tinf=20.0)
+    assert out is not T and out._t.data_ptr() != T._t.data_ptr()
+    assert np.array_equal(cp.asnumpy(T), c["T0"])
+
+
+def test_mask_mutation_and_rebinding_are_seen(g, cp):
+    """Layer birth: grid.mask mutated in place on the device (quick_compare_layer_birth_robin_v3.py:
+    272-277) and rebound to a host array (waam_from_stl_v7_mm.py:494-495)."""
+    from oracle import cart
+    shape = (16, 17, 40)
+    nx, ny, nz = shape
+    mask = np.zeros(shape, bool)
+    mask[:, :, :20] = cases.build_cyl_mask(nx, ny, 20, cases.DX, 0.4 * nx * cases.DX)
+    T0 = np.full(shape, 20.0)
+    kappa = cases.K / (cases.RHO * cases.CP)
+    dt = 2.0 * cases.DX ** 2 / kappa
+    bcs = dict(robin_h={f: 30.0 for f in cart.FACES})
+    mat_h = cart.Material(cases.RHO, cases.CP, cases.K)
+    grid_d = g.Grid3D(nx, ny, nz, cases.DX, mask)
+    mat_d = g.Material(cases.RHO, cases.CP, cases.K)
+    Td = cp.asarray(T0)
+    Th = T0.copy()
+    mh = mask.copy()
+    for birth in range(3):
+        k0, k1 = 20 + 5 * birth, 25 + 5 * birth
+        born = np.zeros(shape, bool)
+        born[:, :, k0:k1] = mask[:, :, :1]
+        # host side (oracle)
+        Th[born] = 1000.0
+        mh |= born
+        grid_h = cart.Grid3D(nx, ny, nz, cases.DX, mh)
+        ph = cart.precompute_coeff_packs_unified(grid_h, mat_h, **bcs)
+        # device side, alternating the two mutation styles
+        if birth % 2 == 0:
+            bd = cp.asarray(born)
+            Td[bd] = 1000.0
+            grid_d.mask[bd] = True
+        else:
+            idx = np.where(born)
+            Td[idx] = 1000.0
+            grid_d.mask = mh.copy()
+        pd = g.precompute_coeff_packs_unified(grid_d, mat_d, **bcs)
+        for _ in range(2):
+            Th = cart.adi_step_numba_coeff(Th, grid_h, mat_h, cart.Params(dt, 0.5), ph, Tinf=20.0)
+            Td = g.adi_step_gpu_coeff(Td, grid_d, mat_d, g.Params(dt, 0.5), pd, Tinf=20.0)
+        assert cases.rel_l2(cp.asnumpy(Td), Th, mh) <= TOL
+
+
+def test_shape_errors(g, cp):
+    with pytest.raises(AssertionError):
+        g.Grid3D(4, 4, 4, 1e-3, np.ones((4, 4, 5), bool))
+    grid = g.Grid3D(4, 4, 4, 1e-3, np.ones((4, 4, 4), bool))
+    mat = g.Material(1.0, 1.0, 1.0)
+    packs = g.precompute_coeff_packs_unified(grid, mat)
+    with pytest.raises(ValueError):
+        g.adi_step_gpu_coeff(cp.zeros((4, 4, 5)), grid, mat, g.Params(1e-3), packs)
+    with pytest.raises(TypeError):
+        g.adi_step_gpu_coeff(cp.zeros((4, 4, 4), dtype=cp.float32), grid, mat, g.Params(1e-3), packs)
+
+
+# ---- size-independent properties at the benchmark's full size (512^3) -------------------
+@pytest.fixture(scope="module")
+def big(g, cp):
+    import torch
+    n = 512
+    mask = torch.zeros((n, n, n), dtype=torch.bool, device="cuda")
+    mask[:, :, :504] = True
+    mask[:16, :256, 504:] = True            # single_track_on_plate.py:113-114,159
+    grid = g.Grid3D.__new__(g.Grid3D)
+    grid.nx = grid.ny = grid.nz = n
+    grid.dx = 1e-3
+    grid.mask = cp.ndarray(mask)
+    mat = g.Material(7800.0, 500.0, 25.0)
+    return grid, mat
+
+
+def test_full_size_heat_conservation_and_void(g, cp, big):
+    """Insulated body (no Robin/Neumann/Dirichlet): every directional operator has zero column
+    sums, so the ADI step conserves the sum over active cells; void cells pass through."""
+    import torch
+    grid, mat = big
+    packs = g.precompute_coeff_packs_unified(grid, mat)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    T = torch.rand(grid.mask.shape, dtype=torch.float64, device="cuda", generator=gen) * 1380.0 + 20.0
+    out = g.adi_step_gpu_coeff(cp.ndarray(T), grid, mat, g.Params(0.02, 0.5), packs, Tinf=20.0)._t
+    m = grid.mask._t
+    s0, s1 = T[m].sum().item(), out[m].sum().item()
+    assert abs(s1 - s0) <= 1e-12 * abs(s0)
+    assert torch.equal(out[~m], T[~m])
+
+
+def test_full_size_linearity_and_ambient_fixed_point(g, cp, big):
+    import torch
+    grid, mat = big
+    h = {f: 10.0 for f in ("x-", "x+", "y-", "y+", "z-", "z+")}
+    packs = g.precompute_coeff_packs_unified(grid, mat, robin_h=h)
+    prm = g.Params(0.02, 0.5)
+    m = grid.mask._t
+    # a field at the ambient temperature stays there
+    T = torch.full(m.shape, 20.0, dtype=torch.float64, device="cuda")
+    out = g.adi_step_gpu_coeff(cp.ndarray(T), grid, mat, prm, packs, Tinf=20.0)._t
+    assert (out[m] - 20.0).abs().max().item() <= 1e-11
+    # linear in T when Tinf = 0
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.rand(m.shape, dtype=torch.float64, device="cuda", generator=gen)
+    B = torch.rand(m.shape, dtype=torch.float64, device="cuda", generator=gen)
+    step = lambda X: g.adi_step_gpu_coeff(cp.ndarray(X), grid, mat, prm, packs, Tinf=0.0)._t
+    lhs = step(2.0 * A - 3.0 * B)
+    rhs = 2.0 * step(A) - 3.0 * step(B)
+    err = ((lhs - rhs)[m].norm() / rhs[m].norm()).item()
+    assert err <= 1e-13

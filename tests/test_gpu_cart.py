@@ -179,6 +179,8 @@ def test_mask_mutation_and_rebinding_are_seen(g, cp):
         if birth % 2 == 0:
             bd = cp.asarray(born)
             Td[bd] = 1000.0
+            if not isinstance(grid_d.mask, cp.ndarray):   # rebound to a host array last birth
+                grid_d.mask = cp.asarray(grid_d.mask)
             grid_d.mask[bd] = True
         else:
             idx = np.where(born)

@@ -354,5 +354,12 @@ def adi_step_host(Tn, grid, mat, params, packs, Tinf=0.0, nsteps=1):
     return out
 
 
+def set_option(name, value):
+    """Engine tuning knob (adi_set_option): 'm' chunk length (16|32), 'kt' / 'lt' lines per
+    block of the strided / z sweeps; 0 restores the default."""
+    _capi.check(_engine.lib().adi_set_option(_engine.context(), str(name).encode(), int(value)),
+                "adi_set_option")
+
+
 def launch_count():
     return int(_engine.lib().adi_launch_count(_engine.context()))

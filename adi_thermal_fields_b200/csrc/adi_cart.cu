@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 
+#define ADI_CART_MISC_KERNELS
 #include "adi_cart.cuh"
 #include "adi_ctx.h"
 
@@ -10,8 +11,6 @@ using namespace adi;
 
 namespace {
 
-constexpr int kM = 16;          // cells per thread-chunk
-constexpr int kMaxThreads = 512;
 
 int check_cart(adi_ctx *ctx, const char *who)
 {
@@ -59,68 +58,17 @@ int ensure_code(adi_ctx *ctx, cudaStream_t st)
     return ADI_OK;
 }
 
-template <typename K>
-int launch(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const SweepArgs &a, adi_ctx *ctx)
-{
-    if (smem > 48 * 1024)
-        ADI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, block, smem, st>>>(a);
-    ctx->launches++;
-    ADI_CUDA(cudaGetLastError());
-    return ADI_OK;
+}  // namespace
+
+// adi_sweep_x.cu / adi_sweep_y.cu / adi_sweep_z.cu (one translation unit per sweep so that the
+// template instantiations compile in parallel)
+namespace adi {
+int launch_sweep_x(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, bool expl, cudaStream_t st);
+int launch_sweep_y(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, cudaStream_t st);
+int launch_sweep_z(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, cudaStream_t st);
 }
 
-template <int AXIS>
-int launch_strided(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, bool expl, cudaStream_t st)
-{
-    const int n = AXIS == 0 ? a.nx : a.ny;
-    const int other = AXIS == 0 ? a.ny : a.nx;
-    const int P = (n + kM - 1) / kM;
-    int KT = 32;
-    while (KT > 4 && KT * P > 256) KT >>= 1;
-    if (ctx->opt_kt > 0) KT = (int)ctx->opt_kt;
-    if (KT * P > kMaxThreads || P > kMaxThreads) {
-        set_error("adi_cart_step: line too long for the register-resident sweep (n > 2048)");
-        return ADI_EINVAL;
-    }
-    dim3 block(KT, P), grid((a.nz + KT - 1) / KT, other);
-    const size_t smem = (size_t)6 * KT * P * sizeof(double);
-#define ADI_GO(CM, EX, XP) return launch(k_sweep_strided<AXIS, kM, CM, EX, XP>, grid, block, smem, st, a, ctx)
-    if (AXIS == 0 && expl) {
-        if (dense) { if (extra) ADI_GO(2, true, (AXIS == 0)); else ADI_GO(2, false, (AXIS == 0)); }
-        else       { if (extra) ADI_GO(1, true, (AXIS == 0)); else ADI_GO(1, false, (AXIS == 0)); }
-    } else {
-        if (dense) { if (extra) ADI_GO(2, true, false); else ADI_GO(2, false, false); }
-        else       { if (extra) ADI_GO(1, true, false); else ADI_GO(1, false, false); }
-    }
-#undef ADI_GO
-}
-
-int launch_z(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, cudaStream_t st)
-{
-    const int P = (a.nz + kM - 1) / kM;
-    if (P > kMaxThreads) {
-        set_error("adi_cart_step: z line too long for the register-resident sweep");
-        return ADI_EINVAL;
-    }
-    int LT = std::max(1, 256 / P);
-    if (ctx->opt_lt > 0) LT = (int)ctx->opt_lt;
-    LT = std::min(LT, kMaxThreads / P);
-    const size_t nlines = (size_t)a.nx * a.ny;
-    dim3 block(P, LT), grid((unsigned)((nlines + LT - 1) / LT));
-    const size_t LS = (size_t)P * zpad<kM>();
-    const size_t smem = ((dense ? 2 : 1) * LT * LS + 6 * (size_t)P * LT) * sizeof(double) + (size_t)LT * P * kM;
-    if (smem > 227 * 1024) {
-        set_error("adi_cart_step: z tile does not fit shared memory");
-        return ADI_EINVAL;
-    }
-    if (dense) {
-        if (extra) return launch(k_sweep_z<kM, 2, true>, grid, block, smem, st, a, ctx);
-        return launch(k_sweep_z<kM, 2, false>, grid, block, smem, st, a, ctx);
-    }
-    if (extra) return launch(k_sweep_z<kM, 1, true>, grid, block, smem, st, a, ctx);
-    return launch(k_sweep_z<kM, 1, false>, grid, block, smem, st, a, ctx);
-}
+namespace {
 
 int ensure_stage(adi_ctx *ctx, size_t cells)
 {
@@ -236,9 +184,9 @@ int adi_cart_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, 
         a.k.h_hi = ctx->scalar_robin ? ctx->face_coeff[2 * axis + 1] : 0.0;
         const bool dense = p.coeff != nullptr;
         const bool extra = p.q != nullptr || p.dirm != nullptr;
-        if (axis == 0) rc = launch_strided<0>(ctx, a, dense, extra, expl, st);
-        else if (axis == 1) rc = launch_strided<1>(ctx, a, dense, extra, false, st);
-        else rc = launch_z(ctx, a, dense, extra, st);
+        if (axis == 0) rc = launch_sweep_x(ctx, a, dense, extra, expl, st);
+        else if (axis == 1) rc = launch_sweep_y(ctx, a, dense, extra, st);
+        else rc = launch_sweep_z(ctx, a, dense, extra, st);
         if (rc) return rc;
         rc = prof_mark(ctx, axis + 1, st);
         if (rc) return rc;

@@ -4,10 +4,11 @@
 // K0 k_build_code      mask (+dir_mask) -> 1-byte neighbour code per cell
 // K1 k_sweep_strided   x sweep (stride ny*nz, explicit stage fused) and y sweep (stride nz):
 //                      lanes run along z, so every load/store of a warp is a run of
-//                      contiguous 8-byte cells (64-256 B rows); each thread keeps a
-//                      16-cell chunk of its line in registers
+//                      contiguous 8-byte cells (64-256 B rows); each thread keeps an
+//                      M-cell chunk of its line in registers and the pivot reciprocals in a
+//                      conflict-free shared-memory column
 // K3 k_sweep_z         z sweep (contiguous axis): the tile of lines is staged through
-//                      padded shared memory with coalesced 16-byte accesses, then the same
+//                      XOR-swizzled shared memory with 16-byte cp.async copies, then the same
 //                      register-resident chunk solve runs with lanes along the line
 // K7 k_build_packs     precompute_coeff_packs_unified on the device
 #pragma once
@@ -18,8 +19,8 @@
 namespace adi {
 
 struct SweepArgs {
-    const double *__restrict__ in;
-    double *__restrict__ out;
+    const double *in;                  // may alias out (y and z sweeps run in place)
+    double *out;
     const uint8_t *__restrict__ code;
     const double *__restrict__ coeff;  // CMODE 2
     const double *__restrict__ q;      // EXTRA, may be null
@@ -28,6 +29,7 @@ struct SweepArgs {
     SweepConst k;
 };
 
+#ifdef ADI_CART_MISC_KERNELS  // defined by adi_cart.cu, the one unit that launches K0/K7
 // ------------------------------------------------------------------------------------
 // K0: neighbour code.  One thread per cell; the six neighbour bytes come from L1/L2.
 // ------------------------------------------------------------------------------------
@@ -43,24 +45,27 @@ __global__ void k_build_code(const uint8_t *__restrict__ mask, const uint8_t *__
         const int j = (int)(ij % ny);
         const int i = (int)(ij / ny);
         unsigned c = 0;
-        if (mask[idx]) {
+        if (mask[idx]) {  // a void cell keeps code 0
             c = CB_SELF;
             if (dirm && dirm[idx]) c |= CB_DIR;
+            if (i > 0 && mask[idx - snx]) c |= CB_XM;
+            if (i + 1 < nx && mask[idx + snx]) c |= CB_XP;
+            if (j > 0 && mask[idx - nz]) c |= CB_YM;
+            if (j + 1 < ny && mask[idx + nz]) c |= CB_YP;
+            if (k > 0 && mask[idx - 1]) c |= CB_ZM;
+            if (k + 1 < nz && mask[idx + 1]) c |= CB_ZP;
         }
-        if (i > 0 && mask[idx - snx]) c |= CB_XM;
-        if (i + 1 < nx && mask[idx + snx]) c |= CB_XP;
-        if (j > 0 && mask[idx - nz]) c |= CB_YM;
-        if (j + 1 < ny && mask[idx + nz]) c |= CB_YP;
-        if (k > 0 && mask[idx - 1]) c |= CB_ZM;
-        if (k + 1 < nz && mask[idx + 1]) c |= CB_ZP;
         code[idx] = (uint8_t)c;
     }
 }
 
+#endif  // ADI_CART_MISC_KERNELS (K0)
+
 // ------------------------------------------------------------------------------------
 // Reduced-system solve shared by all sweeps: exchange through shared memory.
 // red: 6*NTH doubles.  ridx: this thread's slot; rstep: slot distance between consecutive
-// chunks of the same line.  Returns S_p in r.D and S_{p-1} in *Sl.
+// chunks of the same line.  Returns S_p and S_{p-1} (*Sl).  Ends with every thread past
+// its last read of red only after the caller's next __syncthreads().
 // ------------------------------------------------------------------------------------
 template <int M>
 __device__ __forceinline__ double solve_reduced(const Chunk<M> &ch, const First &f, double *red,
@@ -112,82 +117,152 @@ __device__ __forceinline__ double solve_reduced(const Chunk<M> &ch, const First 
 // grid = (ceil(nz/KT), ny) for AXIS 0 and (ceil(nz/KT), nx) for AXIS 1.
 // EXPL (AXIS 0 only): the input is T^n and the explicit stage
 // R0 = T + beta*(Lx+Ly+Lz) (adi3d_numba_coeff.py:298) is applied while loading.
+// Shared memory: rv[M][NTH] pivot reciprocals, red[6*NTH] reduced-system exchange.
 // ------------------------------------------------------------------------------------
-template <int AXIS, int M, int CMODE, bool EXTRA, bool EXPL>
-__global__ void __launch_bounds__(512, 1) k_sweep_strided(const SweepArgs a)
+template <int M>
+struct StridedOps {
+    const double *coeff, *qp, *dvp;  // already offset to the chunk's first cell; may be null
+    unsigned sl;  // stride between consecutive cells of the line (elements)
+    int nv;       // valid cells of this chunk (0 for an out-of-range lane)
+    double *sm;   // &column[tid]: factor store, slot s of cell e at sm[(NS*e + s)*NTH]
+    int NTH;
+    __device__ __forceinline__ double coef(int e) const { return e < nv ? coeff[e * sl] : 0.0; }
+    __device__ __forceinline__ double q(int e) const { return (qp && e < nv) ? qp[e * sl] : 0.0; }
+    __device__ __forceinline__ double dirv(int e) const { return (dvp && e < nv) ? dvp[e * sl] : 0.0; }
+    __device__ __forceinline__ void put2(int e, double la, double u) { sm[(2 * e) * NTH] = la; sm[(2 * e + 1) * NTH] = u; }
+    __device__ __forceinline__ double la(int e) const { return sm[(2 * e) * NTH]; }
+    __device__ __forceinline__ double u(int e) const { return sm[(2 * e + 1) * NTH]; }
+    __device__ __forceinline__ void put1(int e, double v) { sm[e * NTH] = v; }
+    __device__ __forceinline__ double rinv(int e) const { return sm[e * NTH]; }
+};
+
+template <int AXIS, int M, int NS, int CMODE, bool EXTRA, bool EXPL, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
 {
-    extern __shared__ double red[];
+    extern __shared__ double smem[];
     const int KT = blockDim.x, P = blockDim.y;
     const int kk = threadIdx.x, p = threadIdx.y;
     const int NTH = KT * P;
+    const int tid = p * KT + kk;
     const int k = blockIdx.x * KT + kk;
-    const bool lane_ok = k < a.nz;
     const int n = (AXIS == 0) ? a.nx : a.ny;
-    const size_t sline = (AXIS == 0) ? (size_t)a.ny * a.nz : (size_t)a.nz;
-    const size_t base = ((AXIS == 0) ? (size_t)blockIdx.y * a.nz : (size_t)blockIdx.y * a.ny * a.nz) + k;
+    const unsigned sl = (AXIS == 0) ? (unsigned)a.ny * (unsigned)a.nz : (unsigned)a.nz;
     constexpr unsigned LO = (AXIS == 0) ? CB_XM : CB_YM;
     constexpr unsigned HI = (AXIS == 0) ? CB_XP : CB_YP;
     const int t0 = p * M;
+    const int nv = (k < a.nz) ? min(max(n - t0, 0), M) : 0;
+    // first cell of the chunk (clamped in-range so that pointer arithmetic stays valid)
+    const size_t idx0 = ((AXIS == 0) ? (size_t)blockIdx.y * a.nz : (size_t)blockIdx.y * a.ny * a.nz) +
+                        (size_t)min(k, a.nz - 1) + (size_t)min(t0, n - 1) * sl;
+    double *red = smem + (size_t)NS * M * NTH;
+    const double *tp = a.in + idx0;
 
     Chunk<M> ch;
-    double Q[EXTRA ? M : 1], DV[EXTRA ? M : 1];
+    {
+        const uint8_t *cp = a.code + idx0;
 #pragma unroll
-    for (int e = 0; e < M; ++e) {
-        const bool ok = lane_ok && (t0 + e) < n;
-        const size_t idx = base + (size_t)(t0 + e) * sline;
-        ch.code[e] = ok ? (unsigned)a.code[idx] : 0u;
-        ch.T[e] = ok ? a.in[idx] : 0.0;
-        ch.Cc[e] = (CMODE == 2 && ok) ? a.coeff[idx] : 0.0;
-        if (EXTRA) {
-            Q[e] = (a.q && ok) ? a.q[idx] : 0.0;
-            DV[e] = (a.dirv && ok && (ch.code[e] & CB_DIR)) ? a.dirv[idx] : 0.0;
-        }
+        for (int e = 0; e < M; ++e) ch.set_code(e, e < nv ? (unsigned)cp[e * sl] : 0u);
+#pragma unroll
+        for (int e = 0; e < M; ++e) ch.T[e] = e < nv ? tp[e * sl] : 0.0;
+#pragma unroll
+        for (int e = 0; e < M; ++e) ch.T[e] = ch.active(e) ? ch.T[e] : 0.0;  // load rule (adi_core.h)
     }
     if (EXPL) {
-        const double *__restrict__ in = a.in;
-        const unsigned c0 = ch.code[0], cl = ch.code[M - 1];
-        double prev = ((c0 & CB_SELF) && (c0 & CB_XM)) ? in[base + (size_t)(t0 - 1) * sline] : 0.0;
-        const double nxt = ((cl & CB_SELF) && (cl & CB_XP)) ? in[base + (size_t)(t0 + M) * sline] : 0.0;
+        // neighbour values are only ever loaded where the code says the neighbour is active
+        const unsigned c0 = ch.code(0), cl = ch.code(M - 1);
+        double prev = (c0 & CB_XM) ? *(tp - sl) : 0.0;
+        const double nxt = (cl & CB_XP) ? tp[M * sl] : 0.0;
+        const int sy = a.nz;
 #pragma unroll
         for (int e = 0; e < M; ++e) {
-            const unsigned c = ch.code[e];
-            const size_t idx = base + (size_t)(t0 + e) * sline;
-            const bool act = (c & CB_SELF) != 0;
-            const double ym = (act && (c & CB_YM)) ? in[idx - a.nz] : 0.0;
-            const double yp = (act && (c & CB_YP)) ? in[idx + a.nz] : 0.0;
-            const double zm = (act && (c & CB_ZM)) ? in[idx - 1] : 0.0;
-            const double zp = (act && (c & CB_ZP)) ? in[idx + 1] : 0.0;
+            const unsigned c = ch.code(e);
+            const double *pc = tp + e * sl;
+            const double ym = (c & CB_YM) ? *(pc - sy) : 0.0;
+            const double yp = (c & CB_YP) ? *(pc + sy) : 0.0;
+            const double zm = (c & CB_ZM) ? *(pc - 1) : 0.0;
+            const double zp = (c & CB_ZP) ? *(pc + 1) : 0.0;
+            // x neighbours come from the chunk registers: already 0 where void; a void cell
+            // itself (code 0, T 0) must stay 0 whatever its neighbours hold
             const double xp = (e < M - 1) ? ch.T[e + 1] : nxt;
             const double r0 = explicit_r0(c, ch.T[e], prev, xp, ym, yp, zm, zp, a.k);
             prev = ch.T[e];
-            ch.T[e] = r0;
+            ch.T[e] = (c & CB_SELF) ? r0 : 0.0;
         }
     }
 
-    const First f = chunk_forward<M, CMODE, EXTRA>(ch, Q, DV, LO, HI, a.k);
-    double Sl;
-    const double S = solve_reduced<M>(ch, f, red, NTH, p * KT + kk, KT, p, P, &Sl);
-    chunk_backward<M>(ch, Sl, S);
+    StridedOps<M> ops;
+    ops.coeff = (CMODE == 2) ? a.coeff + idx0 : nullptr;
+    ops.qp = (EXTRA && a.q) ? a.q + idx0 : nullptr;
+    ops.dvp = (EXTRA && a.dirv) ? a.dirv + idx0 : nullptr;
+    ops.sl = sl;
+    ops.nv = nv;
+    ops.sm = smem + tid;
+    ops.NTH = NTH;
 
+    const First f = chunk_forward<M, CMODE, EXTRA, NS>(ch, ops, LO, HI, a.k);
+    double Sl;
+    const double S = solve_reduced<M>(ch, f, red, NTH, tid, KT, p, P, &Sl);
+    chunk_backward<M, EXTRA, NS>(ch, ops, LO, HI, a.k.g, Sl, S);
+
+    double *op = a.out + idx0;
+    if (a.in == a.out) {
+        // in place: void cells are simply not written
 #pragma unroll
-    for (int e = 0; e < M; ++e) {
-        const bool ok = lane_ok && (t0 + e) < n;
-        if (ok) a.out[base + (size_t)(t0 + e) * sline] = ch.T[e];
+        for (int e = 0; e < M; ++e)
+            if (e < nv && ch.active(e)) op[e * sl] = ch.T[e];
+    } else {
+        // out of place: void cells take the input bits (adi3d_gpu_coeff.py:229)
+#pragma unroll
+        for (int e = 0; e < M; ++e)
+            if (e < nv) op[e * sl] = ch.active(e) ? ch.T[e] : tp[e * sl];
     }
 }
 
 // ------------------------------------------------------------------------------------
 // K3: sweep along z (contiguous).  blockDim = (P chunks, LT lines); grid = ceil(nx*ny/LT).
-// Shared memory: sT[LT][P*(M+2)] (+ sC when CMODE 2), sCode[LT][P*M], red[6*NTH].
-// The +2 padding per chunk makes the per-thread 16-byte reads of a quarter warp hit
-// eight different 16-byte bank groups (stride 144 B).
+// Shared memory: sT[LT][P*M] and sC[LT][P*M] (field / coefficient tiles; sC then holds the
+// pivot reciprocals), sCode[LT][P*M].  Inside each chunk the 16-byte pairs are stored at
+// position j ^ (p & 7): the per-thread 16-byte reads of a quarter warp (8 consecutive
+// chunks, 128 B apart) then hit eight different bank groups, without padding.
+// The reduced-system exchange buffer aliases sT while the chunk lives in registers.
 // ------------------------------------------------------------------------------------
-template <int M>
-__host__ __device__ constexpr int zpad() { return M + 2; }
-
-template <int M, int CMODE, bool EXTRA>
-__global__ void __launch_bounds__(512, 1) k_sweep_z(const SweepArgs a)
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, int src_bytes)
 {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int M>
+__device__ __forceinline__ int zslot(int chunk, int pair)
+{
+    constexpr int SW = (M / 2 >= 8) ? 7 : (M / 2 - 1);
+    return chunk * M + 2 * (pair ^ (chunk & SW));
+}
+
+template <int M>
+struct TileOps {
+    double *c;          // this chunk's coefficient slots, then la (NS 2) / rinv (NS 1)
+    double *uu;         // this chunk's u slots (NS 2)
+    int sw;             // p & SW
+    const double *qp, *dvp;
+    int nv;
+    __device__ __forceinline__ int at(int e) const { return 2 * ((e >> 1) ^ sw) + (e & 1); }
+    __device__ __forceinline__ double coef(int e) const { return c[at(e)]; }
+    __device__ __forceinline__ double q(int e) const { return (qp && e < nv) ? qp[e] : 0.0; }
+    __device__ __forceinline__ double dirv(int e) const { return (dvp && e < nv) ? dvp[e] : 0.0; }
+    __device__ __forceinline__ void put2(int e, double la, double u) { c[at(e)] = la; uu[at(e)] = u; }
+    __device__ __forceinline__ double la(int e) const { return c[at(e)]; }
+    __device__ __forceinline__ double u(int e) const { return uu[at(e)]; }
+    __device__ __forceinline__ void put1(int e, double v) { c[at(e)] = v; }
+    __device__ __forceinline__ double rinv(int e) const { return c[at(e)]; }
+};
+
+// smem: sT[LT][RL] | sC[LT][RL] | (NS 2: sU[LT][RL]) | sCode[LT][RL bytes]
+template <int M, int NS, int CMODE, bool EXTRA, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const int vec)
+{
+    static_assert(M % 4 == 0, "chunk length must be a multiple of 4");
     extern __shared__ double smem[];
     const int P = blockDim.x, LT = blockDim.y;
     const int p = threadIdx.x, ln = threadIdx.y;
@@ -196,118 +271,142 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(const SweepArgs a)
     const int nz = a.nz;
     const size_t nlines = (size_t)a.nx * a.ny;
     const size_t L0 = (size_t)blockIdx.x * LT;
-    const int LS = P * zpad<M>();  // doubles per staged line
+    const int RL = P * M;  // doubles per staged line
     double *sT = smem;
-    double *sC = sT + (size_t)LT * LS;
-    double *red = sC + (CMODE == 2 ? (size_t)LT * LS : 0);
-    uint8_t *sCode = reinterpret_cast<uint8_t *>(red + 6 * NTH);
+    double *sC = sT + (size_t)LT * RL;
+    double *sU = sC + (size_t)LT * RL;
+    uint8_t *sCode = reinterpret_cast<uint8_t *>(sU + (NS == 2 ? (size_t)LT * RL : 0));
+    double *red = sT;
+    constexpr int SW = (M / 2 >= 8) ? 7 : (M / 2 - 1);
 
-    // ---- stage in (coalesced) ----
-    const bool vec2 = (nz & 1) == 0;
-    for (int l = 0; l < LT; ++l) {
-        const size_t line = L0 + l;
-        const bool lok = line < nlines;
-        const size_t g0 = line * (size_t)nz;
-        if (vec2) {
-            for (int tv = tid; tv < (nz >> 1); tv += NTH) {
-                const int t = tv << 1;
-                const int so = l * LS + (t / M) * zpad<M>() + (t % M);
-                double2 v = make_double2(0.0, 0.0);
-                if (lok) v = *reinterpret_cast<const double2 *>(a.in + g0 + t);
-                *reinterpret_cast<double2 *>(sT + so) = v;
-                if (CMODE == 2) {
-                    double2 c = make_double2(0.0, 0.0);
-                    if (lok) c = *reinterpret_cast<const double2 *>(a.coeff + g0 + t);
-                    *reinterpret_cast<double2 *>(sC + so) = c;
-                }
-            }
-        } else {
-            for (int t = tid; t < nz; t += NTH) {
-                const int so = l * LS + (t / M) * zpad<M>() + (t % M);
-                sT[so] = lok ? a.in[g0 + t] : 0.0;
-                if (CMODE == 2) sC[so] = lok ? a.coeff[g0 + t] : 0.0;
+    // ---- stage in ----
+    const int ppl = RL / 2;  // 16-byte pairs per staged line
+    if (vec) {
+        for (int l = 0; l < LT; ++l) {
+            const size_t line = L0 + l;
+            const bool lok = line < nlines;
+            const double *srcT = a.in + (lok ? line * (size_t)nz : 0);
+            const double *srcC = (CMODE == 2) ? a.coeff + (lok ? line * (size_t)nz : 0) : nullptr;
+            for (int pl = tid; pl < ppl; pl += NTH) {
+                const int dst = l * RL + zslot<M>(pl / (M / 2), pl % (M / 2));
+                const int z = 2 * pl;
+                const bool ok = lok && z < nz;
+                cp_async16(sT + dst, srcT + (ok ? z : 0), ok ? 16 : 0);
+                if (CMODE == 2) cp_async16(sC + dst, srcC + (ok ? z : 0), ok ? 16 : 0);
             }
         }
-        if ((nz & 15) == 0 && P * M == nz) {
-            for (int tv = tid; tv < (nz >> 4); tv += NTH) {
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (lok) v = *reinterpret_cast<const uint4 *>(a.code + g0 + (tv << 4));
-                *reinterpret_cast<uint4 *>(sCode + (size_t)l * P * M + (tv << 4)) = v;
+    } else {
+        for (int l = 0; l < LT; ++l) {
+            const size_t line = L0 + l;
+            const bool lok = line < nlines;
+            for (int z = tid; z < RL; z += NTH) {
+                const int dst = l * RL + zslot<M>(z / M, (z % M) >> 1) + (z & 1);
+                const bool ok = lok && z < nz;
+                sT[dst] = ok ? a.in[line * (size_t)nz + z] : 0.0;
+                if (CMODE == 2) sC[dst] = ok ? a.coeff[line * (size_t)nz + z] : 0.0;
             }
-        } else {
-            for (int t = tid; t < P * M; t += NTH)
-                sCode[(size_t)l * P * M + t] = (lok && t < nz) ? a.code[g0 + t] : (uint8_t)0;
         }
     }
+    if (vec && (nz & 15) == 0) {
+        for (int l = 0; l < LT; ++l) {
+            const size_t line = L0 + l;
+            const bool lok = line < nlines;
+            for (int c16 = tid; c16 < RL / 16; c16 += NTH) {
+                const bool ok = lok && 16 * c16 < nz;
+                cp_async16(sCode + (size_t)l * RL + 16 * c16, a.code + (ok ? line * (size_t)nz + 16 * c16 : 0),
+                           ok ? 16 : 0);
+            }
+        }
+    } else {
+        for (int l = 0; l < LT; ++l) {
+            const size_t line = L0 + l;
+            const bool lok = line < nlines;
+            for (int z = tid; z < RL; z += NTH)
+                sCode[(size_t)l * RL + z] = (lok && z < nz) ? a.code[line * (size_t)nz + z] : (uint8_t)0;
+        }
+    }
+    cp_async_wait_all();
     __syncthreads();
 
     // ---- chunk to registers ----
     Chunk<M> ch;
-    double Q[EXTRA ? M : 1], DV[EXTRA ? M : 1];
-    const int so0 = ln * LS + p * zpad<M>();
+    double *myT = sT + (size_t)ln * RL + p * M;
     {
-        const uint8_t *cb = sCode + (size_t)ln * P * M + p * M;
+        const unsigned *cb = reinterpret_cast<const unsigned *>(sCode + (size_t)ln * RL + p * M);
 #pragma unroll
-        for (int e = 0; e < M; e += 4) {
-            const unsigned w = *reinterpret_cast<const unsigned *>(cb + e);
-            ch.code[e] = w & 0xffu;
-            ch.code[e + 1] = (w >> 8) & 0xffu;
-            ch.code[e + 2] = (w >> 16) & 0xffu;
-            ch.code[e + 3] = w >> 24;
-        }
+        for (int w = 0; w < M / 4; ++w) ch.cw[w] = cb[w];
 #pragma unroll
-        for (int e = 0; e < M; e += 2) {
-            const double2 v = *reinterpret_cast<const double2 *>(sT + so0 + e);
-            ch.T[e] = v.x;
-            ch.T[e + 1] = v.y;
-            if (CMODE == 2) {
-                const double2 c = *reinterpret_cast<const double2 *>(sC + so0 + e);
-                ch.Cc[e] = c.x;
-                ch.Cc[e + 1] = c.y;
-            } else {
-                ch.Cc[e] = 0.0;
-                ch.Cc[e + 1] = 0.0;
-            }
+        for (int j = 0; j < M / 2; ++j) {
+            const double2 v = *reinterpret_cast<const double2 *>(myT + 2 * (j ^ (p & SW)));
+            ch.T[2 * j] = ch.active(2 * j) ? v.x : 0.0;          // load rule (adi_core.h)
+            ch.T[2 * j + 1] = ch.active(2 * j + 1) ? v.y : 0.0;
         }
     }
-    if (EXTRA) {
-        const size_t line = L0 + ln;
-        const size_t g0 = line * (size_t)nz + (size_t)p * M;
-#pragma unroll
-        for (int e = 0; e < M; ++e) {
-            const bool ok = line < nlines && (p * M + e) < nz;
-            Q[e] = (a.q && ok) ? a.q[g0 + e] : 0.0;
-            DV[e] = (a.dirv && ok && (ch.code[e] & CB_DIR)) ? a.dirv[g0 + e] : 0.0;
-        }
+    __syncthreads();  // sT is reused as the reduced-system exchange buffer from here on
+
+    TileOps<M> ops;
+    ops.c = sC + (size_t)ln * RL + p * M;
+    ops.uu = sU + (size_t)ln * RL + p * M;
+    ops.sw = p & SW;
+    {
+        const size_t line = min(L0 + ln, nlines - 1);
+        const size_t g0 = line * (size_t)nz + (size_t)min(p * M, nz - 1);
+        ops.qp = (EXTRA && a.q) ? a.q + g0 : nullptr;
+        ops.dvp = (EXTRA && a.dirv) ? a.dirv + g0 : nullptr;
+        ops.nv = (L0 + ln < nlines) ? min(max(nz - p * M, 0), M) : 0;
     }
 
-    const First f = chunk_forward<M, CMODE, EXTRA>(ch, Q, DV, CB_ZM, CB_ZP, a.k);
+    const First f = chunk_forward<M, CMODE, EXTRA, NS>(ch, ops, CB_ZM, CB_ZP, a.k);
     double Sl;
     const double S = solve_reduced<M>(ch, f, red, NTH, tid, 1, p, P, &Sl);
-    chunk_backward<M>(ch, Sl, S);
+    chunk_backward<M, EXTRA, NS>(ch, ops, CB_ZM, CB_ZP, a.k.g, Sl, S);
+    __syncthreads();  // everybody is done reading the exchange buffer
 
     // ---- results back through shared memory (each thread owns its slots) ----
+    // The sweep runs in place, so void cells must keep the bits they have in global memory:
+    // the copy-out below only writes cells whose staged code is active.
 #pragma unroll
-    for (int e = 0; e < M; e += 2)
-        *reinterpret_cast<double2 *>(sT + so0 + e) = make_double2(ch.T[e], ch.T[e + 1]);
+    for (int j = 0; j < M / 2; ++j)
+        *reinterpret_cast<double2 *>(myT + 2 * (j ^ (p & SW))) = make_double2(ch.T[2 * j], ch.T[2 * j + 1]);
     __syncthreads();
-    for (int l = 0; l < LT; ++l) {
-        const size_t line = L0 + l;
-        if (line >= nlines) break;
-        const size_t g0 = line * (size_t)nz;
-        if (vec2) {
-            for (int tv = tid; tv < (nz >> 1); tv += NTH) {
-                const int t = tv << 1;
-                const int so = l * LS + (t / M) * zpad<M>() + (t % M);
-                *reinterpret_cast<double2 *>(a.out + g0 + t) = *reinterpret_cast<const double2 *>(sT + so);
+    const bool inplace = (a.in == a.out);
+    if (vec) {
+        for (int l = 0; l < LT; ++l) {
+            const size_t line = L0 + l;
+            if (line >= nlines) break;
+            for (int pl = tid; pl < ppl; pl += NTH) {
+                const int z = 2 * pl;
+                if (z >= nz) break;
+                const double2 v = *reinterpret_cast<const double2 *>(sT + l * RL + zslot<M>(pl / (M / 2), pl % (M / 2)));
+                const unsigned cc = *reinterpret_cast<const unsigned short *>(sCode + (size_t)l * RL + z);
+                const size_t g = line * (size_t)nz + z;
+                const bool a0 = cc & 1u, a1 = (cc >> 8) & 1u;
+                if (a0 && a1) {
+                    *reinterpret_cast<double2 *>(a.out + g) = v;
+                } else if (inplace) {
+                    if (a0) a.out[g] = v.x;
+                    if (a1) a.out[g + 1] = v.y;
+                } else {
+                    a.out[g] = a0 ? v.x : a.in[g];
+                    a.out[g + 1] = a1 ? v.y : a.in[g + 1];
+                }
             }
-        } else {
-            for (int t = tid; t < nz; t += NTH)
-                a.out[g0 + t] = sT[l * LS + (t / M) * zpad<M>() + (t % M)];
+        }
+    } else {
+        for (int l = 0; l < LT; ++l) {
+            const size_t line = L0 + l;
+            if (line >= nlines) break;
+            for (int z = tid; z < nz; z += NTH) {
+                const size_t g = line * (size_t)nz + z;
+                const bool act = sCode[(size_t)l * RL + z] & 1u;
+                if (act) a.out[g] = sT[l * RL + zslot<M>(z / M, (z % M) >> 1) + (z & 1)];
+                else if (!inplace) a.out[g] = a.in[g];
+            }
         }
     }
 }
 
+#ifdef ADI_CART_MISC_KERNELS
 // ------------------------------------------------------------------------------------
 // K7: exposed_mask / precompute_coeff_packs_unified (adi3d_gpu_coeff.py:31-110).
 // ------------------------------------------------------------------------------------
@@ -387,5 +486,6 @@ __global__ void k_exposed_mask(const uint8_t *__restrict__ mask, uint8_t *__rest
         out[idx] = (uint8_t)((exposed_bits(mask, idx, i, j, k, nx, ny, nz) >> face) & 1u);
     }
 }
+#endif  // ADI_CART_MISC_KERNELS (K7)
 
 }  // namespace adi

@@ -3,21 +3,28 @@
 // One ADI sweep solves, for every grid line along the swept axis, the tridiagonal system
 // the reference assembles in sweep_axis0/1/2 (adi3d_numba_coeff.py:133-237; un-compressed
 // form: adi3d_gpu_coeff.py:154-191).  A line of n cells is cut into P = ceil(n/M) chunks of
-// M cells; one THREAD owns one chunk and keeps it in registers:
+// M cells; one THREAD owns one chunk.  The last cell of a chunk is its separator S_p, the
+// M-1 cells before it are its interior.
 //
-//   phase 1  forward elimination over the chunk's M-1 interior cells with the coupling to
-//            the previous chunk kept symbolic (spike v'), then a backward recurrence that
-//            yields the first interior cell as  x_0 = Y0 - V0*S_{p-1} - W0*S_p ;
-//   phase 2  the chunk's LAST cell is its separator S_p; substituting the neighbours'
-//            relations into its row gives one row of a P-unknown tridiagonal system,
-//            which the P threads of the line solve together by parallel cyclic reduction
-//            (ceil(log2 P) steps, exchanged through shared memory);
-//   phase 3  back substitution inside the chunk with S_{p-1}, S_p known.
+//   phase 1  one forward pass over the interior: the row (a,b,c,d) of each cell is built
+//            from the neighbour code and the operands, eliminated against its left
+//            neighbour (Thomas, normalised form), and three running sums give the first
+//            interior cell as an affine function of the two separators around the chunk,
+//                x_0 = Y + V*S_{p-1} + W*S_p ,
+//            likewise the last one, x_{M-2} = Yl + Vl*S_{p-1} + Wl*S_p.
+//            Kept per cell: the scaled right-hand side d_e/den_e (registers, in place of
+//            T) and the two normalised couplings aa_e/den_e, cc_e/den_e (shared memory);
+//            for long lines only 1/den_e is kept and the couplings are rebuilt from the code.
+//   phase 2  substituting the neighbours' relations into the separator rows gives a
+//            P-unknown tridiagonal system per line, solved by the P threads of the line
+//            with parallel cyclic reduction (ceil(log2 P) steps);
+//   phase 3  with S_{p-1}, S_p known: forward elimination of d once more (now with the
+//            true left boundary value) and back substitution.
 //
-// Each cell is therefore read once and written once; nothing is spilled to HBM.
-// Void cells (mask false) are identity rows that are never coupled to anything and come
-// out bit-identical to the input (the reference never touches them); no value of a void
-// cell ever enters arithmetic that reaches an active cell (they may hold NaN).
+// Each cell is read once and written once; nothing is spilled to HBM.
+// Void cells (mask false) are identity rows that are never coupled to anything; their
+// values are never loaded into the arithmetic (they may hold NaN) and never stored, so they
+// come out bit-identical to the input (the reference never touches them).
 //
 // The functions are __host__ __device__ so that tests/ can run the very same code on the
 // CPU (csrc/host_emulation.cpp) against the oracle.
@@ -36,9 +43,10 @@ using std::fma;
 
 namespace adi {
 
-// Per-cell neighbour code, built once per mask change (kernel build_code):
+// Per-cell neighbour code, built once per mask change (kernel k_build_code):
 // bit0 = cell active; bits 1..6 = neighbour across x-,x+,y-,y+,z-,z+ exists and is active;
-// bit7 = Dirichlet cell of this axis' pack (dir_mask & mask).
+// bit7 = Dirichlet cell of this axis' pack (dir_mask & mask).  A void cell has code 0, so a
+// set neighbour or Dirichlet bit implies an active cell.
 enum : unsigned {
     CB_SELF = 1u, CB_XM = 2u, CB_XP = 4u, CB_YM = 8u, CB_YP = 16u, CB_ZM = 32u, CB_ZP = 64u,
     CB_DIR = 128u
@@ -47,15 +55,14 @@ enum : unsigned {
 ADI_HD double frcp(double x)
 {
 #if defined(__CUDA_ARCH__) && !defined(ADI_EXACT_DIV)
-    // MUFU.RCP64H seed (>= 20 good bits) + two Newton steps in residual form: ~1 ulp,
-    // branch-free.  Pivots here are >= 1 (diagonally dominant M-matrix rows), never denormal.
+    // MUFU.RCP64H seed (>= 20 good bits) + one cubically convergent step
+    // r' = r + r*(e + e^2), e = 1 - x*r  (|1 - x*r'| = |e|^3 <= 2^-60): ~1 ulp, branch-free.
+    // Pivots here are >= 1 (diagonally dominant M-matrix rows), never denormal or huge.
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 #else
     return 1.0 / x;
 #endif
@@ -81,6 +88,15 @@ struct Row {
     bool active;
 };
 
+// Couplings of a row to its '-' / '+' neighbour along the swept axis: present when the cell
+// and that neighbour are active and the cell is not a Dirichlet cell (:151-158; the
+// neighbours of a Dirichlet cell still couple TO it).
+template <bool EXTRA>
+ADI_HD bool couples(unsigned code, unsigned nb)
+{
+    return EXTRA ? ((code & (nb | CB_DIR)) == nb) : ((code & nb) != 0);
+}
+
 // lo/hi: bit masks of the '-' / '+' neighbour along the swept axis.
 // CMODE 0: no Robin term; 1: scalar per face, derived from the code; 2: dense coeff value cval.
 template <int CMODE, bool EXTRA>
@@ -89,8 +105,6 @@ ADI_HD Row make_row(unsigned code, unsigned lo, unsigned hi, double Tval, double
 {
     Row r;
     r.active = (code & CB_SELF) != 0;
-    const bool L = r.active && (code & lo);
-    const bool R = r.active && (code & hi);
     double c = 0.0;
     if (CMODE == 1) {
         // exposed on a face <=> active and no active neighbour across it (:38-55);
@@ -101,21 +115,21 @@ ADI_HD Row make_row(unsigned code, unsigned lo, unsigned hi, double Tval, double
         c = sel(r.active, cval, 0.0);
     }
     const double q = EXTRA ? sel(r.active, qval, 0.0) : 0.0;
-    r.aa = sel(L, k.g, 0.0);
-    r.cc = sel(R, k.g, 0.0);
+    r.aa = sel((code & lo) != 0, k.g, 0.0);
+    r.cc = sel((code & hi) != 0, k.g, 0.0);
     const double nn = r.aa + r.cc;                 // theta*gam*nnb
     const double dtc = k.dt * c;
     r.b = (1.0 + nn) + dtc;                        // :155
     r.d = fma(k.dt, q, Tval) + dtc * k.Tinf;       // :162
     if (EXTRA) {
-        if (r.active && (code & CB_DIR)) {         // :157-158
+        if (code & CB_DIR) {                       // :157-158
             r.aa = 0.0; r.cc = 0.0; r.b = 1.0; r.d = dirval;
         }
     }
     return r;
 }
 
-// Relation handed to the previous chunk: x_first = Y - V*S_{p-1} - W*S_p  (all finite).
+// Affine relation of a chunk's first interior cell: x_0 = Y + V*S_{p-1} + W*S_p.
 struct First {
     double Y, V, W;
 };
@@ -125,70 +139,73 @@ struct Red {
     double A, C, D;
 };
 
-// Chunk state held in registers across the phases.  T[e] holds, in turn, the input value,
-// the eliminated right-hand side d'_e and finally the solution; Cc[e] holds coeff then c'_e;
-// Vp[e] holds the spike v'_e.  code[e] are the neighbour codes.
+// Chunk state held in registers across the phases.  T[e] holds, in turn, the input value
+// (0 for a void cell -- see load rule below), the row's scaled right-hand side and finally the
+// solution.  cw packs the neighbour codes, four cells per word.
+//
+// Load rule: the caller puts 0.0 into T[e] of void cells (and of padding cells beyond the
+// line end, which carry code 0).  Void rows are then exact identity rows with zero
+// right-hand side and zero couplings, so no select is needed anywhere downstream; the
+// caller never stores T[e] of a void cell (the output keeps / is given the input bits).
 template <int M>
 struct Chunk {
     double T[M];
-    double Cc[M];
-    double Vp[M];
-    unsigned code[M];
-    // separator row pieces kept from phase 1 to phase 2
+    unsigned cw[(M + 3) / 4];
+    // separator row and last-interior relation, kept from phase 1 to phase 2
     double s_aa, s_cc, s_b, s_d;
     double Yl, Vl, Wl;
-    bool s_active;
+
+    ADI_HD unsigned code(int e) const { return (cw[e >> 2] >> (8 * (e & 3))) & 0xffu; }
+    ADI_HD bool active(int e) const { return (cw[e >> 2] >> (8 * (e & 3))) & 1u; }
+    ADI_HD void set_code(int e, unsigned c)
+    {
+        if ((e & 3) == 0) cw[e >> 2] = c;
+        else cw[e >> 2] |= c << (8 * (e & 3));
+    }
 };
 
-// Phase 1.  Q[e]/DV[e] (Neumann flux, Dirichlet value) are only read when EXTRA.
-template <int M, int CMODE, bool EXTRA>
-ADI_HD First chunk_forward(Chunk<M> &ch, const double *Q, const double *DV, unsigned lo, unsigned hi,
-                           const SweepConst &k)
+// Operand access of one chunk.  OPS provides
+//   double coef(int e)            dense Robin coefficient of cell e (CMODE 2)
+//   double q(int e), dirv(int e)  Neumann flux / Dirichlet value (EXTRA)
+//   per-cell factor store between phase 1 and phase 3:
+//     NS == 2:  put2(e, la, u), la(e), u(e)     la = aa/den, u = cc/den
+//     NS == 1:  put1(e, rinv), rinv(e)          rinv = 1/den (long lines: half the storage)
+// with e a compile-time constant after unrolling.
+
+// Phase 1.
+template <int M, int CMODE, bool EXTRA, int NS, class OPS>
+ADI_HD First chunk_forward(Chunk<M> &ch, OPS &ops, unsigned lo, unsigned hi, const SweepConst &k)
 {
-    double cprev = 0.0, dprev = 0.0, vprev = 0.0;
+    double uprev = 0.0, dprev = 0.0, vprev = 1.0, alpha = 1.0;
+    First f;
+    f.Y = 0.0; f.V = 0.0; f.W = 0.0;
 #pragma unroll
     for (int e = 0; e < M - 1; ++e) {
-        const Row r = make_row<CMODE, EXTRA>(ch.code[e], lo, hi, ch.T[e], ch.Cc[e],
-                                             EXTRA ? Q[e] : 0.0, EXTRA ? DV[e] : 0.0, k);
-        double den, vp;
-        if (e == 0) {
-            den = r.b;                       // the coupling aa to S_{p-1} stays symbolic
-        } else {
-            den = fma(r.aa, cprev, r.b);     // b - a*c'_{e-1}
-        }
+        const Row r = make_row<CMODE, EXTRA>(ch.code(e), lo, hi, ch.T[e], CMODE == 2 ? ops.coef(e) : 0.0,
+                                             EXTRA ? ops.q(e) : 0.0, EXTRA ? ops.dirv(e) : 0.0, k);
+        // e == 0: the coupling aa to S_{p-1} stays symbolic (uprev = dprev = 0, vprev = 1)
+        const double den = fma(-r.aa, uprev, r.b);      // b - a*c'_{e-1}
         const double rinv = frcp(den);
-        const double cp = -r.cc * rinv;      // c'_e = c/den  (<= 0)
-        const double dp = (e == 0 ? r.d : fma(r.aa, dprev, r.d)) * rinv;
-        if (e == 0) vp = -r.aa * rinv;       // v'_0 = a_0/den
-        else vp = r.aa * vprev * rinv;       // v'_e = -a_e v'_{e-1}/den
-        ch.Cc[e] = cp;
-        ch.Vp[e] = vp;
-        if (r.active) ch.T[e] = dp;          // a void cell keeps its input bits
-        cprev = cp;
-        vprev = vp;
-        dprev = sel(r.active, dp, 0.0);      // never let a void value travel
+        const double u = r.cc * rinv;                   // -c'_e  (>= 0)
+        const double la = r.aa * rinv;
+        const double ds = r.d * rinv;
+        const double dp = fma(la, dprev, ds);           // d'_e with S_{p-1} = 0
+        const double vp = la * vprev;                   // coefficient of S_{p-1} in x_e
+        if (NS == 2) { ops.put2(e, la, u); ch.T[e] = ds; }
+        else { ops.put1(e, rinv); ch.T[e] = r.d; }
+        f.Y = fma(alpha, dp, f.Y);
+        f.V = fma(alpha, vp, f.V);
+        alpha = alpha * u;
+        uprev = u; dprev = dp; vprev = vp;
     }
+    f.W = alpha;
+    ch.Yl = dprev; ch.Vl = vprev; ch.Wl = uprev;        // x_{M-2} = Yl + Vl*S_{p-1} + Wl*S_p
     {
         const int e = M - 1;
-        const Row r = make_row<CMODE, EXTRA>(ch.code[e], lo, hi, ch.T[e], ch.Cc[e],
-                                             EXTRA ? Q[e] : 0.0, EXTRA ? DV[e] : 0.0, k);
-        ch.s_aa = r.aa; ch.s_cc = r.cc; ch.s_b = r.b; ch.s_d = sel(r.active, r.d, 0.0);
-        ch.s_active = r.active;
+        const Row r = make_row<CMODE, EXTRA>(ch.code(e), lo, hi, ch.T[e], CMODE == 2 ? ops.coef(e) : 0.0,
+                                             EXTRA ? ops.q(e) : 0.0, EXTRA ? ops.dirv(e) : 0.0, k);
+        ch.s_aa = r.aa; ch.s_cc = r.cc; ch.s_b = r.b; ch.s_d = r.d;
     }
-    // backward recurrence for (Y,V,W) of the first interior cell
-    const bool actl = (ch.code[M - 2] & CB_SELF) != 0;
-    double Y = sel(actl, ch.T[M - 2], 0.0), V = ch.Vp[M - 2], W = ch.Cc[M - 2];
-    ch.Yl = Y; ch.Vl = V; ch.Wl = W;
-#pragma unroll
-    for (int e = M - 3; e >= 0; --e) {
-        const bool act = (ch.code[e] & CB_SELF) != 0;
-        const double cp = ch.Cc[e];
-        Y = sel(act, fma(-cp, Y, ch.T[e]), 0.0);
-        V = fma(-cp, V, ch.Vp[e]);
-        W = -cp * W;
-    }
-    First f;
-    f.Y = Y; f.V = V; f.W = W;
     return f;
 }
 
@@ -197,15 +214,15 @@ ADI_HD First chunk_forward(Chunk<M> &ch, const double *Q, const double *DV, unsi
 template <int M>
 ADI_HD Red chunk_reduced_row(const Chunk<M> &ch, const First &nx)
 {
-    // a_s x_{M-2} + b_s S_p + c_s x_0^{(p+1)} = d_s,   a_s=-s_aa, c_s=-s_cc,
-    // x_{M-2} = Yl - Vl S_{p-1} - Wl S_p,   x_0^{(p+1)} = nx.Y - nx.V S_p - nx.W S_{p+1}
-    const double A = ch.s_aa * ch.Vl;
-    const double B = fma(ch.s_aa, ch.Wl, ch.s_b) + ch.s_cc * nx.V;
-    const double C = ch.s_cc * nx.W;
-    const double D = fma(ch.s_aa, ch.Yl, ch.s_d) + ch.s_cc * nx.Y;
+    // -aa_s x_{M-2} + b_s S_p - cc_s x_0^{(p+1)} = d_s
+    // x_{M-2} = Yl + Vl S_{p-1} + Wl S_p,   x_0^{(p+1)} = nx.Y + nx.V S_p + nx.W S_{p+1}
+    const double B = fma(-ch.s_cc, nx.V, fma(-ch.s_aa, ch.Wl, ch.s_b));
+    const double D = fma(ch.s_cc, nx.Y, fma(ch.s_aa, ch.Yl, ch.s_d));
     const double rB = frcp(B);
     Red r;
-    r.A = A * rB; r.C = C * rB; r.D = D * rB;
+    r.A = -(ch.s_aa * ch.Vl) * rB;
+    r.C = -(ch.s_cc * nx.W) * rB;
+    r.D = D * rB;
     return r;
 }
 
@@ -223,43 +240,57 @@ ADI_HD Red pcr_step(const Red &me, const Red &lo, const Red &hi)
     return r;
 }
 
-// Phase 3: Sl = S_{p-1} (0 for the first chunk), S = S_p.  Leaves the solution in ch.T.
-template <int M>
-ADI_HD void chunk_backward(Chunk<M> &ch, double Sl, double S)
+// Phase 3: Sl = S_{p-1} (0 for the first chunk), S = S_p.  Leaves the solution in ch.T
+// (0 in void cells, which the caller does not store).
+template <int M, bool EXTRA, int NS, class OPS>
+ADI_HD void chunk_backward(Chunk<M> &ch, OPS &ops, unsigned lo, unsigned hi, double g, double Sl, double S)
 {
-    double xn = sel(ch.s_active, S, 0.0);
-    if (ch.s_active) ch.T[M - 1] = S;
+    double dprev = Sl;
+#pragma unroll
+    for (int e = 0; e < M - 1; ++e) {
+        double dp;
+        if (NS == 2) {
+            dp = fma(ops.la(e), dprev, ch.T[e]);
+        } else {
+            const double aa = sel(couples<EXTRA>(ch.code(e), lo), g, 0.0);
+            dp = fma(aa, dprev, ch.T[e]) * ops.rinv(e);
+        }
+        ch.T[e] = dp;
+        dprev = dp;
+    }
+    double xn = S;   // a void separator solves to exactly 0 (identity row, zero rhs)
+    ch.T[M - 1] = S;
 #pragma unroll
     for (int e = M - 2; e >= 0; --e) {
-        const bool act = (ch.code[e] & CB_SELF) != 0;
-        double x = fma(-ch.Vp[e], Sl, ch.T[e]);
-        x = fma(-ch.Cc[e], xn, x);
-        if (act) ch.T[e] = x;
-        xn = sel(act, x, 0.0);
+        double u;
+        if (NS == 2) u = ops.u(e);
+        else u = sel(couples<EXTRA>(ch.code(e), hi), g, 0.0) * ops.rinv(e);
+        const double x = fma(u, xn, ch.T[e]);
+        ch.T[e] = x;
+        xn = x;
     }
 }
 
-// Explicit stage (adi3d_numba_coeff.py:240-288,298) for one cell:
+// Number (as a double) of the two neighbour bits `bits` set in `code`.
+ADI_HD double nb_count(unsigned code, unsigned bits)
+{
+#if defined(__CUDA_ARCH__)
+    return (double)__popc(code & bits);
+#else
+    return (double)__builtin_popcount(code & bits);
+#endif
+}
+
+// Explicit stage (adi3d_numba_coeff.py:240-288,298) for one ACTIVE cell:
 // R0 = T + beta*((Lx+Ly)+Lz), L* = ((sum of active neighbours, '-' first) - cnt*T)/dx^2.
-// The caller supplies neighbour values (ignored where the code bit is clear).
+// The caller supplies neighbour values that are 0.0 where the code bit is clear.
 ADI_HD double explicit_r0(unsigned code, double T, double xm, double xp, double ym, double yp,
                           double zm, double zp, const SweepConst &k)
 {
-    if (!(code & CB_SELF)) return T;
-    double s, c, L[3];
-    s = 0.0; c = 0.0;
-    if (code & CB_XM) { s += xm; c += 1.0; }
-    if (code & CB_XP) { s += xp; c += 1.0; }
-    L[0] = (s - c * T) * k.invdx2;
-    s = 0.0; c = 0.0;
-    if (code & CB_YM) { s += ym; c += 1.0; }
-    if (code & CB_YP) { s += yp; c += 1.0; }
-    L[1] = (s - c * T) * k.invdx2;
-    s = 0.0; c = 0.0;
-    if (code & CB_ZM) { s += zm; c += 1.0; }
-    if (code & CB_ZP) { s += zp; c += 1.0; }
-    L[2] = (s - c * T) * k.invdx2;
-    return T + k.beta * ((L[0] + L[1]) + L[2]);
+    const double L0 = ((xm + xp) - nb_count(code, CB_XM | CB_XP) * T) * k.invdx2;
+    const double L1 = ((ym + yp) - nb_count(code, CB_YM | CB_YP) * T) * k.invdx2;
+    const double L2 = ((zm + zp) - nb_count(code, CB_ZM | CB_ZP) * T) * k.invdx2;
+    return T + k.beta * ((L0 + L1) + L2);
 }
 
 }  // namespace adi

@@ -1,0 +1,43 @@
+// adi_sweep_z.cu -- z sweep (contiguous axis), in place (adi3d_numba_coeff.py:301).
+#include <stdint.h>
+
+#include "adi_launch.h"
+
+namespace adi {
+
+int launch_sweep_z(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, cudaStream_t st)
+{
+    Shape s;
+    int rc = pick_shape(ctx, a.nz, 0, &s);
+    if (rc) return rc;
+    // lines per block: fill the block, but keep the staged tiles small enough for two
+    // resident blocks per SM where the line length allows it
+    const size_t line_bytes = (size_t)s.P * s.M * (8 * (1 + s.NS) + 1);  // T + factor tiles + codes
+    const size_t budget = s.var == VAR_32L ? 220 * 1024 : 110 * 1024;
+    int LT = s.W;
+    while (LT > 1 && LT * line_bytes > budget) LT >>= 1;
+    if (ctx->opt_lt > 0) LT = (int)std::min<long>(ctx->opt_lt, s.W);
+    const size_t smem = LT * line_bytes;
+    if (smem > 227 * 1024) {
+        set_error("adi_cart_step: z tile does not fit shared memory");
+        return ADI_EINVAL;
+    }
+    const size_t nlines = (size_t)a.nx * a.ny;
+    dim3 block(s.P, LT), grid((unsigned)((nlines + LT - 1) / LT));
+    const int vec = ((a.nz & 1) == 0 && (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.coeff |
+                                          (uintptr_t)a.code) & 15) == 0) ? 1 : 0;
+#define ADI_GO(M, NS, MAXT, MINB)                                                                          \
+    {                                                                                                  \
+        if (dense) {                                                                                   \
+            if (extra) return launch(k_sweep_z<M, NS, 2, true, MAXT, MINB>, grid, block, smem, st, ctx, a, vec);  \
+            return launch(k_sweep_z<M, NS, 2, false, MAXT, MINB>, grid, block, smem, st, ctx, a, vec);            \
+        }                                                                                              \
+        if (extra) return launch(k_sweep_z<M, NS, 1, true, MAXT, MINB>, grid, block, smem, st, ctx, a, vec);      \
+        return launch(k_sweep_z<M, NS, 1, false, MAXT, MINB>, grid, block, smem, st, ctx, a, vec);                \
+    }
+    ADI_FOR_VARIANT(s.var, ADI_GO)
+#undef ADI_GO
+    return ADI_OK;
+}
+
+}  // namespace adi

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "adi_core.h"
@@ -14,30 +15,46 @@ using namespace adi;
 
 namespace {
 
-constexpr int M = 16;
+template <int M>
+struct HostOps {
+    const double *coeff, *qp, *dvp;  // offset to the chunk's first cell; may be null
+    size_t stride;
+    int nv;
+    double f[2 * M];                 // factor store (shared memory on the device)
+    double coef(int e) const { return (coeff && e < nv) ? coeff[(size_t)e * stride] : 0.0; }
+    double q(int e) const { return (qp && e < nv) ? qp[(size_t)e * stride] : 0.0; }
+    double dirv(int e) const { return (dvp && e < nv) ? dvp[(size_t)e * stride] : 0.0; }
+    void put2(int e, double la, double u) { f[2 * e] = la; f[2 * e + 1] = u; }
+    double la(int e) const { return f[2 * e]; }
+    double u(int e) const { return f[2 * e + 1]; }
+    void put1(int e, double v) { f[e] = v; }
+    double rinv(int e) const { return f[e]; }
+};
 
-template <int CMODE, bool EXTRA>
+template <int M, int NS, int CMODE, bool EXTRA>
 void sweep_line(double *T, const uint8_t *code, const double *coeff, const double *q,
                 const double *dirv, size_t base, size_t stride, int n, unsigned LO, unsigned HI,
                 const SweepConst &k)
 {
     const int P = (n + M - 1) / M;
     std::vector<Chunk<M>> ch(P);
+    std::vector<HostOps<M>> ops(P);
     std::vector<First> fi(P);
     std::vector<Red> red(P), nxt(P);
     for (int p = 0; p < P; ++p) {
-        double Q[M], DV[M];
+        const size_t idx0 = base + (size_t)p * M * stride;
+        ops[p].coeff = coeff ? coeff + idx0 : nullptr;
+        ops[p].qp = q ? q + idx0 : nullptr;
+        ops[p].dvp = dirv ? dirv + idx0 : nullptr;
+        ops[p].stride = stride;
+        ops[p].nv = std::min(std::max(n - p * M, 0), M);
         for (int e = 0; e < M; ++e) {
-            const int t = p * M + e;
-            const bool ok = t < n;
-            const size_t idx = base + (size_t)t * stride;
-            ch[p].code[e] = ok ? code[idx] : 0u;
-            ch[p].T[e] = ok ? T[idx] : 0.0;
-            ch[p].Cc[e] = (CMODE == 2 && ok) ? coeff[idx] : 0.0;
-            Q[e] = (q && ok) ? q[idx] : 0.0;
-            DV[e] = (dirv && ok && (ch[p].code[e] & CB_DIR)) ? dirv[idx] : 0.0;
+            const bool ok = e < ops[p].nv;
+            const size_t idx = idx0 + (size_t)e * stride;
+            ch[p].set_code(e, ok ? code[idx] : 0u);
+            ch[p].T[e] = (ok && (code[idx] & CB_SELF)) ? T[idx] : 0.0;   // load rule
         }
-        fi[p] = chunk_forward<M, CMODE, EXTRA>(ch[p], Q, DV, LO, HI, k);
+        fi[p] = chunk_forward<M, CMODE, EXTRA, NS>(ch[p], ops[p], LO, HI, k);
     }
     for (int p = 0; p < P; ++p) {
         First nx;
@@ -57,11 +74,23 @@ void sweep_line(double *T, const uint8_t *code, const double *coeff, const doubl
         red.swap(nxt);
     }
     for (int p = 0; p < P; ++p) {
-        chunk_backward<M>(ch[p], p > 0 ? red[p - 1].D : 0.0, red[p].D);
-        for (int e = 0; e < M; ++e) {
-            const int t = p * M + e;
-            if (t < n) T[base + (size_t)t * stride] = ch[p].T[e];
-        }
+        chunk_backward<M, EXTRA, NS>(ch[p], ops[p], LO, HI, k.g, p > 0 ? red[p - 1].D : 0.0, red[p].D);
+        for (int e = 0; e < ops[p].nv; ++e)
+            if (ch[p].active(e)) T[base + ((size_t)p * M + e) * stride] = ch[p].T[e];
+    }
+}
+
+template <int M, int NS>
+void sweep_line_any(bool dense, bool extra, double *T, const uint8_t *code, const double *coeff,
+                    const double *q, const double *dirv, size_t base, size_t stride, int n, unsigned LO,
+                    unsigned HI, const SweepConst &k)
+{
+    if (dense) {
+        if (extra) sweep_line<M, NS, 2, true>(T, code, coeff, q, dirv, base, stride, n, LO, HI, k);
+        else sweep_line<M, NS, 2, false>(T, code, coeff, nullptr, nullptr, base, stride, n, LO, HI, k);
+    } else {
+        if (extra) sweep_line<M, NS, 1, true>(T, code, nullptr, q, dirv, base, stride, n, LO, HI, k);
+        else sweep_line<M, NS, 1, false>(T, code, nullptr, nullptr, nullptr, base, stride, n, LO, HI, k);
     }
 }
 
@@ -81,23 +110,25 @@ void emu_build_code(const uint8_t *mask, const uint8_t *dirm, uint8_t *code, int
                 if (mask[idx]) {
                     c = CB_SELF;
                     if (dirm && dirm[idx]) c |= CB_DIR;
+                    if (i > 0 && mask[idx - snx]) c |= CB_XM;
+                    if (i + 1 < nx && mask[idx + snx]) c |= CB_XP;
+                    if (j > 0 && mask[idx - nz]) c |= CB_YM;
+                    if (j + 1 < ny && mask[idx + nz]) c |= CB_YP;
+                    if (k > 0 && mask[idx - 1]) c |= CB_ZM;
+                    if (k + 1 < nz && mask[idx + 1]) c |= CB_ZP;
                 }
-                if (i > 0 && mask[idx - snx]) c |= CB_XM;
-                if (i + 1 < nx && mask[idx + snx]) c |= CB_XP;
-                if (j > 0 && mask[idx - nz]) c |= CB_YM;
-                if (j + 1 < ny && mask[idx + nz]) c |= CB_YP;
-                if (k > 0 && mask[idx - 1]) c |= CB_ZM;
-                if (k + 1 < nz && mask[idx + 1]) c |= CB_ZP;
                 code[idx] = (uint8_t)c;
             }
 }
 
 // One full step with the operand conventions of adi_cart_step (adi_b200.h).
 // coeff[a]/q[a]/dirm[a]/dirv[a] may be NULL; face_coeff != NULL selects the scalar Robin mode.
+// variant: 0 = M 16 / two factors per cell, 1 = M 32 / one factor per cell (adi_launch.h)
 int emu_cart_step(const double *Tin, double *Tout, const uint8_t *mask, int nx, int ny, int nz,
                   double dx, double dt, double theta, double kappa, double Tinf,
                   const double *const coeff[3], const uint8_t *const dirm[3],
-                  const double *const dirv[3], const double *const q[3], const double *face_coeff)
+                  const double *const dirv[3], const double *const q[3], const double *face_coeff,
+                  int variant)
 {
     const size_t n = (size_t)nx * ny * nz;
     std::vector<uint8_t> code(n ? n : 1);
@@ -114,16 +145,15 @@ int emu_cart_step(const double *Tin, double *Tout, const uint8_t *mask, int nx, 
     for (size_t idx = 0; idx < n; ++idx) {
         const unsigned c = code[idx];
         double v[6] = {0, 0, 0, 0, 0, 0};
-        if (c & CB_SELF) {
-            if (c & CB_XM) v[0] = Tin[idx - snx];
-            if (c & CB_XP) v[1] = Tin[idx + snx];
-            if (c & CB_YM) v[2] = Tin[idx - nz];
-            if (c & CB_YP) v[3] = Tin[idx + nz];
-            if (c & CB_ZM) v[4] = Tin[idx - 1];
-            if (c & CB_ZP) v[5] = Tin[idx + 1];
-        }
-        Tout[idx] = (k.beta != 0.0) ? explicit_r0(c, Tin[idx], v[0], v[1], v[2], v[3], v[4], v[5], k)
-                                    : Tin[idx];
+        if (c & CB_XM) v[0] = Tin[idx - snx];
+        if (c & CB_XP) v[1] = Tin[idx + snx];
+        if (c & CB_YM) v[2] = Tin[idx - nz];
+        if (c & CB_YP) v[3] = Tin[idx + nz];
+        if (c & CB_ZM) v[4] = Tin[idx - 1];
+        if (c & CB_ZP) v[5] = Tin[idx + 1];
+        Tout[idx] = (k.beta != 0.0 && (c & CB_SELF))
+                        ? explicit_r0(c, Tin[idx], v[0], v[1], v[2], v[3], v[4], v[5], k)
+                        : Tin[idx];
     }
     for (int axis = 0; axis < 3; ++axis) {
         if (axis > 0) emu_build_code(mask, dirm[axis], code.data(), nx, ny, nz);
@@ -142,13 +172,12 @@ int emu_cart_step(const double *Tin, double *Tout, const uint8_t *mask, int nx, 
                 if (axis == 0) base = (size_t)u * nz + v;
                 else if (axis == 1) base = (size_t)u * snx + v;
                 else base = ((size_t)u * ny + v) * nz;
-                if (dense) {
-                    if (extra) sweep_line<2, true>(Tout, code.data(), coeff[axis], q[axis], dirv[axis], base, stride, len, LO, HI, k);
-                    else sweep_line<2, false>(Tout, code.data(), coeff[axis], nullptr, nullptr, base, stride, len, LO, HI, k);
-                } else {
-                    if (extra) sweep_line<1, true>(Tout, code.data(), nullptr, q[axis], dirv[axis], base, stride, len, LO, HI, k);
-                    else sweep_line<1, false>(Tout, code.data(), nullptr, nullptr, nullptr, base, stride, len, LO, HI, k);
-                }
+                if (variant == 0)
+                    sweep_line_any<16, 2>(dense, extra, Tout, code.data(), coeff[axis], q[axis], dirv[axis], base,
+                                          stride, len, LO, HI, k);
+                else
+                    sweep_line_any<32, 1>(dense, extra, Tout, code.data(), coeff[axis], q[axis], dirv[axis], base,
+                                          stride, len, LO, HI, k);
             }
     }
     return 0;

@@ -232,6 +232,9 @@ def run_ours(args):
     eng.bind(grid); eng.set_mask(grid); eng.set_packs(packs)
     ctx = eng.context()
     kappa = K / (RHO * CP)
+    for o in args.opt:
+        name, _, val = o.partition("=")
+        _capi.check(L.adi_set_option(ctx, name.encode(), int(val)), "adi_set_option")
     A = T0.clone()
     B = torch.empty_like(A)
     stream = torch.cuda.current_stream()
@@ -379,6 +382,8 @@ def main():
     ap.add_argument("--cpu-ny", type=int, default=128, help="y extent of the CPU-baseline sample slab")
     ap.add_argument("--ref-ny", type=int, default=64, help="y extent of the --impl reference sample slab")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="engine tuning option (adi_set_option), e.g. --opt m=32 --opt kt=16")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -29,7 +29,7 @@ def _ptr(a, ty):
 
 
 def cart_step(T, mask, dx, dt, theta, kappa, Tinf, coeff=(None,) * 3, dirm=(None,) * 3,
-              dirv=(None,) * 3, q=(None,) * 3, face_coeff=None):
+              dirv=(None,) * 3, q=(None,) * 3, face_coeff=None, variant=0):
     L = lib()
     T = np.ascontiguousarray(T, dtype=np.float64)
     nx, ny, nz = T.shape
@@ -55,10 +55,10 @@ def cart_step(T, mask, dx, dt, theta, kappa, Tinf, coeff=(None,) * 3, dirm=(None
     if face_coeff is not None:
         fc = np.ascontiguousarray(face_coeff, dtype=np.float64)
     L.emu_cart_step.argtypes = [dp, dp, bp, C.c_int, C.c_int, C.c_int] + [C.c_double] * 5 + \
-        [C.POINTER(dp), C.POINTER(bp), C.POINTER(dp), C.POINTER(dp), dp]
+        [C.POINTER(dp), C.POINTER(bp), C.POINTER(dp), C.POINTER(dp), dp, C.c_int]
     rc = L.emu_cart_step(_ptr(T, C.c_double), _ptr(out, C.c_double), _ptr(m8, C.c_uint8), nx, ny, nz,
                          dx, dt, theta, kappa, Tinf, arr3(coeff, C.c_double, np.float64),
                          arr3(dirm, C.c_uint8, np.bool_), arr3(dirv, C.c_double, np.float64),
-                         arr3(q, C.c_double, np.float64), _ptr(fc, C.c_double))
+                         arr3(q, C.c_double, np.float64), _ptr(fc, C.c_double), int(variant))
     assert rc == 0
     return out

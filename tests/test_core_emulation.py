@@ -21,8 +21,9 @@ def _packs(c):
     return cart.precompute_coeff_packs_unified(grid, mat, robin_Tinf=c["Tinf"], **c["bcs"])
 
 
+@pytest.mark.parametrize("variant", [0, 1], ids=["M16_two_factors", "M32_one_factor"])
 @pytest.mark.parametrize("name", sorted(cases.CART_CASES))
-def test_emulated_kernel_matches_reference(name, golden_dir):
+def test_emulated_kernel_matches_reference(name, variant, golden_dir):
     c = cases.build_cart_case(name)
     g = np.load(os.path.join(golden_dir, f"cart_{name}.npz"))
     packs = _packs(c)
@@ -34,7 +35,7 @@ def test_emulated_kernel_matches_reference(name, golden_dir):
                           coeff=[p.coeff for p in packs],
                           dirm=[p.dir_mask if has_dir else None for p in packs],
                           dirv=[p.dir_val if has_dir else None for p in packs],
-                          q=[p.qflux if p.qflux.any() else None for p in packs])
+                          q=[p.qflux if p.qflux.any() else None for p in packs], variant=variant)
     m = c["mask"]
     assert cases.rel_l2(T, g["T_out"], m) <= TOL
     assert np.array_equal(T[~m], c["T0"][~m], equal_nan=True)

@@ -256,3 +256,65 @@ def test_full_size_linearity_and_ambient_fixed_point(g, cp, big):
     rhs = 2.0 * step(A) - 3.0 * step(B)
     err = ((lhs - rhs)[m].norm() / rhs[m].norm()).item()
     assert err <= 1e-13
+
+
+def _oracle_case(shape, seed, theta=0.5, cfl=1.3, holes=True):
+    """Seeded case checked against the oracle directly (no golden file): dense per-face Robin h,
+    a Neumann face, Dirichlet plane, random holes, NaN in the void."""
+    from oracle import cart
+    nx, ny, nz = shape
+    mask = np.ones(shape, bool)
+    if holes:
+        mask &= cases.splitmix_uniform(seed, shape) > 0.15
+    T0 = 20.0 + 900.0 * cases.splitmix_uniform(seed + 1, shape)
+    T0[~mask] = np.nan
+    kappa = cases.K / (cases.RHO * cases.CP)
+    dt = cfl * cases.DX ** 2 / kappa
+    h = {f: 400.0 * cases.splitmix_uniform(seed + 2 + i, shape) for i, f in enumerate(cart.FACES)}
+    dm = cases.splitmix_uniform(seed + 20, shape) < 0.02
+    bcs = dict(robin_h=h, neumann={"z-": 2.0e5, "x+": 1.0e5}, dir_mask=dm, dir_value=333.0)
+    return dict(shape=shape, mask=mask, T0=T0, dt=dt, theta=theta, bcs=bcs, kappa=kappa)
+
+
+def _both(g, cp, c, nsteps=2, Tinf=20.0):
+    from oracle import cart
+    nx, ny, nz = c["shape"]
+    gh = cart.Grid3D(nx, ny, nz, cases.DX, c["mask"])
+    mh = cart.Material(cases.RHO, cases.CP, cases.K)
+    ph = cart.precompute_coeff_packs_unified(gh, mh, **c["bcs"])
+    gd = g.Grid3D(nx, ny, nz, cases.DX, c["mask"])
+    md = g.Material(cases.RHO, cases.CP, cases.K)
+    pd = g.precompute_coeff_packs_unified(gd, md, **c["bcs"])
+    Th, Td = c["T0"], cp.asarray(c["T0"])
+    for _ in range(nsteps):
+        Th = cart.adi_step_numba_coeff(Th, gh, mh, cart.Params(c["dt"], c["theta"]), ph, Tinf=Tinf)
+        Td = g.adi_step_gpu_coeff(Td, gd, md, g.Params(c["dt"], c["theta"]), pd, Tinf=Tinf)
+    Td = cp.asnumpy(Td)
+    m = c["mask"]
+    assert cases.rel_l2(Td, Th, m) <= TOL
+    assert np.array_equal(Td[~m], c["T0"][~m], equal_nan=True)
+
+
+@pytest.mark.parametrize("shape", [(1100, 3, 6), (5, 1300, 4), (3, 4, 2100), (600, 7, 520), (2, 2050, 34)])
+def test_long_lines_select_the_M32_variants(shape, g, cp):
+    """Lines of 513..1024 cells run the M=32 / 256-thread kernels, 1025..4096 the 512-thread ones."""
+    _both(g, cp, _oracle_case(shape, seed=4000 + shape[0]))
+
+
+@pytest.mark.parametrize("opts", [dict(m=32), dict(m=32, kt=16), dict(kt=4), dict(lt=2), dict(m=32, lt=4)])
+@pytest.mark.parametrize("shape", [(40, 67, 130), (96, 33, 64)])
+def test_kernel_variant_options_agree(shape, opts, g, cp):
+    """Every tunable launch shape (adi_set_option) gives the same answer."""
+    for k, v in opts.items():
+        g.set_option(k, v)
+    try:
+        _both(g, cp, _oracle_case(shape, seed=5000 + shape[2]), nsteps=1)
+        _both(g, cp, _oracle_case(shape, seed=5100 + shape[2], theta=1.0, cfl=40.0), nsteps=1)
+    finally:
+        for k in opts:
+            g.set_option(k, 0)
+
+
+def test_ragged_and_tiny_grids(g, cp):
+    for shape in [(1, 1, 1), (2, 1, 3), (1, 17, 1), (16, 16, 16), (17, 33, 15), (31, 2, 47)]:
+        _both(g, cp, _oracle_case(shape, seed=6000 + sum(shape), holes=shape != (1, 1, 1)), nsteps=1)

@@ -119,26 +119,67 @@ __device__ __forceinline__ double solve_reduced(const Chunk<M> &ch, const First 
 // R0 = T + beta*(Lx+Ly+Lz) (adi3d_numba_coeff.py:298) is applied while loading.
 // Shared memory: rv[M][NTH] pivot reciprocals, red[6*NTH] reduced-system exchange.
 // ------------------------------------------------------------------------------------
-template <int M>
+// ---- small PTX helpers -----------------------------------------------------------------
+// Loads are written as volatile asm so that the compiler keeps them, in program order, in
+// front of the cp.async group and its wait: every global operand of a chunk is then in
+// flight at once (one memory round trip per thread).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double ldg_f64(const void *p)
+{
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ldg_u8(const void *p)
+{
+    unsigned v;
+    asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cp_async8(unsigned dst_smem, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, int src_bytes)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Shared-memory columns of the strided sweeps: slot s of cell e of thread tid lives at
+// col[(s*M + e)*NTH] (col = smem + tid), so a warp access is a run of consecutive doubles.
+//   slot 0  dense coefficient (staged with cp.async)  ->  la (NS 2) / rinv (NS 1)
+//   slot 1  [explicit stage: y- neighbour row]        ->  u  (NS 2)
+//   slot 2  [explicit stage: y+ neighbour row]        ->  reduced-system exchange buffer
+template <int M, bool STAGED>
 struct StridedOps {
     const double *coeff, *qp, *dvp;  // already offset to the chunk's first cell; may be null
     unsigned sl;  // stride between consecutive cells of the line (elements)
     int nv;       // valid cells of this chunk (0 for an out-of-range lane)
-    double *sm;   // &column[tid]: factor store, slot s of cell e at sm[(NS*e + s)*NTH]
+    double *col;
     int NTH;
-    __device__ __forceinline__ double coef(int e) const { return e < nv ? coeff[e * sl] : 0.0; }
+    __device__ __forceinline__ double coef(int e) const
+    {
+        if (STAGED) return col[e * NTH];
+        return e < nv ? coeff[e * sl] : 0.0;
+    }
     __device__ __forceinline__ double q(int e) const { return (qp && e < nv) ? qp[e * sl] : 0.0; }
     __device__ __forceinline__ double dirv(int e) const { return (dvp && e < nv) ? dvp[e * sl] : 0.0; }
-    __device__ __forceinline__ void put2(int e, double la, double u) { sm[(2 * e) * NTH] = la; sm[(2 * e + 1) * NTH] = u; }
-    __device__ __forceinline__ double la(int e) const { return sm[(2 * e) * NTH]; }
-    __device__ __forceinline__ double u(int e) const { return sm[(2 * e + 1) * NTH]; }
-    __device__ __forceinline__ void put1(int e, double v) { sm[e * NTH] = v; }
-    __device__ __forceinline__ double rinv(int e) const { return sm[e * NTH]; }
+    __device__ __forceinline__ void put2(int e, double la, double u) { col[e * NTH] = la; col[(M + e) * NTH] = u; }
+    __device__ __forceinline__ double la(int e) const { return col[e * NTH]; }
+    __device__ __forceinline__ double u(int e) const { return col[(M + e) * NTH]; }
+    __device__ __forceinline__ void put1(int e, double v) { col[e * NTH] = v; }
+    __device__ __forceinline__ double rinv(int e) const { return col[e * NTH]; }
 };
 
 template <int AXIS, int M, int NS, int CMODE, bool EXTRA, bool EXPL, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
 {
+    // STAGED: every global operand of the chunk is requested up front -- T and codes into
+    // registers, the coefficient and (explicit stage) the y/z neighbour values with cp.async
+    // into the thread's shared-memory column -- so the thread pays one memory round trip.
+    constexpr bool STAGED = (NS == 2);
     extern __shared__ double smem[];
     const int KT = blockDim.x, P = blockDim.y;
     const int kk = threadIdx.x, p = threadIdx.y;
@@ -154,20 +195,101 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
     // first cell of the chunk (clamped in-range so that pointer arithmetic stays valid)
     const size_t idx0 = ((AXIS == 0) ? (size_t)blockIdx.y * a.nz : (size_t)blockIdx.y * a.ny * a.nz) +
                         (size_t)min(k, a.nz - 1) + (size_t)min(t0, n - 1) * sl;
-    double *red = smem + (size_t)NS * M * NTH;
+    double *col = smem + tid;
+    double *red = smem + (size_t)2 * M * NTH;             // NS 1: behind slot 0 and a spare slot
+    double *halo = smem + (size_t)3 * M * NTH;            // [2][M][P], explicit stage only
     const double *tp = a.in + idx0;
 
     Chunk<M> ch;
-    {
+    double xprev = 0.0, xnext = 0.0;
+    if (STAGED) {
+        // Cells beyond the chunk's valid range (line end / z tile end) re-read the last valid
+        // cell (or the clamped first one): their code is forced to 0, so the values are
+        // never used.  Likewise neighbour rows outside the domain re-read the cell itself.
+        const int nvm1 = max(nv - 1, 0);
+        const unsigned sl8 = sl * 8u;
+        const char *tb = reinterpret_cast<const char *>(tp);
+        {
+            const uint8_t *cb = a.code + idx0;
+#pragma unroll
+            for (int e = 0; e < M; ++e) {
+                const unsigned cv = ldg_u8(cb + (size_t)((unsigned)min(e, nvm1) * sl));
+                ch.set_code(e, e < nv ? cv : 0u);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < M; ++e) ch.T[e] = ldg_f64(tb + (size_t)((unsigned)min(e, nvm1) * sl8));
+        const unsigned scol = smem_u32(col);
+        const unsigned nth8 = (unsigned)NTH * 8u;
+        if (CMODE == 2) {
+            const char *cf = reinterpret_cast<const char *>(a.coeff + idx0);
+#pragma unroll
+            for (int e = 0; e < M; ++e) cp_async8(scol + e * nth8, cf + (size_t)((unsigned)min(e, nvm1) * sl8));
+        }
+        if (EXPL) {
+            // AXIS 0: blockIdx.y is the y index
+            const long long ym_off = blockIdx.y > 0 ? -8ll * a.nz : 0ll;
+            const long long yp_off = (int)blockIdx.y + 1 < a.ny ? 8ll * a.nz : 0ll;
+#pragma unroll
+            for (int e = 0; e < M; ++e) {
+                const char *pc = tb + (size_t)((unsigned)min(e, nvm1) * sl8);
+                cp_async8(scol + (M + e) * nth8, pc + ym_off);
+                cp_async8(scol + (2 * M + e) * nth8, pc + yp_off);
+            }
+            if (kk == 0) {
+                const long long off = k > 0 ? -8ll : 0ll;
+                const unsigned sh = smem_u32(halo + p);
+#pragma unroll
+                for (int e = 0; e < M; ++e)
+                    cp_async8(sh + e * (unsigned)P * 8u, tb + (size_t)((unsigned)min(e, nvm1) * sl8) + off);
+            }
+            if (kk == KT - 1) {
+                const long long off = (k + 1 < a.nz && nv > 0) ? 8ll : 0ll;
+                const unsigned sh = smem_u32(halo + M * P + p);
+#pragma unroll
+                for (int e = 0; e < M; ++e)
+                    cp_async8(sh + e * (unsigned)P * 8u, tb + (size_t)((unsigned)min(e, nvm1) * sl8) + off);
+            }
+            xprev = ldg_f64(tb - ((nv > 0 && t0 > 0) ? (long long)sl8 : 0ll));
+            xnext = ldg_f64(tb + ((nv == M && t0 + M < n) ? (long long)M * sl8 : 0ll));
+        }
+        // The barrier keeps every load above it (the compiler would otherwise sink them next
+        // to their uses, one memory round trip per batch); the wait comes after it.
+        __syncthreads();
+        cp_async_wait_all();
+    } else {
         const uint8_t *cp = a.code + idx0;
 #pragma unroll
         for (int e = 0; e < M; ++e) ch.set_code(e, e < nv ? (unsigned)cp[e * sl] : 0u);
 #pragma unroll
         for (int e = 0; e < M; ++e) ch.T[e] = e < nv ? tp[e * sl] : 0.0;
-#pragma unroll
-        for (int e = 0; e < M; ++e) ch.T[e] = ch.active(e) ? ch.T[e] : 0.0;  // load rule (adi_core.h)
     }
-    if (EXPL) {
+#pragma unroll
+    for (int e = 0; e < M; ++e) ch.T[e] = ch.active(e) ? ch.T[e] : 0.0;  // load rule (adi_core.h)
+
+    if (EXPL && STAGED) {
+        double prev = (ch.code(0) & CB_XM) ? xprev : 0.0;
+        const double nxt = (ch.code(M - 1) & CB_XP) ? xnext : 0.0;
+#pragma unroll
+        for (int e = 0; e < M; ++e) {
+            const unsigned c = ch.code(e);
+            const double ymr = col[(M + e) * NTH], ypr = col[(2 * M + e) * NTH];
+            const double ym = (c & CB_YM) ? ymr : 0.0;
+            const double yp = (c & CB_YP) ? ypr : 0.0;
+            // z neighbours: the adjacent lanes hold them (already 0 where void); the first /
+            // last lane of the z tile takes the staged halo value instead
+            double zm = __shfl_up_sync(0xffffffffu, ch.T[e], 1);
+            double zp = __shfl_down_sync(0xffffffffu, ch.T[e], 1);
+            if (kk == 0) zm = (c & CB_ZM) ? halo[e * P + p] : 0.0;
+            if (kk == KT - 1) zp = (c & CB_ZP) ? halo[(M + e) * P + p] : 0.0;
+            // x neighbours come from the chunk registers: already 0 where void; a void cell
+            // itself (code 0, T 0) must stay 0 whatever its neighbours hold
+            const double xp = (e < M - 1) ? ch.T[e + 1] : nxt;
+            const double r0 = explicit_r0(c, ch.T[e], prev, xp, ym, yp, zm, zp, a.k);
+            prev = ch.T[e];
+            ch.T[e] = (c & CB_SELF) ? r0 : 0.0;
+        }
+    } else if (EXPL) {
         // neighbour values are only ever loaded where the code says the neighbour is active
         const unsigned c0 = ch.code(0), cl = ch.code(M - 1);
         double prev = (c0 & CB_XM) ? *(tp - sl) : 0.0;
@@ -181,8 +303,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
             const double yp = (c & CB_YP) ? *(pc + sy) : 0.0;
             const double zm = (c & CB_ZM) ? *(pc - 1) : 0.0;
             const double zp = (c & CB_ZP) ? *(pc + 1) : 0.0;
-            // x neighbours come from the chunk registers: already 0 where void; a void cell
-            // itself (code 0, T 0) must stay 0 whatever its neighbours hold
             const double xp = (e < M - 1) ? ch.T[e + 1] : nxt;
             const double r0 = explicit_r0(c, ch.T[e], prev, xp, ym, yp, zm, zp, a.k);
             prev = ch.T[e];
@@ -190,16 +310,17 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
         }
     }
 
-    StridedOps<M> ops;
+    StridedOps<M, STAGED> ops;
     ops.coeff = (CMODE == 2) ? a.coeff + idx0 : nullptr;
     ops.qp = (EXTRA && a.q) ? a.q + idx0 : nullptr;
     ops.dvp = (EXTRA && a.dirv) ? a.dirv + idx0 : nullptr;
     ops.sl = sl;
     ops.nv = nv;
-    ops.sm = smem + tid;
+    ops.col = col;
     ops.NTH = NTH;
 
     const First f = chunk_forward<M, CMODE, EXTRA, NS>(ch, ops, LO, HI, a.k);
+    if (EXPL && STAGED) __syncthreads();  // slot 2 (other threads' y+ values) becomes the exchange buffer
     double Sl;
     const double S = solve_reduced<M>(ch, f, red, NTH, tid, KT, p, P, &Sl);
     chunk_backward<M, EXTRA, NS>(ch, ops, LO, HI, a.k.g, Sl, S);
@@ -226,12 +347,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
 // chunks, 128 B apart) then hit eight different bank groups, without padding.
 // The reduced-system exchange buffer aliases sT while the chunk lives in registers.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, int src_bytes)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(dst_smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int M>
 __device__ __forceinline__ int zslot(int chunk, int pair)

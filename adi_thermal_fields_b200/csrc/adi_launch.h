@@ -31,7 +31,11 @@ inline int pick_shape(adi_ctx *ctx, int n, long opt_w, Shape *s)
     const int P = (n + M - 1) / M;
     int W = 32;
     while (W > 1 && W * P > maxt) W >>= 1;
-    if (opt_w > 0) W = (int)std::min<long>(opt_w, maxt / P);
+    if (opt_w > 0) {
+        int w = 1;
+        while (2 * w <= opt_w && 2 * w <= 32 && 2 * w * P <= maxt) w <<= 1;  // power of two
+        W = w;
+    }
     if (W < 1) W = 1;
     s->var = var; s->M = M; s->NS = var == VAR_16 ? 2 : 1; s->P = P; s->W = W;
     return ADI_OK;

@@ -13,7 +13,7 @@ int launch_sweep_z(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, cud
     // lines per block: fill the block, but keep the staged tiles small enough for two
     // resident blocks per SM where the line length allows it
     const size_t line_bytes = (size_t)s.P * s.M * (8 * (1 + s.NS) + 1);  // T + factor tiles + codes
-    const size_t budget = s.var == VAR_32L ? 220 * 1024 : 110 * 1024;
+    const size_t budget = s.var == VAR_32L ? 220 * 1024 : 28 * 1024;  // small blocks overlap best (measured)
     int LT = s.W;
     while (LT > 1 && LT * line_bytes > budget) LT >>= 1;
     if (ctx->opt_lt > 0) LT = (int)std::min<long>(ctx->opt_lt, s.W);

@@ -1,12 +1,14 @@
 #!/bin/bash
 # Runs on the B200 box: GPU tests, then short device-resident bench runs over launch-shape options.
-tag=${1:-t}
+# usage: tools/gpu_tune.sh tag "opts1" "opts2" ...
+tag=${1:-t}; shift
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/${tag}_pytest.log
 tail -8 gpurun_out/${tag}_pytest.log
 : > gpurun_out/${tag}_tune.jsonl
-for o in "" "--opt kt=4" "--opt m=32" "--opt m=32 --opt kt=16" "--opt lt=4" "--opt lt=2" "--opt m=32 --opt lt=4"; do
+if [ $# -eq 0 ]; then set -- ""; fi
+for o in "$@"; do
   echo "== $o" | tee -a gpurun_out/${tag}_tune.jsonl
   timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --e2e-steps 1 $o 2>>gpurun_out/${tag}_tune.err | tee -a gpurun_out/${tag}_tune.jsonl | python -c "
 import sys,json

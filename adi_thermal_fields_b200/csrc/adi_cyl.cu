@@ -1,8 +1,516 @@
-// placeholder, replaced below
+// adi_cyl.cu -- cylindrical (r, phi, z) backward-Euler ADI step on sm_100a
+// (adi3d_cyl_phi_v3.py:332-350, scheme "be") and its activation-mask wrapper
+// (quick_spiral_deposition_gif_v5.py:31-70).
+//
+// K4 k_cyl_strided   r sweep (stride nphi*nz_pitch) and periodic phi sweep (stride nz_pitch):
+//                    lanes run along z, so a warp's loads/stores are runs of contiguous cells;
+//                    each thread keeps one chunk of its line in registers
+// K6 k_cyl_z         z sweep (contiguous): a tile of lines is staged through padded shared
+//                    memory (conflict-free column reads), then the same chunk solve runs with
+//                    the threads of a line side by side
+// All matrix work is tabulated on the host (adi_tab_core.h); the kernels stream right-hand
+// sides.  The r sweep applies the prologue of the step (source term :339, void clamp of
+// adi_step_masked :55-57), the z sweep its epilogue (void / axis clamps :61-68).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
 #include "adi_ctx.h"
-namespace adi { void cyl_release(adi_ctx *) {} }
-extern "C" {
-int adi_cyl_bind(adi_ctx *, int, int, int, int, double, double, double) { adi::set_error("cyl: not built"); return ADI_ESTATE; }
-int adi_cyl_step(adi_ctx *, const double *, double *, const adi_cyl_params *, const uint8_t *, const double *, void *) { adi::set_error("cyl: not built"); return ADI_ESTATE; }
-int adi_cyl_step_host(adi_ctx *, const double *, double *, int, const adi_cyl_params *, const uint8_t *, const double *, void *) { adi::set_error("cyl: not built"); return ADI_ESTATE; }
+#include "adi_tab_core.h"
+
+namespace adi {
+
+struct CylTables {
+    // cache key: everything the tables depend on
+    adi_cyl_params key;
+    bool valid = false;
+    int nr = 0, nphi = 0, nz = 0, M = 0;
+    TabGeom gr, gp, gz;
+    double *d_blob = nullptr;  // [r blob | z blob | nr phi blobs]
+    int *d_geom = nullptr;     // [r ints | z ints | phi ints]
+    size_t blob_cap = 0, geom_cap = 0;
+    size_t off_r = 0, off_z = 0, off_p = 0;   // blob offsets (doubles)
+    size_t goff_r = 0, goff_z = 0, goff_p = 0;  // geom offsets (ints)
+    double add_r = 0.0;
+    ZEnd bot, top;
+};
+
+void cyl_release(adi_ctx *ctx)
+{
+    if (!ctx->cyl) return;
+    if (ctx->cyl->d_blob) cudaFree(ctx->cyl->d_blob);
+    if (ctx->cyl->d_geom) cudaFree(ctx->cyl->d_geom);
+    delete ctx->cyl;
+    ctx->cyl = nullptr;
 }
+
+struct CylArgs {
+    const double *in;       // may alias out (phi and z sweeps run in place)
+    double *out;
+    const double *blob;     // table blob of blockIdx.y == 0
+    const int *geom;
+    long long blob_stride;  // doubles between the blobs of consecutive blockIdx.y (phi: per ring)
+    TabGeom g;
+    int nz;                 // valid cells along z (lanes of the strided sweeps / line length of z)
+    long long cell_stride;  // between consecutive cells of a strided line
+    long long outer_stride; // between consecutive blockIdx.y planes (strided) / lines (z)
+    long long nlines;       // z sweep: number of lines
+    int nphi;               // z sweep: line / nphi = ring index
+    // prologue (r sweep)
+    const uint8_t *active;  // NULL: unmasked
+    double T_void, T_inner;
+    const double *S;        // NULL: no source
+    double dt, rho_cp;
+    // right-hand side boundary terms: first / last cell of the line
+    int set_first, set_last;
+    double val_first, val_last;
+};
+
+__device__ __forceinline__ void load_tables(const CylArgs &a, double *sTab, int *sGeom, int tid, int nth,
+                                            const double *blob)
+{
+    for (int i = tid; i < a.g.ndbl; i += nth) sTab[i] = blob[i];
+    for (int i = tid; i < 3 * a.g.P; i += nth) sGeom[i] = a.geom[i];
+}
+
+// Reduced system over the P chunks of a line.  ex: 3*NTH doubles; slot(q) = index of chunk q of
+// this thread's line.  Returns S_p, *Sl = S_{p-1}.
+template <class SLOT>
+__device__ __forceinline__ double cyl_reduced(const CylArgs &a, const double *sTab, double *ex, int NTH,
+                                              int p, double ds, double Y, double Yl, SLOT slot, double *Sl)
+{
+    const int P = a.g.P, cyc = a.g.cyclic;
+    double *sY = ex + 2 * NTH;
+    sY[slot(p)] = Y;
+    __syncthreads();
+    const double Ynext = sY[slot(tab_hi(p, 1, P, cyc))];
+    double D = tab_reduced_rhs(sTab[a.g.o_t0 + p], sTab[a.g.o_t1 + p], sTab[a.g.o_t2 + p], ds, Yl, Ynext);
+    int cur = 0;
+    for (int l = 0; l < a.g.levels; ++l) {
+        const int s = 1 << l;
+        double *b = ex + cur * NTH;
+        b[slot(p)] = D;
+        __syncthreads();
+        const double Dlo = b[slot(tab_lo(p, s, P, cyc))];
+        const double Dhi = b[slot(tab_hi(p, s, P, cyc))];
+        const double *R = sTab + a.g.o_lvl + l * 3 * P;
+        D = tab_level(R[p], R[P + p], R[2 * P + p], D, Dlo, Dhi);
+        cur ^= 1;
+    }
+    double *b = ex + cur * NTH;
+    b[slot(p)] = D;
+    __syncthreads();
+    *Sl = b[slot(tab_lo(p, 1, P, cyc))];
+    return D;
+}
+
+// ------------------------------------------------------------------------------------
+// K4: strided sweeps.  blockDim = (KT lanes along z, P chunks); grid = (ceil(nz/KT), nouter).
+// PRO: r sweep of the step -- applies the void clamp and the source term while loading.
+// ------------------------------------------------------------------------------------
+template <int M, bool PRO>
+__global__ void __launch_bounds__(256) k_cyl_strided(const CylArgs a)
+{
+    extern __shared__ double smem[];
+    const int KT = blockDim.x, P = blockDim.y;
+    const int kk = threadIdx.x, p = threadIdx.y;
+    const int NTH = KT * P, tid = p * KT + kk;
+    double *sTab = smem;
+    double *ex = sTab + a.g.ndbl;
+    int *sGeom = reinterpret_cast<int *>(ex + 3 * NTH);
+    load_tables(a, sTab, sGeom, tid, NTH, a.blob + (size_t)blockIdx.y * a.blob_stride);
+
+    const int k = blockIdx.x * KT + kk;
+    const bool lane_ok = k < a.nz;
+    const size_t base = (size_t)blockIdx.y * a.outer_stride + (size_t)min(k, a.nz - 1);
+    __syncthreads();
+    const int cb = sGeom[p], endp = sGeom[P + p], len = sGeom[2 * P + p];
+    const int n = a.g.n;
+
+    double d[M];
+#pragma unroll
+    for (int e = 0; e < M; ++e) {
+        const int i = endp - (M - 1 - e);
+        const bool ok = lane_ok && e >= M - len;
+        double v = 0.0;
+        if (ok) {
+            const size_t g = base + (size_t)i * a.cell_stride;
+            v = a.in[g];
+            if (PRO) {
+                if (a.active && !a.active[g]) v = a.T_void;              // T_work[~active] = T_void
+                if (a.S) v = __dadd_rn(v, __dmul_rn(a.dt, __ddiv_rn(a.S[g], a.rho_cp)));  // :339
+            }
+            if (i == 0) v = a.set_first ? a.val_first : __dadd_rn(v, a.val_first);
+            if (i == n - 1) v = a.set_last ? a.val_last : __dadd_rn(v, a.val_last);
+        }
+        d[e] = v;
+    }
+    double Yl;
+    const double Y = tab_forward<M>(d, sTab + a.g.o_rinv + cb, sTab + a.g.o_la + cb, sTab + a.g.o_alpha + cb, &Yl);
+    double Sl;
+    const double S = cyl_reduced(a, sTab, ex, NTH, p, d[M - 1], Y, Yl, [=](int q) { return q * KT + kk; }, &Sl);
+    tab_backward<M>(d, sTab + a.g.o_u + cb, sTab + a.g.o_v + cb, Sl, S);
+#pragma unroll
+    for (int e = 0; e < M; ++e) {
+        const int i = endp - (M - 1 - e);
+        if (lane_ok && e >= M - len) a.out[base + (size_t)i * a.cell_stride] = d[e];
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K6: z sweep.  blockDim = (P chunks, LT lines); grid = ceil(nlines/LT).
+// Staged line layout: cell z at z + (z >> 4) (one pad per 16 cells: chunk starts 16 apart land
+// 17 doubles apart, so the 64-bit column reads of a half warp hit 16 different bank pairs).
+// EPI: last sweep of a masked step -- void cells := T_void, void axis cells := T_inner.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ int zphys(int z) { return z + (z >> 4); }
+
+template <int M, bool EPI>
+__global__ void __launch_bounds__(256) k_cyl_z(const CylArgs a)
+{
+    extern __shared__ double smem[];
+    const int P = blockDim.x, LT = blockDim.y;
+    const int p = threadIdx.x, ln = threadIdx.y;
+    const int NTH = P * LT, tid = ln * P + p;
+    const int nz = a.nz, n = nz;
+    const int RL = zphys(nz - 1) + 1;  // doubles per staged line
+    double *sTab = smem;
+    double *ex = sTab + a.g.ndbl;
+    double *sT = ex + 3 * NTH;
+    int *sGeom = reinterpret_cast<int *>(sT + (size_t)LT * RL);
+    load_tables(a, sTab, sGeom, tid, NTH, a.blob);
+
+    const long long L0 = (long long)blockIdx.x * LT;
+    for (int l = 0; l < LT; ++l) {
+        const long long line = L0 + l;
+        if (line >= a.nlines) break;
+        const double *src = a.in + (size_t)line * a.outer_stride;
+        for (int z = tid; z < nz; z += NTH) sT[(size_t)l * RL + zphys(z)] = src[z];
+    }
+    __syncthreads();
+    const int cb = sGeom[p], endp = sGeom[P + p], len = sGeom[2 * P + p];
+    const bool line_ok = L0 + ln < a.nlines;
+    double *myT = sT + (size_t)ln * RL;
+
+    double d[M];
+#pragma unroll
+    for (int e = 0; e < M; ++e) {
+        const int i = endp - (M - 1 - e);
+        double v = 0.0;
+        if (line_ok && e >= M - len) {
+            v = myT[zphys(i)];
+            if (i == 0) v = a.set_first ? a.val_first : __dadd_rn(v, a.val_first);
+            if (i == n - 1) v = a.set_last ? a.val_last : __dadd_rn(v, a.val_last);
+        }
+        d[e] = v;
+    }
+    double Yl;
+    const double Y = tab_forward<M>(d, sTab + a.g.o_rinv + cb, sTab + a.g.o_la + cb, sTab + a.g.o_alpha + cb, &Yl);
+    double Sl;
+    const double S = cyl_reduced(a, sTab, ex, NTH, p, d[M - 1], Y, Yl, [=](int q) { return ln * P + q; }, &Sl);
+    tab_backward<M>(d, sTab + a.g.o_u + cb, sTab + a.g.o_v + cb, Sl, S);
+#pragma unroll
+    for (int e = 0; e < M; ++e) {
+        const int i = endp - (M - 1 - e);
+        if (line_ok && e >= M - len) myT[zphys(i)] = d[e];
+    }
+    __syncthreads();
+    for (int l = 0; l < LT; ++l) {
+        const long long line = L0 + l;
+        if (line >= a.nlines) break;
+        double *dst = a.out + (size_t)line * a.outer_stride;
+        const uint8_t *act = EPI ? a.active + (size_t)line * a.outer_stride : nullptr;
+        const double vv = (EPI && line / a.nphi == 0) ? a.T_inner : a.T_void;  // :61-68
+        for (int z = tid; z < nz; z += NTH) {
+            double v = sT[(size_t)l * RL + zphys(z)];
+            if (EPI && !act[z]) v = vv;
+            dst[z] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+static bool same_key(const adi_cyl_params &x, const adi_cyl_params &y)
+{
+    // T_void / T_inner do not enter the tables
+    return x.dt == y.dt && x.rho == y.rho && x.cp == y.cp && x.k == y.k && x.h_r == y.h_r &&
+           x.Tinf_r == y.Tinf_r && x.kind_bot == y.kind_bot && x.kind_top == y.kind_top &&
+           x.h_bot == y.h_bot && x.h_top == y.h_top && x.Tinf_bot == y.Tinf_bot &&
+           x.Tinf_top == y.Tinf_top && x.T_bot == y.T_bot && x.T_top == y.T_top;
+}
+
+static int pick_M(int n) { return n <= 512 ? 16 : 32; }
+
+static int ensure_tables(adi_ctx *ctx, const adi_cyl_params &prm, cudaStream_t st)
+{
+    if (!ctx->cyl) ctx->cyl = new CylTables();
+    CylTables &T = *ctx->cyl;
+    const int nr = ctx->nr, nphi = ctx->nphi, nz = ctx->cnz;
+    if (T.valid && T.nr == nr && T.nphi == nphi && T.nz == nz && same_key(T.key, prm)) return ADI_OK;
+    if (prm.kind_bot < 0 || prm.kind_bot > 2) { set_error("unknown zbc.kind_bot"); return ADI_EINVAL; }
+    if (prm.kind_top < 0 || prm.kind_top > 2) { set_error("unknown zbc.kind_top"); return ADI_EINVAL; }
+    const double alpha = prm.k / (prm.rho * prm.cp);  // Material.alpha :49-50
+
+    T.gr = tab_geom(nr, pick_M(nr), false, false);
+    T.gz = tab_geom(nz, pick_M(nz), false, false);
+    const bool phi = nphi > 1;
+    if (phi) T.gp = tab_geom(nphi, pick_M(nphi), true, true);
+    else memset(&T.gp, 0, sizeof(T.gp));
+    if (T.gr.P > 64 || T.gz.P > 64 || (phi && T.gp.P > 64)) {
+        set_error("adi_cyl_step: line too long for the register-resident sweep (n > 2048)");
+        return ADI_EINVAL;
+    }
+    T.off_r = 0;
+    T.off_z = T.off_r + T.gr.ndbl;
+    T.off_p = T.off_z + T.gz.ndbl;
+    const size_t ndbl = T.off_p + (phi ? (size_t)nr * T.gp.ndbl : 0);
+    T.goff_r = 0;
+    T.goff_z = T.goff_r + 3 * T.gr.P;
+    T.goff_p = T.goff_z + 3 * T.gz.P;
+    const size_t nint = T.goff_p + (phi ? 3 * T.gp.P : 0);
+
+    std::vector<double> blob(ndbl);
+    std::vector<int> geom(nint);
+    {
+        std::vector<double> a(nr), b(nr), c(nr);
+        T.add_r = cyl_rows_r(nr, ctx->dr, alpha, prm.k, prm.dt, prm.h_r, prm.Tinf_r, a.data(), b.data(), c.data());
+        int *gi = geom.data() + T.goff_r;
+        tab_partition(T.gr, false, gi, gi + T.gr.P, gi + 2 * T.gr.P);
+        tab_build(T.gr, gi, gi + T.gr.P, gi + 2 * T.gr.P, a.data(), b.data(), c.data(), blob.data() + T.off_r);
+    }
+    {
+        std::vector<double> a(nz), b(nz), c(nz);
+        cyl_rows_z(nz, ctx->dz, alpha, prm.k, prm.dt, prm.kind_bot, prm.kind_top, prm.h_bot, prm.h_top,
+                   prm.Tinf_bot, prm.Tinf_top, prm.T_bot, prm.T_top, a.data(), b.data(), c.data(), &T.bot, &T.top);
+        int *gi = geom.data() + T.goff_z;
+        tab_partition(T.gz, false, gi, gi + T.gz.P, gi + 2 * T.gz.P);
+        tab_build(T.gz, gi, gi + T.gz.P, gi + 2 * T.gz.P, a.data(), b.data(), c.data(), blob.data() + T.off_z);
+    }
+    if (phi) {
+        std::vector<double> a(nphi), b(nphi), c(nphi);
+        int *gi = geom.data() + T.goff_p;
+        tab_partition(T.gp, true, gi, gi + T.gp.P, gi + 2 * T.gp.P);
+        for (int ir = 0; ir < nr; ++ir) {
+            const double f = cyl_fac_phi(ir, ctx->dr, ctx->dphi, alpha, prm.dt);
+            for (int j = 0; j < nphi; ++j) { a[j] = -f; b[j] = 1.0 + 2.0 * f; c[j] = -f; }
+            tab_build(T.gp, gi, gi + T.gp.P, gi + 2 * T.gp.P, a.data(), b.data(), c.data(),
+                      blob.data() + T.off_p + (size_t)ir * T.gp.ndbl);
+        }
+    }
+    // the previous tables may still be in use by kernels queued on `st`: stream-ordered frees
+    if (T.blob_cap < ndbl) {
+        if (T.d_blob) { ADI_CUDA(cudaStreamSynchronize(st)); ADI_CUDA(cudaFree(T.d_blob)); }
+        T.d_blob = nullptr;
+        ADI_CUDA(cudaMalloc(&T.d_blob, ndbl * sizeof(double)));
+        T.blob_cap = ndbl;
+    }
+    if (T.geom_cap < nint) {
+        if (T.d_geom) { ADI_CUDA(cudaStreamSynchronize(st)); ADI_CUDA(cudaFree(T.d_geom)); }
+        T.d_geom = nullptr;
+        ADI_CUDA(cudaMalloc(&T.d_geom, nint * sizeof(int)));
+        T.geom_cap = nint;
+    }
+    // pageable sources: the copies are staged before the calls return
+    ADI_CUDA(cudaMemcpyAsync(T.d_blob, blob.data(), ndbl * sizeof(double), cudaMemcpyHostToDevice, st));
+    ADI_CUDA(cudaMemcpyAsync(T.d_geom, geom.data(), nint * sizeof(int), cudaMemcpyHostToDevice, st));
+    ADI_CUDA(cudaStreamSynchronize(st));
+    T.key = prm; T.nr = nr; T.nphi = nphi; T.nz = nz; T.valid = true;
+    return ADI_OK;
+}
+
+template <typename K>
+static int launch_cyl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, adi_ctx *ctx, const CylArgs &a)
+{
+    if (smem > 227 * 1024) {
+        set_error("adi_cyl_step: tile does not fit shared memory");
+        return ADI_EINVAL;
+    }
+    if (smem > 48 * 1024)
+        ADI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, block, smem, st>>>(a);
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
+    return ADI_OK;
+}
+
+static int lanes_for(adi_ctx *ctx, int P, int nz)
+{
+    int KT = 32;
+    while (KT > 1 && KT * P > 256) KT >>= 1;
+    if (ctx->opt_kt > 0) {
+        int w = 1;
+        while (2 * w <= ctx->opt_kt && 2 * w <= 32 && 2 * w * P <= 256) w <<= 1;
+        KT = w;
+    }
+    while (KT > 1 && KT / 2 >= nz) KT >>= 1;
+    return KT;
+}
+
+static int launch_strided(adi_ctx *ctx, CylArgs &a, bool pro, int nouter, cudaStream_t st)
+{
+    const int P = a.g.P;
+    const int KT = lanes_for(ctx, P, a.nz);
+    dim3 block(KT, P), grid((a.nz + KT - 1) / KT, nouter);
+    const size_t nth = (size_t)KT * P;
+    const size_t smem = ((size_t)a.g.ndbl + 3 * nth) * sizeof(double) + 3 * (size_t)P * sizeof(int);
+    if (a.g.M == 16) {
+        if (pro) return launch_cyl(k_cyl_strided<16, true>, grid, block, smem, st, ctx, a);
+        return launch_cyl(k_cyl_strided<16, false>, grid, block, smem, st, ctx, a);
+    }
+    if (pro) return launch_cyl(k_cyl_strided<32, true>, grid, block, smem, st, ctx, a);
+    return launch_cyl(k_cyl_strided<32, false>, grid, block, smem, st, ctx, a);
+}
+
+static int launch_z(adi_ctx *ctx, CylArgs &a, bool epi, cudaStream_t st)
+{
+    const int P = a.g.P;
+    int LT = 32;
+    while (LT > 1 && LT * P > 256) LT >>= 1;
+    const int RL = a.nz - 1 + ((a.nz - 1) >> 4) + 1;
+    const size_t fixed = (size_t)a.g.ndbl * sizeof(double) + 3 * (size_t)P * sizeof(int);
+    auto bytes = [&](int lt) { return fixed + ((size_t)3 * lt * P + (size_t)lt * RL) * sizeof(double); };
+    if (ctx->opt_lt > 0) LT = (int)std::min<long>(std::max<long>(ctx->opt_lt, 1), LT);
+    while (LT > 1 && bytes(LT) > 100 * 1024) LT >>= 1;
+    while (LT > 1 && (long long)(LT / 2) >= a.nlines) LT >>= 1;
+    dim3 block(P, LT), grid((unsigned)((a.nlines + LT - 1) / LT));
+    const size_t smem = bytes(LT);
+    if (a.g.M == 16) {
+        if (epi) return launch_cyl(k_cyl_z<16, true>, grid, block, smem, st, ctx, a);
+        return launch_cyl(k_cyl_z<16, false>, grid, block, smem, st, ctx, a);
+    }
+    if (epi) return launch_cyl(k_cyl_z<32, true>, grid, block, smem, st, ctx, a);
+    return launch_cyl(k_cyl_z<32, false>, grid, block, smem, st, ctx, a);
+}
+
+static int ensure_aux(adi_ctx *ctx, size_t cells)
+{
+    if (ctx->stage_aux_cells >= cells && ctx->stage_mask) return ADI_OK;
+    if (ctx->stage_mask) cudaFree(ctx->stage_mask);
+    if (ctx->stage_src) cudaFree(ctx->stage_src);
+    ctx->stage_mask = nullptr; ctx->stage_src = nullptr;
+    ADI_CUDA(cudaMalloc(&ctx->stage_mask, std::max<size_t>(cells, 1)));
+    ADI_CUDA(cudaMalloc(&ctx->stage_src, std::max<size_t>(cells, 1) * sizeof(double)));
+    ctx->stage_aux_cells = cells;
+    return ADI_OK;
+}
+
+}  // namespace adi
+
+using namespace adi;
+
+extern "C" {
+
+int adi_cyl_bind(adi_ctx *ctx, int nr, int nphi, int nz, int nz_pitch, double dr, double dphi, double dz)
+{
+    if (!ctx) return ADI_EINVAL;
+    if (nr < 1 || nphi < 1 || nz < 1 || nz_pitch < nz || !(dr > 0.0) || !(dz > 0.0) || !(dphi > 0.0)) {
+        set_error("adi_cyl_bind: bad grid");
+        return ADI_EINVAL;
+    }
+    ADI_CUDA(cudaSetDevice(ctx->device));
+    ctx->nr = nr; ctx->nphi = nphi; ctx->cnz = nz; ctx->nz_pitch = nz_pitch;
+    ctx->dr = dr; ctx->dphi = dphi; ctx->dz = dz;
+    ctx->cyl_bound = true;
+    if (ctx->cyl) ctx->cyl->valid = false;
+    return ADI_OK;
+}
+
+int adi_cyl_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_cyl_params *p,
+                 const uint8_t *d_active, const double *d_S, void *stream)
+{
+    if (!ctx || !p) { set_error("adi_cyl_step: NULL argument"); return ADI_EINVAL; }
+    if (!ctx->cyl_bound) { set_error("adi_cyl_step: adi_cyl_bind has not been called"); return ADI_ESTATE; }
+    if (!d_Tin || !d_Tout || d_Tin == d_Tout) {
+        set_error("adi_cyl_step: Tin/Tout must be distinct device arrays");
+        return ADI_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_tables(ctx, *p, st);
+    if (rc) return rc;
+    const CylTables &T = *ctx->cyl;
+    const int nr = ctx->nr, nphi = ctx->nphi, nz = ctx->cnz;
+    const long long pitch = ctx->nz_pitch;
+
+    CylArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nz = nz;
+    a.nphi = nphi;
+    a.T_void = p->T_void; a.T_inner = p->T_inner;
+    rc = prof_mark(ctx, 0, st);
+    if (rc) return rc;
+
+    // r sweep  (:341-344): Tin -> Tout, prologue fused
+    a.in = d_Tin; a.out = d_Tout;
+    a.blob = T.d_blob + T.off_r; a.geom = T.d_geom + T.goff_r; a.blob_stride = 0; a.g = T.gr;
+    a.cell_stride = (long long)nphi * pitch; a.outer_stride = pitch;
+    a.active = d_active; a.S = d_S; a.dt = p->dt; a.rho_cp = p->rho * p->cp;
+    a.set_first = 0; a.val_first = 0.0;
+    a.set_last = 0; a.val_last = (p->h_r != 0.0) ? T.add_r : 0.0;
+    if (nr == 1) { a.val_first = 0.0; }  // first == last: both branches apply in order, like the reference
+    rc = launch_strided(ctx, a, d_active != nullptr || d_S != nullptr, nphi, st);
+    if (rc) return rc;
+    rc = prof_mark(ctx, 1, st);
+    if (rc) return rc;
+
+    // phi sweep (:346), in place; nphi == 1 is the identity (:309-310)
+    a.in = d_Tout; a.active = nullptr; a.S = nullptr;
+    a.set_first = a.set_last = 0; a.val_first = a.val_last = 0.0;
+    if (nphi > 1) {
+        a.blob = T.d_blob + T.off_p; a.geom = T.d_geom + T.goff_p; a.blob_stride = T.gp.ndbl; a.g = T.gp;
+        a.cell_stride = pitch; a.outer_stride = (long long)nphi * pitch;
+        rc = launch_strided(ctx, a, false, nr, st);
+        if (rc) return rc;
+    }
+    rc = prof_mark(ctx, 2, st);
+    if (rc) return rc;
+
+    // z sweep (:348-350), in place, epilogue fused
+    a.blob = T.d_blob + T.off_z; a.geom = T.d_geom + T.goff_z; a.blob_stride = 0; a.g = T.gz;
+    a.outer_stride = pitch; a.nlines = (long long)nr * nphi;
+    a.active = d_active;
+    a.set_first = T.bot.set; a.val_first = T.bot.val;
+    a.set_last = T.top.set; a.val_last = T.top.val;
+    rc = launch_z(ctx, a, d_active != nullptr, st);
+    if (rc) return rc;
+    rc = prof_mark(ctx, 3, st);
+    if (rc) return rc;
+    if (ctx->opt_sync_check) ADI_CUDA(cudaStreamSynchronize(st));
+    return ADI_OK;
+}
+
+int adi_cyl_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int nsteps,
+                      const adi_cyl_params *p, const uint8_t *h_active, const double *h_S, void *stream)
+{
+    if (!ctx || !p || !h_Tin || !h_Tout || nsteps < 1) { set_error("adi_cyl_step_host: bad arguments"); return ADI_EINVAL; }
+    if (!ctx->cyl_bound) { set_error("adi_cyl_step_host: adi_cyl_bind has not been called"); return ADI_ESTATE; }
+    if (ctx->nz_pitch != ctx->cnz) { set_error("adi_cyl_step_host: host arrays are dense (nz_pitch must equal nz)"); return ADI_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ncell = (size_t)ctx->nr * ctx->nphi * ctx->cnz;
+    if (ctx->stage_cells < ncell || !ctx->stage[0]) {
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+            ctx->stage[i] = nullptr;
+            ADI_CUDA(cudaMalloc(&ctx->stage[i], ncell * sizeof(double)));
+        }
+        ctx->stage_cells = ncell;
+    }
+    int rc = ensure_aux(ctx, ncell);
+    if (rc) return rc;
+    ADI_CUDA(cudaMemcpyAsync(ctx->stage[0], h_Tin, ncell * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (h_active) ADI_CUDA(cudaMemcpyAsync(ctx->stage_mask, h_active, ncell, cudaMemcpyHostToDevice, st));
+    if (h_S) ADI_CUDA(cudaMemcpyAsync(ctx->stage_src, h_S, ncell * sizeof(double), cudaMemcpyHostToDevice, st));
+    int cur = 0;
+    for (int s = 0; s < nsteps; ++s) {
+        rc = adi_cyl_step(ctx, ctx->stage[cur], ctx->stage[cur ^ 1], p, h_active ? ctx->stage_mask : nullptr,
+                          h_S ? ctx->stage_src : nullptr, stream);
+        if (rc) return rc;
+        cur ^= 1;
+    }
+    ADI_CUDA(cudaMemcpyAsync(h_Tout, ctx->stage[cur], ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
+    ADI_CUDA(cudaStreamSynchronize(st));
+    return ADI_OK;
+}
+
+}  // extern "C"

@@ -184,3 +184,125 @@ int emu_cart_step(const double *Tin, double *Tout, const uint8_t *mask, int nx, 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// Cylindrical path: the table-driven solve of adi_tab_core.h, one "thread" after another.
+// ---------------------------------------------------------------------------------------
+#include "adi_tab_core.h"
+
+namespace {
+
+template <int M>
+void tab_line(double *T, size_t base, size_t stride, const TabGeom &g, const int *geom, const double *blob,
+              int set_first, double val_first, int set_last, double val_last)
+{
+    const int P = g.P;
+    const int *cbase = geom, *end = geom + P, *len = geom + 2 * P;
+    std::vector<double> d((size_t)P * M), Y(P), Yl(P), D(P), Dn(P);
+    for (int p = 0; p < P; ++p) {
+        double (&dd)[M] = *reinterpret_cast<double (*)[M]>(&d[(size_t)p * M]);
+        for (int e = 0; e < M; ++e) {
+            const int i = end[p] - (M - 1 - e);
+            double v = 0.0;
+            if (e >= M - len[p]) {
+                v = T[base + (size_t)i * stride];
+                if (i == 0) v = set_first ? val_first : v + val_first;
+                if (i == g.n - 1) v = set_last ? val_last : v + val_last;
+            }
+            dd[e] = v;
+        }
+        Y[p] = tab_forward<M>(dd, blob + g.o_rinv + cbase[p], blob + g.o_la + cbase[p],
+                              blob + g.o_alpha + cbase[p], &Yl[p]);
+    }
+    for (int p = 0; p < P; ++p)
+        D[p] = tab_reduced_rhs(blob[g.o_t0 + p], blob[g.o_t1 + p], blob[g.o_t2 + p], d[(size_t)p * M + M - 1], Yl[p],
+                               Y[tab_hi(p, 1, P, g.cyclic)]);
+    for (int l = 0; l < g.levels; ++l) {
+        const int s = 1 << l;
+        const double *R = blob + g.o_lvl + (size_t)l * 3 * P;
+        for (int p = 0; p < P; ++p)
+            Dn[p] = tab_level(R[p], R[P + p], R[2 * P + p], D[p], D[tab_lo(p, s, P, g.cyclic)],
+                              D[tab_hi(p, s, P, g.cyclic)]);
+        D.swap(Dn);
+    }
+    for (int p = 0; p < P; ++p) {
+        double (&dd)[M] = *reinterpret_cast<double (*)[M]>(&d[(size_t)p * M]);
+        tab_backward<M>(dd, blob + g.o_u + cbase[p], blob + g.o_v + cbase[p], D[tab_lo(p, 1, P, g.cyclic)], D[p]);
+        for (int e = 0; e < M; ++e) {
+            const int i = end[p] - (M - 1 - e);
+            if (e >= M - len[p]) T[base + (size_t)i * stride] = dd[e];
+        }
+    }
+}
+
+void tab_line_any(int M, double *T, size_t base, size_t stride, const TabGeom &g, const int *geom,
+                  const double *blob, int sf, double vf, int sl, double vl)
+{
+    if (M == 16) tab_line<16>(T, base, stride, g, geom, blob, sf, vf, sl, vl);
+    else if (M == 8) tab_line<8>(T, base, stride, g, geom, blob, sf, vf, sl, vl);
+    else if (M == 4) tab_line<4>(T, base, stride, g, geom, blob, sf, vf, sl, vl);
+    else tab_line<32>(T, base, stride, g, geom, blob, sf, vf, sl, vl);
+}
+
+}  // namespace
+
+extern "C" {
+
+// prm: dt, rho, cp, k, h_r, Tinf_r, h_bot, h_top, Tinf_bot, Tinf_top, T_bot, T_top, T_void, T_inner
+int emu_cyl_step(const double *Tin, double *Tout, int nr, int nphi, int nz, double dr, double dphi, double dz,
+                 const double *prm, int kind_bot, int kind_top, const uint8_t *active, const double *S, int M)
+{
+    const double dt = prm[0], rho = prm[1], cp = prm[2], k = prm[3], h_r = prm[4], Tinf_r = prm[5];
+    const double alpha = k / (rho * cp);
+    const size_t ncell = (size_t)nr * nphi * nz;
+    for (size_t g = 0; g < ncell; ++g) {
+        double v = Tin[g];
+        if (active && !active[g]) v = prm[12];
+        if (S) v = v + dt * (S[g] / (rho * cp));
+        Tout[g] = v;
+    }
+    {
+        const TabGeom g = tab_geom(nr, M, false, false);
+        std::vector<int> geom(3 * g.P);
+        std::vector<double> blob(g.ndbl), a(nr), b(nr), c(nr);
+        const double add = cyl_rows_r(nr, dr, alpha, k, dt, h_r, Tinf_r, a.data(), b.data(), c.data());
+        tab_partition(g, false, geom.data(), geom.data() + g.P, geom.data() + 2 * g.P);
+        tab_build(g, geom.data(), geom.data() + g.P, geom.data() + 2 * g.P, a.data(), b.data(), c.data(), blob.data());
+        for (int j = 0; j < nphi; ++j)
+            for (int kz = 0; kz < nz; ++kz)
+                tab_line_any(M, Tout, (size_t)j * nz + kz, (size_t)nphi * nz, g, geom.data(), blob.data(), 0, 0.0, 0,
+                             h_r != 0.0 ? add : 0.0);
+    }
+    if (nphi > 1) {
+        const TabGeom g = tab_geom(nphi, M, true, true);
+        std::vector<int> geom(3 * g.P);
+        std::vector<double> blob(g.ndbl), a(nphi), b(nphi), c(nphi);
+        tab_partition(g, true, geom.data(), geom.data() + g.P, geom.data() + 2 * g.P);
+        for (int ir = 0; ir < nr; ++ir) {
+            const double f = cyl_fac_phi(ir, dr, dphi, alpha, dt);
+            for (int j = 0; j < nphi; ++j) { a[j] = -f; b[j] = 1.0 + 2.0 * f; c[j] = -f; }
+            tab_build(g, geom.data(), geom.data() + g.P, geom.data() + 2 * g.P, a.data(), b.data(), c.data(), blob.data());
+            for (int kz = 0; kz < nz; ++kz)
+                tab_line_any(M, Tout, (size_t)ir * nphi * nz + kz, (size_t)nz, g, geom.data(), blob.data(), 0, 0.0, 0, 0.0);
+        }
+    }
+    {
+        const TabGeom g = tab_geom(nz, M, false, false);
+        std::vector<int> geom(3 * g.P);
+        std::vector<double> blob(g.ndbl), a(nz), b(nz), c(nz);
+        ZEnd bot, top;
+        if (cyl_rows_z(nz, dz, alpha, k, dt, kind_bot, kind_top, prm[6], prm[7], prm[8], prm[9], prm[10], prm[11],
+                       a.data(), b.data(), c.data(), &bot, &top))
+            return -1;
+        tab_partition(g, false, geom.data(), geom.data() + g.P, geom.data() + 2 * g.P);
+        tab_build(g, geom.data(), geom.data() + g.P, geom.data() + 2 * g.P, a.data(), b.data(), c.data(), blob.data());
+        for (size_t line = 0; line < (size_t)nr * nphi; ++line)
+            tab_line_any(M, Tout, line * nz, 1, g, geom.data(), blob.data(), bot.set, bot.val, top.set, top.val);
+    }
+    if (active)
+        for (size_t g = 0; g < ncell; ++g)
+            if (!active[g]) Tout[g] = (g / ((size_t)nphi * nz) == 0) ? prm[13] : prm[12];
+    return 0;
+}
+
+}  // extern "C"

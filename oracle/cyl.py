@@ -260,3 +260,14 @@ def adi_step_masked(Tn, grid, mat, prm, robin_outer, zbc, active, robin_inner=No
     out[void] = float(robin_void.T_inf)
     out[0, void[0]] = float(robin_inner.T_inf)
     return out
+
+
+def build_grid_annular(R_out, wall_thickness, height, z_back, nr, nphi, dz_override=None):
+    """quick_spiral_deposition_gif_v5.py:74-80 (with a GridCyl that accepts R_in)."""
+    import math
+    R_in = max(0.0, R_out - wall_thickness)
+    dr = (R_out - R_in) / float(nr)
+    dz = dr if (dz_override is None or dz_override <= 0.0) else float(dz_override)
+    nz = int(round((z_back + height) / dz))
+    dphi = (2.0 * math.pi) / max(1, nphi)
+    return GridCyl(nr, nphi, nz, dr, dphi, dz, R_out, R_in=R_in), R_in, R_out, dz

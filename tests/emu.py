@@ -16,7 +16,7 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(ROOT, "tests", "_emu.so")
-        srcs = [os.path.join(CSRC, f) for f in ("host_emulation.cpp", "adi_core.h")]
+        srcs = [os.path.join(CSRC, f) for f in ("host_emulation.cpp", "adi_core.h", "adi_tab_core.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
                             "-o", so, srcs[0]], check=True)
@@ -60,5 +60,30 @@ def cart_step(T, mask, dx, dt, theta, kappa, Tinf, coeff=(None,) * 3, dirm=(None
                          dx, dt, theta, kappa, Tinf, arr3(coeff, C.c_double, np.float64),
                          arr3(dirm, C.c_uint8, np.bool_), arr3(dirv, C.c_double, np.float64),
                          arr3(q, C.c_double, np.float64), _ptr(fc, C.c_double), int(variant))
+    assert rc == 0
+    return out
+
+
+KINDS = {"neumann0": 0, "dirichlet": 1, "robin": 2}
+
+
+def cyl_step(c, M=16):
+    """One cylindrical BE step of case dict `c` (tests/cases.build_cyl_case) through the
+    host-compiled table-driven solve (csrc/adi_tab_core.h)."""
+    L = lib()
+    T = np.ascontiguousarray(c["T0"], dtype=np.float64)
+    out = np.empty_like(T)
+    z = c["zbc"]
+    prm = np.array([c["dt"], c["rho"], c["cp"], c["k"], c["h_r"], c["Tinf_r"], z["h_bot"], z["h_top"],
+                    z["T_inf_bot"], z["T_inf_top"], z["T_bot"], z["T_top"], c["T_void"], c["T_inner"]],
+                   dtype=np.float64)
+    act = None if c.get("active") is None else np.ascontiguousarray(c["active"], dtype=np.bool_).view(np.uint8)
+    S = None if c.get("S") is None else np.ascontiguousarray(c["S"], dtype=np.float64)
+    dp, bp = C.POINTER(C.c_double), C.POINTER(C.c_uint8)
+    L.emu_cyl_step.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, dp,
+                               C.c_int, C.c_int, bp, dp, C.c_int]
+    rc = L.emu_cyl_step(_ptr(T, C.c_double), _ptr(out, C.c_double), c["nr"], c["nphi"], c["nz"], c["dr"],
+                        c["dphi"], c["dz"], _ptr(prm, C.c_double), KINDS[z["kind_bot"]], KINDS[z["kind_top"]],
+                        _ptr(act, C.c_uint8), _ptr(S, C.c_double), int(M))
     assert rc == 0
     return out

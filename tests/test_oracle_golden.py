@@ -167,3 +167,13 @@ def test_cyl_birth_sequence(golden_dir):
         frames.append(y)
     assert np.array_equal(np.array(frames), g["frames"], equal_nan=True)
     assert np.array_equal(T, g["T_final"])
+
+
+def test_spiral_simulation_oracle_bit_exact(golden_dir):
+    """The deposition event loop of the reference's only test (tests/test_spiral_vs_analytic.py:
+    17-120) run on the oracle reproduces the unmodified reference's snapshots bit for bit."""
+    import spiral_loop
+    g = np.load(os.path.join(golden_dir, "spiral_sim.npz"))
+    snaps, acts = spiral_loop.run(cyl, g["times"])
+    assert np.array_equal(np.array(acts), g["active"])
+    assert np.array_equal(np.array(snaps), g["snapshots"])

@@ -11,6 +11,8 @@
 // All matrix work is tabulated on the host (adi_tab_core.h); the kernels stream right-hand
 // sides.  The r sweep applies the prologue of the step (source term :339, void clamp of
 // adi_step_masked :55-57), the z sweep its epilogue (void / axis clamps :61-68).
+#include <stdint.h>
+
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -66,35 +68,44 @@ struct CylArgs {
     double val_first, val_last;
 };
 
-__device__ __forceinline__ void load_tables(const CylArgs &a, double *sTab, int *sGeom, int tid, int nth,
-                                            const double *blob)
+__device__ __forceinline__ void cyl_cp_async8(double *dst_smem, const double *src)
 {
-    for (int i = tid; i < a.g.ndbl; i += nth) sTab[i] = blob[i];
-    for (int i = tid; i < 3 * a.g.P; i += nth) sGeom[i] = a.geom[i];
+    const unsigned s = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cyl_cp_async16(void *dst_smem, const void *src)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cyl_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // Reduced system over the P chunks of a line.  ex: 3*NTH doubles; slot(q) = index of chunk q of
-// this thread's line.  Returns S_p, *Sl = S_{p-1}.
+// this thread's line.  tab: this line's table blob (global, read through L1).
+// Returns S_p, *Sl = S_{p-1}.
 template <class SLOT>
-__device__ __forceinline__ double cyl_reduced(const CylArgs &a, const double *sTab, double *ex, int NTH,
-                                              int p, double ds, double Y, double Yl, SLOT slot, double *Sl)
+__device__ __forceinline__ double cyl_reduced(const TabGeom &g, const double *__restrict__ tab, double *ex,
+                                              int NTH, int p, double ds, double Y, double Yl, SLOT slot,
+                                              double *Sl)
 {
-    const int P = a.g.P, cyc = a.g.cyclic;
+    const int P = g.P, cyc = g.cyclic;
+    const double t0 = tab_ld(tab + g.o_t0 + p), t1 = tab_ld(tab + g.o_t1 + p), t2 = tab_ld(tab + g.o_t2 + p);
     double *sY = ex + 2 * NTH;
     sY[slot(p)] = Y;
     __syncthreads();
     const double Ynext = sY[slot(tab_hi(p, 1, P, cyc))];
-    double D = tab_reduced_rhs(sTab[a.g.o_t0 + p], sTab[a.g.o_t1 + p], sTab[a.g.o_t2 + p], ds, Yl, Ynext);
+    double D = tab_reduced_rhs(t0, t1, t2, ds, Yl, Ynext);
     int cur = 0;
-    for (int l = 0; l < a.g.levels; ++l) {
+    for (int l = 0; l < g.levels; ++l) {
         const int s = 1 << l;
+        const double *R = tab + g.o_lvl + l * 3 * P;
+        const double cr = tab_ld(R + p), ca = tab_ld(R + P + p), cc = tab_ld(R + 2 * P + p);
         double *b = ex + cur * NTH;
         b[slot(p)] = D;
         __syncthreads();
         const double Dlo = b[slot(tab_lo(p, s, P, cyc))];
         const double Dhi = b[slot(tab_hi(p, s, P, cyc))];
-        const double *R = sTab + a.g.o_lvl + l * 3 * P;
-        D = tab_level(R[p], R[P + p], R[2 * P + p], D, Dlo, Dhi);
+        D = tab_level(cr, ca, cc, D, Dlo, Dhi);
         cur ^= 1;
     }
     double *b = ex + cur * NTH;
@@ -107,124 +118,180 @@ __device__ __forceinline__ double cyl_reduced(const CylArgs &a, const double *sT
 // ------------------------------------------------------------------------------------
 // K4: strided sweeps.  blockDim = (KT lanes along z, P chunks); grid = (ceil(nz/KT), nouter).
 // PRO: r sweep of the step -- applies the void clamp and the source term while loading.
+// Shared memory: 3*NTH doubles (reduced-system exchange) only.
 // ------------------------------------------------------------------------------------
 template <int M, bool PRO>
-__global__ void __launch_bounds__(256) k_cyl_strided(const CylArgs a)
+__global__ void __launch_bounds__(256, 2) k_cyl_strided(const CylArgs a)
 {
     extern __shared__ double smem[];
     const int KT = blockDim.x, P = blockDim.y;
     const int kk = threadIdx.x, p = threadIdx.y;
-    const int NTH = KT * P, tid = p * KT + kk;
-    double *sTab = smem;
-    double *ex = sTab + a.g.ndbl;
-    int *sGeom = reinterpret_cast<int *>(ex + 3 * NTH);
-    load_tables(a, sTab, sGeom, tid, NTH, a.blob + (size_t)blockIdx.y * a.blob_stride);
+    const int NTH = KT * P;
+    const double *__restrict__ tab = a.blob + (size_t)blockIdx.y * a.blob_stride;
+    const int cb = __ldg(a.geom + p), endp = __ldg(a.geom + P + p), len = __ldg(a.geom + 2 * P + p);
 
     const int k = blockIdx.x * KT + kk;
     const bool lane_ok = k < a.nz;
     const size_t base = (size_t)blockIdx.y * a.outer_stride + (size_t)min(k, a.nz - 1);
-    __syncthreads();
-    const int cb = sGeom[p], endp = sGeom[P + p], len = sGeom[2 * P + p];
     const int n = a.g.n;
+    // slot e holds cell i0 + e; cells before the chunk's first one (e < M - len) are padding.
+    // Padding slots re-read the chunk's first cell (always in range) and are zeroed afterwards.
+    const int i0 = endp - (M - 1);
+    const int efirst = M - len;
+    const double *src = a.in + base;
 
     double d[M];
 #pragma unroll
-    for (int e = 0; e < M; ++e) {
-        const int i = endp - (M - 1 - e);
-        const bool ok = lane_ok && e >= M - len;
-        double v = 0.0;
-        if (ok) {
-            const size_t g = base + (size_t)i * a.cell_stride;
-            v = a.in[g];
-            if (PRO) {
-                if (a.active && !a.active[g]) v = a.T_void;              // T_work[~active] = T_void
-                if (a.S) v = __dadd_rn(v, __dmul_rn(a.dt, __ddiv_rn(a.S[g], a.rho_cp)));  // :339
-            }
-            if (i == 0) v = a.set_first ? a.val_first : __dadd_rn(v, a.val_first);
-            if (i == n - 1) v = a.set_last ? a.val_last : __dadd_rn(v, a.val_last);
+    for (int e = 0; e < M; ++e) d[e] = src[(size_t)(i0 + max(e, efirst)) * a.cell_stride];
+    if (PRO) {
+        if (a.active) {  // T_work[~active] = T_void
+            const uint8_t *am = a.active + base;
+            unsigned bits = 0;
+#pragma unroll
+            for (int e = 0; e < M; ++e) bits |= (am[(size_t)(i0 + max(e, efirst)) * a.cell_stride] ? 1u : 0u) << e;
+#pragma unroll
+            for (int e = 0; e < M; ++e) d[e] = ((bits >> e) & 1u) ? d[e] : a.T_void;
         }
-        d[e] = v;
+        if (a.S) {       // R0 = Tn + dt*(S/(rho*cp))  :339
+            const double *sp = a.S + base;
+            double sv[M];
+#pragma unroll
+            for (int e = 0; e < M; ++e) sv[e] = sp[(size_t)(i0 + max(e, efirst)) * a.cell_stride];
+#pragma unroll
+            for (int e = 0; e < M; ++e) d[e] = __dadd_rn(d[e], __dmul_rn(a.dt, __ddiv_rn(sv[e], a.rho_cp)));
+        }
     }
-    double Yl;
-    const double Y = tab_forward<M>(d, sTab + a.g.o_rinv + cb, sTab + a.g.o_la + cb, sTab + a.g.o_alpha + cb, &Yl);
-    double Sl;
-    const double S = cyl_reduced(a, sTab, ex, NTH, p, d[M - 1], Y, Yl, [=](int q) { return q * KT + kk; }, &Sl);
-    tab_backward<M>(d, sTab + a.g.o_u + cb, sTab + a.g.o_v + cb, Sl, S);
 #pragma unroll
     for (int e = 0; e < M; ++e) {
-        const int i = endp - (M - 1 - e);
-        if (lane_ok && e >= M - len) a.out[base + (size_t)i * a.cell_stride] = d[e];
+        const int i = i0 + e;
+        double v = d[e];
+        if (i == 0) v = a.set_first ? a.val_first : __dadd_rn(v, a.val_first);
+        if (i == n - 1) v = a.set_last ? a.val_last : __dadd_rn(v, a.val_last);
+        d[e] = (lane_ok && e >= efirst) ? v : 0.0;
     }
+    double Yl;
+    const double Y = tab_forward<M>(d, tab + a.g.o_rinv + cb, tab + a.g.o_la + cb, tab + a.g.o_alpha + cb, &Yl);
+    double Sl;
+    const double S = cyl_reduced(a.g, tab, smem, NTH, p, d[M - 1], Y, Yl, [=](int q) { return q * KT + kk; }, &Sl);
+    tab_backward<M>(d, tab + a.g.o_u + cb, tab + a.g.o_v + cb, Sl, S);
+    double *dst = a.out + base;
+#pragma unroll
+    for (int e = 0; e < M; ++e)
+        if (lane_ok && e >= efirst) dst[(size_t)(i0 + e) * a.cell_stride] = d[e];
 }
 
 // ------------------------------------------------------------------------------------
 // K6: z sweep.  blockDim = (P chunks, LT lines); grid = ceil(nlines/LT).
-// Staged line layout: cell z at z + (z >> 4) (one pad per 16 cells: chunk starts 16 apart land
-// 17 doubles apart, so the 64-bit column reads of a half warp hit 16 different bank pairs).
+// The tile of LT lines is staged with cp.async (every byte of the tile in flight at once) and
+// each thread then pulls its chunk out of shared memory.
+//   VEC  (nz a multiple of M, 16-byte aligned lines): 16-byte copies; inside each block of 16
+//        cells the 16-byte pairs are stored at pair ^ (chunk & 7), so the double2 column reads of
+//        8 neighbouring chunks hit 8 different bank groups;
+//   else 8-byte copies into a padded line (cell z at z + (z >> 4)): conflict-free 64-bit reads.
 // EPI: last sweep of a masked step -- void cells := T_void, void axis cells := T_inner.
+// Shared memory: ex[3*NTH] | sT[LT][RL] | (EPI && VEC) sMask[LT][nz]
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ int zphys(int z) { return z + (z >> 4); }
+template <int M>
+__device__ __forceinline__ int zswz(int z)
+{
+    return (z & ~15) | ((((z >> 1) & 7) ^ ((z / M) & 7)) << 1) | (z & 1);
+}
 
-template <int M, bool EPI>
-__global__ void __launch_bounds__(256) k_cyl_z(const CylArgs a)
+template <int M, bool EPI, bool VEC>
+__global__ void __launch_bounds__(256, 2) k_cyl_z(const CylArgs a)
 {
     extern __shared__ double smem[];
     const int P = blockDim.x, LT = blockDim.y;
     const int p = threadIdx.x, ln = threadIdx.y;
     const int NTH = P * LT, tid = ln * P + p;
     const int nz = a.nz, n = nz;
-    const int RL = zphys(nz - 1) + 1;  // doubles per staged line
-    double *sTab = smem;
-    double *ex = sTab + a.g.ndbl;
+    const int RL = VEC ? nz : zphys(nz - 1) + 1;  // doubles per staged line
+    double *ex = smem;
     double *sT = ex + 3 * NTH;
-    int *sGeom = reinterpret_cast<int *>(sT + (size_t)LT * RL);
-    load_tables(a, sTab, sGeom, tid, NTH, a.blob);
+    uint8_t *sMask = reinterpret_cast<uint8_t *>(sT + (size_t)LT * RL);
+    const double *__restrict__ tab = a.blob;
 
     const long long L0 = (long long)blockIdx.x * LT;
-    for (int l = 0; l < LT; ++l) {
-        const long long line = L0 + l;
-        if (line >= a.nlines) break;
-        const double *src = a.in + (size_t)line * a.outer_stride;
-        for (int z = tid; z < nz; z += NTH) sT[(size_t)l * RL + zphys(z)] = src[z];
+    const int nl = (int)min((long long)LT, a.nlines - L0);
+    if (VEC) {
+        const int ppl = nz >> 1;
+        for (int l = 0; l < nl; ++l) {
+            const double *src = a.in + (size_t)(L0 + l) * a.outer_stride;
+            for (int pl = tid; pl < ppl; pl += NTH) cyl_cp_async16(sT + (size_t)l * RL + zswz<M>(2 * pl), src + 2 * pl);
+            if (EPI) {
+                const uint8_t *am = a.active + (size_t)(L0 + l) * a.outer_stride;
+                for (int c = tid; c < (nz >> 4); c += NTH) cyl_cp_async16(sMask + (size_t)l * nz + 16 * c, am + 16 * c);
+            }
+        }
+    } else {
+        for (int l = 0; l < nl; ++l) {
+            const double *src = a.in + (size_t)(L0 + l) * a.outer_stride;
+            for (int z = tid; z < nz; z += NTH) cyl_cp_async8(sT + (size_t)l * RL + zphys(z), src + z);
+        }
     }
+    const int cb = __ldg(a.geom + p), endp = __ldg(a.geom + P + p), len = __ldg(a.geom + 2 * P + p);
+    cyl_cp_async_wait();
     __syncthreads();
-    const int cb = sGeom[p], endp = sGeom[P + p], len = sGeom[2 * P + p];
-    const bool line_ok = L0 + ln < a.nlines;
+    const bool line_ok = ln < nl;
     double *myT = sT + (size_t)ln * RL;
+    const int i0 = endp - (M - 1), efirst = M - len;
 
     double d[M];
+    if (VEC) {  // every chunk is full and starts at p*M
+#pragma unroll
+        for (int j = 0; j < M / 2; ++j) {
+            const double2 v = *reinterpret_cast<const double2 *>(myT + zswz<M>(p * M + 2 * j));
+            d[2 * j] = v.x; d[2 * j + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < M; ++e) d[e] = myT[zphys(i0 + max(e, efirst))];
+    }
 #pragma unroll
     for (int e = 0; e < M; ++e) {
-        const int i = endp - (M - 1 - e);
-        double v = 0.0;
-        if (line_ok && e >= M - len) {
-            v = myT[zphys(i)];
-            if (i == 0) v = a.set_first ? a.val_first : __dadd_rn(v, a.val_first);
-            if (i == n - 1) v = a.set_last ? a.val_last : __dadd_rn(v, a.val_last);
-        }
-        d[e] = v;
+        const int i = i0 + e;
+        double v = d[e];
+        if (i == 0) v = a.set_first ? a.val_first : __dadd_rn(v, a.val_first);
+        if (i == n - 1) v = a.set_last ? a.val_last : __dadd_rn(v, a.val_last);
+        d[e] = (line_ok && e >= efirst) ? v : 0.0;
     }
     double Yl;
-    const double Y = tab_forward<M>(d, sTab + a.g.o_rinv + cb, sTab + a.g.o_la + cb, sTab + a.g.o_alpha + cb, &Yl);
+    const double Y = tab_forward<M>(d, tab + a.g.o_rinv + cb, tab + a.g.o_la + cb, tab + a.g.o_alpha + cb, &Yl);
     double Sl;
-    const double S = cyl_reduced(a, sTab, ex, NTH, p, d[M - 1], Y, Yl, [=](int q) { return ln * P + q; }, &Sl);
-    tab_backward<M>(d, sTab + a.g.o_u + cb, sTab + a.g.o_v + cb, Sl, S);
+    const double S = cyl_reduced(a.g, tab, ex, NTH, p, d[M - 1], Y, Yl, [=](int q) { return ln * P + q; }, &Sl);
+    tab_backward<M>(d, tab + a.g.o_u + cb, tab + a.g.o_v + cb, Sl, S);
+    if (VEC) {
 #pragma unroll
-    for (int e = 0; e < M; ++e) {
-        const int i = endp - (M - 1 - e);
-        if (line_ok && e >= M - len) myT[zphys(i)] = d[e];
+        for (int j = 0; j < M / 2; ++j)
+            *reinterpret_cast<double2 *>(myT + zswz<M>(p * M + 2 * j)) = make_double2(d[2 * j], d[2 * j + 1]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < M; ++e)
+            if (e >= efirst) myT[zphys(i0 + e)] = d[e];
     }
     __syncthreads();
-    for (int l = 0; l < LT; ++l) {
+    for (int l = 0; l < nl; ++l) {
         const long long line = L0 + l;
-        if (line >= a.nlines) break;
         double *dst = a.out + (size_t)line * a.outer_stride;
-        const uint8_t *act = EPI ? a.active + (size_t)line * a.outer_stride : nullptr;
         const double vv = (EPI && line / a.nphi == 0) ? a.T_inner : a.T_void;  // :61-68
-        for (int z = tid; z < nz; z += NTH) {
-            double v = sT[(size_t)l * RL + zphys(z)];
-            if (EPI && !act[z]) v = vv;
-            dst[z] = v;
+        if (VEC) {
+            for (int pl = tid; pl < (nz >> 1); pl += NTH) {
+                double2 v = *reinterpret_cast<const double2 *>(sT + (size_t)l * RL + zswz<M>(2 * pl));
+                if (EPI) {
+                    const unsigned m2 = *reinterpret_cast<const unsigned short *>(sMask + (size_t)l * nz + 2 * pl);
+                    if (!(m2 & 0xffu)) v.x = vv;
+                    if (!(m2 >> 8)) v.y = vv;
+                }
+                *reinterpret_cast<double2 *>(dst + 2 * pl) = v;
+            }
+        } else {
+            const uint8_t *act = EPI ? a.active + (size_t)line * a.outer_stride : nullptr;
+            for (int z = tid; z < nz; z += NTH) {
+                double v = sT[(size_t)l * RL + zphys(z)];
+                if (EPI && !act[z]) v = vv;
+                dst[z] = v;
+            }
         }
     }
 }
@@ -241,27 +308,44 @@ static bool same_key(const adi_cyl_params &x, const adi_cyl_params &y)
            x.Tinf_top == y.Tinf_top && x.T_bot == y.T_bot && x.T_top == y.T_top;
 }
 
-static int pick_M(int n) { return n <= 512 ? 16 : 32; }
+static int pick_M(adi_ctx *ctx, int n)
+{
+    if (ctx->opt_m == 16 && n <= 1024) return 16;
+    if (ctx->opt_m == 32) return 32;
+    return n <= 512 ? 16 : 32;
+}
 
 static int ensure_tables(adi_ctx *ctx, const adi_cyl_params &prm, cudaStream_t st)
 {
     if (!ctx->cyl) ctx->cyl = new CylTables();
     CylTables &T = *ctx->cyl;
     const int nr = ctx->nr, nphi = ctx->nphi, nz = ctx->cnz;
-    if (T.valid && T.nr == nr && T.nphi == nphi && T.nz == nz && same_key(T.key, prm)) return ADI_OK;
+    if (T.valid && T.nr == nr && T.nphi == nphi && T.nz == nz && T.M == (int)ctx->opt_m && same_key(T.key, prm)) return ADI_OK;
     if (prm.kind_bot < 0 || prm.kind_bot > 2) { set_error("unknown zbc.kind_bot"); return ADI_EINVAL; }
     if (prm.kind_top < 0 || prm.kind_top > 2) { set_error("unknown zbc.kind_top"); return ADI_EINVAL; }
     const double alpha = prm.k / (prm.rho * prm.cp);  // Material.alpha :49-50
 
-    T.gr = tab_geom(nr, pick_M(nr), false, false);
-    T.gz = tab_geom(nz, pick_M(nz), false, false);
     const bool phi = nphi > 1;
-    if (phi) T.gp = tab_geom(nphi, pick_M(nphi), true, true);
+    TabSet sr, sz;
+    {
+        std::vector<double> a(nr), b(nr), c(nr);
+        T.add_r = cyl_rows_r(nr, ctx->dr, alpha, prm.k, prm.dt, prm.h_r, prm.Tinf_r, a.data(), b.data(), c.data());
+        sr = tab_make(nr, pick_M(ctx, nr), false, a.data(), b.data(), c.data());
+    }
+    {
+        std::vector<double> a(nz), b(nz), c(nz);
+        cyl_rows_z(nz, ctx->dz, alpha, prm.k, prm.dt, prm.kind_bot, prm.kind_top, prm.h_bot, prm.h_top,
+                   prm.Tinf_bot, prm.Tinf_top, prm.T_bot, prm.T_top, a.data(), b.data(), c.data(), &T.bot, &T.top);
+        sz = tab_make(nz, pick_M(ctx, nz), false, a.data(), b.data(), c.data());
+    }
+    T.gr = sr.g; T.gz = sz.g;
+    if (phi) T.gp = tab_geom(nphi, pick_M(ctx, nphi), true, true);
     else memset(&T.gp, 0, sizeof(T.gp));
     if (T.gr.P > 64 || T.gz.P > 64 || (phi && T.gp.P > 64)) {
         set_error("adi_cyl_step: line too long for the register-resident sweep (n > 2048)");
         return ADI_EINVAL;
     }
+    // blobs are padded to 16 bytes apart so that every table starts 8-byte aligned anyway
     T.off_r = 0;
     T.off_z = T.off_r + T.gr.ndbl;
     T.off_p = T.off_z + T.gz.ndbl;
@@ -273,21 +357,10 @@ static int ensure_tables(adi_ctx *ctx, const adi_cyl_params &prm, cudaStream_t s
 
     std::vector<double> blob(ndbl);
     std::vector<int> geom(nint);
-    {
-        std::vector<double> a(nr), b(nr), c(nr);
-        T.add_r = cyl_rows_r(nr, ctx->dr, alpha, prm.k, prm.dt, prm.h_r, prm.Tinf_r, a.data(), b.data(), c.data());
-        int *gi = geom.data() + T.goff_r;
-        tab_partition(T.gr, false, gi, gi + T.gr.P, gi + 2 * T.gr.P);
-        tab_build(T.gr, gi, gi + T.gr.P, gi + 2 * T.gr.P, a.data(), b.data(), c.data(), blob.data() + T.off_r);
-    }
-    {
-        std::vector<double> a(nz), b(nz), c(nz);
-        cyl_rows_z(nz, ctx->dz, alpha, prm.k, prm.dt, prm.kind_bot, prm.kind_top, prm.h_bot, prm.h_top,
-                   prm.Tinf_bot, prm.Tinf_top, prm.T_bot, prm.T_top, a.data(), b.data(), c.data(), &T.bot, &T.top);
-        int *gi = geom.data() + T.goff_z;
-        tab_partition(T.gz, false, gi, gi + T.gz.P, gi + 2 * T.gz.P);
-        tab_build(T.gz, gi, gi + T.gz.P, gi + 2 * T.gz.P, a.data(), b.data(), c.data(), blob.data() + T.off_z);
-    }
+    std::copy(sr.blob.begin(), sr.blob.end(), blob.begin() + T.off_r);
+    std::copy(sz.blob.begin(), sz.blob.end(), blob.begin() + T.off_z);
+    std::copy(sr.geom.begin(), sr.geom.end(), geom.begin() + T.goff_r);
+    std::copy(sz.geom.begin(), sz.geom.end(), geom.begin() + T.goff_z);
     if (phi) {
         std::vector<double> a(nphi), b(nphi), c(nphi);
         int *gi = geom.data() + T.goff_p;
@@ -316,6 +389,7 @@ static int ensure_tables(adi_ctx *ctx, const adi_cyl_params &prm, cudaStream_t s
     ADI_CUDA(cudaMemcpyAsync(T.d_blob, blob.data(), ndbl * sizeof(double), cudaMemcpyHostToDevice, st));
     ADI_CUDA(cudaMemcpyAsync(T.d_geom, geom.data(), nint * sizeof(int), cudaMemcpyHostToDevice, st));
     ADI_CUDA(cudaStreamSynchronize(st));
+    T.M = (int)ctx->opt_m;
     T.key = prm; T.nr = nr; T.nphi = nphi; T.nz = nz; T.valid = true;
     return ADI_OK;
 }
@@ -354,7 +428,7 @@ static int launch_strided(adi_ctx *ctx, CylArgs &a, bool pro, int nouter, cudaSt
     const int KT = lanes_for(ctx, P, a.nz);
     dim3 block(KT, P), grid((a.nz + KT - 1) / KT, nouter);
     const size_t nth = (size_t)KT * P;
-    const size_t smem = ((size_t)a.g.ndbl + 3 * nth) * sizeof(double) + 3 * (size_t)P * sizeof(int);
+    const size_t smem = 3 * nth * sizeof(double);
     if (a.g.M == 16) {
         if (pro) return launch_cyl(k_cyl_strided<16, true>, grid, block, smem, st, ctx, a);
         return launch_cyl(k_cyl_strided<16, false>, grid, block, smem, st, ctx, a);
@@ -365,23 +439,39 @@ static int launch_strided(adi_ctx *ctx, CylArgs &a, bool pro, int nouter, cudaSt
 
 static int launch_z(adi_ctx *ctx, CylArgs &a, bool epi, cudaStream_t st)
 {
-    const int P = a.g.P;
+    const int P = a.g.P, M = a.g.M;
+    // 16-byte path: every chunk full and aligned
+    const bool vec = (a.nz % M) == 0 && (a.outer_stride % 2) == 0 &&
+                     ((((uintptr_t)a.in | (uintptr_t)a.out) & 15) == 0) &&
+                     (!epi || ((a.outer_stride % 16) == 0 && ((uintptr_t)a.active & 15) == 0));
+    const int RL = vec ? a.nz : a.nz - 1 + ((a.nz - 1) >> 4) + 1;
+    auto bytes = [&](int lt) {
+        return ((size_t)3 * lt * P + (size_t)lt * RL) * sizeof(double) + ((vec && epi) ? (size_t)lt * a.nz : 0);
+    };
+    // small blocks: many resident tiles per SM keep loads, solves and stores of different tiles
+    // overlapped
     int LT = 32;
-    while (LT > 1 && LT * P > 256) LT >>= 1;
-    const int RL = a.nz - 1 + ((a.nz - 1) >> 4) + 1;
-    const size_t fixed = (size_t)a.g.ndbl * sizeof(double) + 3 * (size_t)P * sizeof(int);
-    auto bytes = [&](int lt) { return fixed + ((size_t)3 * lt * P + (size_t)lt * RL) * sizeof(double); };
-    if (ctx->opt_lt > 0) LT = (int)std::min<long>(std::max<long>(ctx->opt_lt, 1), LT);
+    while (LT > 1 && LT * P > 64) LT >>= 1;
+    if (ctx->opt_lt > 0) {
+        LT = 1;
+        while (2 * LT <= ctx->opt_lt && 2 * LT * P <= 256) LT <<= 1;
+    }
     while (LT > 1 && bytes(LT) > 100 * 1024) LT >>= 1;
     while (LT > 1 && (long long)(LT / 2) >= a.nlines) LT >>= 1;
     dim3 block(P, LT), grid((unsigned)((a.nlines + LT - 1) / LT));
     const size_t smem = bytes(LT);
-    if (a.g.M == 16) {
-        if (epi) return launch_cyl(k_cyl_z<16, true>, grid, block, smem, st, ctx, a);
-        return launch_cyl(k_cyl_z<16, false>, grid, block, smem, st, ctx, a);
+#define ADI_ZGO(MM)                                                                                   \
+    {                                                                                                 \
+        if (vec) {                                                                                    \
+            if (epi) return launch_cyl(k_cyl_z<MM, true, true>, grid, block, smem, st, ctx, a);       \
+            return launch_cyl(k_cyl_z<MM, false, true>, grid, block, smem, st, ctx, a);               \
+        }                                                                                             \
+        if (epi) return launch_cyl(k_cyl_z<MM, true, false>, grid, block, smem, st, ctx, a);          \
+        return launch_cyl(k_cyl_z<MM, false, false>, grid, block, smem, st, ctx, a);                  \
     }
-    if (epi) return launch_cyl(k_cyl_z<32, true>, grid, block, smem, st, ctx, a);
-    return launch_cyl(k_cyl_z<32, false>, grid, block, smem, st, ctx, a);
+    if (M == 16) ADI_ZGO(16)
+    ADI_ZGO(32)
+#undef ADI_ZGO
 }
 
 static int ensure_aux(adi_ctx *ctx, size_t cells)

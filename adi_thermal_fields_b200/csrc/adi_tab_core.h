@@ -67,7 +67,16 @@ inline int tab_pick_P(int n, int M, bool cyclic)
     return P;
 }
 
+inline TabGeom tab_geom_nvar(int n, int M, bool cyclic, int nvar);
+
 inline TabGeom tab_geom(int n, int M, bool cyclic, bool uniform)
+{
+    const int P = tab_pick_P(n, M, cyclic);
+    // uniform (translation-invariant) lines: chunks of equal length share their cell tables
+    return tab_geom_nvar(n, M, cyclic, uniform ? ((n % P) ? 2 : 1) : P);
+}
+
+inline TabGeom tab_geom_nvar(int n, int M, bool cyclic, int nvar)
 {
     TabGeom g;
     g.n = n; g.M = M; g.cyclic = cyclic ? 1 : 0;
@@ -78,8 +87,7 @@ inline TabGeom tab_geom(int n, int M, bool cyclic, bool uniform)
     } else {
         while ((1 << g.levels) < g.P) g.levels++;
     }
-    // uniform (translation-invariant) lines: chunks of equal length share their cell tables
-    g.nvar = uniform ? ((n % g.P) ? 2 : 1) : g.P;
+    g.nvar = nvar;
     int o = 0;
     g.o_rinv = o; o += g.nvar * M;
     g.o_la = o; o += g.nvar * M;
@@ -188,6 +196,64 @@ inline void tab_build(const TabGeom &g, const int *cbase, const int *end, const 
     }
 }
 
+// Table read: through the read-only (L1) path on the device -- every block of an SM walks the
+// same few KB of tables while the field data streams past L1 (cp.async.cg / plain stores).
+ADI_HD double tab_ld(const double *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// One table set (host).  tab_make builds the tables of a line whose rows are arbitrary and then
+// merges chunks whose cell tables are bit-identical (e.g. all interior chunks of a z line), so
+// the set stays small enough to live in L1.
+struct TabSet {
+    TabGeom g;
+    std::vector<double> blob;
+    std::vector<int> geom;  // cbase[P], end[P], len[P]
+};
+
+inline TabSet tab_make(int n, int M, bool cyclic, const double *a, const double *b, const double *c)
+{
+    TabSet full;
+    full.g = tab_geom(n, M, cyclic, false);
+    const int P = full.g.P;
+    full.geom.resize(3 * P);
+    full.blob.resize(full.g.ndbl);
+    int *cb = full.geom.data(), *en = cb + P, *ln = cb + 2 * P;
+    tab_partition(full.g, false, cb, en, ln);
+    tab_build(full.g, cb, en, ln, a, b, c, full.blob.data());
+    const int offs[5] = {full.g.o_rinv, full.g.o_la, full.g.o_alpha, full.g.o_u, full.g.o_v};
+    std::vector<int> var(P), rep;
+    for (int p = 0; p < P; ++p) {
+        int found = -1;
+        for (size_t v = 0; v < rep.size() && found < 0; ++v) {
+            bool same = true;
+            for (int t = 0; t < 5 && same; ++t)
+                for (int e = 0; e < M && same; ++e)
+                    same = full.blob[offs[t] + p * M + e] == full.blob[offs[t] + rep[v] * M + e];
+            if (same) found = (int)v;
+        }
+        if (found < 0) { rep.push_back(p); found = (int)rep.size() - 1; }
+        var[p] = found;
+    }
+    TabSet out;
+    out.g = tab_geom_nvar(n, M, cyclic, (int)rep.size());
+    out.geom = full.geom;
+    out.blob.assign(out.g.ndbl, 0.0);
+    const int offn[5] = {out.g.o_rinv, out.g.o_la, out.g.o_alpha, out.g.o_u, out.g.o_v};
+    for (size_t v = 0; v < rep.size(); ++v)
+        for (int t = 0; t < 5; ++t)
+            for (int e = 0; e < M; ++e) out.blob[offn[t] + v * M + e] = full.blob[offs[t] + rep[v] * M + e];
+    for (int p = 0; p < P; ++p) out.geom[p] = var[p] * M;
+    for (int i = 0; i < 3 * P; ++i) out.blob[out.g.o_t0 + i] = full.blob[full.g.o_t0 + i];
+    for (int i = 0; i < out.g.levels * 3 * P; ++i) out.blob[out.g.o_lvl + i] = full.blob[full.g.o_lvl + i];
+    return out;
+}
+
 // Neighbour chunk indices of the reduced system (clamped where the coefficient is zero).
 ADI_HD int tab_lo(int p, int s, int P, int cyclic) { return cyclic ? ((p - s) & (P - 1)) : (p - s >= 0 ? p - s : 0); }
 ADI_HD int tab_hi(int p, int s, int P, int cyclic) { return cyclic ? ((p + s) & (P - 1)) : (p + s < P ? p + s : P - 1); }
@@ -201,10 +267,10 @@ ADI_HD double tab_forward(double (&d)[M], const double *rinv, const double *la, 
     double dp = 0.0, Y = 0.0;
 #pragma unroll
     for (int e = 0; e < M - 1; ++e) {
-        const double ds = d[e] * rinv[e];
-        dp = fma(la[e], dp, ds);
+        const double ds = d[e] * tab_ld(rinv + e);
+        dp = fma(tab_ld(la + e), dp, ds);
         d[e] = dp;
-        Y = fma(alpha[e], dp, Y);
+        Y = fma(tab_ld(alpha + e), dp, Y);
     }
     *Yl = dp;
     return Y;
@@ -230,7 +296,7 @@ ADI_HD void tab_backward(double (&d)[M], const double *u, const double *v, doubl
     d[M - 1] = S;
 #pragma unroll
     for (int e = M - 2; e >= 0; --e) {
-        const double x = fma(u[e], xn, fma(v[e], Sl, d[e]));
+        const double x = fma(tab_ld(u + e), xn, fma(tab_ld(v + e), Sl, d[e]));
         d[e] = x;
         xn = x;
     }

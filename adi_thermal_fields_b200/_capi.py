@@ -18,6 +18,8 @@ SYMBOLS = (
     "adi_cart_step", "adi_cart_step_host", "adi_cart_build_packs", "adi_cart_exposed_mask",
     "adi_set_option", "adi_launch_count", "adi_profile_reset", "adi_profile_read",
     "adi_cyl_bind", "adi_cyl_step", "adi_cyl_step_host",
+    "adi_cart_set_slab", "adi_cart_set_mask_halo", "adi_cart_pack_zplanes", "adi_cart_step_xy",
+    "adi_cart_zsweep_reduce", "adi_cart_zsweep_finish",
 )
 
 
@@ -73,6 +75,12 @@ def load():
     L.adi_launch_count.restype = C.c_long
     L.adi_profile_reset.argtypes = [vp]
     L.adi_profile_read.argtypes = [vp, C.POINTER(dbl), C.POINTER(C.c_long)]
+    L.adi_cart_set_slab.argtypes = [vp, C.c_int, C.c_int]
+    L.adi_cart_set_mask_halo.argtypes = [vp, bp, bp]
+    L.adi_cart_pack_zplanes.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    L.adi_cart_step_xy.argtypes = [vp, dp, dp, dp, dp, dbl, dbl, dbl, dbl, vp]
+    L.adi_cart_zsweep_reduce.argtypes = [vp, dp, dp, dbl, dbl, dbl, dbl, vp]
+    L.adi_cart_zsweep_finish.argtypes = [vp, dp, dp, dbl, dbl, dbl, dbl, vp]
     L.adi_cyl_bind.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dbl, dbl, dbl]
     L.adi_cyl_step.argtypes = [vp, dp, dp, C.POINTER(CylParams), bp, dp, vp]
     L.adi_cyl_step_host.argtypes = [vp, vp, vp, C.c_int, C.POINTER(CylParams), vp, vp, vp]

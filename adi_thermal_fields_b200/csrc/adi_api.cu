@@ -75,6 +75,7 @@ int adi_ctx_destroy(adi_ctx *ctx)
         if (ctx->code_buf[a]) cudaFree(ctx->code_buf[a]);
     for (int a = 0; a < 2; ++a)
         if (ctx->stage[a]) cudaFree(ctx->stage[a]);
+    if (ctx->d_ghost) cudaFree(ctx->d_ghost);
     if (ctx->stage_mask) cudaFree(ctx->stage_mask);
     if (ctx->stage_src) cudaFree(ctx->stage_src);
     adi::cyl_release(ctx);

@@ -48,7 +48,7 @@ int ensure_code(adi_ctx *ctx, cudaStream_t st)
         const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, 148 * 64);
         for (int a = 0; a < ncodes; ++a) {
             k_build_code<<<blocks, threads, 0, st>>>(ctx->d_mask, ctx->pack[a].dirm, ctx->code_buf[a],
-                                                     ctx->nx, ctx->ny, ctx->nz);
+                                                     ctx->nx, ctx->ny, ctx->nz, ctx->d_mask_lo, ctx->d_mask_hi);
             ctx->launches++;
         }
         ADI_CUDA(cudaGetLastError());
@@ -65,7 +65,7 @@ int ensure_code(adi_ctx *ctx, cudaStream_t st)
 namespace adi {
 int launch_sweep_x(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, bool expl, cudaStream_t st);
 int launch_sweep_y(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, cudaStream_t st);
-int launch_sweep_z(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, cudaStream_t st);
+int launch_sweep_z(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, int zmode, cudaStream_t st);
 }
 
 namespace {
@@ -97,6 +97,8 @@ int adi_cart_bind(adi_ctx *ctx, int nx, int ny, int nz, double dx)
     ctx->nx = nx; ctx->ny = ny; ctx->nz = nz; ctx->dx = dx;
     ctx->cart_bound = true;
     ctx->d_mask = nullptr;
+    ctx->d_mask_lo = ctx->d_mask_hi = nullptr;
+    ctx->slab_rank = 0; ctx->slab_nranks = 1;
     for (int a = 0; a < 3; ++a) ctx->pack[a] = Pack();
     ctx->scalar_robin = false;
     ctx->code_dirty = true;
@@ -143,19 +145,15 @@ int adi_cart_set_robin_scalar(adi_ctx *ctx, const double face_coeff[6])
     return ADI_OK;
 }
 
-int adi_cart_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, double theta,
-                  double kappa, double Tinf, void *stream)
+// Sweeps `first`..`last` (0 = explicit stage + x, 1 = y, 2 = z) of one step.
+// zmode: 0 whole z lines, 1 z-slab pass 1 (interface relations -> d_iface), 2 z-slab pass 2.
+static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, double theta,
+                      double kappa, double Tinf, int first, int last, int zmode, const double *d_Tlo,
+                      const double *d_Thi, double *d_iface, const double *d_ghost, cudaStream_t st)
 {
-    int rc = check_cart(ctx, "adi_cart_step");
-    if (rc) return rc;
-    if (!d_Tin || !d_Tout || d_Tin == d_Tout) {
-        set_error("adi_cart_step: Tin/Tout must be distinct device arrays");
-        return ADI_EINVAL;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
     const size_t ncell = (size_t)ctx->nx * ctx->ny * ctx->nz;
     if (ncell == 0) return ADI_OK;
-    rc = ensure_code(ctx, st);
+    int rc = ensure_code(ctx, st);
     if (rc) return rc;
 
     // adi3d_numba_coeff.py:291-292,298 -- scalars in the reference's evaluation order
@@ -168,11 +166,10 @@ int adi_cart_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, 
     a.k.Tinf = Tinf;
     a.k.beta = dt * kappa * (1.0 - theta);
     a.k.invdx2 = 1.0 / (dx * dx);
+    a.zlo = d_Tlo; a.zhi = d_Thi; a.iface = d_iface; a.ghost = d_ghost;
     const bool expl = a.k.beta != 0.0;
 
-    rc = prof_mark(ctx, 0, st);
-    if (rc) return rc;
-    for (int axis = 0; axis < 3; ++axis) {
+    for (int axis = first; axis <= last; ++axis) {
         const Pack &p = ctx->pack[axis];
         a.in = axis == 0 ? d_Tin : d_Tout;  // y and z sweeps run in place on Tout
         a.out = d_Tout;
@@ -186,13 +183,140 @@ int adi_cart_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, 
         const bool extra = p.q != nullptr || p.dirm != nullptr;
         if (axis == 0) rc = launch_sweep_x(ctx, a, dense, extra, expl, st);
         else if (axis == 1) rc = launch_sweep_y(ctx, a, dense, extra, st);
-        else rc = launch_sweep_z(ctx, a, dense, extra, st);
+        else rc = launch_sweep_z(ctx, a, dense, extra, zmode, st);
         if (rc) return rc;
-        rc = prof_mark(ctx, axis + 1, st);
-        if (rc) return rc;
+        if (zmode != 1) {
+            rc = prof_mark(ctx, axis + 1, st);
+            if (rc) return rc;
+        }
     }
     if (ctx->opt_sync_check) ADI_CUDA(cudaStreamSynchronize(st));
     return ADI_OK;
+}
+
+int adi_cart_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, double theta,
+                  double kappa, double Tinf, void *stream)
+{
+    int rc = check_cart(ctx, "adi_cart_step");
+    if (rc) return rc;
+    if (!d_Tin || !d_Tout || d_Tin == d_Tout) {
+        set_error("adi_cart_step: Tin/Tout must be distinct device arrays");
+        return ADI_EINVAL;
+    }
+    if (ctx->slab_nranks > 1) {
+        set_error("adi_cart_step: this context holds a z slab; use adi_cart_step_xy + adi_cart_zsweep_*");
+        return ADI_ESTATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = prof_mark(ctx, 0, st);
+    if (rc) return rc;
+    return run_sweeps(ctx, d_Tin, d_Tout, dt, theta, kappa, Tinf, 0, 2, 0, nullptr, nullptr, nullptr, nullptr, st);
+}
+
+// ---- z-slab decomposition ---------------------------------------------------
+
+int adi_cart_set_slab(adi_ctx *ctx, int rank, int nranks)
+{
+    int rc = check_cart(ctx, "adi_cart_set_slab");
+    if (rc) return rc;
+    if (nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks) {
+        set_error("adi_cart_set_slab: need 0 <= rank < nranks <= 16");
+        return ADI_EINVAL;
+    }
+    ctx->slab_rank = rank; ctx->slab_nranks = nranks;
+    return ADI_OK;
+}
+
+int adi_cart_set_mask_halo(adi_ctx *ctx, const uint8_t *d_mask_lo, const uint8_t *d_mask_hi)
+{
+    int rc = check_cart(ctx, "adi_cart_set_mask_halo");
+    if (rc) return rc;
+    ctx->d_mask_lo = d_mask_lo; ctx->d_mask_hi = d_mask_hi;
+    ctx->code_dirty = true;
+    return ADI_OK;
+}
+
+int adi_cart_pack_zplanes(adi_ctx *ctx, const void *d_field, int elem_bytes, void *d_lo_out, void *d_hi_out,
+                          void *stream)
+{
+    int rc = check_cart(ctx, "adi_cart_pack_zplanes");
+    if (rc) return rc;
+    if (!d_field || (elem_bytes != 1 && elem_bytes != 8)) {
+        set_error("adi_cart_pack_zplanes: field is NULL or element size is not 1 / 8");
+        return ADI_EINVAL;
+    }
+    const size_t nlines = (size_t)ctx->nx * ctx->ny;
+    if (!nlines || !ctx->nz) return ADI_OK;
+    const int threads = 256;
+    const int blocks = (int)std::min<size_t>((nlines + threads - 1) / threads, 148 * 16);
+    if (elem_bytes == 8)
+        k_pack_zplanes<double><<<blocks, threads, 0, (cudaStream_t)stream>>>((const double *)d_field, (double *)d_lo_out,
+                                                                         (double *)d_hi_out, nlines, ctx->nz);
+    else
+        k_pack_zplanes<uint8_t><<<blocks, threads, 0, (cudaStream_t)stream>>>((const uint8_t *)d_field, (uint8_t *)d_lo_out,
+                                                                          (uint8_t *)d_hi_out, nlines, ctx->nz);
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
+    return ADI_OK;
+}
+
+int adi_cart_step_xy(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const double *d_Tlo, const double *d_Thi,
+                     double dt, double theta, double kappa, double Tinf, void *stream)
+{
+    int rc = check_cart(ctx, "adi_cart_step_xy");
+    if (rc) return rc;
+    if (!d_Tin || !d_Tout || d_Tin == d_Tout) {
+        set_error("adi_cart_step_xy: Tin/Tout must be distinct device arrays");
+        return ADI_EINVAL;
+    }
+    if ((ctx->d_mask_lo && !d_Tlo) || (ctx->d_mask_hi && !d_Thi)) {
+        set_error("adi_cart_step_xy: a neighbouring slab is bound (mask halo) but its T plane is missing");
+        return ADI_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = prof_mark(ctx, 0, st);
+    if (rc) return rc;
+    return run_sweeps(ctx, d_Tin, d_Tout, dt, theta, kappa, Tinf, 0, 1, 0, ctx->d_mask_lo ? d_Tlo : nullptr,
+                      ctx->d_mask_hi ? d_Thi : nullptr, nullptr, nullptr, st);
+}
+
+int adi_cart_zsweep_reduce(adi_ctx *ctx, double *d_T, double *d_iface, double dt, double theta, double kappa,
+                           double Tinf, void *stream)
+{
+    int rc = check_cart(ctx, "adi_cart_zsweep_reduce");
+    if (rc) return rc;
+    if (!d_T || !d_iface) {
+        set_error("adi_cart_zsweep_reduce: NULL argument");
+        return ADI_EINVAL;
+    }
+    return run_sweeps(ctx, d_T, d_T, dt, theta, kappa, Tinf, 2, 2, 1, nullptr, nullptr, d_iface, nullptr,
+                      (cudaStream_t)stream);
+}
+
+int adi_cart_zsweep_finish(adi_ctx *ctx, double *d_T, const double *d_iface_all, double dt, double theta,
+                           double kappa, double Tinf, void *stream)
+{
+    int rc = check_cart(ctx, "adi_cart_zsweep_finish");
+    if (rc) return rc;
+    if (!d_T || !d_iface_all) {
+        set_error("adi_cart_zsweep_finish: NULL argument");
+        return ADI_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nlines = (size_t)ctx->nx * ctx->ny;
+    if (!nlines || !ctx->nz) return ADI_OK;
+    if (ctx->ghost_lines < nlines) {
+        if (ctx->d_ghost) { ADI_CUDA(cudaStreamSynchronize(st)); ADI_CUDA(cudaFree(ctx->d_ghost)); }
+        ctx->d_ghost = nullptr;
+        ADI_CUDA(cudaMalloc(&ctx->d_ghost, 2 * nlines * sizeof(double)));
+        ctx->ghost_lines = nlines;
+    }
+    const int threads = 128;
+    const int blocks = (int)std::min<size_t>((nlines + threads - 1) / threads, 148 * 32);
+    k_iface_solve<<<blocks, threads, 0, st>>>(d_iface_all, ctx->d_ghost, nlines, ctx->slab_nranks, ctx->slab_rank);
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
+    return run_sweeps(ctx, d_T, d_T, dt, theta, kappa, Tinf, 2, 2, 2, nullptr, nullptr, nullptr, ctx->d_ghost, st);
 }
 
 int adi_cart_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int nsteps, double dt,
@@ -235,6 +359,7 @@ int adi_cart_build_packs(adi_ctx *ctx, double rho, double cp, const int h_kind[6
     }
     PackArgs a;
     a.mask = ctx->d_mask;
+    a.mlo = ctx->d_mask_lo; a.mhi = ctx->d_mask_hi;
     a.nx = ctx->nx; a.ny = ctx->ny; a.nz = ctx->nz;
     const double dx = ctx->dx;
     a.A = dx * dx;
@@ -282,7 +407,7 @@ int adi_cart_exposed_mask(adi_ctx *ctx, int face, uint8_t *d_out, void *stream)
     const int threads = 256;
     const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, 148 * 64);
     k_exposed_mask<<<blocks, threads, 0, (cudaStream_t)stream>>>(ctx->d_mask, d_out, face, ctx->nx,
-                                                                ctx->ny, ctx->nz);
+                                                                ctx->ny, ctx->nz, ctx->d_mask_lo, ctx->d_mask_hi);
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
     return ADI_OK;

@@ -27,6 +27,11 @@ struct SweepArgs {
     const double *__restrict__ dirv;   // EXTRA, may be null
     int nx, ny, nz;
     SweepConst k;
+    // z-slab decomposition (all NULL / 0 on a single GPU)
+    const double *__restrict__ zlo;    // T plane below this slab (nx*ny), explicit stage
+    const double *__restrict__ zhi;    // T plane above this slab
+    double *iface;                     // z sweep pass 1 out: [6][nx*ny]
+    const double *__restrict__ ghost;  // z sweep pass 2 in:  [2][nx*ny] (L, R per line)
 };
 
 #ifdef ADI_CART_MISC_KERNELS  // defined by adi_cart.cu, the one unit that launches K0/K7
@@ -34,7 +39,8 @@ struct SweepArgs {
 // K0: neighbour code.  One thread per cell; the six neighbour bytes come from L1/L2.
 // ------------------------------------------------------------------------------------
 __global__ void k_build_code(const uint8_t *__restrict__ mask, const uint8_t *__restrict__ dirm,
-                             uint8_t *__restrict__ code, int nx, int ny, int nz)
+                             uint8_t *__restrict__ code, int nx, int ny, int nz,
+                             const uint8_t *__restrict__ mlo, const uint8_t *__restrict__ mhi)
 {
     const size_t n = (size_t)nx * ny * nz;
     const size_t snx = (size_t)ny * nz;
@@ -52,8 +58,9 @@ __global__ void k_build_code(const uint8_t *__restrict__ mask, const uint8_t *__
             if (i + 1 < nx && mask[idx + snx]) c |= CB_XP;
             if (j > 0 && mask[idx - nz]) c |= CB_YM;
             if (j + 1 < ny && mask[idx + nz]) c |= CB_YP;
-            if (k > 0 && mask[idx - 1]) c |= CB_ZM;
-            if (k + 1 < nz && mask[idx + 1]) c |= CB_ZP;
+            // across a slab boundary the neighbour is the adjacent rank's mask plane
+            if (k > 0 ? mask[idx - 1] : (mlo && mlo[ij])) c |= CB_ZM;
+            if (k + 1 < nz ? mask[idx + 1] : (mhi && mhi[ij])) c |= CB_ZP;
         }
         code[idx] = (uint8_t)c;
     }
@@ -67,10 +74,12 @@ __global__ void k_build_code(const uint8_t *__restrict__ mask, const uint8_t *__
 // chunks of the same line.  Returns S_p and S_{p-1} (*Sl).  Ends with every thread past
 // its last read of red only after the caller's next __syncthreads().
 // ------------------------------------------------------------------------------------
-template <int M>
+// GHOST (z-slab decomposition, pass 2): the line continues on the adjacent ranks; their
+// boundary values Lg (= S_{-1}) and Rg (the cell after the last separator) are known.
+template <int M, bool GHOST = false>
 __device__ __forceinline__ double solve_reduced(const Chunk<M> &ch, const First &f, double *red,
                                                 int NTH, int ridx, int rstep, int p, int P,
-                                                double *Sl)
+                                                double *Sl, double Lg = 0.0, double Rg = 0.0)
 {
     red[ridx] = f.Y;
     red[NTH + ridx] = f.V;
@@ -82,8 +91,14 @@ __device__ __forceinline__ double solve_reduced(const Chunk<M> &ch, const First 
         nx.Y = red[ridx + rstep];
         nx.V = red[NTH + ridx + rstep];
         nx.W = red[2 * NTH + ridx + rstep];
+    } else if (GHOST) {
+        nx = ghost_first();
     }
     Red r = chunk_reduced_row(ch, nx);
+    if (GHOST) {
+        if (p == 0) r.D = fma(-r.A, Lg, r.D);        // the PCR below ignores A_0 and C_{P-1}
+        if (p == P - 1) r.D = fma(-r.C, Rg, r.D);
+    }
     int cur = 1;
     for (int s = 1; s < P; s <<= 1) {
         double *b = red + cur * 3 * NTH;
@@ -108,8 +123,52 @@ __device__ __forceinline__ double solve_reduced(const Chunk<M> &ch, const First 
     double *b = red + cur * 3 * NTH;
     b[ridx] = r.D;
     __syncthreads();
-    *Sl = (p > 0) ? b[ridx - rstep] : 0.0;
+    *Sl = (p > 0) ? b[ridx - rstep] : (GHOST ? Lg : 0.0);
     return r.D;
+}
+
+// z-slab decomposition, pass 1: the separators as affine functions of the two ghosts.
+// red: 10*NTH doubles (two buffers of five columns); the First exchange uses the first 3*NTH.
+template <int M>
+__device__ __forceinline__ Red3 solve_reduced3(const Chunk<M> &ch, const First &f, double *red, int NTH,
+                                               int ridx, int rstep, int p, int P)
+{
+    red[ridx] = f.Y;
+    red[NTH + ridx] = f.V;
+    red[2 * NTH + ridx] = f.W;
+    __syncthreads();
+    First nx = ghost_first();
+    if (p + 1 < P) {
+        nx.Y = red[ridx + rstep];
+        nx.V = red[NTH + ridx + rstep];
+        nx.W = red[2 * NTH + ridx + rstep];
+    }
+    Red3 r = reduced_row3(chunk_reduced_row(ch, nx), p, P);
+    __syncthreads();  // everybody has read the First values: the buffers are reused below
+    int cur = 0;
+    for (int s = 1; s < P; s <<= 1) {
+        double *b = red + cur * 5 * NTH;
+        b[ridx] = r.A;
+        b[NTH + ridx] = r.C;
+        b[2 * NTH + ridx] = r.D;
+        b[3 * NTH + ridx] = r.DL;
+        b[4 * NTH + ridx] = r.DR;
+        __syncthreads();
+        Red3 lo, hi;
+        lo.A = lo.C = lo.D = lo.DL = lo.DR = 0.0;
+        hi = lo;
+        if (p - s >= 0) {
+            const int o = ridx - s * rstep;
+            lo.A = b[o]; lo.C = b[NTH + o]; lo.D = b[2 * NTH + o]; lo.DL = b[3 * NTH + o]; lo.DR = b[4 * NTH + o];
+        }
+        if (p + s < P) {
+            const int o = ridx + s * rstep;
+            hi.A = b[o]; hi.C = b[NTH + o]; hi.D = b[2 * NTH + o]; hi.DL = b[3 * NTH + o]; hi.DR = b[4 * NTH + o];
+        }
+        r = pcr_step3(r, lo, hi);
+        cur ^= 1;
+    }
+    return r;
 }
 
 // ------------------------------------------------------------------------------------
@@ -200,6 +259,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
     double *halo = smem + (size_t)3 * M * NTH;            // [2][M][P], explicit stage only
     const double *tp = a.in + idx0;
 
+    // last lane of the z tile, or the lane holding the last cell of the line
+    const bool hi_edge = (k == a.nz - 1) || (kk == KT - 1 && k < a.nz - 1);
     Chunk<M> ch;
     double xprev = 0.0, xnext = 0.0;
     if (STAGED) {
@@ -236,19 +297,30 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
                 cp_async8(scol + (M + e) * nth8, pc + ym_off);
                 cp_async8(scol + (2 * M + e) * nth8, pc + yp_off);
             }
+            // z halo of the tile: the cell before its first lane / after its last valid lane.  At a
+            // slab boundary (k == 0 / k == nz-1 with an adjacent rank) it comes from the T plane
+            // received from that rank; a.zlo / a.zhi are (nx, ny) planes.
             if (kk == 0) {
                 const long long off = k > 0 ? -8ll : 0ll;
                 const unsigned sh = smem_u32(halo + p);
+                const bool pl = (k == 0) && a.zlo;
+                const char *zb = reinterpret_cast<const char *>(a.zlo) + ((size_t)min(t0, n - 1) * a.ny + blockIdx.y) * 8;
+                const size_t zs = (size_t)a.ny * 8;
 #pragma unroll
                 for (int e = 0; e < M; ++e)
-                    cp_async8(sh + e * (unsigned)P * 8u, tb + (size_t)((unsigned)min(e, nvm1) * sl8) + off);
+                    cp_async8(sh + e * (unsigned)P * 8u,
+                              pl ? zb + (size_t)min(e, nvm1) * zs : tb + (size_t)((unsigned)min(e, nvm1) * sl8) + off);
             }
-            if (kk == KT - 1) {
+            if (hi_edge) {
                 const long long off = (k + 1 < a.nz && nv > 0) ? 8ll : 0ll;
                 const unsigned sh = smem_u32(halo + M * P + p);
+                const bool pl = (k == a.nz - 1) && a.zhi;
+                const char *zb = reinterpret_cast<const char *>(a.zhi) + ((size_t)min(t0, n - 1) * a.ny + blockIdx.y) * 8;
+                const size_t zs = (size_t)a.ny * 8;
 #pragma unroll
                 for (int e = 0; e < M; ++e)
-                    cp_async8(sh + e * (unsigned)P * 8u, tb + (size_t)((unsigned)min(e, nvm1) * sl8) + off);
+                    cp_async8(sh + e * (unsigned)P * 8u,
+                              pl ? zb + (size_t)min(e, nvm1) * zs : tb + (size_t)((unsigned)min(e, nvm1) * sl8) + off);
             }
             xprev = ldg_f64(tb - ((nv > 0 && t0 > 0) ? (long long)sl8 : 0ll));
             xnext = ldg_f64(tb + ((nv == M && t0 + M < n) ? (long long)M * sl8 : 0ll));
@@ -281,7 +353,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
             double zm = __shfl_up_sync(0xffffffffu, ch.T[e], 1);
             double zp = __shfl_down_sync(0xffffffffu, ch.T[e], 1);
             if (kk == 0) zm = (c & CB_ZM) ? halo[e * P + p] : 0.0;
-            if (kk == KT - 1) zp = (c & CB_ZP) ? halo[(M + e) * P + p] : 0.0;
+            if (hi_edge) zp = (c & CB_ZP) ? halo[(M + e) * P + p] : 0.0;
             // x neighbours come from the chunk registers: already 0 where void; a void cell
             // itself (code 0, T 0) must stay 0 whatever its neighbours hold
             const double xp = (e < M - 1) ? ch.T[e + 1] : nxt;
@@ -301,8 +373,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
             const double *pc = tp + e * sl;
             const double ym = (c & CB_YM) ? *(pc - sy) : 0.0;
             const double yp = (c & CB_YP) ? *(pc + sy) : 0.0;
-            const double zm = (c & CB_ZM) ? *(pc - 1) : 0.0;
-            const double zp = (c & CB_ZP) ? *(pc + 1) : 0.0;
+            // at a slab boundary the z neighbour lives in the plane received from the adjacent rank
+            const double zm = (c & CB_ZM) ? (k > 0 ? *(pc - 1) : a.zlo[(size_t)(t0 + e) * a.ny + blockIdx.y]) : 0.0;
+            const double zp = (c & CB_ZP) ? (k + 1 < a.nz ? *(pc + 1) : a.zhi[(size_t)(t0 + e) * a.ny + blockIdx.y]) : 0.0;
             const double xp = (e < M - 1) ? ch.T[e + 1] : nxt;
             const double r0 = explicit_r0(c, ch.T[e], prev, xp, ym, yp, zm, zp, a.k);
             prev = ch.T[e];
@@ -374,7 +447,10 @@ struct TileOps {
 };
 
 // smem: sT[LT][RL] | sC[LT][RL] | (NS 2: sU[LT][RL]) | sCode[LT][RL bytes]
-template <int M, int NS, int CMODE, bool EXTRA, int MAXT, int MINB>
+// ZMODE 0: whole line on this GPU.  1: z-slab pass 1 -- writes the interface relation of each
+// local line segment to a.iface and leaves the field untouched.  2: z-slab pass 2 -- finishes the
+// segment with the ghost values a.ghost.  ZMODE != 0 needs nz % M == 0 (last cell = a separator).
+template <int M, int NS, int CMODE, bool EXTRA, int MAXT, int MINB, int ZMODE = 0>
 __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const int vec)
 {
     static_assert(M % 4 == 0, "chunk length must be a multiple of 4");
@@ -472,8 +548,31 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
     }
 
     const First f = chunk_forward<M, CMODE, EXTRA, NS>(ch, ops, CB_ZM, CB_ZP, a.k);
-    double Sl;
-    const double S = solve_reduced<M>(ch, f, red, NTH, tid, 1, p, P, &Sl);
+    if (ZMODE == 1) {
+        const Red3 r = solve_reduced3<M>(ch, f, red, NTH, tid, 1, p, P);
+        const size_t line = L0 + ln;
+        if (line < nlines) {
+            // x_first = f.Y + f.V*L + f.W*S_0,  x_last = S_{P-1}   (adi_core.h, Iface)
+            if (p == 0) {
+                a.iface[line] = fma(f.W, r.D, f.Y);
+                a.iface[nlines + line] = fma(f.W, r.DL, f.V);
+                a.iface[2 * nlines + line] = f.W * r.DR;
+            }
+            if (p == P - 1) {
+                a.iface[3 * nlines + line] = r.D;
+                a.iface[4 * nlines + line] = r.DL;
+                a.iface[5 * nlines + line] = r.DR;
+            }
+        }
+        return;
+    }
+    double Sl, Lg = 0.0, Rg = 0.0;
+    if (ZMODE == 2) {
+        const size_t line = min(L0 + ln, nlines - 1);
+        if (p == 0) Lg = a.ghost[line];
+        if (p == P - 1) Rg = a.ghost[nlines + line];
+    }
+    const double S = solve_reduced<M, ZMODE == 2>(ch, f, red, NTH, tid, 1, p, P, &Sl, Lg, Rg);
     chunk_backward<M, EXTRA, NS>(ch, ops, CB_ZM, CB_ZP, a.k.g, Sl, S);
     __syncthreads();  // everybody is done reading the exchange buffer
 
@@ -523,11 +622,45 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
 
 #ifdef ADI_CART_MISC_KERNELS
 // ------------------------------------------------------------------------------------
+// K8: z-slab exchange helpers.
+// k_pack_zplanes: first and last z plane of a field / mask into contiguous (nx, ny) buffers
+// (the messages of the halo exchange).  k_iface_solve: every rank solves, per line, the
+// 2*nranks-unknown inter-rank system from the gathered interface relations
+// all[rank][6][nlines] and keeps its own two ghost values ghost[2][nlines].
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_pack_zplanes(const T *__restrict__ f, T *__restrict__ lo, T *__restrict__ hi, size_t nlines, int nz)
+{
+    for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < nlines; l += (size_t)gridDim.x * blockDim.x) {
+        if (lo) lo[l] = f[l * nz];
+        if (hi) hi[l] = f[l * nz + nz - 1];
+    }
+}
+
+__global__ void k_iface_solve(const double *__restrict__ all, double *__restrict__ ghost, size_t nlines,
+                              int nranks, int rank)
+{
+    for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < nlines; l += (size_t)gridDim.x * blockDim.x) {
+        double Lg, Rg;
+        iface_solve([&](int r) {
+            const double *q = all + (size_t)r * 6 * nlines + l;
+            Iface v;
+            v.yf = q[0]; v.vf = q[nlines]; v.wf = q[2 * nlines];
+            v.yl = q[3 * nlines]; v.vl = q[4 * nlines]; v.wl = q[5 * nlines];
+            return v;
+        }, nranks, rank, &Lg, &Rg);
+        ghost[l] = Lg;
+        ghost[nlines + l] = Rg;
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // K7: exposed_mask / precompute_coeff_packs_unified (adi3d_gpu_coeff.py:31-110).
 // ------------------------------------------------------------------------------------
 struct PackArgs {
     const uint8_t *mask;
     int nx, ny, nz;
+    const uint8_t *mlo, *mhi;  // mask planes of the adjacent z slabs (NULL: domain boundary)
     double A, Ccell;  // dx*dx, rho*cp*dx^3 (adi3d_numba_coeff.py:69-71)
     int h_kind[6];
     double h_scalar[6];
@@ -540,7 +673,9 @@ struct PackArgs {
 };
 
 __device__ __forceinline__ unsigned exposed_bits(const uint8_t *__restrict__ mask, size_t idx, int i,
-                                                 int j, int k, int nx, int ny, int nz)
+                                                 int j, int k, int nx, int ny, int nz,
+                                                 const uint8_t *__restrict__ mlo = nullptr,
+                                                 const uint8_t *__restrict__ mhi = nullptr)
 {
     // bit f set <=> cell active and neighbour across face f void or outside (:38-55)
     if (!mask[idx]) return 0u;
@@ -550,8 +685,9 @@ __device__ __forceinline__ unsigned exposed_bits(const uint8_t *__restrict__ mas
     if (!(i + 1 < nx && mask[idx + snx])) b |= 2u;
     if (!(j > 0 && mask[idx - nz])) b |= 4u;
     if (!(j + 1 < ny && mask[idx + nz])) b |= 8u;
-    if (!(k > 0 && mask[idx - 1])) b |= 16u;
-    if (!(k + 1 < nz && mask[idx + 1])) b |= 32u;
+    const size_t ij = (size_t)i * ny + j;
+    if (!(k > 0 ? mask[idx - 1] : (mlo && mlo[ij]))) b |= 16u;
+    if (!(k + 1 < nz ? mask[idx + 1] : (mhi && mhi[ij]))) b |= 32u;
     return b;
 }
 
@@ -564,7 +700,7 @@ __global__ void k_build_packs(const PackArgs a)
         const size_t ij = idx / a.nz;
         const int j = (int)(ij % a.ny);
         const int i = (int)(ij / a.ny);
-        const unsigned ex = exposed_bits(a.mask, idx, i, j, k, a.nx, a.ny, a.nz);
+        const unsigned ex = exposed_bits(a.mask, idx, i, j, k, a.nx, a.ny, a.nz, a.mlo, a.mhi);
 #pragma unroll
         for (int ax = 0; ax < 3; ++ax) {
             double c = 0.0, q = 0.0;
@@ -589,7 +725,8 @@ __global__ void k_build_packs(const PackArgs a)
 }
 
 __global__ void k_exposed_mask(const uint8_t *__restrict__ mask, uint8_t *__restrict__ out, int face,
-                               int nx, int ny, int nz)
+                               int nx, int ny, int nz, const uint8_t *__restrict__ mlo,
+                               const uint8_t *__restrict__ mhi)
 {
     const size_t n = (size_t)nx * ny * nz;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
@@ -598,7 +735,7 @@ __global__ void k_exposed_mask(const uint8_t *__restrict__ mask, uint8_t *__rest
         const size_t ij = idx / nz;
         const int j = (int)(ij % ny);
         const int i = (int)(ij / ny);
-        out[idx] = (uint8_t)((exposed_bits(mask, idx, i, j, k, nx, ny, nz) >> face) & 1u);
+        out[idx] = (uint8_t)((exposed_bits(mask, idx, i, j, k, nx, ny, nz, mlo, mhi) >> face) & 1u);
     }
 }
 #endif  // ADI_CART_MISC_KERNELS (K7)

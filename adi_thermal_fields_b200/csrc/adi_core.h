@@ -240,6 +240,83 @@ ADI_HD Red pcr_step(const Red &me, const Red &lo, const Red &hi)
     return r;
 }
 
+// ---- z-slab decomposition (multi-GPU z sweep) ---------------------------------------------
+// A rank holds the cells [z0, z1) of every z line.  Its segment couples to the last cell of the
+// rank below (ghost value L) and to the first cell of the rank above (ghost value R) through
+// the ZM bit of its first cell and the ZP bit of its last cell (the neighbour code is built
+// with the neighbours' mask planes).  Pass 1 carries the separators as affine functions of
+// the two ghosts, S_p = D + DL*L + DR*R, through the same PCR: three right-hand-side columns.
+struct Red3 {
+    double A, C, D, DL, DR;
+};
+
+// Reduced row of chunk p of P with the ghost couplings moved to the right-hand side columns.
+ADI_HD Red3 reduced_row3(const Red &r, int p, int P)
+{
+    Red3 q;
+    q.A = r.A; q.C = r.C; q.D = r.D; q.DL = 0.0; q.DR = 0.0;
+    if (p == 0) { q.DL = -r.A; q.A = 0.0; }          // A_0 multiplies S_{-1} = L
+    if (p == P - 1) { q.DR = -r.C; q.C = 0.0; }      // C_{P-1} multiplies the ghost R
+    return q;
+}
+
+ADI_HD Red3 pcr_step3(const Red3 &me, const Red3 &lo, const Red3 &hi)
+{
+    const double B = fma(-me.C, hi.A, fma(-me.A, lo.C, 1.0));
+    const double rB = frcp(B);
+    Red3 r;
+    r.A = (-me.A * lo.A) * rB;
+    r.C = (-me.C * hi.C) * rB;
+    r.D = fma(-me.C, hi.D, fma(-me.A, lo.D, me.D)) * rB;
+    r.DL = fma(-me.C, hi.DL, fma(-me.A, lo.DL, me.DL)) * rB;
+    r.DR = fma(-me.C, hi.DR, fma(-me.A, lo.DR, me.DR)) * rB;
+    return r;
+}
+
+// The `First` relation a ghost cell presents to the last chunk: x = 0 + 0*S_p + 1*R.
+ADI_HD First ghost_first()
+{
+    First f;
+    f.Y = 0.0; f.V = 0.0; f.W = 1.0;
+    return f;
+}
+
+// Interface relation of a rank's segment of one line:
+//   x_first = yf + vf*L + wf*R,   x_last = yl + vl*L + wl*R.
+struct Iface {
+    double yf, vf, wf, yl, vl, wl;
+};
+
+// Inter-rank system of one line (R ranks, 2R unknowns), solved by every rank for its own two
+// ghosts.  get(r) returns rank r's Iface.  L = x_last of rank-1, Rg = x_first of rank+1
+// (0 beyond the ends: the couplings there are zero).
+template <class GET>
+ADI_HD void iface_solve(GET get, int nranks, int rank, double *Lout, double *Rout)
+{
+    // forward: l_r = al + be*f_{r+1},  f_r = ga + de*f_{r+1}
+    double al[16], be[16], ga[16], de[16];
+    double alp = 0.0, bep = 0.0;   // l_{-1} = 0
+    for (int r = 0; r < nranks; ++r) {
+        const Iface q = get(r);
+        const double den = 1.0 - q.vf * bep;
+        ga[r] = (q.yf + q.vf * alp) / den;
+        de[r] = q.wf / den;
+        al[r] = q.yl + q.vl * (alp + bep * ga[r]);
+        be[r] = q.wl + q.vl * bep * de[r];
+        alp = al[r]; bep = be[r];
+    }
+    // backward
+    double fnext = 0.0, Lv = 0.0, Rv = 0.0;
+    for (int r = nranks - 1; r >= 0; --r) {
+        const double f = ga[r] + de[r] * fnext;
+        const double l = al[r] + be[r] * fnext;
+        if (r == rank + 1) Rv = f;
+        if (r == rank - 1) Lv = l;
+        fnext = f;
+    }
+    *Lout = Lv; *Rout = Rv;
+}
+
 // Phase 3: Sl = S_{p-1} (0 for the first chunk), S = S_p.  Leaves the solution in ch.T
 // (0 in void cells, which the caller does not store).
 template <int M, bool EXTRA, int NS, class OPS>

@@ -54,6 +54,11 @@ struct adi_ctx {
     uint8_t *code_buf[3] = {nullptr, nullptr, nullptr};
     size_t code_cells = 0;
     bool code_dirty = true;
+    // z-slab decomposition: mask planes of the adjacent slabs (borrowed), scratch for the ghosts
+    int slab_rank = 0, slab_nranks = 1;
+    const uint8_t *d_mask_lo = nullptr, *d_mask_hi = nullptr;
+    double *d_ghost = nullptr;
+    size_t ghost_lines = 0;
     // host-array convenience path
     double *stage[2] = {nullptr, nullptr};
     size_t stage_cells = 0;

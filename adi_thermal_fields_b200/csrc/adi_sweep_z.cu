@@ -5,11 +5,16 @@
 
 namespace adi {
 
-int launch_sweep_z(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, cudaStream_t st)
+template <int ZMODE>
+static int launch_sweep_z_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, cudaStream_t st)
 {
     Shape s;
     int rc = pick_shape(ctx, a.nz, 0, &s);
     if (rc) return rc;
+    if (ZMODE != 0 && a.nz % s.M != 0) {
+        set_error("adi_cart_zsweep_*: the local z extent must be a multiple of the chunk length (16; 32 for nz > 512)");
+        return ADI_EINVAL;
+    }
     // lines per block: fill the block, but keep the staged tiles small enough for two
     // resident blocks per SM where the line length allows it
     const size_t line_bytes = (size_t)s.P * s.M * (8 * (1 + s.NS) + 1);  // T + factor tiles + codes
@@ -29,15 +34,22 @@ int launch_sweep_z(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, cud
 #define ADI_GO(M, NS, MAXT, MINB)                                                                          \
     {                                                                                                  \
         if (dense) {                                                                                   \
-            if (extra) return launch(k_sweep_z<M, NS, 2, true, MAXT, MINB>, grid, block, smem, st, ctx, a, vec);  \
-            return launch(k_sweep_z<M, NS, 2, false, MAXT, MINB>, grid, block, smem, st, ctx, a, vec);            \
+            if (extra) return launch(k_sweep_z<M, NS, 2, true, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, a, vec);  \
+            return launch(k_sweep_z<M, NS, 2, false, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, a, vec);            \
         }                                                                                              \
-        if (extra) return launch(k_sweep_z<M, NS, 1, true, MAXT, MINB>, grid, block, smem, st, ctx, a, vec);      \
-        return launch(k_sweep_z<M, NS, 1, false, MAXT, MINB>, grid, block, smem, st, ctx, a, vec);                \
+        if (extra) return launch(k_sweep_z<M, NS, 1, true, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, a, vec);      \
+        return launch(k_sweep_z<M, NS, 1, false, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, a, vec);                \
     }
     ADI_FOR_VARIANT(s.var, ADI_GO)
 #undef ADI_GO
     return ADI_OK;
+}
+
+int launch_sweep_z(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, int zmode, cudaStream_t st)
+{
+    if (zmode == 1) return launch_sweep_z_mode<1>(ctx, a, dense, extra, st);
+    if (zmode == 2) return launch_sweep_z_mode<2>(ctx, a, dense, extra, st);
+    return launch_sweep_z_mode<0>(ctx, a, dense, extra, st);
 }
 
 }  // namespace adi

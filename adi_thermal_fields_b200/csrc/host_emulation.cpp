@@ -34,7 +34,7 @@ struct HostOps {
 template <int M, int NS, int CMODE, bool EXTRA>
 void sweep_line(double *T, const uint8_t *code, const double *coeff, const double *q,
                 const double *dirv, size_t base, size_t stride, int n, unsigned LO, unsigned HI,
-                const SweepConst &k)
+                const SweepConst &k, int zmode = 0, Iface *iface = nullptr, double Lg = 0.0, double Rg = 0.0)
 {
     const int P = (n + M - 1) / M;
     std::vector<Chunk<M>> ch(P);
@@ -56,11 +56,37 @@ void sweep_line(double *T, const uint8_t *code, const double *coeff, const doubl
         }
         fi[p] = chunk_forward<M, CMODE, EXTRA, NS>(ch[p], ops[p], LO, HI, k);
     }
+    if (zmode == 1) {  // z-slab pass 1: separators as affine functions of the ghosts (solve_reduced3)
+        std::vector<Red3> r3(P), n3(P);
+        for (int p = 0; p < P; ++p)
+            r3[p] = reduced_row3(chunk_reduced_row(ch[p], p + 1 < P ? fi[p + 1] : ghost_first()), p, P);
+        for (int s = 1; s < P; s <<= 1) {
+            for (int p = 0; p < P; ++p) {
+                Red3 lo, hi;
+                lo.A = lo.C = lo.D = lo.DL = lo.DR = 0.0;
+                hi = lo;
+                if (p - s >= 0) lo = r3[p - s];
+                if (p + s < P) hi = r3[p + s];
+                n3[p] = pcr_step3(r3[p], lo, hi);
+            }
+            r3.swap(n3);
+        }
+        iface->yf = fma(fi[0].W, r3[0].D, fi[0].Y);
+        iface->vf = fma(fi[0].W, r3[0].DL, fi[0].V);
+        iface->wf = fi[0].W * r3[0].DR;
+        iface->yl = r3[P - 1].D; iface->vl = r3[P - 1].DL; iface->wl = r3[P - 1].DR;
+        return;
+    }
     for (int p = 0; p < P; ++p) {
         First nx;
         nx.Y = nx.V = nx.W = 0.0;
         if (p + 1 < P) nx = fi[p + 1];
+        else if (zmode == 2) nx = ghost_first();
         red[p] = chunk_reduced_row(ch[p], nx);
+        if (zmode == 2) {
+            if (p == 0) red[p].D = fma(-red[p].A, Lg, red[p].D);
+            if (p == P - 1) red[p].D = fma(-red[p].C, Rg, red[p].D);
+        }
     }
     for (int s = 1; s < P; s <<= 1) {
         for (int p = 0; p < P; ++p) {
@@ -74,7 +100,7 @@ void sweep_line(double *T, const uint8_t *code, const double *coeff, const doubl
         red.swap(nxt);
     }
     for (int p = 0; p < P; ++p) {
-        chunk_backward<M, EXTRA, NS>(ch[p], ops[p], LO, HI, k.g, p > 0 ? red[p - 1].D : 0.0, red[p].D);
+        chunk_backward<M, EXTRA, NS>(ch[p], ops[p], LO, HI, k.g, p > 0 ? red[p - 1].D : (zmode == 2 ? Lg : 0.0), red[p].D);
         for (int e = 0; e < ops[p].nv; ++e)
             if (ch[p].active(e)) T[base + ((size_t)p * M + e) * stride] = ch[p].T[e];
     }
@@ -83,14 +109,15 @@ void sweep_line(double *T, const uint8_t *code, const double *coeff, const doubl
 template <int M, int NS>
 void sweep_line_any(bool dense, bool extra, double *T, const uint8_t *code, const double *coeff,
                     const double *q, const double *dirv, size_t base, size_t stride, int n, unsigned LO,
-                    unsigned HI, const SweepConst &k)
+                    unsigned HI, const SweepConst &k, int zmode = 0, Iface *iface = nullptr, double Lg = 0.0,
+                    double Rg = 0.0)
 {
     if (dense) {
-        if (extra) sweep_line<M, NS, 2, true>(T, code, coeff, q, dirv, base, stride, n, LO, HI, k);
-        else sweep_line<M, NS, 2, false>(T, code, coeff, nullptr, nullptr, base, stride, n, LO, HI, k);
+        if (extra) sweep_line<M, NS, 2, true>(T, code, coeff, q, dirv, base, stride, n, LO, HI, k, zmode, iface, Lg, Rg);
+        else sweep_line<M, NS, 2, false>(T, code, coeff, nullptr, nullptr, base, stride, n, LO, HI, k, zmode, iface, Lg, Rg);
     } else {
-        if (extra) sweep_line<M, NS, 1, true>(T, code, nullptr, q, dirv, base, stride, n, LO, HI, k);
-        else sweep_line<M, NS, 1, false>(T, code, nullptr, nullptr, nullptr, base, stride, n, LO, HI, k);
+        if (extra) sweep_line<M, NS, 1, true>(T, code, nullptr, q, dirv, base, stride, n, LO, HI, k, zmode, iface, Lg, Rg);
+        else sweep_line<M, NS, 1, false>(T, code, nullptr, nullptr, nullptr, base, stride, n, LO, HI, k, zmode, iface, Lg, Rg);
     }
 }
 
@@ -119,6 +146,107 @@ void emu_build_code(const uint8_t *mask, const uint8_t *dirm, uint8_t *code, int
                 }
                 code[idx] = (uint8_t)c;
             }
+}
+
+// the same with the mask planes of the adjacent z slabs (adi_cart_set_mask_halo)
+void emu_build_code_halo(const uint8_t *mask, const uint8_t *dirm, uint8_t *code, int nx, int ny, int nz,
+                         const uint8_t *mlo, const uint8_t *mhi)
+{
+    emu_build_code(mask, dirm, code, nx, ny, nz);
+    if (!nz) return;
+    for (size_t ij = 0; ij < (size_t)nx * ny; ++ij) {
+        if (mlo && mlo[ij] && mask[ij * nz]) code[ij * nz] |= CB_ZM;
+        if (mhi && mhi[ij] && mask[ij * nz + nz - 1]) code[ij * nz + nz - 1] |= CB_ZP;
+    }
+}
+
+// z-slab phases with the operand conventions of adi_cart_step_xy / adi_cart_zsweep_reduce /
+// adi_cart_zsweep_finish (adi_b200.h).  phase 0: explicit stage + x + y sweeps, Tin -> Tout;
+// phase 1: interface relations of the z lines of Tout -> iface[6][nx*ny];
+// phase 2: inter-rank solve from iface_all[nranks][6][nx*ny] + local finish of Tout in place.
+int emu_cart_slab(const double *Tin, double *Tout, const uint8_t *mask, int nx, int ny, int nz,
+                  double dx, double dt, double theta, double kappa, double Tinf,
+                  const double *const coeff[3], const uint8_t *const dirm[3],
+                  const double *const dirv[3], const double *const q[3], const double *face_coeff,
+                  int variant, const uint8_t *mlo, const uint8_t *mhi, const double *Tlo, const double *Thi,
+                  int phase, double *iface, const double *iface_all, int rank, int nranks)
+{
+    const size_t n = (size_t)nx * ny * nz, nlines = (size_t)nx * ny;
+    std::vector<uint8_t> code(n ? n : 1);
+    SweepConst k;
+    const double gam = kappa * dt / (dx * dx);
+    k.g = theta * gam;
+    k.dt = dt;
+    k.Tinf = Tinf;
+    k.beta = dt * kappa * (1.0 - theta);
+    k.invdx2 = 1.0 / (dx * dx);
+    const size_t snx = (size_t)ny * nz;
+    const int M = variant == 0 ? 16 : 32;
+    if (phase == 0) {
+        emu_build_code_halo(mask, dirm[0], code.data(), nx, ny, nz, mlo, mhi);
+        for (size_t idx = 0; idx < n; ++idx) {
+            const unsigned c = code[idx];
+            const size_t ij = idx / nz;
+            const int kz = (int)(idx % nz);
+            double v[6] = {0, 0, 0, 0, 0, 0};
+            if (c & CB_XM) v[0] = Tin[idx - snx];
+            if (c & CB_XP) v[1] = Tin[idx + snx];
+            if (c & CB_YM) v[2] = Tin[idx - nz];
+            if (c & CB_YP) v[3] = Tin[idx + nz];
+            if (c & CB_ZM) v[4] = kz > 0 ? Tin[idx - 1] : Tlo[ij];
+            if (c & CB_ZP) v[5] = kz + 1 < nz ? Tin[idx + 1] : Thi[ij];
+            Tout[idx] = (k.beta != 0.0 && (c & CB_SELF))
+                            ? explicit_r0(c, Tin[idx], v[0], v[1], v[2], v[3], v[4], v[5], k)
+                            : Tin[idx];
+        }
+    }
+    const int a0 = phase == 0 ? 0 : 2, a1 = phase == 0 ? 1 : 2;
+    for (int axis = a0; axis <= a1; ++axis) {
+        if (axis > 0 || phase != 0) emu_build_code_halo(mask, dirm[axis], code.data(), nx, ny, nz, mlo, mhi);
+        k.h_lo = face_coeff ? face_coeff[2 * axis] : 0.0;
+        k.h_hi = face_coeff ? face_coeff[2 * axis + 1] : 0.0;
+        const int len = axis == 0 ? nx : (axis == 1 ? ny : nz);
+        const size_t stride = axis == 0 ? snx : (axis == 1 ? (size_t)nz : 1);
+        const unsigned LO = axis == 0 ? CB_XM : (axis == 1 ? CB_YM : CB_ZM);
+        const unsigned HI = axis == 0 ? CB_XP : (axis == 1 ? CB_YP : CB_ZP);
+        const int n1 = axis == 0 ? ny : nx, n2 = axis == 2 ? ny : nz;
+        const bool dense = coeff[axis] != nullptr;
+        const bool extra = q[axis] != nullptr || dirm[axis] != nullptr;
+        if (axis == 2 && len % M != 0) return -2;
+        for (int u = 0; u < n1; ++u)
+            for (int v = 0; v < n2; ++v) {
+                size_t base;
+                if (axis == 0) base = (size_t)u * nz + v;
+                else if (axis == 1) base = (size_t)u * snx + v;
+                else base = ((size_t)u * ny + v) * nz;
+                int zmode = 0;
+                Iface f;
+                double Lg = 0.0, Rg = 0.0;
+                const size_t line = (size_t)u * ny + v;
+                if (axis == 2) {
+                    zmode = phase;
+                    if (phase == 2)
+                        iface_solve([&](int r) {
+                            const double *qq = iface_all + (size_t)r * 6 * nlines + line;
+                            Iface w;
+                            w.yf = qq[0]; w.vf = qq[nlines]; w.wf = qq[2 * nlines];
+                            w.yl = qq[3 * nlines]; w.vl = qq[4 * nlines]; w.wl = qq[5 * nlines];
+                            return w;
+                        }, nranks, rank, &Lg, &Rg);
+                }
+                if (variant == 0)
+                    sweep_line_any<16, 2>(dense, extra, Tout, code.data(), coeff[axis], q[axis], dirv[axis], base,
+                                          stride, len, LO, HI, k, zmode, &f, Lg, Rg);
+                else
+                    sweep_line_any<32, 1>(dense, extra, Tout, code.data(), coeff[axis], q[axis], dirv[axis], base,
+                                          stride, len, LO, HI, k, zmode, &f, Lg, Rg);
+                if (axis == 2 && phase == 1) {
+                    iface[line] = f.yf; iface[nlines + line] = f.vf; iface[2 * nlines + line] = f.wf;
+                    iface[3 * nlines + line] = f.yl; iface[4 * nlines + line] = f.vl; iface[5 * nlines + line] = f.wl;
+                }
+            }
+    }
+    return 0;
 }
 
 // One full step with the operand conventions of adi_cart_step (adi_b200.h).

@@ -1,0 +1,357 @@
+# -*- coding: utf-8 -*-
+"""z-slab decomposition of the Cartesian ADI step across GPUs (BASELINE north_star).
+
+The reference is single-process; this is the multi-GPU form of `adi_step_gpu_coeff`
+(adi3d_gpu_coeff.py:213-230): rank r of R owns the z planes [z0_r, z1_r) of every array.
+
+  * x and y sweeps are rank-local (lines never cross slabs);
+  * the explicit stage (adi3d_numba_coeff.py:274-288,298) needs one T plane from each adjacent
+    rank per step, the neighbour code one MASK plane per side whenever the mask changes;
+  * the z sweep (adi3d_numba_coeff.py:205-237) is a partitioned tridiagonal solve: every rank
+    reduces its segment of each line to an interface relation (pass 1), the relations are
+    all-gathered (6 doubles per line and rank), every rank solves the 2R-unknown inter-rank
+    system per line and finishes its segment (pass 2).
+
+One process per GPU; `torch.distributed` (NCCL over NVLink) is the plumbing for the two
+exchanges, the arithmetic runs in libadi_b200.so.  `LocalComm` runs R virtual ranks as threads of
+one process on one device (used by the single-GPU tests and to measure the cost of the split
+itself); `backend=` is a test seam (tests/ plug in the host emulation of the kernels for the
+gloo tests on CPU) -- the default backend is the CUDA library and raises without it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _capi
+
+FACES = ("x-", "x+", "y-", "y+", "z-", "z+")
+
+
+def split_z(nz, world):
+    """Balanced slab extents: list of (z0, z1)."""
+    q, r = divmod(nz, world)
+    out, z = [], 0
+    for i in range(world):
+        n = q + (1 if i < r else 0)
+        out.append((z, z + n))
+        z += n
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# communicators
+# --------------------------------------------------------------------------------------------
+class TorchDistComm:
+    """Ranks = processes of a torch.distributed group (NCCL for CUDA tensors, gloo for CPU)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def exchange_planes(self, lo, hi, recv_lo, recv_hi):
+        """Send `hi` up / `lo` down; receive the plane below into recv_lo, above into recv_hi."""
+        dist = self.dist
+        ops = []
+        if self.rank + 1 < self.world:
+            ops.append(dist.P2POp(dist.isend, hi, self._peer(self.rank + 1), self.group))
+            ops.append(dist.P2POp(dist.irecv, recv_hi, self._peer(self.rank + 1), self.group))
+        if self.rank > 0:
+            ops.append(dist.P2POp(dist.isend, lo, self._peer(self.rank - 1), self.group))
+            ops.append(dist.P2POp(dist.irecv, recv_lo, self._peer(self.rank - 1), self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def _peer(self, r):
+        return r if self.group is None else self.dist.get_global_rank(self.group, r)
+
+    def all_gather(self, out, inp):
+        try:
+            self.dist.all_gather_into_tensor(out, inp, group=self.group)
+        except (RuntimeError, NotImplementedError):
+            parts = list(out.view(self.world, -1).unbind(0))
+            self.dist.all_gather(parts, inp.view(-1), group=self.group)
+
+
+class LocalComm:
+    """R virtual ranks = R threads of this process sharing one device (and its current stream, so
+    every hand-over is stream-ordered).  comm = LocalComm(R); comm.view(r) is rank r's handle."""
+
+    def __init__(self, world):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [dict() for _ in range(world)]
+
+    def view(self, rank):
+        return _LocalView(self, rank)
+
+    def run(self, fn):
+        """Run fn(rank_view) on every virtual rank; returns the list of results."""
+        res, err = [None] * self.world, []
+        dev = torch.cuda.current_device() if torch.cuda.is_available() else None
+
+        def go(r):
+            try:
+                if dev is not None:
+                    torch.cuda.set_device(dev)
+                res[r] = fn(self.view(r))
+            except BaseException as e:  # noqa: BLE001
+                err.append(e)
+                self.barrier.abort()
+
+        th = [threading.Thread(target=go, args=(r,)) for r in range(self.world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if err:
+            raise err[0]
+        return res
+
+
+class _LocalView:
+    def __init__(self, comm, rank):
+        self.c, self.rank, self.world = comm, rank, comm.world
+
+    def exchange_planes(self, lo, hi, recv_lo, recv_hi):
+        s = self.c.slots
+        s[self.rank]["lo"], s[self.rank]["hi"] = lo, hi
+        self.c.barrier.wait()
+        if self.rank > 0:
+            recv_lo.copy_(s[self.rank - 1]["hi"])
+        if self.rank + 1 < self.world:
+            recv_hi.copy_(s[self.rank + 1]["lo"])
+        self.c.barrier.wait()
+
+    def all_gather(self, out, inp):
+        s = self.c.slots
+        s[self.rank]["ag"] = inp
+        self.c.barrier.wait()
+        o = out.view(self.world, -1)
+        for r in range(self.world):
+            o[r].copy_(s[r]["ag"].view(-1))
+        self.c.barrier.wait()
+
+
+# --------------------------------------------------------------------------------------------
+# CUDA backend (the product path)
+# --------------------------------------------------------------------------------------------
+class CudaBackend:
+    """One engine context per (virtual) rank; all arithmetic through the C ABI."""
+
+    def __init__(self):
+        if not torch.cuda.is_available():
+            raise RuntimeError("adi_thermal_fields_b200.slab: no CUDA device (there is no CPU fallback)")
+        self.L = _capi.load()
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        h = C.c_void_p()
+        _capi.check(self.L.adi_ctx_create(self.dev.index, C.byref(h)), "adi_ctx_create")
+        self.ctx = h
+        self.hold = None
+
+    def _st(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.dev)
+
+    def asarray(self, x, dtype):
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+        return t.to(device=self.dev, dtype=dtype).contiguous()
+
+    def bind(self, nx, ny, nz, dx, mask, rank, world):
+        L = self.L
+        _capi.check(L.adi_cart_bind(self.ctx, nx, ny, nz, dx), "adi_cart_bind")
+        _capi.check(L.adi_cart_set_slab(self.ctx, rank, world), "adi_cart_set_slab")
+        _capi.check(L.adi_cart_set_mask(self.ctx, mask.data_ptr()), "adi_cart_set_mask")
+
+    def pack_planes(self, field, lo, hi):
+        _capi.check(self.L.adi_cart_pack_zplanes(self.ctx, field.data_ptr(), field.element_size(),
+                                                 lo.data_ptr(), hi.data_ptr(), self._st()), "adi_cart_pack_zplanes")
+
+    def set_mask_halo(self, lo, hi):
+        _capi.check(self.L.adi_cart_set_mask_halo(self.ctx, None if lo is None else lo.data_ptr(),
+                                                  None if hi is None else hi.data_ptr()), "adi_cart_set_mask_halo")
+
+    def mark_mask_changed(self, mask):
+        _capi.check(self.L.adi_cart_set_mask(self.ctx, mask.data_ptr()), "adi_cart_set_mask")
+
+    def build_packs(self, rho, cp, hk, hs, hf, qk, qs, qf, shape):
+        """-> (coeff[3], q[3]) device arrays or None (k_build_packs, halo-aware exposed faces)."""
+        dense_h = any(k == 2 for k in hk)
+        have_q = any(k != 0 for k in qk)
+        if not (dense_h or have_q):
+            return [None] * 3, [None] * 3
+        coeffs = [self.empty(shape, torch.float64) if dense_h else None for _ in range(3)]
+        qs_out = [self.empty(shape, torch.float64) if (qk[2 * a] or qk[2 * a + 1]) else None for a in range(3)]
+        vp = C.c_void_p
+        hfp = (vp * 6)(*[None if a is None else a.data_ptr() for a in hf])
+        qfp = (vp * 6)(*[None if a is None else a.data_ptr() for a in qf])
+        ptr = [None if a is None else a.data_ptr() for a in coeffs + qs_out]
+        _capi.check(self.L.adi_cart_build_packs(self.ctx, rho, cp, (C.c_int * 6)(*hk), (C.c_double * 6)(*hs), hfp,
+                                                (C.c_int * 6)(*qk), (C.c_double * 6)(*qs), qfp, *ptr, self._st()),
+                    "adi_cart_build_packs")
+        return coeffs, qs_out
+
+    def set_packs(self, packs, face_coeff):
+        """packs: 3 x (coeff|None, dir_mask|None, dir_val|None, q|None) device arrays."""
+        self.hold = packs
+        for a, (c, dm, dv, q) in enumerate(packs):
+            p = [None if x is None else x.data_ptr() for x in (c, dm, dv, q)]
+            _capi.check(self.L.adi_cart_set_pack(self.ctx, a, *p), "adi_cart_set_pack")
+        if face_coeff is not None:
+            _capi.check(self.L.adi_cart_set_robin_scalar(self.ctx, (C.c_double * 6)(*face_coeff)),
+                        "adi_cart_set_robin_scalar")
+
+    def step_xy(self, Tin, Tout, Tlo, Thi, dt, theta, kappa, Tinf):
+        _capi.check(self.L.adi_cart_step_xy(self.ctx, Tin.data_ptr(), Tout.data_ptr(),
+                                            None if Tlo is None else Tlo.data_ptr(),
+                                            None if Thi is None else Thi.data_ptr(), dt, theta, kappa, Tinf,
+                                            self._st()), "adi_cart_step_xy")
+
+    def zsweep_reduce(self, T, iface, dt, theta, kappa, Tinf):
+        _capi.check(self.L.adi_cart_zsweep_reduce(self.ctx, T.data_ptr(), iface.data_ptr(), dt, theta, kappa, Tinf,
+                                                  self._st()), "adi_cart_zsweep_reduce")
+
+    def zsweep_finish(self, T, iface_all, dt, theta, kappa, Tinf):
+        _capi.check(self.L.adi_cart_zsweep_finish(self.ctx, T.data_ptr(), iface_all.data_ptr(), dt, theta, kappa,
+                                                  Tinf, self._st()), "adi_cart_zsweep_finish")
+
+    def launch_count(self):
+        return int(self.L.adi_launch_count(self.ctx))
+
+    def set_option(self, name, value):
+        _capi.check(self.L.adi_set_option(self.ctx, str(name).encode(), int(value)), "adi_set_option")
+
+    def profile(self, on):
+        self.L.adi_set_option(self.ctx, b"profile", 1 if on else 0)
+        self.L.adi_profile_reset(self.ctx)
+
+    def profile_read(self):
+        ms = (C.c_double * 3)()
+        n = C.c_long()
+        self.L.adi_profile_read(self.ctx, ms, C.byref(n))
+        return [ms[i] for i in range(3)], n.value
+
+    def close(self):
+        if self.ctx is not None:
+            self.L.adi_ctx_destroy(self.ctx)
+            self.ctx = None
+
+
+# --------------------------------------------------------------------------------------------
+# the slab stepper
+# --------------------------------------------------------------------------------------------
+class SlabGrid3D:
+    """Local slab of a Cartesian grid: Grid3D(nx,ny,nz,dx,mask) (adi3d_gpu_coeff.py:6-12) with
+    nz / mask the LOCAL extent, plus the communicator that links it to the adjacent slabs."""
+
+    def __init__(self, nx, ny, nz_local, dx, mask_local, comm, backend=None):
+        self.nx, self.ny, self.nz, self.dx = int(nx), int(ny), int(nz_local), float(dx)
+        self.comm = comm
+        self.rank, self.world = comm.rank, comm.world
+        self.be = backend if backend is not None else CudaBackend()
+        be = self.be
+        self.mask = be.asarray(mask_local, torch.bool)
+        assert tuple(self.mask.shape) == (self.nx, self.ny, self.nz)
+        pl = (self.nx, self.ny)
+        self._m_lo, self._m_hi = be.empty(pl, torch.bool), be.empty(pl, torch.bool)      # to send
+        self.mask_lo, self.mask_hi = be.empty(pl, torch.bool), be.empty(pl, torch.bool)  # received
+        self._t_lo, self._t_hi = be.empty(pl, torch.float64), be.empty(pl, torch.float64)
+        self.T_lo, self.T_hi = be.empty(pl, torch.float64), be.empty(pl, torch.float64)
+        self.iface = be.empty((6, self.nx * self.ny), torch.float64)
+        self.iface_all = be.empty((self.world, 6, self.nx * self.ny), torch.float64)
+        be.bind(self.nx, self.ny, self.nz, self.dx, self.mask, self.rank, self.world)
+        self.sync_mask()
+
+    def sync_mask(self):
+        """Call after the local mask changed (layer births): refreshes the adjacent ranks' view of
+        it.  Collective: every rank of the group must call it."""
+        be = self.be
+        be.mark_mask_changed(self.mask)
+        be.pack_planes(self.mask, self._m_lo, self._m_hi)
+        self.comm.exchange_planes(self._m_lo, self._m_hi, self.mask_lo, self.mask_hi)
+        be.set_mask_halo(self.mask_lo if self.rank > 0 else None,
+                         self.mask_hi if self.rank + 1 < self.world else None)
+
+
+class SlabPacks:
+    def __init__(self, packs, face_coeff):
+        self.packs, self.face_coeff = packs, face_coeff
+
+
+def precompute_coeff_packs_unified(grid, mat, dir_mask=None, dir_value=None, neumann=None, robin_h=None,
+                                   robin_Tinf=None):
+    """precompute_coeff_packs_unified (adi3d_gpu_coeff.py:50-110) for a slab: all field arguments
+    are the LOCAL slabs of the global fields; faces at slab boundaries are exposed only where
+    the adjacent rank's cell is void."""
+    be = grid.be
+    shape = (grid.nx, grid.ny, grid.nz)
+
+    def classify(v):
+        if v is None:
+            return 0, 0.0, None
+        if np.isscalar(v):
+            return 1, float(v), None
+        a = be.asarray(v, torch.float64)
+        if tuple(a.shape) != shape:
+            raise ValueError("field shape does not match the slab")
+        return 2, 0.0, a
+
+    hk, hs, hf = [0] * 6, [0.0] * 6, [None] * 6
+    if robin_h is not None:
+        for i, f in enumerate(FACES):
+            v = robin_h.get(f, 0.0) if isinstance(robin_h, dict) else robin_h
+            hk[i], hs[i], hf[i] = classify(v)
+    qk, qs, qf = [0] * 6, [0.0] * 6, [None] * 6
+    if neumann is not None:
+        for f, v in neumann.items():
+            if f not in FACES:
+                raise ValueError("bad face")
+            i = FACES.index(f)
+            qk[i], qs[i], qf[i] = classify(v)
+    dm = None if dir_mask is None else be.asarray(dir_mask, torch.bool)
+    if dm is not None and not bool(dm.any()):
+        dm = None
+    dv = None
+    if dm is not None:
+        if dir_value is None:
+            dv = torch.zeros_like(dm, dtype=torch.float64)
+        elif np.isscalar(dir_value):
+            dv = torch.full_like(dm, float(dir_value), dtype=torch.float64)
+        else:
+            dv = be.asarray(dir_value, torch.float64)
+    coeffs, qouts = be.build_packs(mat.rho, mat.cp, hk, hs, hf, qk, qs, qf, shape)
+    A = grid.dx * grid.dx
+    Ccell = mat.rho * mat.cp * grid.dx ** 3
+    face_coeff = None
+    if coeffs[0] is None:
+        face_coeff = [(hs[i] * A / Ccell) if hk[i] == 1 else 0.0 for i in range(6)]
+    return SlabPacks([(coeffs[a], dm, dv, qouts[a]) for a in range(3)], face_coeff)
+
+
+def adi_step_gpu_coeff(Tn, grid, mat, params, packs, Tinf=0.0, out=None):
+    """One ADI theta-step of the slab (collective over grid.comm).  Returns a new local array."""
+    be, comm = grid.be, grid.comm
+    kappa = mat.k / (mat.rho * mat.cp)
+    dt, theta = float(params.dt), float(params.theta)
+    T = Tn
+    if out is None:
+        out = be.empty(tuple(T.shape), torch.float64)
+    be.set_packs(packs.packs, packs.face_coeff)
+    lo_ok, hi_ok = grid.rank > 0, grid.rank + 1 < grid.world
+    if theta != 1.0:   # the explicit stage is the only consumer of the T halo (beta = 0 at theta = 1)
+        be.pack_planes(T, grid._t_lo, grid._t_hi)
+        comm.exchange_planes(grid._t_lo, grid._t_hi, grid.T_lo, grid.T_hi)
+    be.step_xy(T, out, grid.T_lo if lo_ok else None, grid.T_hi if hi_ok else None, dt, theta, kappa, float(Tinf))
+    be.zsweep_reduce(out, grid.iface, dt, theta, kappa, float(Tinf))
+    comm.all_gather(grid.iface_all, grid.iface)
+    be.zsweep_finish(out, grid.iface_all, dt, theta, kappa, float(Tinf))
+    return out

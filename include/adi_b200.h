@@ -90,6 +90,37 @@ int adi_cart_build_packs(adi_ctx *ctx, double rho, double cp, const int h_kind[6
                          void *stream);
 /* exposed_mask(mask, face)  adi3d_gpu_coeff.py:31-48; face index 0..5 as above. */
 int adi_cart_exposed_mask(adi_ctx *ctx, int face, uint8_t *d_out, void *stream);
+/* ---- z-slab decomposition of the Cartesian grid across GPUs (BASELINE north_star; the
+ * reference is single-process: this is the multi-GPU form of adi_step_gpu_coeff,
+ * adi3d_gpu_coeff.py:213-230).  Rank r of R holds the planes [z0_r, z1_r) of every array; the
+ * context is bound (adi_cart_bind) with the LOCAL nz.  x and y sweeps are local.  Per step the
+ * host exchanges one T plane per side (explicit stage, adi3d_numba_coeff.py:274-288) and the
+ * interface relations of the z sweep (adi3d_numba_coeff.py:205-237 solved as a partitioned
+ * tridiagonal system), e.g. with NCCL:
+ *     adi_cart_pack_zplanes(T)            -> send lo plane down / hi plane up
+ *     adi_cart_step_xy(Tin, Tout, Tlo, Thi)
+ *     adi_cart_zsweep_reduce(Tout, iface) -> all-gather iface (6*nx*ny doubles per rank)
+ *     adi_cart_zsweep_finish(Tout, iface_all)
+ * The local nz must be a multiple of 16 (32 when nz > 512). */
+int adi_cart_set_slab(adi_ctx *ctx, int rank, int nranks);
+/* Mask planes (nx*ny bytes) of the slab below / above; NULL at the domain boundary.  Borrowed.
+ * Used by the neighbour code, adi_cart_build_packs and adi_cart_exposed_mask. */
+int adi_cart_set_mask_halo(adi_ctx *ctx, const uint8_t *d_mask_lo, const uint8_t *d_mask_hi);
+/* First / last z plane of a field (elem_bytes 8) or mask (1) into contiguous nx*ny buffers
+ * (either output may be NULL). */
+int adi_cart_pack_zplanes(adi_ctx *ctx, const void *d_field, int elem_bytes, void *d_lo_out,
+                          void *d_hi_out, void *stream);
+/* Explicit stage + x sweep + y sweep; d_Tlo / d_Thi: T planes received from the adjacent ranks. */
+int adi_cart_step_xy(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const double *d_Tlo,
+                     const double *d_Thi, double dt, double theta, double kappa, double Tinf,
+                     void *stream);
+/* z sweep, pass 1: d_iface[6][nx*ny] = (yf,vf,wf,yl,vl,wl) per line; d_T is not modified. */
+int adi_cart_zsweep_reduce(adi_ctx *ctx, double *d_T, double *d_iface, double dt, double theta,
+                           double kappa, double Tinf, void *stream);
+/* z sweep, pass 2: d_iface_all[nranks][6][nx*ny] gathered from all ranks; solves the inter-rank
+ * system per line and finishes the local segments in place. */
+int adi_cart_zsweep_finish(adi_ctx *ctx, double *d_T, const double *d_iface_all, double dt,
+                           double theta, double kappa, double Tinf, void *stream);
 /* Tuning / introspection: kernel variant selection (0 = default) and launch counter. */
 int adi_set_option(adi_ctx *ctx, const char *name, long value);
 long adi_launch_count(adi_ctx *ctx);

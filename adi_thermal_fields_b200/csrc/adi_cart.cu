@@ -1,5 +1,7 @@
 // adi_cart.cu -- Cartesian entry points of the C ABI: operand binding, variant
 // selection and launch of the kernels in adi_cart.cuh.
+#include <stdint.h>
+
 #include <algorithm>
 #include <cstdio>
 
@@ -167,11 +169,28 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
     a.k.beta = dt * kappa * (1.0 - theta);
     a.k.invdx2 = 1.0 / (dx * dx);
     a.zlo = d_Tlo; a.zhi = d_Thi; a.iface = d_iface; a.ghost = d_ghost;
-    const bool expl = a.k.beta != 0.0;
+    bool expl = a.k.beta != 0.0;
+    bool x_in_place = false;
+    if (expl && first == 0 && !ctx->opt_fuse) {
+        // explicit stage as its own streaming pass Tin -> Tout; the x sweep then runs in place
+        a.in = d_Tin; a.out = d_Tout; a.code = ctx->code[0];
+        a.coeff = nullptr; a.q = nullptr; a.dirv = nullptr;
+        const bool vec = (a.nz % 2 == 0) && ((((uintptr_t)d_Tin | (uintptr_t)d_Tout) & 15) == 0) &&
+                         (((uintptr_t)a.code & 1) == 0);
+        const int VEC = vec ? 2 : 1, threads = 128, JT = 16;
+        dim3 grid((unsigned)(((a.nz + VEC - 1) / VEC + threads - 1) / threads), (unsigned)((a.ny + JT - 1) / JT),
+                  (unsigned)a.nx);
+        if (vec) k_explicit<2><<<grid, threads, 0, st>>>(a, JT);
+        else k_explicit<1><<<grid, threads, 0, st>>>(a, JT);
+        ctx->launches++;
+        ADI_CUDA(cudaGetLastError());
+        expl = false;
+        x_in_place = true;
+    }
 
     for (int axis = first; axis <= last; ++axis) {
         const Pack &p = ctx->pack[axis];
-        a.in = axis == 0 ? d_Tin : d_Tout;  // y and z sweeps run in place on Tout
+        a.in = (axis == 0 && !x_in_place) ? d_Tin : d_Tout;  // y and z sweeps run in place on Tout
         a.out = d_Tout;
         a.code = ctx->code[axis];
         a.coeff = p.coeff;

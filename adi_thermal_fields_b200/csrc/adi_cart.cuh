@@ -14,6 +14,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "adi_core.h"
 
 namespace adi {
@@ -621,6 +623,65 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
 }
 
 #ifdef ADI_CART_MISC_KERNELS
+// ------------------------------------------------------------------------------------
+// K1e: explicit stage as a streaming kernel, R0 = T + beta*(Lx+Ly+Lz)T  (adi3d_numba_coeff.py:240-298).
+// Threads run along z (VEC cells each, 16-byte accesses for VEC 2) and march JT rows in y with
+// the y-1 / y / y+1 values of their column in registers; the x-1 / x+1 rows come from the two
+// adjacent x planes (L2 hits: the blocks of neighbouring planes run at the same time), the
+// z neighbours of the thread's first / last cell from the adjacent lanes' lines (L1 hits) or, at
+// a slab boundary, from the T plane received from the adjacent rank.
+// Void cells are copied bit for bit (the reference never touches them).
+// grid = (ceil(nz/VEC/blockDim.x), ceil(ny/JT), nx).
+// ------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(128) k_explicit(const SweepArgs a, const int JT)
+{
+    const int z = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (z >= a.nz) return;
+    const int i = blockIdx.z;
+    const int j0 = blockIdx.y * JT, j1 = min(j0 + JT, a.ny);
+    const size_t snx = (size_t)a.ny * a.nz;
+    size_t idx = ((size_t)i * a.ny + j0) * a.nz + z;
+    typedef typename std::conditional<VEC == 2, double2, double>::type V;
+    auto ldv = [&](size_t g, double (&v)[VEC]) {
+        const V t = *reinterpret_cast<const V *>(a.in + g);
+        if (VEC == 2) { v[0] = reinterpret_cast<const double *>(&t)[0]; v[1] = reinterpret_cast<const double *>(&t)[VEC - 1]; }
+        else v[0] = reinterpret_cast<const double *>(&t)[0];
+    };
+    double prev[VEC], cur[VEC], next[VEC], xm[VEC], xp[VEC], r[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) prev[v] = next[v] = xm[v] = xp[v] = 0.0;
+    if (j0 > 0) ldv(idx - a.nz, prev);
+    ldv(idx, cur);
+    for (int j = j0; j < j1; ++j) {
+        if (j + 1 < a.ny) ldv(idx + a.nz, next);
+        if (i > 0) ldv(idx - snx, xm);
+        if (i + 1 < a.nx) ldv(idx + snx, xp);
+        unsigned cw;
+        if (VEC == 2) cw = *reinterpret_cast<const unsigned short *>(a.code + idx);
+        else cw = a.code[idx];
+        const unsigned c0 = cw & 0xffu, cl = (cw >> (8 * (VEC - 1))) & 0xffu;
+        double zlo_v = 0.0, zhi_v = 0.0;
+        if (c0 & CB_ZM) zlo_v = z > 0 ? a.in[idx - 1] : a.zlo[(size_t)i * a.ny + j];
+        if (cl & CB_ZP) zhi_v = z + VEC < a.nz ? a.in[idx + VEC] : a.zhi[(size_t)i * a.ny + j];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const unsigned c = (cw >> (8 * v)) & 0xffu;
+            const double zm = v == 0 ? zlo_v : ((c & CB_ZM) ? cur[v - 1 < 0 ? 0 : v - 1] : 0.0);
+            const double zp = v == VEC - 1 ? zhi_v : ((c & CB_ZP) ? cur[v + 1 < VEC ? v + 1 : v] : 0.0);
+            const double r0 = explicit_r0(c, (c & CB_SELF) ? cur[v] : 0.0, (c & CB_XM) ? xm[v] : 0.0,
+                                          (c & CB_XP) ? xp[v] : 0.0, (c & CB_YM) ? prev[v] : 0.0,
+                                          (c & CB_YP) ? next[v] : 0.0, zm, zp, a.k);
+            r[v] = (c & CB_SELF) ? r0 : cur[v];
+        }
+        if (VEC == 2) *reinterpret_cast<double2 *>(a.out + idx) = make_double2(r[0], r[VEC - 1]);
+        else a.out[idx] = r[0];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { prev[v] = cur[v]; cur[v] = next[v]; }
+        idx += a.nz;
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // K8: z-slab exchange helpers.
 // k_pack_zplanes: first and last z plane of a field / mask into contiguous (nx, ny) buffers

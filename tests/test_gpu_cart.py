@@ -53,6 +53,22 @@ def test_step_matches_reference(name, g, cp, golden_dir):
         assert cases.rel_l2(trace, gold["trace"], np.isfinite(gold["trace"])) <= TOL
 
 
+@pytest.mark.parametrize("name", sorted(n for n, v in cases.CART_CASES.items() if v[3] != 1.0))
+def test_fused_explicit_stage_variant(name, g, cp, golden_dir):
+    """Engine option fuse=1: the explicit stage (adi3d_numba_coeff.py:298) applied while the x
+    sweep loads its lines, instead of as its own streaming pass."""
+    c = cases.build_cart_case(name)
+    gold = np.load(os.path.join(golden_dir, f"cart_{name}.npz"))
+    g.set_option("fuse", 1)
+    try:
+        T, _, _ = _run(g, cp, c)
+    finally:
+        g.set_option("fuse", 0)
+    m = c["mask"]
+    assert cases.rel_l2(T, gold["T_out"], m) <= TOL
+    assert np.array_equal(T[~m], c["T0"][~m], equal_nan=True)
+
+
 @pytest.mark.parametrize("name", ["holes_combined", "track_mixed", "random_neumann_fields"])
 def test_device_pack_builder_bit_exact(name, g, cp, golden_dir):
     """precompute_coeff_packs_unified on the device (kernel k_build_packs) vs the reference."""

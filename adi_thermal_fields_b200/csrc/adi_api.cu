@@ -22,14 +22,14 @@ void cyl_release(adi_ctx *ctx);  // adi_cyl.cu
 int prof_mark(adi_ctx *ctx, int slot, cudaStream_t st)
 {
     if (!ctx->opt_profile) return ADI_OK;
-    const size_t need = (size_t)(ctx->prof_steps + 1) * 4;
+    const size_t need = (size_t)(ctx->prof_steps + 1) * 5;
     while (ctx->prof_ev.size() < need) {
         cudaEvent_t e;
         ADI_CUDA(cudaEventCreate(&e));
         ctx->prof_ev.push_back(e);
     }
-    ADI_CUDA(cudaEventRecord(ctx->prof_ev[(size_t)ctx->prof_steps * 4 + slot], st));
-    if (slot == 3) ctx->prof_steps++;
+    ADI_CUDA(cudaEventRecord(ctx->prof_ev[(size_t)ctx->prof_steps * 5 + slot], st));
+    if (slot == 4) ctx->prof_steps++;
     return ADI_OK;
 }
 
@@ -146,14 +146,14 @@ int adi_profile_reset(adi_ctx *ctx)
     return ADI_OK;
 }
 
-int adi_profile_read(adi_ctx *ctx, double ms[3], long *nsteps)
+int adi_profile_read(adi_ctx *ctx, double ms[4], long *nsteps)
 {
     if (!ctx || !ms) return ADI_EINVAL;
-    ms[0] = ms[1] = ms[2] = 0.0;
+    ms[0] = ms[1] = ms[2] = ms[3] = 0.0;
     for (long s = 0; s < ctx->prof_steps; ++s) {
-        cudaEvent_t *e = &ctx->prof_ev[(size_t)s * 4];
-        ADI_CUDA(cudaEventSynchronize(e[3]));
-        for (int k = 0; k < 3; ++k) {
+        cudaEvent_t *e = &ctx->prof_ev[(size_t)s * 5];
+        ADI_CUDA(cudaEventSynchronize(e[4]));
+        for (int k = 0; k < 4; ++k) {
             float t = 0.f;
             ADI_CUDA(cudaEventElapsedTime(&t, e[k], e[k + 1]));
             ms[k] += (double)t;

@@ -187,6 +187,10 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
         expl = false;
         x_in_place = true;
     }
+    if (first == 0) {
+        rc = prof_mark(ctx, 1, st);
+        if (rc) return rc;
+    }
 
     for (int axis = first; axis <= last; ++axis) {
         const Pack &p = ctx->pack[axis];
@@ -205,7 +209,7 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
         else rc = launch_sweep_z(ctx, a, dense, extra, zmode, st);
         if (rc) return rc;
         if (zmode != 1) {
-            rc = prof_mark(ctx, axis + 1, st);
+            rc = prof_mark(ctx, axis + 2, st);
             if (rc) return rc;
         }
     }

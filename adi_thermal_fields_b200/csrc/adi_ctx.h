@@ -28,7 +28,8 @@ struct Pack {
 
 struct CylTables;  // adi_cyl.cu
 
-// profile helpers (adi_api.cu): record event #slot (0..3) of the current step
+// profile helpers (adi_api.cu): record event #slot (0..4) of the current step:
+// 0 start, 1 after the explicit stage, 2 after the x|r sweep, 3 after y|phi, 4 after z
 int prof_mark(adi_ctx *ctx, int slot, cudaStream_t st);
 
 }  // namespace adi
@@ -38,7 +39,7 @@ struct adi_ctx {
     long launches = 0;
     // options (adi_set_option)
     long opt_kt = 0, opt_lt = 0, opt_m = 0, opt_sync_check = 0, opt_profile = 0, opt_fuse = 0;
-    // per-sweep timing (adi_profile_*): 4 events per step, read lazily
+    // per-kernel timing (adi_profile_*): 5 events per step, read lazily
     std::vector<cudaEvent_t> prof_ev;
     long prof_steps = 0;
 

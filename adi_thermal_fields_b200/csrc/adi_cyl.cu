@@ -118,10 +118,11 @@ __device__ __forceinline__ double cyl_reduced(const TabGeom &g, const double *__
 // ------------------------------------------------------------------------------------
 // K4: strided sweeps.  blockDim = (KT lanes along z, P chunks); grid = (ceil(nz/KT), nouter).
 // PRO: r sweep of the step -- applies the void clamp and the source term while loading.
+// BCL: the last cell of the line takes a boundary term (outer Robin row of the r sweep).
 // Shared memory: 3*NTH doubles (reduced-system exchange) only.
 // ------------------------------------------------------------------------------------
-template <int M, bool PRO>
-__global__ void __launch_bounds__(256, 2) k_cyl_strided(const CylArgs a)
+template <int M, bool PRO, bool BCL>
+__global__ void __launch_bounds__(256, (M <= 16 ? 3 : 2)) k_cyl_strided(const CylArgs a)
 {
     extern __shared__ double smem[];
     const int KT = blockDim.x, P = blockDim.y;
@@ -132,52 +133,46 @@ __global__ void __launch_bounds__(256, 2) k_cyl_strided(const CylArgs a)
 
     const int k = blockIdx.x * KT + kk;
     const bool lane_ok = k < a.nz;
-    const size_t base = (size_t)blockIdx.y * a.outer_stride + (size_t)min(k, a.nz - 1);
-    const int n = a.g.n;
-    // slot e holds cell i0 + e; cells before the chunk's first one (e < M - len) are padding.
-    // Padding slots re-read the chunk's first cell (always in range) and are zeroed afterwards.
-    const int i0 = endp - (M - 1);
-    const int efirst = M - len;
-    const double *src = a.in + base;
+    // slot e holds cell i0 + e of the line; slots e < efirst are padding (never dereferenced)
+    const int efirst = lane_ok ? M - len : M;
+    // byte offset of slot e: e * cs8 (one 32 x 32 -> 64 bit multiply-add per access)
+    const unsigned cs8 = (unsigned)a.cell_stride * 8u;
+    const long long first = (long long)blockIdx.y * a.outer_stride + min(k, a.nz - 1) + (long long)(endp - (M - 1)) * a.cell_stride;
+    const char *src = reinterpret_cast<const char *>(a.in + first);
 
     double d[M];
 #pragma unroll
-    for (int e = 0; e < M; ++e) d[e] = src[(size_t)(i0 + max(e, efirst)) * a.cell_stride];
+    for (int e = 0; e < M; ++e) d[e] = e >= efirst ? *reinterpret_cast<const double *>(src + (size_t)e * cs8) : 0.0;
     if (PRO) {
         if (a.active) {  // T_work[~active] = T_void
-            const uint8_t *am = a.active + base;
+            const uint8_t *am = a.active + first;
+            const unsigned cs1 = (unsigned)a.cell_stride;
             unsigned bits = 0;
 #pragma unroll
-            for (int e = 0; e < M; ++e) bits |= (am[(size_t)(i0 + max(e, efirst)) * a.cell_stride] ? 1u : 0u) << e;
+            for (int e = 0; e < M; ++e) bits |= ((e >= efirst && am[(size_t)e * cs1]) ? 1u : 0u) << e;
 #pragma unroll
-            for (int e = 0; e < M; ++e) d[e] = ((bits >> e) & 1u) ? d[e] : a.T_void;
+            for (int e = 0; e < M; ++e) d[e] = ((bits >> e) & 1u) ? d[e] : (e >= efirst ? a.T_void : 0.0);
         }
         if (a.S) {       // R0 = Tn + dt*(S/(rho*cp))  :339
-            const double *sp = a.S + base;
-            double sv[M];
+            const char *sp = reinterpret_cast<const char *>(a.S + first);
 #pragma unroll
-            for (int e = 0; e < M; ++e) sv[e] = sp[(size_t)(i0 + max(e, efirst)) * a.cell_stride];
-#pragma unroll
-            for (int e = 0; e < M; ++e) d[e] = __dadd_rn(d[e], __dmul_rn(a.dt, __ddiv_rn(sv[e], a.rho_cp)));
+            for (int e = 0; e < M; ++e)
+                if (e >= efirst)
+                    d[e] = __dadd_rn(d[e], __dmul_rn(a.dt, __ddiv_rn(*reinterpret_cast<const double *>(sp + (size_t)e * cs8), a.rho_cp)));
         }
     }
-#pragma unroll
-    for (int e = 0; e < M; ++e) {
-        const int i = i0 + e;
-        double v = d[e];
-        if (i == 0) v = a.set_first ? a.val_first : __dadd_rn(v, a.val_first);
-        if (i == n - 1) v = a.set_last ? a.val_last : __dadd_rn(v, a.val_last);
-        d[e] = (lane_ok && e >= efirst) ? v : 0.0;
+    if (BCL) {  // the last cell of the line is the separator of the last chunk
+        if (p == P - 1 && lane_ok) d[M - 1] = a.set_last ? a.val_last : __dadd_rn(d[M - 1], a.val_last);
     }
     double Yl;
-    const double Y = tab_forward<M>(d, tab + a.g.o_rinv + cb, tab + a.g.o_la + cb, tab + a.g.o_alpha + cb, &Yl);
+    const double Y = tab_forward<M>(d, tab + a.g.o_f + 2 * cb, tab + a.g.o_alpha + cb, &Yl);
     double Sl;
     const double S = cyl_reduced(a.g, tab, smem, NTH, p, d[M - 1], Y, Yl, [=](int q) { return q * KT + kk; }, &Sl);
-    tab_backward<M>(d, tab + a.g.o_u + cb, tab + a.g.o_v + cb, Sl, S);
-    double *dst = a.out + base;
+    tab_backward<M>(d, tab + a.g.o_b + 2 * cb, Sl, S);
+    char *dst = reinterpret_cast<char *>(a.out + first);
 #pragma unroll
     for (int e = 0; e < M; ++e)
-        if (lane_ok && e >= efirst) dst[(size_t)(i0 + e) * a.cell_stride] = d[e];
+        if (e >= efirst) *reinterpret_cast<double *>(dst + (size_t)e * cs8) = d[e];
 }
 
 // ------------------------------------------------------------------------------------
@@ -199,13 +194,13 @@ __device__ __forceinline__ int zswz(int z)
 }
 
 template <int M, bool EPI, bool VEC>
-__global__ void __launch_bounds__(256, 2) k_cyl_z(const CylArgs a)
+__global__ void __launch_bounds__(256, (M <= 16 ? 3 : 2)) k_cyl_z(const CylArgs a)
 {
     extern __shared__ double smem[];
     const int P = blockDim.x, LT = blockDim.y;
     const int p = threadIdx.x, ln = threadIdx.y;
     const int NTH = P * LT, tid = ln * P + p;
-    const int nz = a.nz, n = nz;
+    const int nz = a.nz;
     const int RL = VEC ? nz : zphys(nz - 1) + 1;  // doubles per staged line
     double *ex = smem;
     double *sT = ex + 3 * NTH;
@@ -235,32 +230,35 @@ __global__ void __launch_bounds__(256, 2) k_cyl_z(const CylArgs a)
     __syncthreads();
     const bool line_ok = ln < nl;
     double *myT = sT + (size_t)ln * RL;
-    const int i0 = endp - (M - 1), efirst = M - len;
+    const int i0 = endp - (M - 1);
+    const int efirst = line_ok ? M - len : M;
 
     double d[M];
     if (VEC) {  // every chunk is full and starts at p*M
 #pragma unroll
         for (int j = 0; j < M / 2; ++j) {
             const double2 v = *reinterpret_cast<const double2 *>(myT + zswz<M>(p * M + 2 * j));
-            d[2 * j] = v.x; d[2 * j + 1] = v.y;
+            d[2 * j] = line_ok ? v.x : 0.0; d[2 * j + 1] = line_ok ? v.y : 0.0;
         }
     } else {
 #pragma unroll
-        for (int e = 0; e < M; ++e) d[e] = myT[zphys(i0 + max(e, efirst))];
+        for (int e = 0; e < M; ++e) d[e] = e >= efirst ? myT[zphys(i0 + e)] : 0.0;
     }
+    if (line_ok) {
+        // boundary rows (build_coeff_z :271-296): the first cell of the line sits in slot efirst of
+        // chunk 0, the last one is the separator of the last chunk; bottom is applied first
+        if (p == 0) {
 #pragma unroll
-    for (int e = 0; e < M; ++e) {
-        const int i = i0 + e;
-        double v = d[e];
-        if (i == 0) v = a.set_first ? a.val_first : __dadd_rn(v, a.val_first);
-        if (i == n - 1) v = a.set_last ? a.val_last : __dadd_rn(v, a.val_last);
-        d[e] = (line_ok && e >= efirst) ? v : 0.0;
+            for (int e = 0; e < M; ++e)
+                if (e == efirst) d[e] = a.set_first ? a.val_first : __dadd_rn(d[e], a.val_first);
+        }
+        if (p == P - 1) d[M - 1] = a.set_last ? a.val_last : __dadd_rn(d[M - 1], a.val_last);
     }
     double Yl;
-    const double Y = tab_forward<M>(d, tab + a.g.o_rinv + cb, tab + a.g.o_la + cb, tab + a.g.o_alpha + cb, &Yl);
+    const double Y = tab_forward<M>(d, tab + a.g.o_f + 2 * cb, tab + a.g.o_alpha + cb, &Yl);
     double Sl;
     const double S = cyl_reduced(a.g, tab, ex, NTH, p, d[M - 1], Y, Yl, [=](int q) { return ln * P + q; }, &Sl);
-    tab_backward<M>(d, tab + a.g.o_u + cb, tab + a.g.o_v + cb, Sl, S);
+    tab_backward<M>(d, tab + a.g.o_b + 2 * cb, Sl, S);
     if (VEC) {
 #pragma unroll
         for (int j = 0; j < M / 2; ++j)
@@ -411,7 +409,10 @@ static int launch_cyl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s
 
 static int lanes_for(adi_ctx *ctx, int P, int nz)
 {
+    // 64-byte rows (8 lanes) in blocks of at least 128 threads: small blocks keep more tiles in
+    // flight per SM (measured: r sweep of 256 cells 0.59 -> 0.51 ms against 16 lanes)
     int KT = 32;
+    while (KT > 8 && KT * P > 128) KT >>= 1;
     while (KT > 1 && KT * P > 256) KT >>= 1;
     if (ctx->opt_kt > 0) {
         int w = 1;
@@ -429,12 +430,23 @@ static int launch_strided(adi_ctx *ctx, CylArgs &a, bool pro, int nouter, cudaSt
     dim3 block(KT, P), grid((a.nz + KT - 1) / KT, nouter);
     const size_t nth = (size_t)KT * P;
     const size_t smem = 3 * nth * sizeof(double);
-    if (a.g.M == 16) {
-        if (pro) return launch_cyl(k_cyl_strided<16, true>, grid, block, smem, st, ctx, a);
-        return launch_cyl(k_cyl_strided<16, false>, grid, block, smem, st, ctx, a);
+    const bool bcl = a.set_last != 0 || a.val_last != 0.0;
+    if ((unsigned long long)a.cell_stride * 8ull >= (1ull << 32)) {
+        set_error("adi_cyl_step: grid too large for 32-bit line strides");
+        return ADI_EINVAL;
     }
-    if (pro) return launch_cyl(k_cyl_strided<32, true>, grid, block, smem, st, ctx, a);
-    return launch_cyl(k_cyl_strided<32, false>, grid, block, smem, st, ctx, a);
+#define ADI_SGO(MM)                                                                             \
+    {                                                                                           \
+        if (pro) {                                                                              \
+            if (bcl) return launch_cyl(k_cyl_strided<MM, true, true>, grid, block, smem, st, ctx, a);   \
+            return launch_cyl(k_cyl_strided<MM, true, false>, grid, block, smem, st, ctx, a);   \
+        }                                                                                       \
+        if (bcl) return launch_cyl(k_cyl_strided<MM, false, true>, grid, block, smem, st, ctx, a);      \
+        return launch_cyl(k_cyl_strided<MM, false, false>, grid, block, smem, st, ctx, a);      \
+    }
+    if (a.g.M == 16) ADI_SGO(16)
+    ADI_SGO(32)
+#undef ADI_SGO
 }
 
 static int launch_z(adi_ctx *ctx, CylArgs &a, bool epi, cudaStream_t st)
@@ -530,6 +542,8 @@ int adi_cyl_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_cy
     a.T_void = p->T_void; a.T_inner = p->T_inner;
     rc = prof_mark(ctx, 0, st);
     if (rc) return rc;
+    rc = prof_mark(ctx, 1, st);
+    if (rc) return rc;
 
     // r sweep  (:341-344): Tin -> Tout, prologue fused
     a.in = d_Tin; a.out = d_Tout;
@@ -541,7 +555,7 @@ int adi_cyl_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_cy
     if (nr == 1) { a.val_first = 0.0; }  // first == last: both branches apply in order, like the reference
     rc = launch_strided(ctx, a, d_active != nullptr || d_S != nullptr, nphi, st);
     if (rc) return rc;
-    rc = prof_mark(ctx, 1, st);
+    rc = prof_mark(ctx, 2, st);
     if (rc) return rc;
 
     // phi sweep (:346), in place; nphi == 1 is the identity (:309-310)
@@ -553,7 +567,7 @@ int adi_cyl_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_cy
         rc = launch_strided(ctx, a, false, nr, st);
         if (rc) return rc;
     }
-    rc = prof_mark(ctx, 2, st);
+    rc = prof_mark(ctx, 3, st);
     if (rc) return rc;
 
     // z sweep (:348-350), in place, epilogue fused
@@ -564,7 +578,7 @@ int adi_cyl_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_cy
     a.set_last = T.top.set; a.val_last = T.top.val;
     rc = launch_z(ctx, a, d_active != nullptr, st);
     if (rc) return rc;
-    rc = prof_mark(ctx, 3, st);
+    rc = prof_mark(ctx, 4, st);
     if (rc) return rc;
     if (ctx->opt_sync_check) ADI_CUDA(cudaStreamSynchronize(st));
     return ADI_OK;

@@ -46,8 +46,10 @@ namespace adi {
 // Geometry and blob layout of one table set (identical for every ring of the phi sweep).
 struct TabGeom {
     int n, M, P, levels, cyclic, nvar;
-    // offsets into the double blob
-    int o_rinv, o_la, o_alpha, o_u, o_v;  // cell tables, nvar*M each
+    // offsets into the double blob (all even: the pair tables are read as 16-byte words)
+    int o_f;      // cell table, forward pass:  {rinv, la} pairs, 2*nvar*M doubles
+    int o_alpha;  // cell table, forward pass:  alpha, nvar*M doubles
+    int o_b;      // cell table, backward pass: {u, v} pairs, 2*nvar*M doubles
     int o_t0, o_t1, o_t2;                 // reduced right-hand side assembly, P each
     int o_lvl;                            // levels * 3 * P: [level][r|a|c][p]
     int ndbl;                             // doubles per blob
@@ -89,16 +91,14 @@ inline TabGeom tab_geom_nvar(int n, int M, bool cyclic, int nvar)
     }
     g.nvar = nvar;
     int o = 0;
-    g.o_rinv = o; o += g.nvar * M;
-    g.o_la = o; o += g.nvar * M;
+    g.o_f = o; o += 2 * g.nvar * M;
+    g.o_b = o; o += 2 * g.nvar * M;
     g.o_alpha = o; o += g.nvar * M;
-    g.o_u = o; o += g.nvar * M;
-    g.o_v = o; o += g.nvar * M;
     g.o_t0 = o; o += g.P;
     g.o_t1 = o; o += g.P;
     g.o_t2 = o; o += g.P;
     g.o_lvl = o; o += g.levels * 3 * g.P;
-    g.ndbl = o;
+    g.ndbl = (o + 1) & ~1;   // even, so that consecutive blobs stay 16-byte aligned
     return g;
 }
 
@@ -122,7 +122,7 @@ inline void tab_build(const TabGeom &g, const int *cbase, const int *end, const 
 {
     const int M = g.M, P = g.P, n = g.n;
     for (int i = 0; i < g.ndbl; ++i) blob[i] = 0.0;
-    for (int v = 0; v < g.nvar * M; ++v) blob[g.o_rinv + v] = 1.0;
+    for (int v = 0; v < g.nvar * M; ++v) blob[g.o_f + 2 * v] = 1.0;   // rinv of padding slots
     std::vector<double> V(P), W(P), Vl(P), Wl(P), A(P), C(P), An(P), Cn(P);
     for (int p = 0; p < P; ++p) {
         const int e0 = M - len[p];
@@ -136,11 +136,11 @@ inline void tab_build(const TabGeom &g, const int *cbase, const int *end, const 
             const double uc = -cpe;
             const double v = la * vprev;
             const int t = cbase[p] + e;
-            blob[g.o_rinv + t] = 1.0 / den;
-            blob[g.o_la + t] = la;
+            blob[g.o_f + 2 * t] = 1.0 / den;
+            blob[g.o_f + 2 * t + 1] = la;
             blob[g.o_alpha + t] = alpha;
-            blob[g.o_u + t] = uc;
-            blob[g.o_v + t] = v;
+            blob[g.o_b + 2 * t] = uc;
+            blob[g.o_b + 2 * t + 1] = v;
             Vsum += alpha * v;
             alpha *= uc;
             cp_prev = cpe; vprev = v; ulast = uc;
@@ -196,7 +196,7 @@ inline void tab_build(const TabGeom &g, const int *cbase, const int *end, const 
     }
 }
 
-// Table read: through the read-only (L1) path on the device -- every block of an SM walks the
+// Table reads: through the read-only (L1) path on the device -- every block of an SM walks the
 // same few KB of tables while the field data streams past L1 (cp.async.cg / plain stores).
 ADI_HD double tab_ld(const double *p)
 {
@@ -205,6 +205,20 @@ ADI_HD double tab_ld(const double *p)
 #else
     return *p;
 #endif
+}
+struct TabPair {
+    double a, b;
+};
+ADI_HD TabPair tab_ld2(const double *p)   // p is 16-byte aligned
+{
+    TabPair r;
+#if defined(__CUDA_ARCH__)
+    const double2 t = __ldg(reinterpret_cast<const double2 *>(p));
+    r.a = t.x; r.b = t.y;
+#else
+    r.a = p[0]; r.b = p[1];
+#endif
+    return r;
 }
 
 // One table set (host).  tab_make builds the tables of a line whose rows are arbitrary and then
@@ -226,17 +240,20 @@ inline TabSet tab_make(int n, int M, bool cyclic, const double *a, const double 
     int *cb = full.geom.data(), *en = cb + P, *ln = cb + 2 * P;
     tab_partition(full.g, false, cb, en, ln);
     tab_build(full.g, cb, en, ln, a, b, c, full.blob.data());
-    const int offs[5] = {full.g.o_rinv, full.g.o_la, full.g.o_alpha, full.g.o_u, full.g.o_v};
+    // per chunk: 2M + 2M + M table doubles
+    auto same_chunk = [&](int p, int q) {
+        for (int e = 0; e < 2 * M; ++e)
+            if (full.blob[full.g.o_f + 2 * p * M + e] != full.blob[full.g.o_f + 2 * q * M + e] ||
+                full.blob[full.g.o_b + 2 * p * M + e] != full.blob[full.g.o_b + 2 * q * M + e]) return false;
+        for (int e = 0; e < M; ++e)
+            if (full.blob[full.g.o_alpha + p * M + e] != full.blob[full.g.o_alpha + q * M + e]) return false;
+        return true;
+    };
     std::vector<int> var(P), rep;
     for (int p = 0; p < P; ++p) {
         int found = -1;
-        for (size_t v = 0; v < rep.size() && found < 0; ++v) {
-            bool same = true;
-            for (int t = 0; t < 5 && same; ++t)
-                for (int e = 0; e < M && same; ++e)
-                    same = full.blob[offs[t] + p * M + e] == full.blob[offs[t] + rep[v] * M + e];
-            if (same) found = (int)v;
-        }
+        for (size_t v = 0; v < rep.size() && found < 0; ++v)
+            if (same_chunk(p, rep[v])) found = (int)v;
         if (found < 0) { rep.push_back(p); found = (int)rep.size() - 1; }
         var[p] = found;
     }
@@ -244,10 +261,13 @@ inline TabSet tab_make(int n, int M, bool cyclic, const double *a, const double 
     out.g = tab_geom_nvar(n, M, cyclic, (int)rep.size());
     out.geom = full.geom;
     out.blob.assign(out.g.ndbl, 0.0);
-    const int offn[5] = {out.g.o_rinv, out.g.o_la, out.g.o_alpha, out.g.o_u, out.g.o_v};
-    for (size_t v = 0; v < rep.size(); ++v)
-        for (int t = 0; t < 5; ++t)
-            for (int e = 0; e < M; ++e) out.blob[offn[t] + v * M + e] = full.blob[offs[t] + rep[v] * M + e];
+    for (size_t v = 0; v < rep.size(); ++v) {
+        for (int e = 0; e < 2 * M; ++e) {
+            out.blob[out.g.o_f + 2 * v * M + e] = full.blob[full.g.o_f + 2 * rep[v] * M + e];
+            out.blob[out.g.o_b + 2 * v * M + e] = full.blob[full.g.o_b + 2 * rep[v] * M + e];
+        }
+        for (int e = 0; e < M; ++e) out.blob[out.g.o_alpha + v * M + e] = full.blob[full.g.o_alpha + rep[v] * M + e];
+    }
     for (int p = 0; p < P; ++p) out.geom[p] = var[p] * M;
     for (int i = 0; i < 3 * P; ++i) out.blob[out.g.o_t0 + i] = full.blob[full.g.o_t0 + i];
     for (int i = 0; i < out.g.levels * 3 * P; ++i) out.blob[out.g.o_lvl + i] = full.blob[full.g.o_lvl + i];
@@ -258,17 +278,17 @@ inline TabSet tab_make(int n, int M, bool cyclic, const double *a, const double 
 ADI_HD int tab_lo(int p, int s, int P, int cyclic) { return cyclic ? ((p - s) & (P - 1)) : (p - s >= 0 ? p - s : 0); }
 ADI_HD int tab_hi(int p, int s, int P, int cyclic) { return cyclic ? ((p + s) & (P - 1)) : (p + s < P ? p + s : P - 1); }
 
-// Phase 1.  rinv/la/alpha already point at the chunk's tables.  d[e] holds the right-hand side
-// (0 in padding slots) and is replaced by dp_e; returns Y, *Yl = dp of the last interior cell.
+// Phase 1.  f / alpha already point at the chunk's tables ({rinv, la} pairs; alpha).  d[e] holds the
+// right-hand side (0 in padding slots) and is replaced by dp_e; returns Y, *Yl = dp of the last
+// interior cell.
 template <int M>
-ADI_HD double tab_forward(double (&d)[M], const double *rinv, const double *la, const double *alpha,
-                          double *Yl)
+ADI_HD double tab_forward(double (&d)[M], const double *f, const double *alpha, double *Yl)
 {
     double dp = 0.0, Y = 0.0;
 #pragma unroll
     for (int e = 0; e < M - 1; ++e) {
-        const double ds = d[e] * tab_ld(rinv + e);
-        dp = fma(tab_ld(la + e), dp, ds);
+        const TabPair t = tab_ld2(f + 2 * e);          // rinv, la
+        dp = fma(t.b, dp, d[e] * t.a);
         d[e] = dp;
         Y = fma(tab_ld(alpha + e), dp, Y);
     }
@@ -288,15 +308,16 @@ ADI_HD double tab_level(double r, double a, double c, double D, double Dlo, doub
     return fma(c, Dhi, fma(a, Dlo, r * D));
 }
 
-// Phase 3.  Leaves the solution in d (padding slots: 0).
+// Phase 3.  b points at the chunk's {u, v} pairs.  Leaves the solution in d (padding slots: 0).
 template <int M>
-ADI_HD void tab_backward(double (&d)[M], const double *u, const double *v, double Sl, double S)
+ADI_HD void tab_backward(double (&d)[M], const double *b, double Sl, double S)
 {
     double xn = S;
     d[M - 1] = S;
 #pragma unroll
     for (int e = M - 2; e >= 0; --e) {
-        const double x = fma(tab_ld(u + e), xn, fma(tab_ld(v + e), Sl, d[e]));
+        const TabPair t = tab_ld2(b + 2 * e);          // u, v
+        const double x = fma(t.a, xn, fma(t.b, Sl, d[e]));
         d[e] = x;
         xn = x;
     }

@@ -339,8 +339,7 @@ void tab_line(double *T, size_t base, size_t stride, const TabGeom &g, const int
             }
             dd[e] = v;
         }
-        Y[p] = tab_forward<M>(dd, blob + g.o_rinv + cbase[p], blob + g.o_la + cbase[p],
-                              blob + g.o_alpha + cbase[p], &Yl[p]);
+        Y[p] = tab_forward<M>(dd, blob + g.o_f + 2 * cbase[p], blob + g.o_alpha + cbase[p], &Yl[p]);
     }
     for (int p = 0; p < P; ++p)
         D[p] = tab_reduced_rhs(blob[g.o_t0 + p], blob[g.o_t1 + p], blob[g.o_t2 + p], d[(size_t)p * M + M - 1], Yl[p],
@@ -355,7 +354,7 @@ void tab_line(double *T, size_t base, size_t stride, const TabGeom &g, const int
     }
     for (int p = 0; p < P; ++p) {
         double (&dd)[M] = *reinterpret_cast<double (*)[M]>(&d[(size_t)p * M]);
-        tab_backward<M>(dd, blob + g.o_u + cbase[p], blob + g.o_v + cbase[p], D[tab_lo(p, 1, P, g.cyclic)], D[p]);
+        tab_backward<M>(dd, blob + g.o_b + 2 * cbase[p], D[tab_lo(p, 1, P, g.cyclic)], D[p]);
         for (int e = 0; e < M; ++e) {
             const int i = end[p] - (M - 1 - e);
             if (e >= M - len[p]) T[base + (size_t)i * stride] = dd[e];

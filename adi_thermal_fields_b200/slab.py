@@ -235,10 +235,10 @@ class CudaBackend:
         self.L.adi_profile_reset(self.ctx)
 
     def profile_read(self):
-        ms = (C.c_double * 3)()
+        ms = (C.c_double * 4)()
         n = C.c_long()
         self.L.adi_profile_read(self.ctx, ms, C.byref(n))
-        return [ms[i] for i in range(3)], n.value
+        return [ms[i] for i in range(4)], n.value
 
     def close(self):
         if self.ctx is not None:

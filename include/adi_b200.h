@@ -126,11 +126,12 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value);
 long adi_launch_count(adi_ctx *ctx);
 /* Per-kernel device timing (the `[time]` prints of quick_compare_neumann_robin_backend.py:
  * 173-186 are the reference's only profiling hook).  After adi_set_option(ctx,"profile",1)
- * every adi_cart_step / adi_cyl_step records CUDA events around its three sweeps on the
- * caller's stream; adi_profile_read synchronises, returns the accumulated milliseconds per
- * sweep (x|r, y|phi, z) and the number of steps since the last adi_profile_reset. */
+ * every adi_cart_step / adi_cyl_step records CUDA events around its kernels on the caller's
+ * stream; adi_profile_read synchronises, returns the accumulated milliseconds per kernel
+ * (explicit stage, x|r sweep, y|phi sweep, z sweep) and the number of steps since the last
+ * adi_profile_reset. */
 int adi_profile_reset(adi_ctx *ctx);
-int adi_profile_read(adi_ctx *ctx, double ms[3], long *nsteps);
+int adi_profile_read(adi_ctx *ctx, double ms[4], long *nsteps);
 
 /* ---- cylindrical path --------------------------------------------------------------- */
 /* GridCyl(nr,nphi,nz,dr,dphi,dz,R)  adi3d_cyl_phi_v3.py:33-43.  nz_pitch >= nz is the

@@ -49,12 +49,12 @@ for _ in range(a.steps):
     gc.adi_step_device(A, grid, mat, prm, rob, zbc, active=act, out=B); A, B = B, A
 e1.record()
 torch.cuda.synchronize()
-ms = (C.c_double * 3)()
+ms = (C.c_double * 4)()
 n = C.c_long()
 L.adi_profile_read(ctx, ms, C.byref(n))
 cells = nr * nphi * nz
-per = [ms[i] / n.value for i in range(3)]
+per = [ms[i] / n.value for i in range(4)]
 tot = e0.elapsed_time(e1) / a.steps
 print(f"cyl {nr}x{nphi}x{nz} masked={a.masked} opts {a.opt}: "
-      + "  ".join(f"{ax} {t:.3f} ms {16 * cells / max(t, 1e-9) / 1e6:.0f} GB/s" for ax, t in zip(("r", "phi", "z"), per))
+      + "  ".join(f"{ax} {t:.3f} ms {16 * cells / max(t, 1e-9) / 1e6:.0f} GB/s" for ax, t in zip(("r", "phi", "z"), per[1:]))
       + f"  | step {tot:.3f} ms  {cells / tot / 1e6:.2f} Gcell-steps/s  {48 * cells / tot / 1e6:.0f} GB/s")

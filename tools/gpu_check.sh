@@ -16,7 +16,11 @@ if [ "${NO_NCU:-0}" != "1" ]; then
 python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/${tag}_ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 9 -c 3 -f -o gpurun_out/${tag}_prof \
+ncu --set full --clock-control none --import-source on -k regex:"k_sweep|k_explicit" -s 12 -c 4 -f -o gpurun_out/${tag}_prof \
     python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/${tag}_ncu2.log 2>&1
 tail -3 gpurun_out/${tag}_ncu2.log
+python tools/cyl_probe.py 256 1024 512 > gpurun_out/${tag}_cyl.log 2>&1; python tools/cyl_probe.py 256 1024 512 --masked >> gpurun_out/${tag}_cyl.log 2>&1; cat gpurun_out/${tag}_cyl.log
+ncu --set full --clock-control none --import-source on -k regex:k_cyl -s 9 -c 3 -f -o gpurun_out/${tag}_prof_cyl \
+    python tools/cyl_probe.py 256 1024 512 --steps 2 > gpurun_out/${tag}_ncu3.log 2>&1
+tail -3 gpurun_out/${tag}_ncu3.log
 fi

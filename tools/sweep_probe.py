@@ -60,12 +60,13 @@ L.adi_profile_reset(ctx)
 for _ in range(a.steps):
     step(A, B); A, B = B, A
 torch.cuda.synchronize()
-ms = (C.c_double * 3)()
+ms = (C.c_double * 4)()
 n = C.c_long()
 L.adi_profile_read(ctx, ms, C.byref(n))
 cells = nx * ny * nz
 bpc = 17 if a.scalar else 25
-per = [ms[i] / n.value for i in range(3)]
+per = [ms[i] / n.value for i in range(4)]
 print(f"shape {nx}x{ny}x{nz} theta {a.theta} {'scalar' if a.scalar else 'dense'} opts {a.opt}: "
-      + "  ".join(f"{ax} {t:.3f} ms {bpc * cells / t / 1e6:.0f} GB/s" for ax, t in zip("xyz", per))
+      + f"expl {per[0]:.3f} ms {17 * cells / max(per[0], 1e-9) / 1e6:.0f} GB/s  "
+      + "  ".join(f"{ax} {t:.3f} ms {bpc * cells / t / 1e6:.0f} GB/s" for ax, t in zip("xyz", per[1:]))
       + f"  | step {sum(per):.3f} ms")

@@ -129,6 +129,7 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
     else if (!strcmp(name, "m")) ctx->opt_m = value;
     else if (!strcmp(name, "sync_check")) ctx->opt_sync_check = value;
     else if (!strcmp(name, "profile")) ctx->opt_profile = value;
+    else if (!strcmp(name, "wide")) ctx->opt_wide = value;  // 1: 512-thread blocks for lines <= 512 cells too
     else if (!strcmp(name, "fuse")) ctx->opt_fuse = value;  // 1: explicit stage fused into the x sweep
     else {
         adi::set_error(std::string("adi_set_option: unknown option ") + name);

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
     const size_t idx0 = ((AXIS == 0) ? (size_t)blockIdx.y * a.nz : (size_t)blockIdx.y * a.ny * a.nz) +
                         (size_t)min(k, a.nz - 1) + (size_t)min(t0, n - 1) * sl;
     double *col = smem + tid;
-    double *red = smem + (size_t)2 * M * NTH;             // NS 1: behind slot 0 and a spare slot
+    double *red = smem + (size_t)NS * M * NTH;            // behind the factor slots
     double *halo = smem + (size_t)3 * M * NTH;            // [2][M][P], explicit stage only
     const double *tp = a.in + idx0;
 

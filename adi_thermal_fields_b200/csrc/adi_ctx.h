@@ -38,7 +38,7 @@ struct adi_ctx {
     int device = 0;
     long launches = 0;
     // options (adi_set_option)
-    long opt_kt = 0, opt_lt = 0, opt_m = 0, opt_sync_check = 0, opt_profile = 0, opt_fuse = 0;
+    long opt_kt = 0, opt_lt = 0, opt_m = 0, opt_sync_check = 0, opt_profile = 0, opt_fuse = 0, opt_wide = 0;
     // per-kernel timing (adi_profile_*): 5 events per step, read lazily
     std::vector<cudaEvent_t> prof_ev;
     long prof_steps = 0;

@@ -15,10 +15,10 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
     if (rc) return rc;
     dim3 block(s.W, s.P), grid((a.nz + s.W - 1) / s.W, other);
     const size_t nth = (size_t)s.W * s.P;
-    // columns: two slots + exchange buffer; the staged explicit stage adds a third slot (which
+    // columns: NS factor slots + exchange buffer; the staged explicit stage adds a third slot (which
     // the exchange buffer then reuses) and the z halo [2][M][P]
     const size_t smem = ((AXIS == 0 && expl && s.NS == 2) ? (size_t)3 * s.M * nth + (size_t)2 * s.M * s.P
-                                                        : (size_t)(2 * s.M + 6) * nth) * sizeof(double);
+                                                        : (size_t)(s.NS * s.M + 6) * nth) * sizeof(double);
     if ((unsigned long long)s.M * (AXIS == 0 ? (unsigned long long)a.ny * a.nz : (unsigned long long)a.nz) >= (1ull << 32)) {
         set_error("adi_cart_step: grid too large for 32-bit in-chunk offsets");
         return ADI_EINVAL;

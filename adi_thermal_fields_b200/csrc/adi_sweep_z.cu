@@ -9,7 +9,7 @@ template <int ZMODE>
 static int launch_sweep_z_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, cudaStream_t st)
 {
     Shape s;
-    int rc = pick_shape(ctx, a.nz, 0, &s);
+    int rc = pick_shape(ctx, a.nz, -1, &s);  // -1: z sweep (no lane-count option)
     if (rc) return rc;
     if (ZMODE != 0 && a.nz % s.M != 0) {
         set_error("adi_cart_zsweep_*: the local z extent must be a multiple of the chunk length (16; 32 for nz > 512)");
@@ -18,7 +18,7 @@ static int launch_sweep_z_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
     // lines per block: fill the block, but keep the staged tiles small enough for two
     // resident blocks per SM where the line length allows it
     const size_t line_bytes = (size_t)s.P * s.M * (8 * (1 + s.NS) + 1);  // T + factor tiles + codes
-    const size_t budget = s.var == VAR_32L ? 220 * 1024 : 28 * 1024;  // small blocks overlap best (measured)
+    const size_t budget = s.var == VAR_32L ? 220 * 1024 : 28 * 1024;  // one 1024-cell line is 25.6 KB  // small blocks overlap best (measured)
     int LT = s.W;
     while (LT > 1 && LT * line_bytes > budget) LT >>= 1;
     if (ctx->opt_lt > 0) LT = (int)std::min<long>(ctx->opt_lt, s.W);

@@ -334,3 +334,32 @@ def test_kernel_variant_options_agree(shape, opts, g, cp):
 def test_ragged_and_tiny_grids(g, cp):
     for shape in [(1, 1, 1), (2, 1, 3), (1, 17, 1), (16, 16, 16), (17, 33, 15), (31, 2, 47)]:
         _both(g, cp, _oracle_case(shape, seed=6000 + sum(shape), holes=shape != (1, 1, 1)), nsteps=1)
+
+
+@pytest.mark.parametrize("shape", [(6, 7, 1000), (700, 5, 16), (5, 1024, 24), (5, 1100, 8), (2100, 3, 8), (3, 4, 1500)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("bk,theta", [("robin6", 0.5), ("combined", 0.5), ("robin_dict3d", 1.0)])
+def test_long_lines(shape, bk, theta, g, cp):
+    """Lines of 513..1024 cells (16-cell chunks, 512-thread blocks) and longer (32-cell chunks),
+    as in BASELINE configs 4 and 5, against the oracle on the same inputs."""
+    from oracle import cart
+    mask = cases.make_mask("cyl_holes" if min(shape[:2]) > 4 else "random", shape, 21)
+    bcs = cases.make_bcs(bk, shape, mask, 21, 20.0)
+    T0 = 20.0 + 1380.0 * cases.splitmix_uniform(22, shape)
+    T0[~mask] = np.nan
+    kappa = cases.K / (cases.RHO * cases.CP)
+    dt = 2.0 * cases.DX ** 2 / kappa
+    nx, ny, nz = shape
+    hg, hm = cart.Grid3D(nx, ny, nz, cases.DX, mask), cart.Material(cases.RHO, cases.CP, cases.K)
+    ref = cart.adi_step_numba_coeff(T0, hg, hm, cart.Params(dt, theta),
+                                    cart.precompute_coeff_packs_unified(hg, hm, **bcs), Tinf=20.0)
+    grid, mat = g.Grid3D(nx, ny, nz, cases.DX, mask), g.Material(cases.RHO, cases.CP, cases.K)
+    packs = g.precompute_coeff_packs_unified(grid, mat, **bcs)
+    for fuse in (0, 1):
+        g.set_option("fuse", fuse)
+        try:
+            out = cp.asnumpy(g.adi_step_gpu_coeff(cp.asarray(T0), grid, mat, g.Params(dt, theta), packs, Tinf=20.0))
+        finally:
+            g.set_option("fuse", 0)
+        assert cases.rel_l2(out, ref, mask) <= TOL
+        assert np.array_equal(out[~mask], T0[~mask], equal_nan=True)

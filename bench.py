@@ -132,6 +132,13 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU legs (oracle) -- the only place bench.py touches oracle/
 # ------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_leg(n, ny_sample, threads, steps=1, check_against=None):
     from oracle import cart
     mask, T0, h = host_inputs(n, ny_sample)
@@ -157,7 +164,8 @@ def run_reference(args):
         return 0
     from oracle import cart
     n = args.size
-    threads = cart.max_threads()
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1: not a property of the box)
+    threads = host_threads()
     # bounded sample: a y-slab of the workload (x and z lines keep their full length)
     ny_s = min(n, args.ref_ny)
     cells = n * ny_s * n
@@ -210,7 +218,7 @@ def run_ours(args):
 
     from adi_thermal_fields_b200 import _capi, adi3d_gpu_coeff as g, devarray as cp
 
-    if world > 1:
+    if world > 1 or args.workload == "c5":
         return run_ours_slab(args, rank, world, local)
     n = args.size
     dev = torch.device("cuda", local)
@@ -350,7 +358,7 @@ def run_ours(args):
     parity = None
     if world == 1 and not args.no_cpu:
         from oracle import cart
-        nth = cart.max_threads()
+        nth = host_threads()
         ny_s = min(n, args.cpu_ny)
         Tref, times, (m_s, T0_s, h_s) = cpu_leg(n, ny_s, nth, steps=1)
         v_all = n * ny_s * n / times[0]
@@ -392,32 +400,58 @@ def run_ours_slab(args, rank, world, local):
     import torch.distributed as dist
     from adi_thermal_fields_b200 import slab
 
-    n = args.size
     dev = torch.device("cuda", local)
-    nzg = n * world
-    z0 = rank * n
-    # plate + track on the global grid (single_track_on_plate.py:113-114,159): plate below
-    # nzg - n/64, track on top of it in the last slab
-    nzp = nzg - max(1, n // 64)
-    kz = torch.arange(z0, z0 + n, device=dev)
-    mask = (kz < nzp)[None, None, :].expand(n, n, n).clone()
-    if rank == world - 1:
-        mask[: max(1, n // 32), : n // 2, (nzp - z0):] = True
-    gen = torch.Generator(device=dev).manual_seed(rank)
-    T0 = torch.full((n, n, n), TINF, dtype=torch.float64, device=dev)
-    T0 = torch.where(mask, 20.0 + 1380.0 * torch.rand((n, n, n), dtype=torch.float64, device=dev, generator=gen), T0)
-    comm = slab.TorchDistComm()
-    grid = slab.SlabGrid3D(n, n, n, DX, mask, comm)
+    comm = slab.TorchDistComm() if world > 1 else slab.LocalComm(1).view(0)
+    c5 = args.workload == "c5"
 
     class Mat:
         rho, cp, k = RHO, CP, K
 
     class Prm:
         dt, theta = DT, THETA
-    gen2 = torch.Generator(device=dev).manual_seed(1234 + rank)
-    h = {f: 10.0 * (0.3 + torch.rand((n, n, n), dtype=torch.float64, device=dev, generator=gen2)) for f in FACES}
-    packs = slab.precompute_coeff_packs_unified(grid, Mat, robin_h=h)
-    del h
+    if c5:
+        # BASELINE configs[4] / SURVEY 8d C5: full mask, scalar Robin h = 10 on the six faces
+        # (coefficients derived from the mask on the fly: 51 B/cell-step), strong scaling
+        nx = ny = 4 * args.size
+        nzg = 2 * args.size
+        nzl = nzg // world
+        mask = torch.ones((nx, ny, nzl), dtype=torch.bool, device=dev)
+        gen = torch.Generator(device=dev).manual_seed(5 + rank)
+        T0 = 20.0 + 1380.0 * torch.rand((nx, ny, nzl), dtype=torch.float64, device=dev, generator=gen)
+        grid = slab.SlabGrid3D(nx, ny, nzl, DX, mask, comm)
+        packs = slab.precompute_coeff_packs_unified(grid, Mat, robin_h={f: 10.0 for f in FACES})
+        bpc = 51.0
+        wl = {"workload": f"synthetic Cartesian {nx}x{ny}x{nzg} (BASELINE configs[4]): full mask, scalar Robin h=10 x6 "
+                          f"(on-the-fly coefficients), theta={THETA}, dt={DT}; strong scaling",
+              "grid": [nx, ny, nzg], "cells": nx * ny * nzg, "bytes_per_cell_step": 51,
+              "l2": "fields (34 GB) exceed the 126 MB L2; no flush needed",
+              "parallelism": f"z-slab x{world}: {nzl} planes per GPU; per step T-plane halos + all-gather of 6 doubles "
+                             f"per z line and rank (NCCL)"}
+        scaling = "strong"
+    else:
+        n = args.size
+        nx = ny = nzl = n
+        nzg = n * world
+        z0 = rank * n
+        # plate + track on the global grid (single_track_on_plate.py:113-114,159): plate below
+        # nzg - n/64, track on top of it in the last slab
+        nzp = nzg - max(1, n // 64)
+        kz = torch.arange(z0, z0 + n, device=dev)
+        mask = (kz < nzp)[None, None, :].expand(n, n, n).clone()
+        if rank == world - 1:
+            mask[: max(1, n // 32), : n // 2, (nzp - z0):] = True
+        gen = torch.Generator(device=dev).manual_seed(rank)
+        T0 = torch.full((n, n, n), TINF, dtype=torch.float64, device=dev)
+        T0 = torch.where(mask, 20.0 + 1380.0 * torch.rand((n, n, n), dtype=torch.float64, device=dev, generator=gen), T0)
+        grid = slab.SlabGrid3D(n, n, n, DX, mask, comm)
+        gen2 = torch.Generator(device=dev).manual_seed(1234 + rank)
+        h = {f: 10.0 * (0.3 + torch.rand((n, n, n), dtype=torch.float64, device=dev, generator=gen2)) for f in FACES}
+        packs = slab.precompute_coeff_packs_unified(grid, Mat, robin_h=h)
+        del h
+        bpc = 75.0
+        wl = workload_config(args, world)
+        scaling = "weak"
+    cells = nx * ny * nzl          # per rank
     for o in args.opt:
         name, _, val = o.partition("=")
         grid.be.set_option(name, int(val))
@@ -432,8 +466,16 @@ def run_ours_slab(args, rank, world, local):
         step(A, B); A, B = B, A
 
     def barrier():
-        dist.barrier()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     grid.be.profile(True)
     sampler = ClockSampler(local)
@@ -452,18 +494,18 @@ def run_ours_slab(args, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
     ms3, nst = grid.be.profile_read()
     grid.be.profile(False)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = allmax(ms_total)
     ms_per_step = ms_total / args.steps
-    cells = n ** 3
     value = world * cells * args.steps / (ms_total * 1e-3)
 
     # e2e: pinned host slabs in and out every step (H2D + step + D2H inside the timed region)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    hin = torch.empty((n, n, n), dtype=torch.float64, pin_memory=True)
-    hout = torch.empty((n, n, n), dtype=torch.float64, pin_memory=True)
-    hin.copy_(T0)
+    if 8 * cells > 12 * 2 ** 30:   # two pinned slabs of > 12 GB each: not attempted
+        e2e_steps = 0
+    hin = torch.empty((nx, ny, nzl) if e2e_steps else (1,), dtype=torch.float64, pin_memory=True)
+    hout = torch.empty((nx, ny, nzl) if e2e_steps else (1,), dtype=torch.float64, pin_memory=True)
+    if e2e_steps:
+        hin.copy_(T0)
     torch.cuda.synchronize()
 
     def host_step():
@@ -472,46 +514,47 @@ def run_ours_slab(args, rank, world, local):
         hout.copy_(B, non_blocking=True)
         torch.cuda.synchronize()
 
-    host_step()
+    if e2e_steps:
+        host_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         host_step()
     t_e2e = time.perf_counter() - t0
-    t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_e2e = float(t.item())
-    e2e_value = world * cells * e2e_steps / t_e2e
+    t_e2e = allmax(t_e2e)
+    e2e_value = world * cells * e2e_steps / t_e2e if e2e_steps else None
 
     if rank == 0:
         peak, peak_src = peaks()
         per = [ms3[i] / max(1, nst) for i in range(4)]
         names = ["k_explicit", "k_sweep_strided<x>", "k_sweep_strided<y>", "k_sweep_z pass1 + all-gather + pass2"]
-        # the z sweep reads the slab twice (pass 1: T + coeff + code, pass 2: the same + write): 17 + 25 B/cell
-        alg = [17.0 * cells, 25.0 * cells, 25.0 * cells, 42.0 * cells]
+        # N>1: the z sweep reads the slab twice (pass 1 without the write)
+        s1 = bpc / 3.0   # one sweep: 25 B/cell dense, 17 B/cell scalar Robin
+        alg = [17.0 * cells, s1 * cells, s1 * cells, (s1 + (s1 - 8.0 if world > 1 else 0.0)) * cells]
         dom = int(np.argmax(per))
         achieved = alg[dom] / (per[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg[dom], "per": "GPU (rank 0)",
                     "kernel_ms": {"explicit": per[0], "x": per[1], "y": per[2], "z": per[3]},
-                    "step_achieved_GBs": 75.0 * cells / (ms_per_step * 1e-3) / 1e9,
-                    "step_frac": 75.0 * cells / (ms_per_step * 1e-3) / 1e9 / peak}
+                    "step_achieved_GBs": bpc * cells / (ms_per_step * 1e-3) / 1e9,
+                    "step_frac": bpc * cells / (ms_per_step * 1e-3) / 1e9 / peak}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": wl,
             "roofline": roofline, "cpu_baseline": None, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * cells * world,
                     "d2h_bytes_per_step": 8 * cells * world, "steps": e2e_steps,
                     "api": "slab.adi_step_gpu_coeff on pinned host slabs (H2D + step + D2H per rank)"},
             "gpu_launches": int(launches), "parity": None,
-            "exchange": {"halo_bytes_per_step_per_boundary": 2 * 8 * n * n,
-                         "allgather_bytes_per_rank_per_step": 6 * 8 * n * n},
+            "exchange": {"halo_bytes_per_step_per_boundary": 2 * 8 * nx * ny,
+                         "allgather_bytes_per_rank_per_step": 6 * 8 * nx * ny},
         }
         print(json.dumps(line), flush=True)
-    dist.barrier()
-    dist.destroy_process_group()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
@@ -522,6 +565,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--workload", default="plate", choices=["plate", "c5"],
+                    help="plate: BASELINE configs[1] (N>1: one size^3 slab per GPU, weak scaling); "
+                         "c5: BASELINE configs[4], 2048x2048x1024 scalar-Robin strong scaling, z-slab over N GPUs")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-ny", type=int, default=128, help="y extent of the CPU-baseline sample slab")
     ap.add_argument("--ref-ny", type=int, default=64, help="y extent of the --impl reference sample slab")

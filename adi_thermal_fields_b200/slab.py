@@ -216,6 +216,10 @@ class CudaBackend:
                                             None if Thi is None else Thi.data_ptr(), dt, theta, kappa, Tinf,
                                             self._st()), "adi_cart_step_xy")
 
+    def step_plain(self, Tin, Tout, dt, theta, kappa, Tinf):
+        _capi.check(self.L.adi_cart_step(self.ctx, Tin.data_ptr(), Tout.data_ptr(), dt, theta, kappa, Tinf,
+                                         self._st()), "adi_cart_step")
+
     def zsweep_reduce(self, T, iface, dt, theta, kappa, Tinf):
         _capi.check(self.L.adi_cart_zsweep_reduce(self.ctx, T.data_ptr(), iface.data_ptr(), dt, theta, kappa, Tinf,
                                                   self._st()), "adi_cart_zsweep_reduce")
@@ -346,6 +350,9 @@ def adi_step_gpu_coeff(Tn, grid, mat, params, packs, Tinf=0.0, out=None):
     if out is None:
         out = be.empty(tuple(T.shape), torch.float64)
     be.set_packs(packs.packs, packs.face_coeff)
+    if grid.world == 1 and hasattr(be, "step_plain"):   # a single slab is the plain step
+        be.step_plain(T, out, dt, theta, kappa, float(Tinf))
+        return out
     lo_ok, hi_ok = grid.rank > 0, grid.rank + 1 < grid.world
     if theta != 1.0:   # the explicit stage is the only consumer of the T halo (beta = 0 at theta = 1)
         be.pack_planes(T, grid._t_lo, grid._t_hi)

@@ -3,6 +3,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 
 #define ADI_CART_MISC_KERNELS
@@ -386,7 +387,7 @@ int adi_cart_build_packs(adi_ctx *ctx, double rho, double cp, const int h_kind[6
     a.nx = ctx->nx; a.ny = ctx->ny; a.nz = ctx->nz;
     const double dx = ctx->dx;
     a.A = dx * dx;
-    const double V = dx * dx * dx;  // dx**3 (adi3d_numba_coeff.py:70)
+    const double V = std::pow(dx, 3.0);  // dx**3 (adi3d_numba_coeff.py:70): Python float power = C pow()
     a.Ccell = rho * cp * V;
     for (int f = 0; f < 6; ++f) {
         a.h_kind[f] = h_kind ? h_kind[f] : 0;

@@ -186,14 +186,39 @@ class ndarray:
         return ndarray(self._t.mean() if axis is None else self._t.mean(dim=axis))
 
     # -- elementwise ---------------------------------------------------------------
+    @staticmethod
+    def _numpy_promote(a, b, op):
+        """NumPy/CuPy promotion where torch differs: a Python float (or true division) meeting a
+        bool / integer array gives float64, not torch's default float32
+        (e.g. `(-theta*gam) * m` with a bool `m`, adi3d_gpu_coeff.py:175-176)."""
+        def nonfloat(t):
+            return isinstance(t, torch.Tensor) and not (t.is_floating_point() or t.is_complex())
+        def pyfloat(x):
+            return isinstance(x, (float, np.floating)) and not isinstance(x, torch.Tensor)
+        if op is torch.true_divide:
+            if nonfloat(a) and not (isinstance(b, torch.Tensor) and b.is_floating_point()):
+                a = a.to(torch.float64)
+            elif nonfloat(b) and not (isinstance(a, torch.Tensor) and a.is_floating_point()):
+                b = b.to(torch.float64)
+        if nonfloat(a) and pyfloat(b):
+            a = a.to(torch.float64)
+        if nonfloat(b) and pyfloat(a):
+            b = b.to(torch.float64)
+        if isinstance(a, np.floating):
+            a = float(a)
+        if isinstance(b, np.floating):
+            b = float(b)
+        return a, b
+
     def _bin(self, other, op):
-        return ndarray(op(self._t, _unwrap(other)))
+        a, b = self._numpy_promote(self._t, _unwrap(other), op)
+        return ndarray(op(a, b))
 
     def _rbin(self, other, op):
-        o = _unwrap(other)
-        if not isinstance(o, torch.Tensor):
-            o = torch.as_tensor(o, device=self._t.device)
-        return ndarray(op(o, self._t))
+        a, b = self._numpy_promote(_unwrap(other), self._t, op)
+        if not isinstance(a, torch.Tensor):
+            a = torch.as_tensor(a, device=self._t.device, dtype=b.dtype if b.is_floating_point() else None)
+        return ndarray(op(a, b))
 
     def __add__(self, o): return self._bin(o, torch.add)
     def __radd__(self, o): return self._bin(o, torch.add)

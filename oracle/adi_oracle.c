@@ -22,6 +22,7 @@
  * (oracle_set_threads) and is reported by the benchmark as `cores`.
  */
 #include <stdint.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -79,7 +80,7 @@ int oracle_precompute_packs(const uint8_t *mask, int nx, int ny, int nz, double 
                             double *q_x, double *q_y, double *q_z)
 {
     const size_t n = (size_t)nx * ny * nz;
-    const double A = dx * dx, V = dx * dx * dx; /* dx**3 */
+    const double A = dx * dx, V = pow(dx, 3.0); /* dx**3: Python float power = C pow() */
     const double Ccell = rho * cp * V;
     double *coeff[3] = {coeff_x, coeff_y, coeff_z};
     double *qq[3] = {q_x, q_y, q_z};

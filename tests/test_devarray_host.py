@@ -62,3 +62,24 @@ def test_where_and_logic():
     assert np.array_equal((~m).get(), [False, True, False])
     assert np.array_equal((m & ~m).get(), [False] * 3)
     cp.cuda.Stream.null  # attribute exists
+
+
+def test_numpy_type_promotion():
+    """Python float x bool / int array -> float64 (torch alone gives float32), true division of
+    integer arrays -> float64: the reference's CuPy code relies on it (adi3d_gpu_coeff.py:175-176)."""
+    import torch
+    from adi_thermal_fields_b200 import devarray as cp
+    old = cp._FORCE_DEVICE
+    cp._FORCE_DEVICE = torch.device("cpu")
+    try:
+        m = cp.asarray(np.array([True, False, True]))
+        i = cp.asarray(np.array([1, 2, 3]))
+        x = 0.1 + 1e-12
+        for got, want in [((-x) * m, (-x) * np.array([True, False, True])), (m * x, np.array([True, False, True]) * x),
+                          (i * x, np.array([1, 2, 3]) * x), (x - i, x - np.array([1, 2, 3])),
+                          (i / 3, np.array([1, 2, 3]) / 3), (1.0 / i, 1.0 / np.array([1, 2, 3])),
+                          (np.float64(x) * m, np.float64(x) * np.array([True, False, True]))]:
+            assert got.dtype == np.float64
+            assert np.array_equal(cp.asnumpy(got), want)
+    finally:
+        cp._FORCE_DEVICE = old

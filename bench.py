@@ -218,6 +218,8 @@ def run_ours(args):
 
     from adi_thermal_fields_b200 import _capi, adi3d_gpu_coeff as g, devarray as cp
 
+    if args.workload == "c4":
+        return run_ours_c4(args, local)
     if world > 1 or args.workload == "c5":
         return run_ours_slab(args, rank, world, local)
     n = args.size
@@ -558,6 +560,108 @@ def run_ours_slab(args, rank, world, local):
     return 0
 
 
+def run_ours_c4(args, local):
+    """BASELINE configs[3] (waam_from_stl_v7_mm at 1024^3; the STL is not in the tree): a
+    synthetic head (ellipsoid + neck cylinder) is deposited bottom-up, `n_per_layer` z planes per birth
+    (activate_layer, waam_from_stl_v7_mm.py:487-495), the packs are rebuilt on the device after every birth
+    (precompute_coeff_packs_unified with per-face dense h fields standing in for voxel_bc_correction's
+    output) and `steps_per_layer` ADI steps follow.  Timed: births + pack rebuilds + steps."""
+    import torch
+    from adi_thermal_fields_b200 import adi3d_gpu_coeff as g, devarray as cp
+
+    n = 2 * args.size
+    dev = torch.device("cuda", local)
+    rho, cp_, k = 7800.0, 490.0, 54.0
+    kappa = k / (rho * cp_)
+    dt = 2000.0 * DX * DX / kappa           # cfl = 2000 (waam_from_stl_v7_mm.py:355-363)
+    ax = (torch.arange(n, device=dev, dtype=torch.float64) + 0.5) / n - 0.5
+    X, Y, Z = ax[:, None, None], ax[None, :, None], ax[None, None, :]
+    full = ((X / 0.35) ** 2 + (Y / 0.42) ** 2 + ((Z - 0.05) / 0.45) ** 2 <= 1.0) | \
+           ((X * X + Y * Y <= 0.12 ** 2) & (Z < -0.3))
+    del X, Y, Z
+    gen = torch.Generator(device=dev).manual_seed(3)
+    h = {f: cp.ndarray(40.0 * (0.3 + torch.rand((n, n, n), dtype=torch.float64, device=dev, generator=gen)))
+         for f in FACES}
+    n_per_layer, steps_per_layer = max(1, n // 64), args.c4_steps_per_layer
+    act = torch.zeros((n, n, n), dtype=torch.bool, device=dev)
+    T = cp.full((n, n, n), TINF, dtype=cp.float64)
+    grid = g.Grid3D.__new__(g.Grid3D)
+    grid.nx = grid.ny = grid.nz = n
+    grid.dx = DX
+    grid.mask = cp.ndarray(act)
+    mat, prm = g.Material(rho, cp_, k), g.Params(dt, THETA)
+    zs = torch.nonzero(full.any(0).any(0)).flatten()
+    k0, k1 = int(zs[0]), int(zs[-1]) + 1
+    layers = [(a, min(a + n_per_layer, k1)) for a in range(k0, k1, n_per_layer)]
+
+    def birth(ks, ke):
+        born = full[:, :, ks:ke] & ~act[:, :, ks:ke]
+        T._t[:, :, ks:ke][born] = 1000.0        # Ts
+        act[:, :, ks:ke] |= born
+        grid.mask = cp.ndarray(act)             # rebinding, as the driver does
+        return g.precompute_coeff_packs_unified(grid, mat, robin_h=h)
+
+    def run(layer_list):
+        nonlocal T
+        nsteps = 0
+        tb = ts = 0.0
+        for ks, ke in layer_list:
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            packs = birth(ks, ke)
+            e1.record()
+            for _ in range(steps_per_layer):
+                T = g.adi_step_gpu_coeff(T, grid, mat, prm, packs, Tinf=TINF)
+                nsteps += 1
+            e2.record()
+            torch.cuda.synchronize()
+            tb += e0.elapsed_time(e1)
+            ts += e1.elapsed_time(e2)
+        return nsteps, tb, ts
+
+    nwarm = max(1, args.warmup // steps_per_layer)
+    run(layers[:nwarm])
+    nlay = max(1, args.steps // steps_per_layer)
+    mid = layers[len(layers) // 2: len(layers) // 2 + nlay]   # mid-build: half of the head is active
+    for ks, ke in layers[nwarm:len(layers) // 2]:             # fast-forward the activation (untimed)
+        born = full[:, :, ks:ke]
+        T._t[:, :, ks:ke][born] = 1000.0
+        act[:, :, ks:ke] |= born
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = g.launch_count()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    nsteps, tb, ts = run(mid)
+    wall = time.perf_counter() - t0
+    launches = g.launch_count() - l0
+    clocks = sampler.stop()
+    cells = n ** 3
+    peak, peak_src = peaks()
+    total_ms = tb + ts
+    line = {
+        "metric": METRIC, "value": cells * nsteps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": nsteps,
+        "warmup": nwarm * steps_per_layer, "ms_per_step": total_ms / nsteps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"waam_from_stl_v7_mm {n}^3 (BASELINE configs[3]), synthetic head (ellipsoid + neck; the STL is "
+                               f"not in the tree), {n_per_layer} z planes per birth, {steps_per_layer} steps per layer, "
+                               f"per-face dense h fields, theta={THETA}, cfl=2000; births + device pack rebuilds inside the timed region",
+                   "grid": [n, n, n], "cells": cells, "bytes_per_cell_step": 75,
+                   "active_fraction_mid_build": float(act.sum().item()) / cells, "parallelism": "single GPU"},
+        "roofline": {"bound": "hbm", "kernel": "whole step (explicit + x + y + z), steady state between births",
+                     "achieved": 75.0 * cells / (ts / nsteps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": 75.0 * cells / (ts / nsteps * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "steady_ms_per_step": ts / nsteps, "birth_ms": tb / len(mid),
+                     "birth_note": "mask update + k_build_packs (6 dense h fields -> 3 coeff fields) + neighbour code rebuild"},
+        "cpu_baseline": None, "clocks": clocks,
+        "e2e": {"value": cells * nsteps / wall, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "api": "adi3d_gpu_coeff.precompute_coeff_packs_unified + adi_step_gpu_coeff (device arrays, host wall clock)"},
+        "gpu_launches": int(launches), "parity": None,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -565,13 +669,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--workload", default="plate", choices=["plate", "c5"],
+    ap.add_argument("--workload", default="plate", choices=["plate", "c5", "c4"],
                     help="plate: BASELINE configs[1] (N>1: one size^3 slab per GPU, weak scaling); "
-                         "c5: BASELINE configs[4], 2048x2048x1024 scalar-Robin strong scaling, z-slab over N GPUs")
+                         "c5: BASELINE configs[4], 2048x2048x1024 scalar-Robin strong scaling, z-slab over N GPUs; "
+                         "c4: BASELINE configs[3], waam 1024^3 synthetic head, layer births with device pack rebuilds (1 GPU)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-ny", type=int, default=128, help="y extent of the CPU-baseline sample slab")
     ap.add_argument("--ref-ny", type=int, default=64, help="y extent of the --impl reference sample slab")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--c4-steps-per-layer", type=int, default=4)
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="engine tuning option (adi_set_option), e.g. --opt m=32 --opt kt=16")
     args = ap.parse_args()

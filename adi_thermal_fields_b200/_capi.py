@@ -20,6 +20,7 @@ SYMBOLS = (
     "adi_cyl_bind", "adi_cyl_step", "adi_cyl_step_host",
     "adi_cart_set_slab", "adi_cart_set_mask_halo", "adi_cart_pack_zplanes", "adi_cart_step_xy",
     "adi_cart_zsweep_reduce", "adi_cart_zsweep_finish",
+    "adi_voxel_project", "adi_voxel_correct",
 )
 
 
@@ -81,6 +82,10 @@ def load():
     L.adi_cart_step_xy.argtypes = [vp, dp, dp, dp, dp, dbl, dbl, dbl, dbl, vp]
     L.adi_cart_zsweep_reduce.argtypes = [vp, dp, dp, dbl, dbl, dbl, dbl, vp]
     L.adi_cart_zsweep_finish.argtypes = [vp, dp, dp, dbl, dbl, dbl, dbl, vp]
+    L.adi_voxel_project.argtypes = [vp, dp, dp, dp, C.c_int, C.POINTER(dbl), dbl, C.c_int, dbl, bp, C.c_int, C.c_int,
+                                    C.c_int, C.POINTER(vp), vp]
+    L.adi_voxel_correct.argtypes = [vp, bp, C.c_int, C.c_int, C.c_int, dbl, C.POINTER(vp), ip, C.POINTER(dbl), C.c_int,
+                                    C.POINTER(vp), C.POINTER(vp), vp]
     L.adi_cyl_bind.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dbl, dbl, dbl]
     L.adi_cyl_step.argtypes = [vp, dp, dp, C.POINTER(CylParams), bp, dp, vp]
     L.adi_cyl_step_host.argtypes = [vp, vp, vp, C.c_int, C.POINTER(CylParams), vp, vp, vp]

@@ -133,6 +133,23 @@ long adi_launch_count(adi_ctx *ctx);
 int adi_profile_reset(adi_ctx *ctx);
 int adi_profile_read(adi_ctx *ctx, double ms[4], long *nsteps);
 
+/* ---- voxel_bc_correction (producer of the per-face dense Robin fields) ------------------
+ * STLBoundaryCorrector.compute_voxel_projected_areas  voxel_bc_correction.py:53-108: triangles
+ * (d_tri[ntri][3][3]), unit normals (d_nrm[ntri][3]) and areas (d_area[ntri]) of the surface mesh are
+ * subdivided and scattered into six per-face projected-area fields d_proj[f] (face order
+ * 'x-','x+','y-','y+','z-','z+'; the caller zero-fills them).  fp64 atomics: the sum into one voxel is
+ * order-dependent at rounding level. */
+int adi_voxel_project(adi_ctx *ctx, const double *d_tri, const double *d_nrm, const double *d_area,
+                      int ntri, const double origin[3], double dx, int max_subdiv, double area_eps,
+                      const uint8_t *d_mask, int nx, int ny, int nz, double *const d_proj[6],
+                      void *stream);
+/* STLBoundaryCorrector.build_corrected_fields  voxel_bc_correction.py:110-168: for every face with
+ * has[f] != 0, robin[f] = base_h[f] * proj[f] / dx^2 and scale[f] = proj[f] / dx^2; with `fallback`,
+ * exposed faces without projected area take base_h[f] / 1.  d_scale (or single entries) may be NULL. */
+int adi_voxel_correct(adi_ctx *ctx, const uint8_t *d_mask, int nx, int ny, int nz, double dx,
+                      const double *const d_proj[6], const int has[6], const double base_h[6],
+                      int fallback, double *const d_robin[6], double *const d_scale[6], void *stream);
+
 /* ---- cylindrical path --------------------------------------------------------------- */
 /* GridCyl(nr,nphi,nz,dr,dphi,dz,R)  adi3d_cyl_phi_v3.py:33-43.  nz_pitch >= nz is the
  * allocated z extent of the fields (layer births grow nz without reallocating,

@@ -278,3 +278,56 @@ def rel_l2(a: np.ndarray, b: np.ndarray, where=None) -> float:
     den = float(np.sqrt(np.sum(b.astype(np.float64) ** 2)))
     num = float(np.sqrt(np.sum((a.astype(np.float64) - b.astype(np.float64)) ** 2)))
     return num / den if den > 0 else num
+
+
+# ----------------------------------------------------------------------------
+# voxel_bc_correction cases: a duck-typed triangle mesh (the four attributes the reference
+# reads: triangles, face_normals, area_faces, triangles_center) of an ellipsoid, and the voxel
+# mask of the same ellipsoid.
+# ----------------------------------------------------------------------------
+class TriMesh:
+    def __init__(self, triangles):
+        self.triangles = np.ascontiguousarray(triangles, dtype=np.float64)
+        e1 = self.triangles[:, 1] - self.triangles[:, 0]
+        e2 = self.triangles[:, 2] - self.triangles[:, 0]
+        n = np.cross(e1, e2)
+        nrm = np.sqrt((n * n).sum(axis=1))
+        self.area_faces = 0.5 * nrm
+        self.face_normals = n / np.maximum(nrm, 1e-300)[:, None]
+        self.triangles_center = self.triangles.mean(axis=1)
+
+
+def ellipsoid_mesh(center, radii, nu=14, nv=24):
+    """Latitude-longitude triangulation, outward normals."""
+    cx, cy, cz = center
+    a, b, c = radii
+
+    def pt(i, j):
+        th = math.pi * i / nu
+        ph = 2.0 * math.pi * (j % nv) / nv
+        return (cx + a * math.sin(th) * math.cos(ph), cy + b * math.sin(th) * math.sin(ph), cz + c * math.cos(th))
+
+    tris = []
+    for i in range(nu):
+        for j in range(nv):
+            p00, p01, p10, p11 = pt(i, j), pt(i, j + 1), pt(i + 1, j), pt(i + 1, j + 1)
+            if i > 0:
+                tris.append((p00, p10, p01))
+            if i < nu - 1:
+                tris.append((p01, p10, p11))
+    return TriMesh(np.array(tris))
+
+
+def build_voxel_bc_case(name="ellipsoid"):
+    shape = (22, 26, 30)
+    dx = 1.0e-3
+    origin = (-2.0e-3, 1.0e-3, 0.5e-3)
+    center = (origin[0] + 0.5 * shape[0] * dx, origin[1] + 0.5 * shape[1] * dx, origin[2] + 0.5 * shape[2] * dx)
+    radii = (0.40 * shape[0] * dx, 0.42 * shape[1] * dx, 0.45 * shape[2] * dx)
+    xs = [origin[d] + (np.arange(shape[d]) + 0.5) * dx for d in range(3)]
+    X, Y, Z = np.meshgrid(*xs, indexing="ij")
+    mask = ((X - center[0]) / radii[0]) ** 2 + ((Y - center[1]) / radii[1]) ** 2 + ((Z - center[2]) / radii[2]) ** 2 <= 1.0
+    mesh = ellipsoid_mesh(center, radii, nu=10 if name == "coarse" else 22, nv=16 if name == "coarse" else 40)
+    base_h = {"x-": 40.0, "x+": 55.0, "y-": 40.0, "y+": 0.0, "z-": 25.0, "z+": 80.0}
+    return dict(name=name, shape=shape, dx=dx, origin=origin, mask=mask, mesh=mesh, base_h=base_h,
+                max_subdiv=6 if name != "coarse" else 4)

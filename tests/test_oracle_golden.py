@@ -177,3 +177,21 @@ def test_spiral_simulation_oracle_bit_exact(golden_dir):
     snaps, acts = spiral_loop.run(cyl, g["times"])
     assert np.array_equal(np.array(acts), g["active"])
     assert np.array_equal(np.array(snaps), g["snapshots"])
+
+
+@pytest.mark.parametrize("name", ["ellipsoid", "coarse"])
+def test_voxel_bc_oracle_bit_exact(name, golden_dir):
+    """oracle/voxel_bc.py against voxel_bc_correction.build_corrected_robin_fields of the unmodified
+    reference on a duck-typed ellipsoid mesh (with and without the fallback to the base coefficient)."""
+    from oracle import voxel_bc
+    c = cases.build_voxel_bc_case(name)
+    g = np.load(os.path.join(golden_dir, f"voxel_bc_{name}.npz"))
+    robin, scale = voxel_bc.build_corrected_robin_fields(c["mesh"], c["mask"], c["origin"], c["dx"], c["base_h"],
+                                                         True, c["max_subdiv"])
+    nofb, _ = voxel_bc.build_corrected_robin_fields(c["mesh"], c["mask"], c["origin"], c["dx"], c["base_h"],
+                                                    False, c["max_subdiv"])
+    assert list(robin) == list(c["base_h"])
+    for f in robin:
+        assert np.array_equal(robin[f], g["robin_" + f])
+        assert np.array_equal(scale[f], g["scale_" + f])
+        assert np.array_equal(nofb[f], g["robin_nofallback_" + f])

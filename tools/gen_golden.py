@@ -210,6 +210,25 @@ def gen_cyl_birth(ref, outdir):
     print(f"[cyl_birth] final nz={grid.nz}, {len(frames)} frames")
 
 
+def gen_voxel_bc(ref, outdir):
+    """voxel_bc_correction.build_corrected_robin_fields on a duck-typed ellipsoid mesh."""
+    import voxel_bc_correction as vb
+    for name in ("ellipsoid", "coarse"):
+        c = cases.build_voxel_bc_case(name)
+        robin, scale = vb.build_corrected_robin_fields(c["mesh"], c["mask"], c["origin"], c["dx"], c["base_h"],
+                                                       fallback_to_base=True, max_subdiv=c["max_subdiv"])
+        robin_nf, _ = vb.build_corrected_robin_fields(c["mesh"], c["mask"], c["origin"], c["dx"], c["base_h"],
+                                                      fallback_to_base=False, max_subdiv=c["max_subdiv"])
+        out = {}
+        for f in robin:
+            out["robin_" + f] = robin[f]
+            out["scale_" + f] = scale[f]
+            out["robin_nofallback_" + f] = robin_nf[f]
+        np.savez_compressed(os.path.join(outdir, f"voxel_bc_{name}.npz"), **out)
+        print(f"[voxel_bc] {name}: {len(c['mesh'].triangles)} triangles, "
+              f"{int(sum((robin[f] > 0).sum() for f in robin))} corrected face entries")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -222,6 +241,7 @@ def main():
     gen_cyl(a.ref, a.out)
     gen_spiral_sim(a.ref, a.out)
     gen_cyl_birth(a.ref, a.out)
+    gen_voxel_bc(a.ref, a.out)
 
 
 if __name__ == "__main__":

@@ -338,8 +338,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
 #pragma unroll
         for (int e = 0; e < M; ++e) ch.T[e] = e < nv ? tp[e * sl] : 0.0;
     }
+    // solid tile rows (all chunks of the warp full and without void / Dirichlet cells): the bulk of a part
+    const bool solid = !EXPL && NS == 2 && __all_sync(0xffffffffu, nv == M && chunk_solid<M>(ch, LO, HI));
+    if (!solid) {
 #pragma unroll
-    for (int e = 0; e < M; ++e) ch.T[e] = ch.active(e) ? ch.T[e] : 0.0;  // load rule (adi_core.h)
+        for (int e = 0; e < M; ++e) ch.T[e] = ch.active(e) ? ch.T[e] : 0.0;  // load rule (adi_core.h)
+    }
 
     if (EXPL && STAGED) {
         double prev = (ch.code(0) & CB_XM) ? xprev : 0.0;
@@ -394,14 +398,19 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
     ops.col = col;
     ops.NTH = NTH;
 
-    const First f = chunk_forward<M, CMODE, EXTRA, NS>(ch, ops, LO, HI, a.k);
+    First f;
+    if (solid) f = chunk_forward<M, CMODE, EXTRA, NS, true>(ch, ops, LO, HI, a.k);
+    else f = chunk_forward<M, CMODE, EXTRA, NS, false>(ch, ops, LO, HI, a.k);
     if (EXPL && STAGED) __syncthreads();  // slot 2 (other threads' y+ values) becomes the exchange buffer
     double Sl;
     const double S = solve_reduced<M>(ch, f, red, NTH, tid, KT, p, P, &Sl);
     chunk_backward<M, EXTRA, NS>(ch, ops, LO, HI, a.k.g, Sl, S);
 
     double *op = a.out + idx0;
-    if (a.in == a.out) {
+    if (solid) {
+#pragma unroll
+        for (int e = 0; e < M; ++e) op[e * sl] = ch.T[e];
+    } else if (a.in == a.out) {
         // in place: void cells are simply not written
 #pragma unroll
         for (int e = 0; e < M; ++e)
@@ -535,6 +544,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
             ch.T[2 * j + 1] = ch.active(2 * j + 1) ? v.y : 0.0;
         }
     }
+    // warps whose chunks are all solid (adi_core.h) take the row arithmetic with the code folded away
+    const bool solid = NS == 2 && __all_sync(0xffffffffu, chunk_solid<M>(ch, CB_ZM, CB_ZP));
     __syncthreads();  // sT is reused as the reduced-system exchange buffer from here on
 
     TileOps<M> ops;
@@ -549,7 +560,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
         ops.nv = (L0 + ln < nlines) ? min(max(nz - p * M, 0), M) : 0;
     }
 
-    const First f = chunk_forward<M, CMODE, EXTRA, NS>(ch, ops, CB_ZM, CB_ZP, a.k);
+    First f;
+    if (solid) f = chunk_forward<M, CMODE, EXTRA, NS, true>(ch, ops, CB_ZM, CB_ZP, a.k);
+    else f = chunk_forward<M, CMODE, EXTRA, NS, false>(ch, ops, CB_ZM, CB_ZP, a.k);
     if (ZMODE == 1) {
         const Red3 r = solve_reduced3<M>(ch, f, red, NTH, tid, 1, p, P);
         const size_t line = L0 + ln;

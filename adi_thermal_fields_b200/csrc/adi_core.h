@@ -172,8 +172,37 @@ struct Chunk {
 //     NS == 1:  put1(e, rinv), rinv(e)          rinv = 1/den (long lines: half the storage)
 // with e a compile-time constant after unrolling.
 
-// Phase 1.
-template <int M, int CMODE, bool EXTRA, int NS, class OPS>
+// A chunk is "solid" when all its M cells are active, none is a Dirichlet cell and every link
+// between two of its cells exists; only the outward links of its first and last cell may be
+// missing.  Solid chunks (all of them in the bulk of a part) skip the per-cell decoding of the
+// neighbour code: the same row arithmetic with the code bits known at compile time.
+template <int M>
+ADI_HD bool chunk_solid(const Chunk<M> &ch, unsigned lo, unsigned hi)
+{
+    static_assert(M % 4 == 0, "codes are packed four per word");
+    const unsigned need = (CB_SELF | lo | hi) * 0x01010101u, care = (CB_SELF | lo | hi | CB_DIR) * 0x01010101u;
+    bool ok = true;
+#pragma unroll
+    for (int w = 0; w < M / 4; ++w) {
+        unsigned c = ch.cw[w];
+        if (w == 0) c |= lo;                               // cell 0 may lack its '-' link
+        if (w == M / 4 - 1) c |= hi << 24;                 // cell M-1 may lack its '+' link
+        ok = ok && ((c & care) == need);
+    }
+    return ok;
+}
+
+// Code of cell e of a solid chunk: a compile-time constant except for the two end cells.
+template <int M>
+ADI_HD unsigned solid_code(const Chunk<M> &ch, int e, unsigned lo, unsigned hi)
+{
+    if (e == 0) return CB_SELF | hi | (ch.code(0) & lo);
+    if (e == M - 1) return CB_SELF | lo | (ch.code(M - 1) & hi);
+    return CB_SELF | lo | hi;
+}
+
+// Phase 1.  SOLID: the chunk passed chunk_solid (same arithmetic, selects folded away).
+template <int M, int CMODE, bool EXTRA, int NS, bool SOLID = false, class OPS>
 ADI_HD First chunk_forward(Chunk<M> &ch, OPS &ops, unsigned lo, unsigned hi, const SweepConst &k)
 {
     double uprev = 0.0, dprev = 0.0, vprev = 1.0, alpha = 1.0;
@@ -181,7 +210,8 @@ ADI_HD First chunk_forward(Chunk<M> &ch, OPS &ops, unsigned lo, unsigned hi, con
     f.Y = 0.0; f.V = 0.0; f.W = 0.0;
 #pragma unroll
     for (int e = 0; e < M - 1; ++e) {
-        const Row r = make_row<CMODE, EXTRA>(ch.code(e), lo, hi, ch.T[e], CMODE == 2 ? ops.coef(e) : 0.0,
+        const Row r = make_row<CMODE, EXTRA>(SOLID ? solid_code<M>(ch, e, lo, hi) : ch.code(e), lo, hi, ch.T[e],
+                                             CMODE == 2 ? ops.coef(e) : 0.0,
                                              EXTRA ? ops.q(e) : 0.0, EXTRA ? ops.dirv(e) : 0.0, k);
         // e == 0: the coupling aa to S_{p-1} stays symbolic (uprev = dprev = 0, vprev = 1)
         const double den = fma(-r.aa, uprev, r.b);      // b - a*c'_{e-1}
@@ -202,7 +232,8 @@ ADI_HD First chunk_forward(Chunk<M> &ch, OPS &ops, unsigned lo, unsigned hi, con
     ch.Yl = dprev; ch.Vl = vprev; ch.Wl = uprev;        // x_{M-2} = Yl + Vl*S_{p-1} + Wl*S_p
     {
         const int e = M - 1;
-        const Row r = make_row<CMODE, EXTRA>(ch.code(e), lo, hi, ch.T[e], CMODE == 2 ? ops.coef(e) : 0.0,
+        const Row r = make_row<CMODE, EXTRA>(SOLID ? solid_code<M>(ch, e, lo, hi) : ch.code(e), lo, hi, ch.T[e],
+                                             CMODE == 2 ? ops.coef(e) : 0.0,
                                              EXTRA ? ops.q(e) : 0.0, EXTRA ? ops.dirv(e) : 0.0, k);
         ch.s_aa = r.aa; ch.s_cc = r.cc; ch.s_b = r.b; ch.s_d = r.d;
     }

@@ -147,11 +147,13 @@ __global__ void __launch_bounds__(256, (M <= 16 ? 3 : 2)) k_cyl_strided(const Cy
         if (a.active) {  // T_work[~active] = T_void
             const uint8_t *am = a.active + first;
             const unsigned cs1 = (unsigned)a.cell_stride;
-            unsigned bits = 0;
+            // unconditional byte loads (padding slots re-read a cell of the chunk), all in flight at once
+            unsigned mb[M];
+            const int elast = M - 1;
 #pragma unroll
-            for (int e = 0; e < M; ++e) bits |= ((e >= efirst && am[(size_t)e * cs1]) ? 1u : 0u) << e;
+            for (int e = 0; e < M; ++e) mb[e] = am[(size_t)min(max(e, efirst), elast) * cs1];
 #pragma unroll
-            for (int e = 0; e < M; ++e) d[e] = ((bits >> e) & 1u) ? d[e] : (e >= efirst ? a.T_void : 0.0);
+            for (int e = 0; e < M; ++e) d[e] = mb[e] ? d[e] : (e >= efirst ? a.T_void : 0.0);
         }
         if (a.S) {       // R0 = Tn + dt*(S/(rho*cp))  :339
             const char *sp = reinterpret_cast<const char *>(a.S + first);

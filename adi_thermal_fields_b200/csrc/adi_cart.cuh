@@ -129,6 +129,39 @@ __device__ __forceinline__ double solve_reduced(const Chunk<M> &ch, const First 
     return r.D;
 }
 
+// The same reduced solve when the P chunks of a line are P consecutive lanes of one warp (z sweep with
+// P a power of two <= 32): the PCR rows travel by warp shuffles -- no shared memory, no block barrier.
+__device__ __forceinline__ double shfl_up_w(double v, int d, int w) { return __shfl_up_sync(0xffffffffu, v, d, w); }
+__device__ __forceinline__ double shfl_dn_w(double v, int d, int w) { return __shfl_down_sync(0xffffffffu, v, d, w); }
+
+template <int M, bool GHOST = false>
+__device__ __forceinline__ double solve_reduced_warp(const Chunk<M> &ch, const First &f, int p, int P, double *Sl,
+                                                     double Lg = 0.0, double Rg = 0.0)
+{
+    First nx;
+    nx.Y = shfl_dn_w(f.Y, 1, P); nx.V = shfl_dn_w(f.V, 1, P); nx.W = shfl_dn_w(f.W, 1, P);
+    if (p + 1 >= P) {
+        if (GHOST) nx = ghost_first();
+        else { nx.Y = 0.0; nx.V = 0.0; nx.W = 0.0; }
+    }
+    Red r = chunk_reduced_row(ch, nx);
+    if (GHOST) {
+        if (p == 0) r.D = fma(-r.A, Lg, r.D);
+        if (p == P - 1) r.D = fma(-r.C, Rg, r.D);
+    }
+    for (int s = 1; s < P; s <<= 1) {
+        Red lo, hi;
+        lo.A = shfl_up_w(r.A, s, P); lo.C = shfl_up_w(r.C, s, P); lo.D = shfl_up_w(r.D, s, P);
+        hi.A = shfl_dn_w(r.A, s, P); hi.C = shfl_dn_w(r.C, s, P); hi.D = shfl_dn_w(r.D, s, P);
+        if (p - s < 0) { lo.A = 0.0; lo.C = 0.0; lo.D = 0.0; }
+        if (p + s >= P) { hi.A = 0.0; hi.C = 0.0; hi.D = 0.0; }
+        r = pcr_step(r, lo, hi);
+    }
+    const double sl = shfl_up_w(r.D, 1, P);
+    *Sl = (p > 0) ? sl : (GHOST ? Lg : 0.0);
+    return r.D;
+}
+
 // z-slab decomposition, pass 1: the separators as affine functions of the two ghosts.
 // red: 10*NTH doubles (two buffers of five columns); the First exchange uses the first 3*NTH.
 template <int M>
@@ -544,6 +577,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
             ch.T[2 * j + 1] = ch.active(2 * j + 1) ? v.y : 0.0;
         }
     }
+    // a line = P consecutive lanes of one warp: warp-shuffle PCR (block-uniform)
+    const bool warp_lines = P <= 32 && (P & (P - 1)) == 0;
     // warps whose chunks are all solid (adi_core.h) take the row arithmetic with the code folded away
     const bool solid = NS == 2 && __all_sync(0xffffffffu, chunk_solid<M>(ch, CB_ZM, CB_ZP));
     __syncthreads();  // sT is reused as the reduced-system exchange buffer from here on
@@ -587,7 +622,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
         if (p == 0) Lg = a.ghost[line];
         if (p == P - 1) Rg = a.ghost[nlines + line];
     }
-    const double S = solve_reduced<M, ZMODE == 2>(ch, f, red, NTH, tid, 1, p, P, &Sl, Lg, Rg);
+    double S;
+    if (warp_lines) S = solve_reduced_warp<M, ZMODE == 2>(ch, f, p, P, &Sl, Lg, Rg);
+    else S = solve_reduced<M, ZMODE == 2>(ch, f, red, NTH, tid, 1, p, P, &Sl, Lg, Rg);
     chunk_backward<M, EXTRA, NS>(ch, ops, CB_ZM, CB_ZP, a.k.g, Sl, S);
     __syncthreads();  // everybody is done reading the exchange buffer
 

@@ -20,7 +20,7 @@ SYMBOLS = (
     "adi_cyl_bind", "adi_cyl_step", "adi_cyl_step_host",
     "adi_cart_set_slab", "adi_cart_set_mask_halo", "adi_cart_pack_zplanes", "adi_cart_step_xy",
     "adi_cart_zsweep_reduce", "adi_cart_zsweep_finish",
-    "adi_voxel_project", "adi_voxel_correct",
+    "adi_voxel_project", "adi_voxel_correct", "adi_cart_step_host_async",
 )
 
 
@@ -68,6 +68,7 @@ def load():
     L.adi_cart_set_robin_scalar.argtypes = [vp, C.POINTER(dbl)]
     L.adi_cart_step.argtypes = [vp, dp, dp, dbl, dbl, dbl, dbl, vp]
     L.adi_cart_step_host.argtypes = [vp, vp, vp, C.c_int, dbl, dbl, dbl, dbl, vp]
+    L.adi_cart_step_host_async.argtypes = [vp, C.c_int, vp, vp, dbl, dbl, dbl, dbl, vp]
     L.adi_cart_build_packs.argtypes = [vp, dbl, dbl, ip, C.POINTER(dbl), C.POINTER(vp),
                                        ip, C.POINTER(dbl), C.POINTER(vp)] + [dp] * 6 + [vp]
     L.adi_cart_exposed_mask.argtypes = [vp, C.c_int, bp, vp]

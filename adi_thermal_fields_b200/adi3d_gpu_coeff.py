@@ -354,6 +354,40 @@ def adi_step_host(Tn, grid, mat, params, packs, Tinf=0.0, nsteps=1):
     return out
 
 
+def adi_step_host_pipelined(fields, grid, mat, params, packs, Tinf=0.0):
+    """One ADI step of each of several independent HOST fields (e.g. an ensemble, or frames that
+    are streamed out while the next input streams in): two staging slots on two CUDA streams keep
+    the upload of one field, the compute of another and the download of a third in flight
+    (adi_cart_step_host_async).  `fields`: sequence of (nx,ny,nz) float64 arrays; returns the list of
+    stepped arrays.  Page-locked inputs/outputs (torch pinned tensors' numpy views) transfer fastest."""
+    shape = (grid.nx, grid.ny, grid.nz)
+    kappa = mat.k / (mat.rho * mat.cp)
+    e = _engine
+    e.bind(grid)
+    e.set_mask(grid)
+    e.set_packs(packs)
+    L, ctx = e.lib(), e.context()
+    ins = [np.ascontiguousarray(f, dtype=np.float64) for f in fields]
+    for f in ins:
+        if f.shape != shape:
+            raise ValueError("field shape does not match the grid")
+    outs = [np.empty(shape, dtype=np.float64) for _ in ins]
+    if ins:  # the first step runs alone: it (re)builds the neighbour code before two streams share it
+        _capi.check(L.adi_cart_step_host(ctx, ins[0].ctypes.data, outs[0].ctypes.data, 1, params.dt, params.theta,
+                                         kappa, float(Tinf), _stream_ptr()), "adi_cart_step_host")
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for i in range(1, len(ins)):
+        s = i & 1
+        if i >= 3:
+            streams[s].synchronize()   # the slot's previous occupant is done
+        _capi.check(L.adi_cart_step_host_async(ctx, s, ins[i].ctypes.data, outs[i].ctypes.data, params.dt,
+                                               params.theta, kappa, float(Tinf), streams[s].cuda_stream),
+                    "adi_cart_step_host_async")
+    for st in streams:
+        st.synchronize()
+    return outs
+
+
 def set_option(name, value):
     """Engine tuning knob (adi_set_option): 'm' chunk length (16|32), 'kt' / 'lt' lines per
     block of the strided / z sweeps; 0 restores the default."""

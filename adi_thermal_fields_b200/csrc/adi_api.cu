@@ -76,6 +76,9 @@ int adi_ctx_destroy(adi_ctx *ctx)
     for (int a = 0; a < 2; ++a)
         if (ctx->stage[a]) cudaFree(ctx->stage[a]);
     if (ctx->d_ghost) cudaFree(ctx->d_ghost);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (ctx->pipe[i][j]) cudaFree(ctx->pipe[i][j]);
     if (ctx->stage_mask) cudaFree(ctx->stage_mask);
     if (ctx->stage_src) cudaFree(ctx->stage_src);
     adi::cyl_release(ctx);

@@ -368,6 +368,32 @@ int adi_cart_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int ns
     return ADI_OK;
 }
 
+int adi_cart_step_host_async(adi_ctx *ctx, int slot, const double *h_Tin, double *h_Tout, double dt,
+                             double theta, double kappa, double Tinf, void *stream)
+{
+    int rc = check_cart(ctx, "adi_cart_step_host_async");
+    if (rc) return rc;
+    if (!h_Tin || !h_Tout || slot < 0 || slot > 1) {
+        set_error("adi_cart_step_host_async: bad arguments (slot must be 0 or 1)");
+        return ADI_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ncell = (size_t)ctx->nx * ctx->ny * ctx->nz;
+    if (ctx->pipe_cells[slot] < ncell || !ctx->pipe[slot][0]) {
+        for (int j = 0; j < 2; ++j) {
+            if (ctx->pipe[slot][j]) { ADI_CUDA(cudaDeviceSynchronize()); ADI_CUDA(cudaFree(ctx->pipe[slot][j])); }
+            ctx->pipe[slot][j] = nullptr;
+            ADI_CUDA(cudaMalloc(&ctx->pipe[slot][j], std::max<size_t>(ncell, 1) * sizeof(double)));
+        }
+        ctx->pipe_cells[slot] = ncell;
+    }
+    ADI_CUDA(cudaMemcpyAsync(ctx->pipe[slot][0], h_Tin, ncell * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = adi_cart_step(ctx, ctx->pipe[slot][0], ctx->pipe[slot][1], dt, theta, kappa, Tinf, stream);
+    if (rc) return rc;
+    ADI_CUDA(cudaMemcpyAsync(h_Tout, ctx->pipe[slot][1], ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return ADI_OK;
+}
+
 int adi_cart_build_packs(adi_ctx *ctx, double rho, double cp, const int h_kind[6],
                          const double h_scalar[6], const double *const d_h_field[6],
                          const int q_kind[6], const double q_scalar[6],

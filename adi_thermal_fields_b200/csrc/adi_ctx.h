@@ -63,6 +63,9 @@ struct adi_ctx {
     // host-array convenience path
     double *stage[2] = {nullptr, nullptr};
     size_t stage_cells = 0;
+    // pipelined host-array path: two slots, each with its own in/out staging pair
+    double *pipe[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    size_t pipe_cells[2] = {0, 0};
 
     // ---- cylindrical ----
     bool cyl_bound = false;

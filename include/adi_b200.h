@@ -78,6 +78,16 @@ int adi_cart_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, 
  * result back and synchronises.  Used for end-to-end timing. */
 int adi_cart_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int nsteps, double dt,
                        double theta, double kappa, double Tinf, void *stream);
+/* Pipelined form of the above for callers that step many independent host fields (or stream
+ * frames out while the next input streams in): asynchronous on `stream`, no synchronisation,
+ * staging buffers of `slot` (0 or 1).  Two slots on two streams overlap the upload of one
+ * step with the compute of the other and the download of the previous result (both PCIe
+ * directions busy).  h_Tin / h_Tout should be pinned; the caller synchronises the stream
+ * (adi_sync) before reading h_Tout or reusing the slot's host buffers.  The neighbour code
+ * must be current (one adi_cart_step / adi_cart_step_host call after the last mask change)
+ * before two streams are used concurrently. */
+int adi_cart_step_host_async(adi_ctx *ctx, int slot, const double *h_Tin, double *h_Tout, double dt,
+                             double theta, double kappa, double Tinf, void *stream);
 /* precompute_coeff_packs_unified  adi3d_gpu_coeff.py:50-110 on the device.
  * For face f: h_kind[f] 0 = no Robin, 1 = scalar h_scalar[f], 2 = device field d_h_field[f];
  * likewise q_* for Neumann (q'' > 0 heats the solid).  Writes the six dense outputs

@@ -363,3 +363,22 @@ def test_long_lines(shape, bk, theta, g, cp):
             g.set_option("fuse", 0)
         assert cases.rel_l2(out, ref, mask) <= TOL
         assert np.array_equal(out[~mask], T0[~mask], equal_nan=True)
+
+
+def test_pipelined_host_fields(g, golden_dir):
+    """adi_cart_step_host_async: five independent host fields through two staging slots / two streams."""
+    c = cases.build_cart_case("holes_combined")
+    nx, ny, nz = c["shape"]
+    grid = g.Grid3D(nx, ny, nz, c["dx"], c["mask"])
+    mat = g.Material(c["rho"], c["cp"], c["k"])
+    packs = g.precompute_coeff_packs_unified(grid, mat, **c["bcs"])
+    prm = g.Params(c["dt"], c["theta"])
+    fields = []
+    for i in range(5):
+        f = c["T0"].copy()
+        f[c["mask"]] += 3.0 * i
+        fields.append(f)
+    outs = g.adi_step_host_pipelined(fields, grid, mat, prm, packs, Tinf=c["Tinf"])
+    for f, o in zip(fields, outs):
+        ref = g.adi_step_host(f, grid, mat, prm, packs, Tinf=c["Tinf"])
+        assert np.array_equal(o, ref, equal_nan=True)

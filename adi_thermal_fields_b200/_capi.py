@@ -81,8 +81,8 @@ def load():
     L.adi_cart_set_mask_halo.argtypes = [vp, bp, bp]
     L.adi_cart_pack_zplanes.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     L.adi_cart_step_xy.argtypes = [vp, dp, dp, dp, dp, dbl, dbl, dbl, dbl, vp]
-    L.adi_cart_zsweep_reduce.argtypes = [vp, dp, dp, dbl, dbl, dbl, dbl, vp]
-    L.adi_cart_zsweep_finish.argtypes = [vp, dp, dp, dbl, dbl, dbl, dbl, vp]
+    L.adi_cart_zsweep_reduce.argtypes = [vp, dp, dp, dp, dbl, dbl, dbl, dbl, vp]
+    L.adi_cart_zsweep_finish.argtypes = [vp, dp, dp, dp, dbl, dbl, dbl, dbl, vp]
     L.adi_voxel_project.argtypes = [vp, dp, dp, dp, C.c_int, C.POINTER(dbl), dbl, C.c_int, dbl, bp, C.c_int, C.c_int,
                                     C.c_int, C.POINTER(vp), vp]
     L.adi_voxel_correct.argtypes = [vp, bp, C.c_int, C.c_int, C.c_int, dbl, C.POINTER(vp), ip, C.POINTER(dbl), C.c_int,

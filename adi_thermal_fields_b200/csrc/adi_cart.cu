@@ -152,7 +152,8 @@ int adi_cart_set_robin_scalar(adi_ctx *ctx, const double face_coeff[6])
 // zmode: 0 whole z lines, 1 z-slab pass 1 (interface relations -> d_iface), 2 z-slab pass 2.
 static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, double theta,
                       double kappa, double Tinf, int first, int last, int zmode, const double *d_Tlo,
-                      const double *d_Thi, double *d_iface, const double *d_ghost, cudaStream_t st)
+                      const double *d_Thi, double *d_iface_dyn, double *d_iface_stat, const double *d_ghost,
+                      cudaStream_t st)
 {
     const size_t ncell = (size_t)ctx->nx * ctx->ny * ctx->nz;
     if (ncell == 0) return ADI_OK;
@@ -169,7 +170,7 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
     a.k.Tinf = Tinf;
     a.k.beta = dt * kappa * (1.0 - theta);
     a.k.invdx2 = 1.0 / (dx * dx);
-    a.zlo = d_Tlo; a.zhi = d_Thi; a.iface = d_iface; a.ghost = d_ghost;
+    a.zlo = d_Tlo; a.zhi = d_Thi; a.iface_dyn = d_iface_dyn; a.iface_stat = d_iface_stat; a.ghost = d_ghost;
     bool expl = a.k.beta != 0.0;
     bool x_in_place = false;
     if (expl && first == 0 && !ctx->opt_fuse) {
@@ -209,7 +210,7 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
         else if (axis == 1) rc = launch_sweep_y(ctx, a, dense, extra, st);
         else rc = launch_sweep_z(ctx, a, dense, extra, zmode, st);
         if (rc) return rc;
-        if (zmode != 1) {
+        if (zmode != 1 && zmode != 3) {
             rc = prof_mark(ctx, axis + 2, st);
             if (rc) return rc;
         }
@@ -234,7 +235,7 @@ int adi_cart_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, 
     cudaStream_t st = (cudaStream_t)stream;
     rc = prof_mark(ctx, 0, st);
     if (rc) return rc;
-    return run_sweeps(ctx, d_Tin, d_Tout, dt, theta, kappa, Tinf, 0, 2, 0, nullptr, nullptr, nullptr, nullptr, st);
+    return run_sweeps(ctx, d_Tin, d_Tout, dt, theta, kappa, Tinf, 0, 2, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st);
 }
 
 // ---- z-slab decomposition ---------------------------------------------------
@@ -301,28 +302,28 @@ int adi_cart_step_xy(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const do
     rc = prof_mark(ctx, 0, st);
     if (rc) return rc;
     return run_sweeps(ctx, d_Tin, d_Tout, dt, theta, kappa, Tinf, 0, 1, 0, ctx->d_mask_lo ? d_Tlo : nullptr,
-                      ctx->d_mask_hi ? d_Thi : nullptr, nullptr, nullptr, st);
+                      ctx->d_mask_hi ? d_Thi : nullptr, nullptr, nullptr, nullptr, st);
 }
 
-int adi_cart_zsweep_reduce(adi_ctx *ctx, double *d_T, double *d_iface, double dt, double theta, double kappa,
-                           double Tinf, void *stream)
+int adi_cart_zsweep_reduce(adi_ctx *ctx, double *d_T, double *d_iface_dyn, double *d_iface_stat, double dt,
+                           double theta, double kappa, double Tinf, void *stream)
 {
     int rc = check_cart(ctx, "adi_cart_zsweep_reduce");
     if (rc) return rc;
-    if (!d_T || !d_iface) {
+    if (!d_T || !d_iface_dyn) {
         set_error("adi_cart_zsweep_reduce: NULL argument");
         return ADI_EINVAL;
     }
-    return run_sweeps(ctx, d_T, d_T, dt, theta, kappa, Tinf, 2, 2, 1, nullptr, nullptr, d_iface, nullptr,
-                      (cudaStream_t)stream);
+    return run_sweeps(ctx, d_T, d_T, dt, theta, kappa, Tinf, 2, 2, d_iface_stat ? 1 : 3, nullptr, nullptr, d_iface_dyn,
+                      d_iface_stat, nullptr, (cudaStream_t)stream);
 }
 
-int adi_cart_zsweep_finish(adi_ctx *ctx, double *d_T, const double *d_iface_all, double dt, double theta,
-                           double kappa, double Tinf, void *stream)
+int adi_cart_zsweep_finish(adi_ctx *ctx, double *d_T, const double *d_dyn_all, const double *d_stat_all, double dt,
+                           double theta, double kappa, double Tinf, void *stream)
 {
     int rc = check_cart(ctx, "adi_cart_zsweep_finish");
     if (rc) return rc;
-    if (!d_T || !d_iface_all) {
+    if (!d_T || !d_dyn_all || !d_stat_all) {
         set_error("adi_cart_zsweep_finish: NULL argument");
         return ADI_EINVAL;
     }
@@ -337,10 +338,10 @@ int adi_cart_zsweep_finish(adi_ctx *ctx, double *d_T, const double *d_iface_all,
     }
     const int threads = 128;
     const int blocks = (int)std::min<size_t>((nlines + threads - 1) / threads, 148 * 32);
-    k_iface_solve<<<blocks, threads, 0, st>>>(d_iface_all, ctx->d_ghost, nlines, ctx->slab_nranks, ctx->slab_rank);
+    k_iface_solve<<<blocks, threads, 0, st>>>(d_dyn_all, d_stat_all, ctx->d_ghost, nlines, ctx->slab_nranks, ctx->slab_rank);
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
-    return run_sweeps(ctx, d_T, d_T, dt, theta, kappa, Tinf, 2, 2, 2, nullptr, nullptr, nullptr, ctx->d_ghost, st);
+    return run_sweeps(ctx, d_T, d_T, dt, theta, kappa, Tinf, 2, 2, 2, nullptr, nullptr, nullptr, nullptr, ctx->d_ghost, st);
 }
 
 int adi_cart_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int nsteps, double dt,

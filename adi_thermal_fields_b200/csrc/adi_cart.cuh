@@ -32,7 +32,8 @@ struct SweepArgs {
     // z-slab decomposition (all NULL / 0 on a single GPU)
     const double *__restrict__ zlo;    // T plane below this slab (nx*ny), explicit stage
     const double *__restrict__ zhi;    // T plane above this slab
-    double *iface;                     // z sweep pass 1 out: [6][nx*ny]
+    double *iface_dyn;                 // z sweep pass 1 out: [2][nx*ny] (yf, yl): right-hand-side part
+    double *iface_stat;                // z sweep pass 1 out: [4][nx*ny] (vf, wf, vl, wl): matrix part (ZMODE 1)
     const double *__restrict__ ghost;  // z sweep pass 2 in:  [2][nx*ny] (L, R per line)
 };
 
@@ -492,7 +493,8 @@ struct TileOps {
 
 // smem: sT[LT][RL] | sC[LT][RL] | (NS 2: sU[LT][RL]) | sCode[LT][RL bytes]
 // ZMODE 0: whole line on this GPU.  1: z-slab pass 1 -- writes the interface relation of each
-// local line segment to a.iface and leaves the field untouched.  2: z-slab pass 2 -- finishes the
+// local line segment to a.iface_dyn / a.iface_stat and leaves the field untouched (3: the
+// right-hand-side part a.iface_dyn only).  2: z-slab pass 2 -- finishes the
 // segment with the ghost values a.ghost.  ZMODE != 0 needs nz % M == 0 (last cell = a separator).
 template <int M, int NS, int CMODE, bool EXTRA, int MAXT, int MINB, int ZMODE = 0>
 __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const int vec)
@@ -604,15 +606,29 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
         if (line < nlines) {
             // x_first = f.Y + f.V*L + f.W*S_0,  x_last = S_{P-1}   (adi_core.h, Iface)
             if (p == 0) {
-                a.iface[line] = fma(f.W, r.D, f.Y);
-                a.iface[nlines + line] = fma(f.W, r.DL, f.V);
-                a.iface[2 * nlines + line] = f.W * r.DR;
+                a.iface_dyn[line] = fma(f.W, r.D, f.Y);
+                a.iface_stat[line] = fma(f.W, r.DL, f.V);
+                a.iface_stat[nlines + line] = f.W * r.DR;
             }
             if (p == P - 1) {
-                a.iface[3 * nlines + line] = r.D;
-                a.iface[4 * nlines + line] = r.DL;
-                a.iface[5 * nlines + line] = r.DR;
+                a.iface_dyn[nlines + line] = r.D;
+                a.iface_stat[2 * nlines + line] = r.DL;
+                a.iface_stat[3 * nlines + line] = r.DR;
             }
+        }
+        return;
+    }
+    if (ZMODE == 3) {
+        // right-hand-side part only (the matrix part is cached by the caller while mask, packs,
+        // dt and theta stay the same): the plain solve with both ghosts at zero
+        double Sl0;
+        double S0;
+        if (warp_lines) S0 = solve_reduced_warp<M, true>(ch, f, p, P, &Sl0, 0.0, 0.0);
+        else S0 = solve_reduced<M, true>(ch, f, red, NTH, tid, 1, p, P, &Sl0, 0.0, 0.0);
+        const size_t line = L0 + ln;
+        if (line < nlines) {
+            if (p == 0) a.iface_dyn[line] = fma(f.W, S0, f.Y);
+            if (p == P - 1) a.iface_dyn[nlines + line] = S0;
         }
         return;
     }
@@ -748,16 +764,18 @@ __global__ void k_pack_zplanes(const T *__restrict__ f, T *__restrict__ lo, T *_
     }
 }
 
-__global__ void k_iface_solve(const double *__restrict__ all, double *__restrict__ ghost, size_t nlines,
-                              int nranks, int rank)
+__global__ void k_iface_solve(const double *__restrict__ dyn, const double *__restrict__ stat,
+                              double *__restrict__ ghost, size_t nlines, int nranks, int rank)
 {
+    // dyn[rank][2][nlines] = (yf, yl), stat[rank][4][nlines] = (vf, wf, vl, wl)
     for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < nlines; l += (size_t)gridDim.x * blockDim.x) {
         double Lg, Rg;
         iface_solve([&](int r) {
-            const double *q = all + (size_t)r * 6 * nlines + l;
+            const double *d = dyn + (size_t)r * 2 * nlines + l;
+            const double *q = stat + (size_t)r * 4 * nlines + l;
             Iface v;
-            v.yf = q[0]; v.vf = q[nlines]; v.wf = q[2 * nlines];
-            v.yl = q[3 * nlines]; v.vl = q[4 * nlines]; v.wl = q[5 * nlines];
+            v.yf = d[0]; v.yl = d[nlines];
+            v.vf = q[0]; v.wf = q[nlines]; v.vl = q[2 * nlines]; v.wl = q[3 * nlines];
             return v;
         }, nranks, rank, &Lg, &Rg);
         ghost[l] = Lg;

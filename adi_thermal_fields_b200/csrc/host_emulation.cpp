@@ -81,7 +81,7 @@ void sweep_line(double *T, const uint8_t *code, const double *coeff, const doubl
         First nx;
         nx.Y = nx.V = nx.W = 0.0;
         if (p + 1 < P) nx = fi[p + 1];
-        else if (zmode == 2) nx = ghost_first();
+        else if (zmode == 2 || zmode == 3) nx = ghost_first();
         red[p] = chunk_reduced_row(ch[p], nx);
         if (zmode == 2) {
             if (p == 0) red[p].D = fma(-red[p].A, Lg, red[p].D);
@@ -98,6 +98,11 @@ void sweep_line(double *T, const uint8_t *code, const double *coeff, const doubl
             nxt[p] = pcr_step(red[p], lo, hi);
         }
         red.swap(nxt);
+    }
+    if (zmode == 3) {  // right-hand-side part of the interface relation only (both ghosts zero)
+        iface->yf = fma(fi[0].W, red[0].D, fi[0].Y);
+        iface->yl = red[P - 1].D;
+        return;
     }
     for (int p = 0; p < P; ++p) {
         chunk_backward<M, EXTRA, NS>(ch[p], ops[p], LO, HI, k.g, p > 0 ? red[p - 1].D : (zmode == 2 ? Lg : 0.0), red[p].D);
@@ -162,14 +167,16 @@ void emu_build_code_halo(const uint8_t *mask, const uint8_t *dirm, uint8_t *code
 
 // z-slab phases with the operand conventions of adi_cart_step_xy / adi_cart_zsweep_reduce /
 // adi_cart_zsweep_finish (adi_b200.h).  phase 0: explicit stage + x + y sweeps, Tin -> Tout;
-// phase 1: interface relations of the z lines of Tout -> iface[6][nx*ny];
-// phase 2: inter-rank solve from iface_all[nranks][6][nx*ny] + local finish of Tout in place.
+// phase 1: interface relations of the z lines of Tout -> iface_dyn[2][nx*ny], iface_stat[4][nx*ny];
+// phase 3: the right-hand-side part iface_dyn only;
+// phase 2: inter-rank solve from dyn_all[nranks][2][nx*ny], stat_all[nranks][4][nx*ny] + local finish in place.
 int emu_cart_slab(const double *Tin, double *Tout, const uint8_t *mask, int nx, int ny, int nz,
                   double dx, double dt, double theta, double kappa, double Tinf,
                   const double *const coeff[3], const uint8_t *const dirm[3],
                   const double *const dirv[3], const double *const q[3], const double *face_coeff,
                   int variant, const uint8_t *mlo, const uint8_t *mhi, const double *Tlo, const double *Thi,
-                  int phase, double *iface, const double *iface_all, int rank, int nranks)
+                  int phase, double *iface_dyn, double *iface_stat, const double *dyn_all, const double *stat_all,
+                  int rank, int nranks)
 {
     const size_t n = (size_t)nx * ny * nz, nlines = (size_t)nx * ny;
     std::vector<uint8_t> code(n ? n : 1);
@@ -227,10 +234,11 @@ int emu_cart_slab(const double *Tin, double *Tout, const uint8_t *mask, int nx, 
                     zmode = phase;
                     if (phase == 2)
                         iface_solve([&](int r) {
-                            const double *qq = iface_all + (size_t)r * 6 * nlines + line;
+                            const double *dd = dyn_all + (size_t)r * 2 * nlines + line;
+                            const double *qq = stat_all + (size_t)r * 4 * nlines + line;
                             Iface w;
-                            w.yf = qq[0]; w.vf = qq[nlines]; w.wf = qq[2 * nlines];
-                            w.yl = qq[3 * nlines]; w.vl = qq[4 * nlines]; w.wl = qq[5 * nlines];
+                            w.yf = dd[0]; w.yl = dd[nlines];
+                            w.vf = qq[0]; w.wf = qq[nlines]; w.vl = qq[2 * nlines]; w.wl = qq[3 * nlines];
                             return w;
                         }, nranks, rank, &Lg, &Rg);
                 }
@@ -240,9 +248,12 @@ int emu_cart_slab(const double *Tin, double *Tout, const uint8_t *mask, int nx, 
                 else
                     sweep_line_any<32, 1>(dense, extra, Tout, code.data(), coeff[axis], q[axis], dirv[axis], base,
                                           stride, len, LO, HI, k, zmode, &f, Lg, Rg);
-                if (axis == 2 && phase == 1) {
-                    iface[line] = f.yf; iface[nlines + line] = f.vf; iface[2 * nlines + line] = f.wf;
-                    iface[3 * nlines + line] = f.yl; iface[4 * nlines + line] = f.vl; iface[5 * nlines + line] = f.wl;
+                if (axis == 2 && (phase == 1 || phase == 3)) {
+                    iface_dyn[line] = f.yf; iface_dyn[nlines + line] = f.yl;
+                    if (phase == 1) {
+                        iface_stat[line] = f.vf; iface_stat[nlines + line] = f.wf;
+                        iface_stat[2 * nlines + line] = f.vl; iface_stat[3 * nlines + line] = f.wl;
+                    }
                 }
             }
     }

@@ -9,8 +9,9 @@ The reference is single-process; this is the multi-GPU form of `adi_step_gpu_coe
     rank per step, the neighbour code one MASK plane per side whenever the mask changes;
   * the z sweep (adi3d_numba_coeff.py:205-237) is a partitioned tridiagonal solve: every rank
     reduces its segment of each line to an interface relation (pass 1), the relations are
-    all-gathered (6 doubles per line and rank), every rank solves the 2R-unknown inter-rank
-    system per line and finishes its segment (pass 2).
+    all-gathered (2 doubles per line and rank per step, plus 4 matrix-only doubles whenever mask,
+    packs, dt or theta change), every rank solves the 2R-unknown inter-rank system per line and
+    finishes its segment (pass 2).
 
 One process per GPU; `torch.distributed` (NCCL over NVLink) is the plumbing for the two
 exchanges, the arithmetic runs in libadi_b200.so.  `LocalComm` runs R virtual ranks as threads of
@@ -220,13 +221,14 @@ class CudaBackend:
         _capi.check(self.L.adi_cart_step(self.ctx, Tin.data_ptr(), Tout.data_ptr(), dt, theta, kappa, Tinf,
                                          self._st()), "adi_cart_step")
 
-    def zsweep_reduce(self, T, iface, dt, theta, kappa, Tinf):
-        _capi.check(self.L.adi_cart_zsweep_reduce(self.ctx, T.data_ptr(), iface.data_ptr(), dt, theta, kappa, Tinf,
+    def zsweep_reduce(self, T, dyn, stat, dt, theta, kappa, Tinf):
+        _capi.check(self.L.adi_cart_zsweep_reduce(self.ctx, T.data_ptr(), dyn.data_ptr(),
+                                                  None if stat is None else stat.data_ptr(), dt, theta, kappa, Tinf,
                                                   self._st()), "adi_cart_zsweep_reduce")
 
-    def zsweep_finish(self, T, iface_all, dt, theta, kappa, Tinf):
-        _capi.check(self.L.adi_cart_zsweep_finish(self.ctx, T.data_ptr(), iface_all.data_ptr(), dt, theta, kappa,
-                                                  Tinf, self._st()), "adi_cart_zsweep_finish")
+    def zsweep_finish(self, T, dyn_all, stat_all, dt, theta, kappa, Tinf):
+        _capi.check(self.L.adi_cart_zsweep_finish(self.ctx, T.data_ptr(), dyn_all.data_ptr(), stat_all.data_ptr(), dt,
+                                                  theta, kappa, Tinf, self._st()), "adi_cart_zsweep_finish")
 
     def launch_count(self):
         return int(self.L.adi_launch_count(self.ctx))
@@ -270,8 +272,11 @@ class SlabGrid3D:
         self.mask_lo, self.mask_hi = be.empty(pl, torch.bool), be.empty(pl, torch.bool)  # received
         self._t_lo, self._t_hi = be.empty(pl, torch.float64), be.empty(pl, torch.float64)
         self.T_lo, self.T_hi = be.empty(pl, torch.float64), be.empty(pl, torch.float64)
-        self.iface = be.empty((6, self.nx * self.ny), torch.float64)
-        self.iface_all = be.empty((self.world, 6, self.nx * self.ny), torch.float64)
+        nl = self.nx * self.ny
+        self.iface_dyn, self.iface_stat = be.empty((2, nl), torch.float64), be.empty((4, nl), torch.float64)
+        self.dyn_all, self.stat_all = be.empty((self.world, 2, nl), torch.float64), be.empty((self.world, 4, nl), torch.float64)
+        self.mask_version = 0
+        self._stat_key = None   # (dt, theta, kappa, packs, mask version) the gathered matrix part belongs to
         be.bind(self.nx, self.ny, self.nz, self.dx, self.mask, self.rank, self.world)
         self.sync_mask()
 
@@ -279,6 +284,7 @@ class SlabGrid3D:
         """Call after the local mask changed (layer births): refreshes the adjacent ranks' view of
         it.  Collective: every rank of the group must call it."""
         be = self.be
+        self.mask_version += 1
         be.mark_mask_changed(self.mask)
         be.pack_planes(self.mask, self._m_lo, self._m_hi)
         self.comm.exchange_planes(self._m_lo, self._m_hi, self.mask_lo, self.mask_hi)
@@ -358,7 +364,15 @@ def adi_step_gpu_coeff(Tn, grid, mat, params, packs, Tinf=0.0, out=None):
         be.pack_planes(T, grid._t_lo, grid._t_hi)
         comm.exchange_planes(grid._t_lo, grid._t_hi, grid.T_lo, grid.T_hi)
     be.step_xy(T, out, grid.T_lo if lo_ok else None, grid.T_hi if hi_ok else None, dt, theta, kappa, float(Tinf))
-    be.zsweep_reduce(out, grid.iface, dt, theta, kappa, float(Tinf))
-    comm.all_gather(grid.iface_all, grid.iface)
-    be.zsweep_finish(out, grid.iface_all, dt, theta, kappa, float(Tinf))
+    # the matrix part of the interface relations (4 of the 6 numbers per line) only changes with
+    # mask, packs, dt or theta: it is computed and gathered once and reused while those stay the same
+    key = (dt, theta, kappa, id(packs), grid.mask_version)
+    fresh = key != grid._stat_key
+    be.zsweep_reduce(out, grid.iface_dyn, grid.iface_stat if fresh else None, dt, theta, kappa, float(Tinf))
+    comm.all_gather(grid.dyn_all, grid.iface_dyn)
+    if fresh:
+        comm.all_gather(grid.stat_all, grid.iface_stat)
+        grid._stat_key = key
+        grid._stat_packs = packs   # keeps id(packs) from being reused by another object
+    be.zsweep_finish(out, grid.dyn_all, grid.stat_all, dt, theta, kappa, float(Tinf))
     return out

@@ -574,7 +574,8 @@ def run_ours_slab(args, rank, world, local):
                     "api": "slab.adi_step_gpu_coeff on pinned host slabs (H2D + step + D2H per rank)"},
             "gpu_launches": int(launches), "parity": None,
             "exchange": {"halo_bytes_per_step_per_boundary": 2 * 8 * nx * ny,
-                         "allgather_bytes_per_rank_per_step": 6 * 8 * nx * ny},
+                         "allgather_bytes_per_rank_per_step": 2 * 8 * nx * ny,
+                         "allgather_bytes_per_rank_on_matrix_change": 4 * 8 * nx * ny},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

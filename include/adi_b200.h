@@ -109,8 +109,9 @@ int adi_cart_exposed_mask(adi_ctx *ctx, int face, uint8_t *d_out, void *stream);
  * tridiagonal system), e.g. with NCCL:
  *     adi_cart_pack_zplanes(T)            -> send lo plane down / hi plane up
  *     adi_cart_step_xy(Tin, Tout, Tlo, Thi)
- *     adi_cart_zsweep_reduce(Tout, iface) -> all-gather iface (6*nx*ny doubles per rank)
- *     adi_cart_zsweep_finish(Tout, iface_all)
+ *     adi_cart_zsweep_reduce(Tout, dyn, stat) -> all-gather dyn (2*nx*ny doubles per rank) and, when the
+ *                                              matrix changed, stat (4*nx*ny)
+ *     adi_cart_zsweep_finish(Tout, dyn_all, stat_all)
  * The local nz must be a multiple of 16 (32 when nz > 512). */
 int adi_cart_set_slab(adi_ctx *ctx, int rank, int nranks);
 /* Mask planes (nx*ny bytes) of the slab below / above; NULL at the domain boundary.  Borrowed.
@@ -124,13 +125,17 @@ int adi_cart_pack_zplanes(adi_ctx *ctx, const void *d_field, int elem_bytes, voi
 int adi_cart_step_xy(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const double *d_Tlo,
                      const double *d_Thi, double dt, double theta, double kappa, double Tinf,
                      void *stream);
-/* z sweep, pass 1: d_iface[6][nx*ny] = (yf,vf,wf,yl,vl,wl) per line; d_T is not modified. */
-int adi_cart_zsweep_reduce(adi_ctx *ctx, double *d_T, double *d_iface, double dt, double theta,
-                           double kappa, double Tinf, void *stream);
-/* z sweep, pass 2: d_iface_all[nranks][6][nx*ny] gathered from all ranks; solves the inter-rank
- * system per line and finishes the local segments in place. */
-int adi_cart_zsweep_finish(adi_ctx *ctx, double *d_T, const double *d_iface_all, double dt,
-                           double theta, double kappa, double Tinf, void *stream);
+/* z sweep, pass 1: the interface relation of every local line segment,
+ *   x_first = yf + vf*L + wf*R,  x_last = yl + vl*L + wl*R   (L, R: the adjacent ranks' boundary values),
+ * as d_iface_dyn[2][nx*ny] = (yf, yl) and d_iface_stat[4][nx*ny] = (vf, wf, vl, wl).  The second
+ * group depends on the matrix only (mask, packs, dt, theta): pass d_iface_stat = NULL to compute the
+ * right-hand-side part alone while those stay the same.  d_T is not modified. */
+int adi_cart_zsweep_reduce(adi_ctx *ctx, double *d_T, double *d_iface_dyn, double *d_iface_stat,
+                           double dt, double theta, double kappa, double Tinf, void *stream);
+/* z sweep, pass 2: d_dyn_all[nranks][2][nx*ny] and d_stat_all[nranks][4][nx*ny] gathered from all
+ * ranks; solves the inter-rank system per line and finishes the local segments in place. */
+int adi_cart_zsweep_finish(adi_ctx *ctx, double *d_T, const double *d_dyn_all, const double *d_stat_all,
+                           double dt, double theta, double kappa, double Tinf, void *stream);
 /* Tuning / introspection: kernel variant selection (0 = default) and launch counter. */
 int adi_set_option(adi_ctx *ctx, const char *name, long value);
 long adi_launch_count(adi_ctx *ctx);

@@ -77,7 +77,7 @@ class HostBackend:
     def set_packs(self, packs, face_coeff):
         self.packs, self.fc = packs, face_coeff
 
-    def _call(self, Tin, Tout, Tlo, Thi, phase, iface, iface_all, dt, theta, kappa, Tinf):
+    def _call(self, Tin, Tout, Tlo, Thi, phase, dyn, stat, dyn_all, stat_all, dt, theta, kappa, Tinf):
         dp, bp = C.POINTER(C.c_double), C.POINTER(C.c_uint8)
 
         def p(t, ty):
@@ -89,24 +89,24 @@ class HostBackend:
         fc = None if self.fc is None else torch.tensor(self.fc, dtype=torch.float64)
         self.L.emu_cart_slab.argtypes = [dp, dp, bp, C.c_int, C.c_int, C.c_int] + [C.c_double] * 5 + \
             [C.POINTER(dp), C.POINTER(bp), C.POINTER(dp), C.POINTER(dp), dp, C.c_int, bp, bp, dp, dp, C.c_int,
-             dp, dp, C.c_int, C.c_int]
+             dp, dp, dp, dp, C.c_int, C.c_int]
         rc = self.L.emu_cart_slab(p(Tin, C.c_double), p(Tout, C.c_double), p(self.mask, C.c_uint8), self.nx, self.ny,
                                   self.nz, self.dx, dt, theta, kappa, Tinf, arr3(0, C.c_double), arr3(1, C.c_uint8),
                                   arr3(2, C.c_double), arr3(3, C.c_double), p(fc, C.c_double), self.variant,
                                   p(self.mlo, C.c_uint8), p(self.mhi, C.c_uint8), p(Tlo, C.c_double),
-                                  p(Thi, C.c_double), phase, p(iface, C.c_double), p(iface_all, C.c_double),
-                                  self.rank, self.world)
+                                  p(Thi, C.c_double), phase, p(dyn, C.c_double), p(stat, C.c_double),
+                                  p(dyn_all, C.c_double), p(stat_all, C.c_double), self.rank, self.world)
         assert rc == 0, rc
         self.launches += 1
 
     def step_xy(self, Tin, Tout, Tlo, Thi, dt, theta, kappa, Tinf):
-        self._call(Tin, Tout, Tlo, Thi, 0, None, None, dt, theta, kappa, Tinf)
+        self._call(Tin, Tout, Tlo, Thi, 0, None, None, None, None, dt, theta, kappa, Tinf)
 
-    def zsweep_reduce(self, T, iface, dt, theta, kappa, Tinf):
-        self._call(T, T, None, None, 1, iface, None, dt, theta, kappa, Tinf)
+    def zsweep_reduce(self, T, dyn, stat, dt, theta, kappa, Tinf):
+        self._call(T, T, None, None, 1 if stat is not None else 3, dyn, stat, None, None, dt, theta, kappa, Tinf)
 
-    def zsweep_finish(self, T, iface_all, dt, theta, kappa, Tinf):
-        self._call(T, T, None, None, 2, None, iface_all, dt, theta, kappa, Tinf)
+    def zsweep_finish(self, T, dyn_all, stat_all, dt, theta, kappa, Tinf):
+        self._call(T, T, None, None, 2, None, None, dyn_all, stat_all, dt, theta, kappa, Tinf)
 
     def launch_count(self):
         return self.launches

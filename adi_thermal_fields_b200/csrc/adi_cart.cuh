@@ -12,6 +12,7 @@
 //                      register-resident chunk solve runs with lanes along the line
 // K7 k_build_packs     precompute_coeff_packs_unified on the device
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <type_traits>
@@ -451,6 +452,151 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
             if (e < nv && ch.active(e)) op[e * sl] = ch.T[e];
     } else {
         // out of place: void cells take the input bits (adi3d_gpu_coeff.py:229)
+#pragma unroll
+        for (int e = 0; e < M; ++e)
+            if (e < nv) op[e * sl] = ch.active(e) ? ch.T[e] : tp[e * sl];
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K1c: strided sweeps of LONG lines (1025..4096 cells) on a thread-block CLUSTER.
+// A line of up to CS*1024 cells is shared by the CS CTAs of a cluster (cluster dims (1,1,CS),
+// blockIdx.z = rank in the cluster): CTA c owns chunks [c*P, (c+1)*P) of every line of the tile and
+// keeps them in registers exactly like K1 (M = 16, two factors per cell in its own shared memory).
+// The reduced system over all CS*P separators is solved by the same PCR; rows held by another CTA
+// are read from ITS shared memory through distributed shared memory (cluster.map_shared_rank), and
+// the per-level barrier is the cluster barrier.  blockDim = (KT, P) with KT*P <= 512, one CTA per SM,
+// 2 (lines <= 2048 cells) or 4 CTAs per line.
+// ------------------------------------------------------------------------------------
+template <int M>
+__device__ __forceinline__ double solve_reduced_cluster(const Chunk<M> &ch, const First &f, double *red, int NTH,
+                                                        int KT, int kk, int p, int P, int c, int CS, double *Sl)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const int ridx = p * KT + kk;
+    const int pg = c * P + p, PT = CS * P;
+    // slot of global chunk q in the exchange buffer `b` of the CTA that owns it
+    auto at = [&](double *b, int q) -> const double * {
+        const int owner = q / P;
+        const double *base = owner == c ? b : cl.map_shared_rank(b, owner);
+        return base + (q - owner * P) * KT + kk;
+    };
+    red[ridx] = f.Y;
+    red[NTH + ridx] = f.V;
+    red[2 * NTH + ridx] = f.W;
+    cl.sync();
+    First nx;
+    nx.Y = 0.0; nx.V = 0.0; nx.W = 0.0;
+    if (pg + 1 < PT) {
+        const double *q = at(red, pg + 1);
+        nx.Y = q[0]; nx.V = q[NTH]; nx.W = q[2 * NTH];
+    }
+    Red r = chunk_reduced_row(ch, nx);
+    int cur = 1;
+    for (int s = 1; s < PT; s <<= 1) {
+        double *b = red + cur * 3 * NTH;
+        b[ridx] = r.A;
+        b[NTH + ridx] = r.C;
+        b[2 * NTH + ridx] = r.D;
+        cl.sync();
+        Red lo, hi;
+        lo.A = lo.C = lo.D = 0.0;
+        hi.A = hi.C = hi.D = 0.0;
+        if (pg - s >= 0) {
+            const double *q = at(b, pg - s);
+            lo.A = q[0]; lo.C = q[NTH]; lo.D = q[2 * NTH];
+        }
+        if (pg + s < PT) {
+            const double *q = at(b, pg + s);
+            hi.A = q[0]; hi.C = q[NTH]; hi.D = q[2 * NTH];
+        }
+        r = pcr_step(r, lo, hi);
+        cur ^= 1;
+    }
+    double *b = red + cur * 3 * NTH;
+    b[ridx] = r.D;
+    cl.sync();
+    *Sl = (pg > 0) ? *at(b, pg - 1) : 0.0;
+    cl.sync();  // no CTA leaves (or reuses the buffer) while a peer may still read its shared memory
+    return r.D;
+}
+
+template <int AXIS, int CMODE, bool EXTRA, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided_cl(const SweepArgs a)
+{
+    constexpr int M = 16, NS = 2;
+    extern __shared__ double smem[];
+    const int KT = blockDim.x, P = blockDim.y;
+    const int kk = threadIdx.x, p = threadIdx.y;
+    const int c = blockIdx.z, CS = gridDim.z;
+    const int NTH = KT * P;
+    const int tid = p * KT + kk;
+    const int k = blockIdx.x * KT + kk;
+    const int n = (AXIS == 0) ? a.nx : a.ny;
+    const unsigned sl = (AXIS == 0) ? (unsigned)a.ny * (unsigned)a.nz : (unsigned)a.nz;
+    constexpr unsigned LO = (AXIS == 0) ? CB_XM : CB_YM;
+    constexpr unsigned HI = (AXIS == 0) ? CB_XP : CB_YP;
+    const int t0 = (c * P + p) * M;
+    const int nv = (k < a.nz) ? min(max(n - t0, 0), M) : 0;
+    const size_t idx0 = ((AXIS == 0) ? (size_t)blockIdx.y * a.nz : (size_t)blockIdx.y * a.ny * a.nz) +
+                        (size_t)min(k, a.nz - 1) + (size_t)min(t0, n - 1) * sl;
+    double *col = smem + tid;
+    double *red = smem + (size_t)NS * M * NTH;
+    const double *tp = a.in + idx0;
+
+    Chunk<M> ch;
+    {
+        const int nvm1 = max(nv - 1, 0);
+        const unsigned sl8 = sl * 8u;
+        const char *tb = reinterpret_cast<const char *>(tp);
+        const uint8_t *cb = a.code + idx0;
+#pragma unroll
+        for (int e = 0; e < M; ++e) {
+            const unsigned cv = ldg_u8(cb + (size_t)((unsigned)min(e, nvm1) * sl));
+            ch.set_code(e, e < nv ? cv : 0u);
+        }
+#pragma unroll
+        for (int e = 0; e < M; ++e) ch.T[e] = ldg_f64(tb + (size_t)((unsigned)min(e, nvm1) * sl8));
+        if (CMODE == 2) {
+            const unsigned scol = smem_u32(col);
+            const unsigned nth8 = (unsigned)NTH * 8u;
+            const char *cf = reinterpret_cast<const char *>(a.coeff + idx0);
+#pragma unroll
+            for (int e = 0; e < M; ++e) cp_async8(scol + e * nth8, cf + (size_t)((unsigned)min(e, nvm1) * sl8));
+        }
+        __syncthreads();
+        cp_async_wait_all();
+    }
+    const bool solid = __all_sync(0xffffffffu, nv == M && chunk_solid<M>(ch, LO, HI));
+    if (!solid) {
+#pragma unroll
+        for (int e = 0; e < M; ++e) ch.T[e] = ch.active(e) ? ch.T[e] : 0.0;  // load rule (adi_core.h)
+    }
+    StridedOps<M, true> ops;
+    ops.coeff = (CMODE == 2) ? a.coeff + idx0 : nullptr;
+    ops.qp = (EXTRA && a.q) ? a.q + idx0 : nullptr;
+    ops.dvp = (EXTRA && a.dirv) ? a.dirv + idx0 : nullptr;
+    ops.sl = sl;
+    ops.nv = nv;
+    ops.col = col;
+    ops.NTH = NTH;
+    First f;
+    if (solid) f = chunk_forward<M, CMODE, EXTRA, NS, true>(ch, ops, LO, HI, a.k);
+    else f = chunk_forward<M, CMODE, EXTRA, NS, false>(ch, ops, LO, HI, a.k);
+    double Sl;
+    const double S = solve_reduced_cluster<M>(ch, f, red, NTH, KT, kk, p, P, c, CS, &Sl);
+    chunk_backward<M, EXTRA, NS>(ch, ops, LO, HI, a.k.g, Sl, S);
+
+    double *op = a.out + idx0;
+    if (solid) {
+#pragma unroll
+        for (int e = 0; e < M; ++e) op[e * sl] = ch.T[e];
+    } else if (a.in == a.out) {
+#pragma unroll
+        for (int e = 0; e < M; ++e)
+            if (e < nv && ch.active(e)) op[e * sl] = ch.T[e];
+    } else {
 #pragma unroll
         for (int e = 0; e < M; ++e)
             if (e < nv) op[e * sl] = ch.active(e) ? ch.T[e] : tp[e * sl];

@@ -463,65 +463,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
 // A line of up to CS*1024 cells is shared by the CS CTAs of a cluster (cluster dims (1,1,CS),
 // blockIdx.z = rank in the cluster): CTA c owns chunks [c*P, (c+1)*P) of every line of the tile and
 // keeps them in registers exactly like K1 (M = 16, two factors per cell in its own shared memory).
-// The reduced system over all CS*P separators is solved by the same PCR; rows held by another CTA
-// are read from ITS shared memory through distributed shared memory (cluster.map_shared_rank), and
-// the per-level barrier is the cluster barrier.  blockDim = (KT, P) with KT*P <= 512, one CTA per SM,
-// 2 (lines <= 2048 cells) or 4 CTAs per line.
+// The separators are solved in two levels (see the kernel body): PCR inside each CTA, then one exchange of
+// the CTAs' interface relations through distributed shared memory (cluster.map_shared_rank) -- two
+// cluster barriers per tile in all.  blockDim = (KT, P) with KT*P <= 512, one CTA per SM, 2 (lines <= 2048
+// cells) or 4 CTAs per line.
 // ------------------------------------------------------------------------------------
-template <int M>
-__device__ __forceinline__ double solve_reduced_cluster(const Chunk<M> &ch, const First &f, double *red, int NTH,
-                                                        int KT, int kk, int p, int P, int c, int CS, double *Sl)
-{
-    namespace cg = cooperative_groups;
-    cg::cluster_group cl = cg::this_cluster();
-    const int ridx = p * KT + kk;
-    const int pg = c * P + p, PT = CS * P;
-    // slot of global chunk q in the exchange buffer `b` of the CTA that owns it
-    auto at = [&](double *b, int q) -> const double * {
-        const int owner = q / P;
-        const double *base = owner == c ? b : cl.map_shared_rank(b, owner);
-        return base + (q - owner * P) * KT + kk;
-    };
-    red[ridx] = f.Y;
-    red[NTH + ridx] = f.V;
-    red[2 * NTH + ridx] = f.W;
-    cl.sync();
-    First nx;
-    nx.Y = 0.0; nx.V = 0.0; nx.W = 0.0;
-    if (pg + 1 < PT) {
-        const double *q = at(red, pg + 1);
-        nx.Y = q[0]; nx.V = q[NTH]; nx.W = q[2 * NTH];
-    }
-    Red r = chunk_reduced_row(ch, nx);
-    int cur = 1;
-    for (int s = 1; s < PT; s <<= 1) {
-        double *b = red + cur * 3 * NTH;
-        b[ridx] = r.A;
-        b[NTH + ridx] = r.C;
-        b[2 * NTH + ridx] = r.D;
-        cl.sync();
-        Red lo, hi;
-        lo.A = lo.C = lo.D = 0.0;
-        hi.A = hi.C = hi.D = 0.0;
-        if (pg - s >= 0) {
-            const double *q = at(b, pg - s);
-            lo.A = q[0]; lo.C = q[NTH]; lo.D = q[2 * NTH];
-        }
-        if (pg + s < PT) {
-            const double *q = at(b, pg + s);
-            hi.A = q[0]; hi.C = q[NTH]; hi.D = q[2 * NTH];
-        }
-        r = pcr_step(r, lo, hi);
-        cur ^= 1;
-    }
-    double *b = red + cur * 3 * NTH;
-    b[ridx] = r.D;
-    cl.sync();
-    *Sl = (pg > 0) ? *at(b, pg - 1) : 0.0;
-    cl.sync();  // no CTA leaves (or reuses the buffer) while a peer may still read its shared memory
-    return r.D;
-}
-
 template <int AXIS, int CMODE, bool EXTRA, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided_cl(const SweepArgs a)
 {
@@ -584,8 +530,44 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided_cl(const SweepArgs
     First f;
     if (solid) f = chunk_forward<M, CMODE, EXTRA, NS, true>(ch, ops, LO, HI, a.k);
     else f = chunk_forward<M, CMODE, EXTRA, NS, false>(ch, ops, LO, HI, a.k);
-    double Sl;
-    const double S = solve_reduced_cluster<M>(ch, f, red, NTH, KT, kk, p, P, c, CS, &Sl);
+    // Two-level solve: (1) inside the CTA, PCR with three right-hand-side columns gives every separator as
+    // an affine function of the CTA's two ghost values (the last cell of the CTA before, the first cell of
+    // the CTA after) -- CTA barriers only; (2) the CS interface relations of a line meet through
+    // distributed shared memory (ONE cluster barrier), each CTA solves the tiny inter-CTA system for its
+    // own ghosts and finishes.  The same scheme links the GPUs of the z-slab decomposition.
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const Red3 r3 = solve_reduced3<M>(ch, f, red, NTH, tid, KT, p, P);
+    double *sI = red + (size_t)10 * NTH;   // [6][KT] interface relation of this CTA's segment, per lane
+    double *sG = sI + 6 * KT;              // [2][KT] ghosts
+    if (p == 0) {
+        sI[kk] = fma(f.W, r3.D, f.Y);
+        sI[KT + kk] = fma(f.W, r3.DL, f.V);
+        sI[2 * KT + kk] = f.W * r3.DR;
+    }
+    if (p == P - 1) {
+        sI[3 * KT + kk] = r3.D;
+        sI[4 * KT + kk] = r3.DL;
+        sI[5 * KT + kk] = r3.DR;
+    }
+    cl.sync();
+    if (p == 0) {
+        double Lg, Rg;
+        iface_solve([&](int rr) {
+            const double *q = (rr == c ? sI : cl.map_shared_rank(sI, rr)) + kk;
+            Iface v;
+            v.yf = q[0]; v.vf = q[KT]; v.wf = q[2 * KT]; v.yl = q[3 * KT]; v.vl = q[4 * KT]; v.wl = q[5 * KT];
+            return v;
+        }, CS, c, &Lg, &Rg);
+        sG[kk] = Lg;
+        sG[KT + kk] = Rg;
+    }
+    cl.sync();  // the peers have read this CTA's relation; the ghosts are visible to the whole CTA
+    const double Lg = sG[kk], Rg = sG[KT + kk];
+    const double S = fma(r3.DR, Rg, fma(r3.DL, Lg, r3.D));
+    red[tid] = S;
+    __syncthreads();
+    const double Sl = p > 0 ? red[tid - KT] : Lg;
     chunk_backward<M, EXTRA, NS>(ch, ops, LO, HI, a.k.g, Sl, S);
 
     double *op = a.out + idx0;

@@ -19,7 +19,7 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
         int KT = 8;
         while (KT > 1 && KT * P > 512) KT >>= 1;
         dim3 block(KT, P), grid((a.nz + KT - 1) / KT, other, CS);
-        const size_t smem = (size_t)(2 * M + 6) * KT * P * sizeof(double);
+        const size_t smem = ((size_t)(2 * M + 10) * KT * P + 8 * KT) * sizeof(double);
         if ((unsigned long long)M * (AXIS == 0 ? (unsigned long long)a.ny * a.nz : (unsigned long long)a.nz) >= (1ull << 32)) {
             set_error("adi_cart_step: grid too large for 32-bit in-chunk offsets");
             return ADI_EINVAL;

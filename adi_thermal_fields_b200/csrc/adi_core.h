@@ -324,28 +324,39 @@ struct Iface {
 template <class GET>
 ADI_HD void iface_solve(GET get, int nranks, int rank, double *Lout, double *Rout)
 {
-    // forward: l_r = al + be*f_{r+1},  f_r = ga + de*f_{r+1}
-    double al[16], be[16], ga[16], de[16];
-    double alp = 0.0, bep = 0.0;   // l_{-1} = 0
-    for (int r = 0; r < nranks; ++r) {
+    // Unknowns per rank r: f_r = x_first, l_r = x_last, with
+    //   f_r = yf + vf*l_{r-1} + wf*f_{r+1},   l_r = yl + vl*l_{r-1} + wl*f_{r+1}.
+    // From the left, ranks 0..rank-1 give  l_{rank-1} = al + be*f_rank;  from the right, ranks
+    // nranks-1..rank+1 give  f_{rank+1} = ga + de*l_rank;  a 2x2 system closes at `rank`.
+    // No arrays: one pass from each side (this runs per line inside the sweep kernels).
+    double al = 0.0, be = 0.0;
+    for (int r = 0; r < rank; ++r) {
         const Iface q = get(r);
-        const double den = 1.0 - q.vf * bep;
-        ga[r] = (q.yf + q.vf * alp) / den;
-        de[r] = q.wf / den;
-        al[r] = q.yl + q.vl * (alp + bep * ga[r]);
-        be[r] = q.wl + q.vl * bep * de[r];
-        alp = al[r]; bep = be[r];
+        const double rd = frcp(1.0 - q.vf * be);
+        const double g = (q.yf + q.vf * al) * rd;      // f_r = g + d*f_{r+1}
+        const double d = q.wf * rd;
+        const double al2 = q.yl + q.vl * (al + be * g);
+        be = q.wl + q.vl * be * d;
+        al = al2;
     }
-    // backward
-    double fnext = 0.0, Lv = 0.0, Rv = 0.0;
-    for (int r = nranks - 1; r >= 0; --r) {
-        const double f = ga[r] + de[r] * fnext;
-        const double l = al[r] + be[r] * fnext;
-        if (r == rank + 1) Rv = f;
-        if (r == rank - 1) Lv = l;
-        fnext = f;
+    double ga = 0.0, de = 0.0;
+    for (int r = nranks - 1; r > rank; --r) {
+        const Iface q = get(r);
+        const double rd = frcp(1.0 - q.wl * de);
+        const double lc = (q.yl + q.wl * ga) * rd;     // l_r = lc + lv*l_{r-1}
+        const double lv = q.vl * rd;
+        const double ga2 = q.yf + q.wf * (ga + de * lc);
+        de = q.vf + q.wf * de * lv;
+        ga = ga2;
     }
-    *Lout = Lv; *Rout = Rv;
+    const Iface q = get(rank);
+    const double a11 = 1.0 - q.vf * be, a12 = -q.wf * de, b1 = q.yf + q.vf * al + q.wf * ga;
+    const double a21 = -q.vl * be, a22 = 1.0 - q.wl * de, b2 = q.yl + q.vl * al + q.wl * ga;
+    const double rdet = frcp(a11 * a22 - a12 * a21);
+    const double fr = (b1 * a22 - a12 * b2) * rdet;
+    const double lr = (a11 * b2 - a21 * b1) * rdet;
+    *Lout = al + be * fr;
+    *Rout = ga + de * lr;
 }
 
 // Phase 3: Sl = S_{p-1} (0 for the first chunk), S = S_p.  Leaves the solution in ch.T

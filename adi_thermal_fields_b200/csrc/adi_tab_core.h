@@ -52,6 +52,8 @@ struct TabGeom {
     int o_b;      // cell table, backward pass: {u, v} pairs, 2*nvar*M doubles
     int o_t0, o_t1, o_t2;                 // reduced right-hand side assembly, P each
     int o_lvl;                            // levels * 3 * P: [level][r|a|c][p]
+    int o_dl, o_dr;                       // z-slab segments: response of separator p to the ghost values, P each
+    int o_misc;                           // [0] W of chunk 0, [1] V of chunk 0 (first-cell relation), 2 doubles
     int ndbl;                             // doubles per blob
     // int blob: cbase[P] (offset of the chunk's cell tables), end[P] (index of the
     // separator along the line), len[P]
@@ -98,6 +100,9 @@ inline TabGeom tab_geom_nvar(int n, int M, bool cyclic, int nvar)
     g.o_t1 = o; o += g.P;
     g.o_t2 = o; o += g.P;
     g.o_lvl = o; o += g.levels * 3 * g.P;
+    g.o_dl = o; o += g.P;
+    g.o_dr = o; o += g.P;
+    g.o_misc = o; o += 2;
     g.ndbl = (o + 1) & ~1;   // even, so that consecutive blobs stay 16-byte aligned
     return g;
 }
@@ -117,8 +122,13 @@ inline void tab_partition(const TabGeom &g, bool uniform, int *cbase, int *end, 
 
 // Host: fill one blob from the line's rows  a[i]*x[i-1] + b[i]*x[i] + c[i]*x[i+1] = d[i].
 // Non-cyclic: a[0] and c[n-1] are ignored.  Cyclic: a[0] couples to x[n-1], c[n-1] to x[0].
+// ghost_lo / ghost_hi (non-cyclic lines only): the line is a SEGMENT of a longer line (z-slab
+// decomposition); a[0] then couples to the ghost value L before the segment and c[n-1] to the ghost R
+// after it.  The tables solve for L = R = 0 and o_dl / o_dr hold the separators' response to the ghosts:
+// S_p = D_p + dl_p*L + dr_p*R.
 inline void tab_build(const TabGeom &g, const int *cbase, const int *end, const int *len,
-                      const double *a, const double *b, const double *c, double *blob)
+                      const double *a, const double *b, const double *c, double *blob,
+                      bool ghost_lo = false, bool ghost_hi = false)
 {
     const int M = g.M, P = g.P, n = g.n;
     for (int i = 0; i < g.ndbl; ++i) blob[i] = 0.0;
@@ -129,7 +139,7 @@ inline void tab_build(const TabGeom &g, const int *cbase, const int *end, const 
         double cp_prev = 0.0, vprev = 1.0, alpha = 1.0, Vsum = 0.0, ulast = 0.0;
         for (int e = e0; e < M - 1; ++e) {
             const int i = end[p] - (M - 1 - e);
-            const double ai = (!g.cyclic && i == 0) ? 0.0 : a[i];
+            const double ai = (!g.cyclic && i == 0 && !ghost_lo) ? 0.0 : a[i];
             const double den = b[i] - ai * cp_prev;
             const double cpe = c[i] / den;
             const double la = -ai / den;
@@ -154,16 +164,26 @@ inline void tab_build(const TabGeom &g, const int *cbase, const int *end, const 
     for (int p = 0; p < P; ++p) {
         const int i = end[p];
         const bool has_next = g.cyclic || p + 1 < P;
+        const bool to_ghost = !has_next && ghost_hi;      // the cell after the last separator is the ghost R
         const int nx = (p + 1) % P;
-        const double aS = (!g.cyclic && i == 0) ? 0.0 : a[i];
-        const double cS = (has_next && (g.cyclic || i < n - 1)) ? c[i] : 0.0;
-        const double B = b[i] + aS * Wl[p] + cS * V[nx];
+        const double aS = (!g.cyclic && i == 0 && !ghost_lo) ? 0.0 : a[i];
+        const double cS = ((has_next && (g.cyclic || i < n - 1)) || to_ghost) ? c[i] : 0.0;
+        const double Vn = to_ghost ? 0.0 : V[nx], Wn = to_ghost ? 1.0 : W[nx];
+        const double B = b[i] + aS * Wl[p] + cS * Vn;
         A[p] = aS * Vl[p] / B;
-        C[p] = cS * W[nx] / B;
+        C[p] = cS * Wn / B;
         blob[g.o_t0 + p] = 1.0 / B;
         blob[g.o_t1 + p] = -aS / B;
-        blob[g.o_t2 + p] = -cS / B;
+        blob[g.o_t2 + p] = to_ghost ? 0.0 : -cS / B;   // the ghost cell contributes no right-hand side of its own
     }
+    // ghost couplings move to right-hand-side columns (the PCR below treats rows beyond the ends as zero)
+    std::vector<double> DL(P, 0.0), DR(P, 0.0), DLn(P), DRn(P);
+    if (!g.cyclic) {
+        DL[0] = -A[0]; A[0] = 0.0;
+        DR[P - 1] = -C[P - 1]; C[P - 1] = 0.0;
+    }
+    blob[g.o_misc] = W[0];
+    blob[g.o_misc + 1] = V[0];
     for (int l = 0; l < g.levels; ++l) {
         const int s = 1 << l;
         double *R = blob + g.o_lvl + (size_t)l * 3 * P;
@@ -191,8 +211,18 @@ inline void tab_build(const TabGeom &g, const int *cbase, const int *end, const 
             }
             R[p] = r; R[P + p] = ca; R[2 * P + p] = cc;
             An[p] = an; Cn[p] = cn;
+            if (!g.cyclic) {
+                const int lo = p - s >= 0 ? p - s : 0, hi = p + s < P ? p + s : P - 1;   // coefficients are 0 where clamped
+                DLn[p] = r * DL[p] + ca * DL[lo] + cc * DL[hi];
+                DRn[p] = r * DR[p] + ca * DR[lo] + cc * DR[hi];
+            }
         }
         A.swap(An); C.swap(Cn);
+        if (!g.cyclic) { DL.swap(DLn); DR.swap(DRn); }
+    }
+    for (int p = 0; p < P; ++p) {
+        blob[g.o_dl + p] = g.cyclic ? 0.0 : DL[p];
+        blob[g.o_dr + p] = g.cyclic ? 0.0 : DR[p];
     }
 }
 
@@ -230,7 +260,8 @@ struct TabSet {
     std::vector<int> geom;  // cbase[P], end[P], len[P]
 };
 
-inline TabSet tab_make(int n, int M, bool cyclic, const double *a, const double *b, const double *c)
+inline TabSet tab_make(int n, int M, bool cyclic, const double *a, const double *b, const double *c,
+                       bool ghost_lo = false, bool ghost_hi = false)
 {
     TabSet full;
     full.g = tab_geom(n, M, cyclic, false);
@@ -239,7 +270,7 @@ inline TabSet tab_make(int n, int M, bool cyclic, const double *a, const double 
     full.blob.resize(full.g.ndbl);
     int *cb = full.geom.data(), *en = cb + P, *ln = cb + 2 * P;
     tab_partition(full.g, false, cb, en, ln);
-    tab_build(full.g, cb, en, ln, a, b, c, full.blob.data());
+    tab_build(full.g, cb, en, ln, a, b, c, full.blob.data(), ghost_lo, ghost_hi);
     // per chunk: 2M + 2M + M table doubles
     auto same_chunk = [&](int p, int q) {
         for (int e = 0; e < 2 * M; ++e)
@@ -271,6 +302,7 @@ inline TabSet tab_make(int n, int M, bool cyclic, const double *a, const double 
     for (int p = 0; p < P; ++p) out.geom[p] = var[p] * M;
     for (int i = 0; i < 3 * P; ++i) out.blob[out.g.o_t0 + i] = full.blob[full.g.o_t0 + i];
     for (int i = 0; i < out.g.levels * 3 * P; ++i) out.blob[out.g.o_lvl + i] = full.blob[full.g.o_lvl + i];
+    for (int i = 0; i < 2 * P + 2; ++i) out.blob[out.g.o_dl + i] = full.blob[full.g.o_dl + i];   // dl | dr | misc
     return out;
 }
 
@@ -394,6 +426,24 @@ inline int cyl_rows_z(int nz, double dz, double alpha, double k, double dt, int 
         a[N] = -fac; b[N] = 1.0 + fac * (1.0 + beta * dz); c[N] = 0.0;
         top->val = (1.0 * alpha * dt) * (beta / dz) * Tinf_top;
     } else return -1;
+    return 0;
+}
+
+// Rows of the z sweep for the segment [z0, z0 + nz_loc) of a line of nz_glob cells: the boundary rows of
+// build_coeff_z only on the segments that hold the global first / last cell, interior rows elsewhere
+// (their end couplings then reach the adjacent segment's cell -- tab_build's ghosts).
+inline int cyl_rows_z_segment(int nz_loc, bool first, bool last, double dz, double alpha, double k, double dt,
+                              int kind_bot, int kind_top, double h_bot, double h_top, double Tinf_bot, double Tinf_top,
+                              double T_bot, double T_top, double *a, double *b, double *c, ZEnd *bot, ZEnd *top)
+{
+    const int rc = cyl_rows_z(nz_loc, dz, alpha, k, dt, kind_bot, kind_top, h_bot, h_top, Tinf_bot, Tinf_top, T_bot,
+                              T_top, a, b, c, bot, top);
+    if (rc) return rc;
+    const double fac = 1.0 * alpha * dt / (dz * dz);
+    // order matters for a one-cell segment: the reference writes the bottom row first, then the top row
+    if (!first) { a[0] = -fac; b[0] = 1.0 + 2.0 * fac; c[0] = -fac; bot->set = 0; bot->val = 0.0; }
+    if (!last) { a[nz_loc - 1] = -fac; b[nz_loc - 1] = 1.0 + 2.0 * fac; c[nz_loc - 1] = -fac; top->set = 0; top->val = 0.0; }
+    if (!first && last && nz_loc == 1) { /* top row written by cyl_rows_z stays, with its a = -fac */ }
     return 0;
 }
 

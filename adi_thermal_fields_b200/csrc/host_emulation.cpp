@@ -331,9 +331,12 @@ int emu_cart_step(const double *Tin, double *Tout, const uint8_t *mask, int nx, 
 
 namespace {
 
+// zm 0: whole line.  zm 1: z-slab pass 1 -- y[0] = yf, y[1] = yl of the segment, nothing stored.
+// zm 2: z-slab pass 2 with the ghost values Lg, Rg.
 template <int M>
 void tab_line(double *T, size_t base, size_t stride, const TabGeom &g, const int *geom, const double *blob,
-              int set_first, double val_first, int set_last, double val_last)
+              int set_first, double val_first, int set_last, double val_last, int zm = 0, double *y = nullptr,
+              double Lg = 0.0, double Rg = 0.0)
 {
     const int P = g.P;
     const int *cbase = geom, *end = geom + P, *len = geom + 2 * P;
@@ -363,9 +366,16 @@ void tab_line(double *T, size_t base, size_t stride, const TabGeom &g, const int
                               D[tab_hi(p, s, P, g.cyclic)]);
         D.swap(Dn);
     }
+    if (zm == 1) {
+        y[0] = fma(blob[g.o_misc], D[0], Y[0]);     // x_first = Y_0 + W_0*S_0 (+ ghost terms)
+        y[1] = D[P - 1];
+        return;
+    }
+    if (zm == 2)
+        for (int p = 0; p < P; ++p) D[p] = fma(blob[g.o_dr + p], Rg, fma(blob[g.o_dl + p], Lg, D[p]));
     for (int p = 0; p < P; ++p) {
         double (&dd)[M] = *reinterpret_cast<double (*)[M]>(&d[(size_t)p * M]);
-        tab_backward<M>(dd, blob + g.o_b + 2 * cbase[p], D[tab_lo(p, 1, P, g.cyclic)], D[p]);
+        tab_backward<M>(dd, blob + g.o_b + 2 * cbase[p], (zm == 2 && p == 0) ? Lg : D[tab_lo(p, 1, P, g.cyclic)], D[p]);
         for (int e = 0; e < M; ++e) {
             const int i = end[p] - (M - 1 - e);
             if (e >= M - len[p]) T[base + (size_t)i * stride] = dd[e];
@@ -374,12 +384,13 @@ void tab_line(double *T, size_t base, size_t stride, const TabGeom &g, const int
 }
 
 void tab_line_any(int M, double *T, size_t base, size_t stride, const TabGeom &g, const int *geom,
-                  const double *blob, int sf, double vf, int sl, double vl)
+                  const double *blob, int sf, double vf, int sl, double vl, int zm = 0, double *y = nullptr,
+                  double Lg = 0.0, double Rg = 0.0)
 {
-    if (M == 16) tab_line<16>(T, base, stride, g, geom, blob, sf, vf, sl, vl);
-    else if (M == 8) tab_line<8>(T, base, stride, g, geom, blob, sf, vf, sl, vl);
-    else if (M == 4) tab_line<4>(T, base, stride, g, geom, blob, sf, vf, sl, vl);
-    else tab_line<32>(T, base, stride, g, geom, blob, sf, vf, sl, vl);
+    if (M == 16) tab_line<16>(T, base, stride, g, geom, blob, sf, vf, sl, vl, zm, y, Lg, Rg);
+    else if (M == 8) tab_line<8>(T, base, stride, g, geom, blob, sf, vf, sl, vl, zm, y, Lg, Rg);
+    else if (M == 4) tab_line<4>(T, base, stride, g, geom, blob, sf, vf, sl, vl, zm, y, Lg, Rg);
+    else tab_line<32>(T, base, stride, g, geom, blob, sf, vf, sl, vl, zm, y, Lg, Rg);
 }
 
 }  // namespace
@@ -387,8 +398,20 @@ void tab_line_any(int M, double *T, size_t base, size_t stride, const TabGeom &g
 extern "C" {
 
 // prm: dt, rho, cp, k, h_r, Tinf_r, h_bot, h_top, Tinf_bot, Tinf_top, T_bot, T_top, T_void, T_inner
+int emu_cyl_step_slab(const double *Tin, double *Tout, int nr, int nphi, int nz, double dr, double dphi, double dz,
+                      const double *prm, int kind_bot, int kind_top, const uint8_t *active, const double *S, int M,
+                      int nslab);
+
 int emu_cyl_step(const double *Tin, double *Tout, int nr, int nphi, int nz, double dr, double dphi, double dz,
                  const double *prm, int kind_bot, int kind_top, const uint8_t *active, const double *S, int M)
+{
+    return emu_cyl_step_slab(Tin, Tout, nr, nphi, nz, dr, dphi, dz, prm, kind_bot, kind_top, active, S, M, 1);
+}
+
+// nslab > 1: the z sweep runs as nslab segments per line (the multi-GPU z-slab algorithm, all "ranks" here)
+int emu_cyl_step_slab(const double *Tin, double *Tout, int nr, int nphi, int nz, double dr, double dphi, double dz,
+                      const double *prm, int kind_bot, int kind_top, const uint8_t *active, const double *S, int M,
+                      int nslab)
 {
     const double dt = prm[0], rho = prm[1], cp = prm[2], k = prm[3], h_r = prm[4], Tinf_r = prm[5];
     const double alpha = k / (rho * cp);
@@ -424,7 +447,7 @@ int emu_cyl_step(const double *Tin, double *Tout, int nr, int nphi, int nz, doub
                 tab_line_any(M, Tout, (size_t)ir * nphi * nz + kz, (size_t)nz, g, geom.data(), blob.data(), 0, 0.0, 0, 0.0);
         }
     }
-    {
+    if (nslab <= 1) {
         const TabGeom g = tab_geom(nz, M, false, false);
         std::vector<int> geom(3 * g.P);
         std::vector<double> blob(g.ndbl), a(nz), b(nz), c(nz);
@@ -436,6 +459,44 @@ int emu_cyl_step(const double *Tin, double *Tout, int nr, int nphi, int nz, doub
         tab_build(g, geom.data(), geom.data() + g.P, geom.data() + 2 * g.P, a.data(), b.data(), c.data(), blob.data());
         for (size_t line = 0; line < (size_t)nr * nphi; ++line)
             tab_line_any(M, Tout, line * nz, 1, g, geom.data(), blob.data(), bot.set, bot.val, top.set, top.val);
+    } else {
+        // z-slab decomposition: nslab segments per line, each with its own tables (ghost couplings at the
+        // inner ends), pass 1 -> inter-segment solve -> pass 2, as the ranks of the multi-GPU path do
+        std::vector<TabSet> ts(nslab);
+        std::vector<ZEnd> bots(nslab), tops(nslab);
+        std::vector<int> z0(nslab + 1, 0);
+        for (int q = 0; q < nslab; ++q) z0[q + 1] = z0[q] + nz / nslab + (q < nz % nslab ? 1 : 0);
+        std::vector<Iface> cst(nslab);
+        for (int q = 0; q < nslab; ++q) {
+            const int nl = z0[q + 1] - z0[q];
+            std::vector<double> a(nl), b(nl), c(nl);
+            if (cyl_rows_z_segment(nl, q == 0, q == nslab - 1, dz, alpha, k, dt, kind_bot, kind_top, prm[6], prm[7], prm[8],
+                                   prm[9], prm[10], prm[11], a.data(), b.data(), c.data(), &bots[q], &tops[q]))
+                return -1;
+            ts[q] = tab_make(nl, M, false, a.data(), b.data(), c.data(), q > 0, q < nslab - 1);
+            const TabGeom &g = ts[q].g;
+            const double *bl = ts[q].blob.data();
+            cst[q].yf = cst[q].yl = 0.0;
+            cst[q].vf = bl[g.o_misc + 1] + bl[g.o_misc] * bl[g.o_dl];      // V_0 + W_0*dl_0
+            cst[q].wf = bl[g.o_misc] * bl[g.o_dr];
+            cst[q].vl = bl[g.o_dl + g.P - 1];
+            cst[q].wl = bl[g.o_dr + g.P - 1];
+        }
+        for (size_t line = 0; line < (size_t)nr * nphi; ++line) {
+            std::vector<Iface> rel(cst);
+            for (int q = 0; q < nslab; ++q) {
+                double y[2];
+                tab_line_any(M, Tout, line * nz + z0[q], 1, ts[q].g, ts[q].geom.data(), ts[q].blob.data(), bots[q].set,
+                             bots[q].val, tops[q].set, tops[q].val, 1, y);
+                rel[q].yf = y[0]; rel[q].yl = y[1];
+            }
+            for (int q = 0; q < nslab; ++q) {
+                double Lg, Rg;
+                iface_solve([&](int r) { return rel[r]; }, nslab, q, &Lg, &Rg);
+                tab_line_any(M, Tout, line * nz + z0[q], 1, ts[q].g, ts[q].geom.data(), ts[q].blob.data(), bots[q].set,
+                             bots[q].val, tops[q].set, tops[q].val, 2, nullptr, Lg, Rg);
+            }
+        }
     }
     if (active)
         for (size_t g = 0; g < ncell; ++g)

@@ -220,6 +220,8 @@ def run_ours(args):
 
     if args.workload == "c4":
         return run_ours_c4(args, local)
+    if args.workload == "cyl":
+        return run_ours_cyl(args, local)
     if world > 1 or args.workload == "c5":
         return run_ours_slab(args, rank, world, local)
     n = args.size
@@ -686,6 +688,112 @@ def run_ours_c4(args, local):
     return 0
 
 
+def run_ours_cyl(args, local):
+    """BASELINE configs[2]: cylindrical r-phi-z grid 256 x 1024 x 512 (at --size 512), periodic phi,
+    RobinR(500, 20), ZBC('neumann0', 'robin'), scheme 'be', dt = min(dr^2, dz^2, (R dphi)^2) / alpha
+    (quick_compare_layer_birth_robin_cyl_v3.py:115,127); layer births grow nz 448 -> 512 by 16 planes on a
+    buffer pre-pitched at 512 before the timed region; timed at nz = 512.  48 B/cell-step."""
+    import math
+    import torch
+    from adi_thermal_fields_b200 import _capi, adi3d_cyl_phi_v3 as gc
+
+    nr, nphi, nzf = args.size // 2, 2 * args.size, args.size
+    dev = torch.device("cuda", local)
+    R = 0.02
+    dr = R / nr
+    dz, dphi = dr, 2.0 * math.pi / nphi
+    mat = gc.Material(7800.0, 490.0, 54.0)
+    dt = min(dr * dr, dz * dz, (R * dphi) ** 2) / mat.alpha
+    rob, zbc = gc.RobinR(500.0, 20.0), gc.ZBC("neumann0", "robin", h_top=500.0, T_inf_top=20.0)
+    prm = gc.Params(dt, 1.0, "be")
+    gen = torch.Generator(device=dev).manual_seed(2)
+    A = torch.full((nr, nphi, nzf), 20.0, dtype=torch.float64, device=dev)
+    B = torch.empty_like(A)
+    nz = nzf - 4 * (nzf // 32)
+    A[:, :, :nz] += 5.0 * torch.rand((nr, nphi, nz), dtype=torch.float64, device=dev, generator=gen)
+    while True:   # births: 16 planes at Ts on top, two steps each, in place on the pitched buffer
+        A[:, :, nz - nzf // 32:nz] = 1000.0
+        g = gc.GridCyl(nr, nphi, nz, dr, dphi, dz, R)
+        for _ in range(2):
+            B.copy_(A)
+            gc.adi_step_device(A, g, mat, prm, rob, zbc, out=B, nz_pitch=nzf)
+            A, B = B, A
+        if nz >= nzf:
+            break
+        nz += nzf // 32
+    grid = gc.GridCyl(nr, nphi, nzf, dr, dphi, dz, R)
+    L, ctx = _capi.load(), gc._engine.context()
+    for o in args.opt:
+        name, _, val = o.partition("=")
+        _capi.check(L.adi_set_option(ctx, name.encode(), int(val)), "adi_set_option")
+    stream = torch.cuda.current_stream()
+    for _ in range(args.warmup):
+        gc.adi_step_device(A, grid, mat, prm, rob, zbc, out=B); A, B = B, A
+    torch.cuda.synchronize()
+    L.adi_set_option(ctx, b"profile", 1)
+    L.adi_profile_reset(ctx)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = gc.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        gc.adi_step_device(A, grid, mat, prm, rob, zbc, out=B); A, B = B, A
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    launches = gc.launch_count() - l0
+    clocks = sampler.stop()
+    ms4 = (C.c_double * 4)()
+    nst = C.c_long()
+    L.adi_profile_read(ctx, ms4, C.byref(nst))
+    L.adi_set_option(ctx, b"profile", 0)
+    cells = nr * nphi * nzf
+    ms_per_step = ms_total / args.steps
+    # e2e: the reference's own calling convention -- host NumPy in, host NumPy out (adi_cyl_step_host)
+    host = A.cpu().numpy()
+    gc.adi_step(host, grid, mat, prm, rob, zbc)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = gc.adi_step(host, grid, mat, prm, rob, zbc)
+    t_e2e = time.perf_counter() - t0
+    peak, peak_src = peaks()
+    per = [ms4[i] / max(1, nst.value) for i in range(1, 4)]
+    names = ["k_cyl_strided<r>", "k_cyl_strided<phi>", "k_cyl_z"]
+    dom = int(np.argmax(per))
+    achieved = 16.0 * cells / (per[dom] * 1e-3) / 1e9
+    # parity of this very state against the oracle on a sub-block is not possible (the solve couples the whole
+    # grid); the golden / oracle parity of the cylindrical path is in tests/test_gpu_cyl.py
+    line = {
+        "metric": METRIC, "value": cells * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cylindrical r-phi-z {nr}x{nphi}x{nzf} (BASELINE configs[2]): periodic phi, RobinR(500,20), "
+                               f"ZBC(neumann0, robin), scheme be, cfl 1; nz grown {nzf - 4 * (nzf // 32)}->{nzf} by births on a pitched "
+                               f"buffer before timing", "grid": [nr, nphi, nzf], "cells": cells, "bytes_per_cell_step": 48,
+                   "l2": "fields (1.07 GB) exceed the 126 MB L2; no flush needed", "parallelism": "single GPU"},
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": 16.0 * cells,
+                     "kernel_ms": {"r": per[0], "phi": per[1], "z": per[2]},
+                     "step_achieved_GBs": 48.0 * cells / (ms_per_step * 1e-3) / 1e9,
+                     "step_frac": 48.0 * cells / (ms_per_step * 1e-3) / 1e9 / peak},
+        "cpu_baseline": None, "clocks": clocks,
+        "e2e": {"value": cells * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * cells, "d2h_bytes_per_step": 8 * cells,
+                "steps": e2e_steps, "api": "adi3d_cyl_phi_v3.adi_step (host NumPy in / out, the reference's calling convention)"},
+        "gpu_launches": int(launches), "parity": None,
+    }
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            line["roofline"]["traffic"] = json.load(open(tp)).get(names[dom].split("<")[0], {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -693,9 +801,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--workload", default="plate", choices=["plate", "c5", "c4"],
+    ap.add_argument("--workload", default="plate", choices=["plate", "c5", "c4", "cyl"],
                     help="plate: BASELINE configs[1] (N>1: one size^3 slab per GPU, weak scaling); "
                          "c5: BASELINE configs[4], 2048x2048x1024 scalar-Robin strong scaling, z-slab over N GPUs; "
+                         "cyl: BASELINE configs[2], cylindrical 256x1024x512 backward-Euler step (1 GPU); "
                          "c4: BASELINE configs[3], waam 1024^3 synthetic head, layer births with device pack rebuilds (1 GPU)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-ny", type=int, default=128, help="y extent of the CPU-baseline sample slab")

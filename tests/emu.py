@@ -67,9 +67,10 @@ def cart_step(T, mask, dx, dt, theta, kappa, Tinf, coeff=(None,) * 3, dirm=(None
 KINDS = {"neumann0": 0, "dirichlet": 1, "robin": 2}
 
 
-def cyl_step(c, M=16):
+def cyl_step(c, M=16, nslab=1):
     """One cylindrical BE step of case dict `c` (tests/cases.build_cyl_case) through the
-    host-compiled table-driven solve (csrc/adi_tab_core.h)."""
+    host-compiled table-driven solve (csrc/adi_tab_core.h).  nslab > 1: the z sweep as nslab segments per
+    line (the z-slab algorithm of the multi-GPU path)."""
     L = lib()
     T = np.ascontiguousarray(c["T0"], dtype=np.float64)
     out = np.empty_like(T)
@@ -80,10 +81,10 @@ def cyl_step(c, M=16):
     act = None if c.get("active") is None else np.ascontiguousarray(c["active"], dtype=np.bool_).view(np.uint8)
     S = None if c.get("S") is None else np.ascontiguousarray(c["S"], dtype=np.float64)
     dp, bp = C.POINTER(C.c_double), C.POINTER(C.c_uint8)
-    L.emu_cyl_step.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, dp,
-                               C.c_int, C.c_int, bp, dp, C.c_int]
-    rc = L.emu_cyl_step(_ptr(T, C.c_double), _ptr(out, C.c_double), c["nr"], c["nphi"], c["nz"], c["dr"],
-                        c["dphi"], c["dz"], _ptr(prm, C.c_double), KINDS[z["kind_bot"]], KINDS[z["kind_top"]],
-                        _ptr(act, C.c_uint8), _ptr(S, C.c_double), int(M))
+    L.emu_cyl_step_slab.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, dp,
+                                    C.c_int, C.c_int, bp, dp, C.c_int, C.c_int]
+    rc = L.emu_cyl_step_slab(_ptr(T, C.c_double), _ptr(out, C.c_double), c["nr"], c["nphi"], c["nz"], c["dr"],
+                             c["dphi"], c["dz"], _ptr(prm, C.c_double), KINDS[z["kind_bot"]], KINDS[z["kind_top"]],
+                             _ptr(act, C.c_uint8), _ptr(S, C.c_double), int(M), int(nslab))
     assert rc == 0
     return out

@@ -49,3 +49,15 @@ def test_phi_rings_worst_case():
     ref = cyl.adi_step(c["T0"], grid, mat, cyl.Params(dt, 1.0, "be"), cyl.RobinR(0.0, 20.0), cyl.ZBC(**c["zbc"]))
     for ir in range(nr):
         assert cases.rel_l2(out[ir], ref[ir]) <= TOL, ir
+
+
+@pytest.mark.parametrize("nslab", [2, 3, 5])
+@pytest.mark.parametrize("name", ["mid_default", "mid_dd", "mid_rr", "mid_rd", "odd_sizes", "big", "big_cfl50", "masked_mid", "mid_source"])
+def test_emulated_cyl_z_slabs_match_reference(name, nslab, golden_dir):
+    """The z sweep cut into nslab segments per line (ghost couplings, tabulated ghost responses,
+    inter-segment solve): the multi-GPU z-slab algorithm of the cylindrical path, against the reference."""
+    c = cases.build_cyl_case(name)
+    g = np.load(os.path.join(golden_dir, f"cyl_{name}.npz"))
+    for M in (4, 16):
+        out = emu.cyl_step(c, M=M, nslab=nslab)
+        assert cases.rel_l2(out, g["T_out"]) <= TOL

@@ -21,6 +21,7 @@ SYMBOLS = (
     "adi_cart_set_slab", "adi_cart_set_mask_halo", "adi_cart_pack_zplanes", "adi_cart_step_xy",
     "adi_cart_zsweep_reduce", "adi_cart_zsweep_finish",
     "adi_voxel_project", "adi_voxel_correct", "adi_cart_step_host_async",
+    "adi_cyl_set_slab", "adi_cyl_step_rphi", "adi_cyl_zsweep_reduce", "adi_cyl_zsweep_finish",
 )
 
 
@@ -89,6 +90,10 @@ def load():
                                     C.POINTER(vp), C.POINTER(vp), vp]
     L.adi_cyl_bind.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dbl, dbl, dbl]
     L.adi_cyl_step.argtypes = [vp, dp, dp, C.POINTER(CylParams), bp, dp, vp]
+    L.adi_cyl_set_slab.argtypes = [vp, C.c_int, C.c_int, ip]
+    L.adi_cyl_step_rphi.argtypes = [vp, dp, dp, C.POINTER(CylParams), bp, dp, vp]
+    L.adi_cyl_zsweep_reduce.argtypes = [vp, dp, C.POINTER(CylParams), dp, vp]
+    L.adi_cyl_zsweep_finish.argtypes = [vp, dp, C.POINTER(CylParams), dp, bp, vp]
     L.adi_cyl_step_host.argtypes = [vp, vp, vp, C.c_int, C.POINTER(CylParams), vp, vp, vp]
     _lib = L
     return L

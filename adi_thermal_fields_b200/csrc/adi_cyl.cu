@@ -15,8 +15,10 @@
 
 #include <algorithm>
 #include <cstring>
+#include <string>
 #include <vector>
 
+#include "adi_core.h"
 #include "adi_ctx.h"
 #include "adi_tab_core.h"
 
@@ -35,6 +37,12 @@ struct CylTables {
     size_t goff_r = 0, goff_z = 0, goff_p = 0;  // geom offsets (ints)
     double add_r = 0.0;
     ZEnd bot, top;
+    // z-slab decomposition
+    int slab_rank = 0, slab_nranks = 1;
+    std::vector<int> slab_nz;          // local nz of every rank
+    double *d_G = nullptr;             // [2][nranks][2] ghost map
+    double *d_ghost = nullptr;         // [2][nlines]
+    size_t ghost_lines = 0;
 };
 
 void cyl_release(adi_ctx *ctx)
@@ -42,6 +50,8 @@ void cyl_release(adi_ctx *ctx)
     if (!ctx->cyl) return;
     if (ctx->cyl->d_blob) cudaFree(ctx->cyl->d_blob);
     if (ctx->cyl->d_geom) cudaFree(ctx->cyl->d_geom);
+    if (ctx->cyl->d_G) cudaFree(ctx->cyl->d_G);
+    if (ctx->cyl->d_ghost) cudaFree(ctx->cyl->d_ghost);
     delete ctx->cyl;
     ctx->cyl = nullptr;
 }
@@ -66,6 +76,9 @@ struct CylArgs {
     // right-hand side boundary terms: first / last cell of the line
     int set_first, set_last;
     double val_first, val_last;
+    // z-slab decomposition (z sweep): pass 1 writes y[2][nlines] = (yf, yl), pass 2 reads ghost[2][nlines]
+    double *y;
+    const double *ghost;
 };
 
 __device__ __forceinline__ void cyl_cp_async8(double *dst_smem, const double *src)
@@ -195,7 +208,9 @@ __device__ __forceinline__ int zswz(int z)
     return (z & ~15) | ((((z >> 1) & 7) ^ ((z / M) & 7)) << 1) | (z & 1);
 }
 
-template <int M, bool EPI, bool VEC>
+// ZM 0: whole lines.  1: z-slab pass 1 -- the right-hand-side part (yf, yl) of each segment's interface
+// relation, nothing stored.  2: z-slab pass 2 -- finishes the segment with the ghost values a.ghost.
+template <int M, bool EPI, bool VEC, int ZM = 0>
 __global__ void __launch_bounds__(256, (M <= 16 ? 3 : 2)) k_cyl_z(const CylArgs a)
 {
     extern __shared__ double smem[];
@@ -259,7 +274,21 @@ __global__ void __launch_bounds__(256, (M <= 16 ? 3 : 2)) k_cyl_z(const CylArgs 
     double Yl;
     const double Y = tab_forward<M>(d, tab + a.g.o_f + 2 * cb, tab + a.g.o_alpha + cb, &Yl);
     double Sl;
-    const double S = cyl_reduced(a.g, tab, ex, NTH, p, d[M - 1], Y, Yl, [=](int q) { return ln * P + q; }, &Sl);
+    double S = cyl_reduced(a.g, tab, ex, NTH, p, d[M - 1], Y, Yl, [=](int q) { return ln * P + q; }, &Sl);
+    if (ZM == 1) {
+        if (line_ok) {
+            const size_t line = (size_t)(L0 + ln);
+            if (p == 0) a.y[line] = fma(tab_ld(tab + a.g.o_misc), S, Y);     // x_first = Y_0 + W_0*S_0 (ghosts at 0)
+            if (p == P - 1) a.y[(size_t)a.nlines + line] = S;
+        }
+        return;
+    }
+    if (ZM == 2) {
+        const size_t line = (size_t)min(L0 + ln, a.nlines - 1);
+        const double Lg = a.ghost[line], Rg = a.ghost[(size_t)a.nlines + line];
+        S = fma(tab_ld(tab + a.g.o_dr + p), Rg, fma(tab_ld(tab + a.g.o_dl + p), Lg, S));
+        Sl = p > 0 ? fma(tab_ld(tab + a.g.o_dr + p - 1), Rg, fma(tab_ld(tab + a.g.o_dl + p - 1), Lg, Sl)) : Lg;
+    }
     tab_backward<M>(d, tab + a.g.o_b + 2 * cb, Sl, S);
     if (VEC) {
 #pragma unroll
@@ -293,6 +322,24 @@ __global__ void __launch_bounds__(256, (M <= 16 ? 3 : 2)) k_cyl_z(const CylArgs 
                 dst[z] = v;
             }
         }
+    }
+}
+
+// Ghost values of every line from the gathered right-hand-side parts: the inter-segment system has
+// line-independent coefficients, so its solution is a fixed linear map (G, 4*nranks doubles, host-built):
+//   L = sum_q G[0][q][0]*yf_q + G[0][q][1]*yl_q,   R likewise with G[1].
+__global__ void k_cyl_ghosts(const double *__restrict__ y_all, const double *__restrict__ G, double *__restrict__ ghost,
+                             size_t nlines, int nranks)
+{
+    for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < nlines; l += (size_t)gridDim.x * blockDim.x) {
+        double Lg = 0.0, Rg = 0.0;
+        for (int q = 0; q < nranks; ++q) {
+            const double yf = y_all[((size_t)q * 2) * nlines + l], yl = y_all[((size_t)q * 2 + 1) * nlines + l];
+            Lg = fma(G[q * 2 + 1], yl, fma(G[q * 2], yf, Lg));
+            Rg = fma(G[2 * nranks + q * 2 + 1], yl, fma(G[2 * nranks + q * 2], yf, Rg));
+        }
+        ghost[l] = Lg;
+        ghost[nlines + l] = Rg;
     }
 }
 
@@ -332,11 +379,43 @@ static int ensure_tables(adi_ctx *ctx, const adi_cyl_params &prm, cudaStream_t s
         T.add_r = cyl_rows_r(nr, ctx->dr, alpha, prm.k, prm.dt, prm.h_r, prm.Tinf_r, a.data(), b.data(), c.data());
         sr = tab_make(nr, pick_M(ctx, nr), false, a.data(), b.data(), c.data());
     }
+    std::vector<double> Gmap;
     {
-        std::vector<double> a(nz), b(nz), c(nz);
-        cyl_rows_z(nz, ctx->dz, alpha, prm.k, prm.dt, prm.kind_bot, prm.kind_top, prm.h_bot, prm.h_top,
-                   prm.Tinf_bot, prm.Tinf_top, prm.T_bot, prm.T_top, a.data(), b.data(), c.data(), &T.bot, &T.top);
-        sz = tab_make(nz, pick_M(ctx, nz), false, a.data(), b.data(), c.data());
+        // z rows: the whole line, or this rank's segment of it with ghost couplings at the inner ends
+        const int R = T.slab_nranks, me = T.slab_rank;
+        auto seg = [&](int q, int nl, ZEnd *bot, ZEnd *top) {
+            std::vector<double> a(nl), b(nl), c(nl);
+            cyl_rows_z_segment(nl, q == 0, q == R - 1, ctx->dz, alpha, prm.k, prm.dt, prm.kind_bot, prm.kind_top, prm.h_bot,
+                               prm.h_top, prm.Tinf_bot, prm.Tinf_top, prm.T_bot, prm.T_top, a.data(), b.data(), c.data(),
+                               bot, top);
+            return tab_make(nl, pick_M(ctx, nl), false, a.data(), b.data(), c.data(), q > 0, q < R - 1);
+        };
+        sz = seg(me, nz, &T.bot, &T.top);
+        if (R > 1) {
+            // line-independent coefficients of every rank's interface relation, then the ghost map of this
+            // rank: the inter-rank solve applied to unit right-hand sides
+            std::vector<Iface> cst(R);
+            for (int q = 0; q < R; ++q) {
+                ZEnd b0, t0;
+                const TabSet tq = q == me ? sz : seg(q, T.slab_nz[q], &b0, &t0);
+                const double *bl = tq.blob.data();
+                cst[q].yf = cst[q].yl = 0.0;
+                cst[q].vf = bl[tq.g.o_misc + 1] + bl[tq.g.o_misc] * bl[tq.g.o_dl];
+                cst[q].wf = bl[tq.g.o_misc] * bl[tq.g.o_dr];
+                cst[q].vl = bl[tq.g.o_dl + tq.g.P - 1];
+                cst[q].wl = bl[tq.g.o_dr + tq.g.P - 1];
+            }
+            Gmap.assign(4 * R, 0.0);
+            for (int q = 0; q < R; ++q)
+                for (int w = 0; w < 2; ++w) {
+                    std::vector<Iface> rel(cst);
+                    (w == 0 ? rel[q].yf : rel[q].yl) = 1.0;
+                    double Lg, Rg;
+                    iface_solve([&](int r) { return rel[r]; }, R, me, &Lg, &Rg);
+                    Gmap[q * 2 + w] = Lg;
+                    Gmap[2 * R + q * 2 + w] = Rg;
+                }
+        }
     }
     T.gr = sr.g; T.gz = sz.g;
     if (phi) T.gp = tab_geom(nphi, pick_M(ctx, nphi), true, true);
@@ -388,6 +467,12 @@ static int ensure_tables(adi_ctx *ctx, const adi_cyl_params &prm, cudaStream_t s
     // pageable sources: the copies are staged before the calls return
     ADI_CUDA(cudaMemcpyAsync(T.d_blob, blob.data(), ndbl * sizeof(double), cudaMemcpyHostToDevice, st));
     ADI_CUDA(cudaMemcpyAsync(T.d_geom, geom.data(), nint * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (!Gmap.empty()) {
+        if (T.d_G) { ADI_CUDA(cudaStreamSynchronize(st)); ADI_CUDA(cudaFree(T.d_G)); }
+        T.d_G = nullptr;
+        ADI_CUDA(cudaMalloc(&T.d_G, Gmap.size() * sizeof(double)));
+        ADI_CUDA(cudaMemcpyAsync(T.d_G, Gmap.data(), Gmap.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     ADI_CUDA(cudaStreamSynchronize(st));
     T.M = (int)ctx->opt_m;
     T.key = prm; T.nr = nr; T.nphi = nphi; T.nz = nz; T.valid = true;
@@ -451,7 +536,7 @@ static int launch_strided(adi_ctx *ctx, CylArgs &a, bool pro, int nouter, cudaSt
 #undef ADI_SGO
 }
 
-static int launch_z(adi_ctx *ctx, CylArgs &a, bool epi, cudaStream_t st)
+static int launch_z(adi_ctx *ctx, CylArgs &a, bool epi, cudaStream_t st, int zm = 0)
 {
     const int P = a.g.P, M = a.g.M;
     // 16-byte path: every chunk full and aligned
@@ -474,17 +559,24 @@ static int launch_z(adi_ctx *ctx, CylArgs &a, bool epi, cudaStream_t st)
     while (LT > 1 && (long long)(LT / 2) >= a.nlines) LT >>= 1;
     dim3 block(P, LT), grid((unsigned)((a.nlines + LT - 1) / LT));
     const size_t smem = bytes(LT);
-#define ADI_ZGO(MM)                                                                                   \
+#define ADI_ZGO1(MM, ZMV)                                                                             \
     {                                                                                                 \
         if (vec) {                                                                                    \
-            if (epi) return launch_cyl(k_cyl_z<MM, true, true>, grid, block, smem, st, ctx, a);       \
-            return launch_cyl(k_cyl_z<MM, false, true>, grid, block, smem, st, ctx, a);               \
+            if (epi) return launch_cyl(k_cyl_z<MM, true, true, ZMV>, grid, block, smem, st, ctx, a);  \
+            return launch_cyl(k_cyl_z<MM, false, true, ZMV>, grid, block, smem, st, ctx, a);          \
         }                                                                                             \
-        if (epi) return launch_cyl(k_cyl_z<MM, true, false>, grid, block, smem, st, ctx, a);          \
-        return launch_cyl(k_cyl_z<MM, false, false>, grid, block, smem, st, ctx, a);                  \
+        if (epi) return launch_cyl(k_cyl_z<MM, true, false, ZMV>, grid, block, smem, st, ctx, a);     \
+        return launch_cyl(k_cyl_z<MM, false, false, ZMV>, grid, block, smem, st, ctx, a);             \
+    }
+#define ADI_ZGO(MM)                     \
+    {                                   \
+        if (zm == 1) ADI_ZGO1(MM, 1)    \
+        if (zm == 2) ADI_ZGO1(MM, 2)    \
+        ADI_ZGO1(MM, 0)                 \
     }
     if (M == 16) ADI_ZGO(16)
     ADI_ZGO(32)
+#undef ADI_ZGO1
 #undef ADI_ZGO
 }
 
@@ -517,23 +609,18 @@ int adi_cyl_bind(adi_ctx *ctx, int nr, int nphi, int nz, int nz_pitch, double dr
     ctx->nr = nr; ctx->nphi = nphi; ctx->cnz = nz; ctx->nz_pitch = nz_pitch;
     ctx->dr = dr; ctx->dphi = dphi; ctx->dz = dz;
     ctx->cyl_bound = true;
-    if (ctx->cyl) ctx->cyl->valid = false;
+    if (ctx->cyl) { ctx->cyl->valid = false; ctx->cyl->slab_rank = 0; ctx->cyl->slab_nranks = 1; ctx->cyl->slab_nz.clear(); }
     return ADI_OK;
 }
 
-int adi_cyl_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_cyl_params *p,
-                 const uint8_t *d_active, const double *d_S, void *stream)
+// phases: bit 0 = r and phi sweeps (Tin -> Tout), bit 1 = z sweep on Tout with mode zm
+// (0 whole lines, 1 z-slab pass 1 -> d_y, 2 z-slab pass 2 with d_y_all)
+static int cyl_run(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_cyl_params *p, const uint8_t *d_active,
+                   const double *d_S, int phases, int zm, double *d_y, const double *d_y_all, cudaStream_t st)
 {
-    if (!ctx || !p) { set_error("adi_cyl_step: NULL argument"); return ADI_EINVAL; }
-    if (!ctx->cyl_bound) { set_error("adi_cyl_step: adi_cyl_bind has not been called"); return ADI_ESTATE; }
-    if (!d_Tin || !d_Tout || d_Tin == d_Tout) {
-        set_error("adi_cyl_step: Tin/Tout must be distinct device arrays");
-        return ADI_EINVAL;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_tables(ctx, *p, st);
     if (rc) return rc;
-    const CylTables &T = *ctx->cyl;
+    CylTables &T = *ctx->cyl;
     const int nr = ctx->nr, nphi = ctx->nphi, nz = ctx->cnz;
     const long long pitch = ctx->nz_pitch;
 
@@ -542,48 +629,146 @@ int adi_cyl_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_cy
     a.nz = nz;
     a.nphi = nphi;
     a.T_void = p->T_void; a.T_inner = p->T_inner;
-    rc = prof_mark(ctx, 0, st);
-    if (rc) return rc;
-    rc = prof_mark(ctx, 1, st);
-    if (rc) return rc;
+    if (phases & 1) {
+        rc = prof_mark(ctx, 0, st);
+        if (rc) return rc;
+        rc = prof_mark(ctx, 1, st);
+        if (rc) return rc;
 
-    // r sweep  (:341-344): Tin -> Tout, prologue fused
-    a.in = d_Tin; a.out = d_Tout;
-    a.blob = T.d_blob + T.off_r; a.geom = T.d_geom + T.goff_r; a.blob_stride = 0; a.g = T.gr;
-    a.cell_stride = (long long)nphi * pitch; a.outer_stride = pitch;
-    a.active = d_active; a.S = d_S; a.dt = p->dt; a.rho_cp = p->rho * p->cp;
-    a.set_first = 0; a.val_first = 0.0;
-    a.set_last = 0; a.val_last = (p->h_r != 0.0) ? T.add_r : 0.0;
-    if (nr == 1) { a.val_first = 0.0; }  // first == last: both branches apply in order, like the reference
-    rc = launch_strided(ctx, a, d_active != nullptr || d_S != nullptr, nphi, st);
-    if (rc) return rc;
-    rc = prof_mark(ctx, 2, st);
-    if (rc) return rc;
+        // r sweep  (:341-344): Tin -> Tout, prologue fused
+        a.in = d_Tin; a.out = d_Tout;
+        a.blob = T.d_blob + T.off_r; a.geom = T.d_geom + T.goff_r; a.blob_stride = 0; a.g = T.gr;
+        a.cell_stride = (long long)nphi * pitch; a.outer_stride = pitch;
+        a.active = d_active; a.S = d_S; a.dt = p->dt; a.rho_cp = p->rho * p->cp;
+        a.set_first = 0; a.val_first = 0.0;
+        a.set_last = 0; a.val_last = (p->h_r != 0.0) ? T.add_r : 0.0;
+        rc = launch_strided(ctx, a, d_active != nullptr || d_S != nullptr, nphi, st);
+        if (rc) return rc;
+        rc = prof_mark(ctx, 2, st);
+        if (rc) return rc;
 
-    // phi sweep (:346), in place; nphi == 1 is the identity (:309-310)
-    a.in = d_Tout; a.active = nullptr; a.S = nullptr;
-    a.set_first = a.set_last = 0; a.val_first = a.val_last = 0.0;
-    if (nphi > 1) {
-        a.blob = T.d_blob + T.off_p; a.geom = T.d_geom + T.goff_p; a.blob_stride = T.gp.ndbl; a.g = T.gp;
-        a.cell_stride = pitch; a.outer_stride = (long long)nphi * pitch;
-        rc = launch_strided(ctx, a, false, nr, st);
+        // phi sweep (:346), in place; nphi == 1 is the identity (:309-310)
+        a.in = d_Tout; a.active = nullptr; a.S = nullptr;
+        a.set_first = a.set_last = 0; a.val_first = a.val_last = 0.0;
+        if (nphi > 1) {
+            a.blob = T.d_blob + T.off_p; a.geom = T.d_geom + T.goff_p; a.blob_stride = T.gp.ndbl; a.g = T.gp;
+            a.cell_stride = pitch; a.outer_stride = (long long)nphi * pitch;
+            rc = launch_strided(ctx, a, false, nr, st);
+            if (rc) return rc;
+        }
+        rc = prof_mark(ctx, 3, st);
         if (rc) return rc;
     }
-    rc = prof_mark(ctx, 3, st);
-    if (rc) return rc;
-
-    // z sweep (:348-350), in place, epilogue fused
-    a.blob = T.d_blob + T.off_z; a.geom = T.d_geom + T.goff_z; a.blob_stride = 0; a.g = T.gz;
-    a.outer_stride = pitch; a.nlines = (long long)nr * nphi;
-    a.active = d_active;
-    a.set_first = T.bot.set; a.val_first = T.bot.val;
-    a.set_last = T.top.set; a.val_last = T.top.val;
-    rc = launch_z(ctx, a, d_active != nullptr, st);
-    if (rc) return rc;
-    rc = prof_mark(ctx, 4, st);
-    if (rc) return rc;
+    if (phases & 2) {
+        // z sweep (:348-350), in place, epilogue fused
+        const size_t nlines = (size_t)nr * nphi;
+        a.in = d_Tout; a.out = d_Tout;
+        a.blob = T.d_blob + T.off_z; a.geom = T.d_geom + T.goff_z; a.blob_stride = 0; a.g = T.gz;
+        a.cell_stride = 0; a.outer_stride = pitch; a.nlines = (long long)nlines;
+        a.active = zm == 1 ? nullptr : d_active;
+        a.S = nullptr;
+        a.set_first = T.bot.set; a.val_first = T.bot.val;
+        a.set_last = T.top.set; a.val_last = T.top.val;
+        a.y = d_y;
+        if (zm == 2) {
+            if (T.ghost_lines < nlines) {
+                if (T.d_ghost) { ADI_CUDA(cudaStreamSynchronize(st)); ADI_CUDA(cudaFree(T.d_ghost)); }
+                T.d_ghost = nullptr;
+                ADI_CUDA(cudaMalloc(&T.d_ghost, 2 * nlines * sizeof(double)));
+                T.ghost_lines = nlines;
+            }
+            const int threads = 128;
+            const int blocks = (int)std::min<size_t>((nlines + threads - 1) / threads, 148 * 32);
+            k_cyl_ghosts<<<blocks, threads, 0, st>>>(d_y_all, T.d_G, T.d_ghost, nlines, T.slab_nranks);
+            ctx->launches++;
+            ADI_CUDA(cudaGetLastError());
+            a.ghost = T.d_ghost;
+        }
+        rc = launch_z(ctx, a, zm != 1 && d_active != nullptr, st, zm);
+        if (rc) return rc;
+        if (zm != 1) {
+            rc = prof_mark(ctx, 4, st);
+            if (rc) return rc;
+        }
+    }
     if (ctx->opt_sync_check) ADI_CUDA(cudaStreamSynchronize(st));
     return ADI_OK;
+}
+
+static int cyl_check(adi_ctx *ctx, const adi_cyl_params *p, const char *who)
+{
+    if (!ctx || !p) { set_error(std::string(who) + ": NULL argument"); return ADI_EINVAL; }
+    if (!ctx->cyl_bound) { set_error(std::string(who) + ": adi_cyl_bind has not been called"); return ADI_ESTATE; }
+    return ADI_OK;
+}
+
+int adi_cyl_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_cyl_params *p,
+                 const uint8_t *d_active, const double *d_S, void *stream)
+{
+    int rc = cyl_check(ctx, p, "adi_cyl_step");
+    if (rc) return rc;
+    if (!d_Tin || !d_Tout || d_Tin == d_Tout) {
+        set_error("adi_cyl_step: Tin/Tout must be distinct device arrays");
+        return ADI_EINVAL;
+    }
+    if (ctx->cyl && ctx->cyl->slab_nranks > 1) {
+        set_error("adi_cyl_step: this context holds a z slab; use adi_cyl_step_rphi + adi_cyl_zsweep_*");
+        return ADI_ESTATE;
+    }
+    return cyl_run(ctx, d_Tin, d_Tout, p, d_active, d_S, 3, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int adi_cyl_set_slab(adi_ctx *ctx, int rank, int nranks, const int *nz_per_rank)
+{
+    if (!ctx || !ctx->cyl_bound) { set_error("adi_cyl_set_slab: adi_cyl_bind has not been called"); return ADI_ESTATE; }
+    if (nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks || (nranks > 1 && !nz_per_rank)) {
+        set_error("adi_cyl_set_slab: need 0 <= rank < nranks <= 16 and the local nz of every rank");
+        return ADI_EINVAL;
+    }
+    if (nranks > 1 && nz_per_rank[rank] != ctx->cnz) {
+        set_error("adi_cyl_set_slab: nz_per_rank[rank] differs from the bound local nz");
+        return ADI_EINVAL;
+    }
+    if (!ctx->cyl) ctx->cyl = new CylTables();
+    CylTables &T = *ctx->cyl;
+    T.slab_rank = rank; T.slab_nranks = nranks;
+    T.slab_nz.assign(nranks, ctx->cnz);
+    for (int q = 0; q < nranks && nz_per_rank; ++q) {
+        if (nz_per_rank[q] < 1) { set_error("adi_cyl_set_slab: every rank needs at least one z plane"); return ADI_EINVAL; }
+        T.slab_nz[q] = nz_per_rank[q];
+    }
+    T.valid = false;
+    return ADI_OK;
+}
+
+int adi_cyl_step_rphi(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_cyl_params *p,
+                      const uint8_t *d_active, const double *d_S, void *stream)
+{
+    int rc = cyl_check(ctx, p, "adi_cyl_step_rphi");
+    if (rc) return rc;
+    if (!d_Tin || !d_Tout || d_Tin == d_Tout) {
+        set_error("adi_cyl_step_rphi: Tin/Tout must be distinct device arrays");
+        return ADI_EINVAL;
+    }
+    return cyl_run(ctx, d_Tin, d_Tout, p, d_active, d_S, 1, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int adi_cyl_zsweep_reduce(adi_ctx *ctx, double *d_T, const adi_cyl_params *p, double *d_y, void *stream)
+{
+    int rc = cyl_check(ctx, p, "adi_cyl_zsweep_reduce");
+    if (rc) return rc;
+    if (!d_T || !d_y) { set_error("adi_cyl_zsweep_reduce: NULL argument"); return ADI_EINVAL; }
+    return cyl_run(ctx, d_T, d_T, p, nullptr, nullptr, 2, 1, d_y, nullptr, (cudaStream_t)stream);
+}
+
+int adi_cyl_zsweep_finish(adi_ctx *ctx, double *d_T, const adi_cyl_params *p, const double *d_y_all,
+                          const uint8_t *d_active, void *stream)
+{
+    int rc = cyl_check(ctx, p, "adi_cyl_zsweep_finish");
+    if (rc) return rc;
+    if (!d_T || !d_y_all) { set_error("adi_cyl_zsweep_finish: NULL argument"); return ADI_EINVAL; }
+    if (!ctx->cyl || ctx->cyl->slab_nranks < 2) { set_error("adi_cyl_zsweep_finish: adi_cyl_set_slab has not been called"); return ADI_ESTATE; }
+    return cyl_run(ctx, d_T, d_T, p, d_active, nullptr, 2, 2, nullptr, d_y_all, (cudaStream_t)stream);
 }
 
 int adi_cyl_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int nsteps,

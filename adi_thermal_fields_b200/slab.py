@@ -376,3 +376,66 @@ def adi_step_gpu_coeff(Tn, grid, mat, params, packs, Tinf=0.0, out=None):
         grid._stat_packs = packs   # keeps id(packs) from being reused by another object
     be.zsweep_finish(out, grid.dyn_all, grid.stat_all, dt, theta, kappa, float(Tinf))
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# cylindrical grid: z-slab decomposition of adi3d_cyl_phi_v3.adi_step (scheme "be")
+# --------------------------------------------------------------------------------------------
+class SlabGridCyl:
+    """Local slab of a cylindrical grid: GridCyl(nr,nphi,nz,dr,dphi,dz,R) (adi3d_cyl_phi_v3.py:33-43) with nz
+    the LOCAL number of z planes; `nz_per_rank` lists the local nz of every rank of `comm`.
+    The r and phi solves are rank-local; only the z solve exchanges data (one all-gather of two doubles per
+    line and rank per step -- the matrix part of the interface relations is line-independent and lives in
+    host-built tables)."""
+
+    def __init__(self, nr, nphi, nz_local, dr, dphi, dz, R, comm, nz_per_rank=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("adi_thermal_fields_b200.slab: no CUDA device (there is no CPU fallback)")
+        self.nr, self.nphi, self.nz = int(nr), int(nphi), int(nz_local)
+        self.dr, self.dphi, self.dz, self.R = float(dr), float(dphi), float(dz), float(R)
+        self.comm, self.rank, self.world = comm, comm.rank, comm.world
+        self.nz_per_rank = [int(v) for v in (nz_per_rank if nz_per_rank is not None else [self.nz] * self.world)]
+        if len(self.nz_per_rank) != self.world or self.nz_per_rank[self.rank] != self.nz:
+            raise ValueError("nz_per_rank does not match the communicator / the local nz")
+        self.L = _capi.load()
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        h = C.c_void_p()
+        _capi.check(self.L.adi_ctx_create(self.dev.index, C.byref(h)), "adi_ctx_create")
+        self.ctx = h
+        _capi.check(self.L.adi_cyl_bind(self.ctx, self.nr, self.nphi, self.nz, self.nz, self.dr, self.dphi, self.dz),
+                    "adi_cyl_bind")
+        _capi.check(self.L.adi_cyl_set_slab(self.ctx, self.rank, self.world, (C.c_int * self.world)(*self.nz_per_rank)),
+                    "adi_cyl_set_slab")
+        nl = self.nr * self.nphi
+        self.y = torch.empty((2, nl), dtype=torch.float64, device=self.dev)
+        self.y_all = torch.empty((self.world, 2, nl), dtype=torch.float64, device=self.dev)
+
+    def launch_count(self):
+        return int(self.L.adi_launch_count(self.ctx))
+
+
+def adi_step_cyl(Tn, grid, mat, prm, robin_r, zbc, S=None, active=None, robin_inner=None, robin_void=None, out=None):
+    """One backward-Euler step of the slab (collective over grid.comm): adi_step
+    (adi3d_cyl_phi_v3.py:332-350) / adi_step_masked (quick_spiral_deposition_gif_v5.py:31-70) on device-resident
+    local arrays (nr, nphi, nz_local).  Returns a new local array."""
+    from . import adi3d_cyl_phi_v3 as gc
+    if active is not None:
+        ri, rv = robin_inner or robin_r, robin_void or robin_r
+        p = gc._params(mat, prm, robin_r, zbc, T_void=float(rv.T_inf), T_inner=float(ri.T_inf))
+    else:
+        p = gc._params(mat, prm, robin_r, zbc)
+    L, ctx = grid.L, grid.ctx
+    st = torch.cuda.current_stream().cuda_stream
+    if out is None:
+        out = torch.empty_like(Tn)
+    a = None if active is None else active.data_ptr()
+    s = None if S is None else S.data_ptr()
+    if grid.world == 1:
+        _capi.check(L.adi_cyl_step(ctx, Tn.data_ptr(), out.data_ptr(), C.byref(p), a, s, st), "adi_cyl_step")
+        return out
+    _capi.check(L.adi_cyl_step_rphi(ctx, Tn.data_ptr(), out.data_ptr(), C.byref(p), a, s, st), "adi_cyl_step_rphi")
+    _capi.check(L.adi_cyl_zsweep_reduce(ctx, out.data_ptr(), C.byref(p), grid.y.data_ptr(), st), "adi_cyl_zsweep_reduce")
+    grid.comm.all_gather(grid.y_all, grid.y)
+    _capi.check(L.adi_cyl_zsweep_finish(ctx, out.data_ptr(), C.byref(p), grid.y_all.data_ptr(), a, st),
+                "adi_cyl_zsweep_finish")
+    return out

@@ -190,6 +190,19 @@ int adi_cyl_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_cy
 int adi_cyl_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int nsteps,
                       const adi_cyl_params *p, const uint8_t *h_active, const double *h_S,
                       void *stream);
+/* z-slab decomposition of the cylindrical grid (multi-GPU form of adi_step, adi3d_cyl_phi_v3.py:332-350):
+ * rank r of R holds the z planes [z0_r, z1_r) of every array and is bound (adi_cyl_bind) with its LOCAL
+ * nz; nz_per_rank lists the local nz of all ranks.  The r and phi solves are rank-local; the z solve
+ * (:348-350) is partitioned: pass 1 gives, per line, the right-hand-side part d_y[2][nr*nphi] = (yf, yl) of
+ * the segment's interface relation (its matrix part is line-independent and tabulated on the host), the
+ * ranks all-gather them into d_y_all[R][2][nr*nphi], pass 2 maps them to the two ghost values of every
+ * line and finishes the segment.  The boundary rows of ZBC apply on the first / last rank only. */
+int adi_cyl_set_slab(adi_ctx *ctx, int rank, int nranks, const int *nz_per_rank);
+int adi_cyl_step_rphi(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_cyl_params *p,
+                      const uint8_t *d_active, const double *d_S, void *stream);
+int adi_cyl_zsweep_reduce(adi_ctx *ctx, double *d_T, const adi_cyl_params *p, double *d_y, void *stream);
+int adi_cyl_zsweep_finish(adi_ctx *ctx, double *d_T, const adi_cyl_params *p, const double *d_y_all,
+                          const uint8_t *d_active, void *stream);
 
 #ifdef __cplusplus
 }

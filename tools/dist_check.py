@@ -40,6 +40,37 @@ for shape, mk, bk, theta, cfl, nsteps in [((24, 20, 16 * world * 2), "cyl_holes"
         ok &= good
         print(f"[dist_check] world={world} shape={shape} {mk}/{bk} theta={theta}: rel_l2={err:.2e} "
               f"void_bit_equal={void} launches/rank={parts[0][3]} {'OK' if good else 'FAIL'}", flush=True)
+# cylindrical path: z-slab decomposition against the oracle on the undivided grid
+from adi_thermal_fields_b200 import adi3d_cyl_phi_v3 as gc  # noqa: E402
+from oracle import cyl  # noqa: E402
+for nr, nphi, nz, kb, kt in [(16, 32, 24 * world, "neumann0", "robin"), (12, 40, 7 * world + 3, "robin", "dirichlet")]:
+    R = 0.02
+    dr = R / nr
+    dphi = 2 * np.pi / nphi
+    mat = gc.Material(cases.C_RHO, cases.C_CP, cases.C_K)
+    dt = 2.0 * dr * dr / mat.alpha
+    T0 = 20.0 + 980.0 * cases.splitmix_uniform(31, (nr, nphi, nz))
+    zk = dict(kind_bot=kb, kind_top=kt, h_bot=180.0, h_top=500.0, T_inf_bot=35.0, T_inf_top=20.0, T_bot=250.0, T_top=60.0)
+    ext = slab.split_z(nz, world)
+    z0, z1 = ext[rank]
+    grid = slab.SlabGridCyl(nr, nphi, z1 - z0, dr, dphi, dr, R, slab.TorchDistComm(), nz_per_rank=[b - a for a, b in ext])
+    T = torch.from_numpy(np.ascontiguousarray(T0[:, :, z0:z1])).cuda()
+    for _ in range(3):
+        T = slab.adi_step_cyl(T, grid, mat, gc.Params(dt, 1.0, "be"), gc.RobinR(500.0, 20.0), gc.ZBC(**zk))
+    parts = [None] * world
+    dist.all_gather_object(parts, (z0, z1, T.cpu().numpy()))
+    if rank == 0:
+        out = np.empty((nr, nphi, nz))
+        for a, b, tt in parts:
+            out[:, :, a:b] = tt
+        ref = T0
+        og, om = cyl.GridCyl(nr, nphi, nz, dr, dphi, dr, R), cyl.Material(mat.rho, mat.cp, mat.k)
+        for _ in range(3):
+            ref = cyl.adi_step(ref, og, om, cyl.Params(dt, 1.0, "be"), cyl.RobinR(500.0, 20.0), cyl.ZBC(**zk))
+        err = cases.rel_l2(out, ref)
+        good = err <= 3e-12
+        ok &= good
+        print(f"[dist_check] world={world} cylindrical {nr}x{nphi}x{nz} zbc={kb}/{kt}: rel_l2={err:.2e} {'OK' if good else 'FAIL'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

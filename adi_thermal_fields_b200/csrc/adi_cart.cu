@@ -25,6 +25,7 @@ int check_cart(adi_ctx *ctx, const char *who)
         set_error(std::string(who) + ": adi_cart_bind has not been called");
         return ADI_ESTATE;
     }
+    ADI_CUDA(cudaSetDevice(ctx->device));   // the context's device, whatever the caller made current
     return ADI_OK;
 }
 

@@ -699,6 +699,7 @@ static int cyl_check(adi_ctx *ctx, const adi_cyl_params *p, const char *who)
 {
     if (!ctx || !p) { set_error(std::string(who) + ": NULL argument"); return ADI_EINVAL; }
     if (!ctx->cyl_bound) { set_error(std::string(who) + ": adi_cyl_bind has not been called"); return ADI_ESTATE; }
+    ADI_CUDA(cudaSetDevice(ctx->device));
     return ADI_OK;
 }
 

@@ -20,8 +20,8 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
         while (KT > 1 && KT * P > 512) KT >>= 1;
         dim3 block(KT, P), grid((a.nz + KT - 1) / KT, other, CS);
         const size_t smem = ((size_t)(2 * M + 10) * KT * P + 8 * KT) * sizeof(double);
-        if ((unsigned long long)M * (AXIS == 0 ? (unsigned long long)a.ny * a.nz : (unsigned long long)a.nz) >= (1ull << 32)) {
-            set_error("adi_cart_step: grid too large for 32-bit in-chunk offsets");
+        if ((unsigned long long)M * 8ull * (AXIS == 0 ? (unsigned long long)a.ny * a.nz : (unsigned long long)a.nz) >= (1ull << 32)) {
+            set_error("adi_cart_step: grid too large for 32-bit in-chunk byte offsets (chunk length x line stride x 8 >= 4 GiB)");
             return ADI_EINVAL;
         }
         cudaLaunchConfig_t cfg = {};
@@ -52,8 +52,8 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
     // the exchange buffer then reuses) and the z halo [2][M][P]
     const size_t smem = ((AXIS == 0 && expl && s.NS == 2) ? (size_t)3 * s.M * nth + (size_t)2 * s.M * s.P
                                                         : (size_t)(s.NS * s.M + 6) * nth) * sizeof(double);
-    if ((unsigned long long)s.M * (AXIS == 0 ? (unsigned long long)a.ny * a.nz : (unsigned long long)a.nz) >= (1ull << 32)) {
-        set_error("adi_cart_step: grid too large for 32-bit in-chunk offsets");
+    if ((unsigned long long)s.M * 8ull * (AXIS == 0 ? (unsigned long long)a.ny * a.nz : (unsigned long long)a.nz) >= (1ull << 32)) {
+        set_error("adi_cart_step: grid too large for 32-bit in-chunk byte offsets (chunk length x line stride x 8 >= 4 GiB)");
         return ADI_EINVAL;
     }
 #define ADI_GO(M, NS, MAXT, MINB)                                                                           \

@@ -136,7 +136,11 @@ int adi_cart_zsweep_reduce(adi_ctx *ctx, double *d_T, double *d_iface_dyn, doubl
  * ranks; solves the inter-rank system per line and finishes the local segments in place. */
 int adi_cart_zsweep_finish(adi_ctx *ctx, double *d_T, const double *d_dyn_all, const double *d_stat_all,
                            double dt, double theta, double kappa, double Tinf, void *stream);
-/* Tuning / introspection: kernel variant selection (0 = default) and launch counter. */
+/* Tuning / introspection: kernel variant selection (0 = default) and launch counter.  Options:
+ *   "kt"    lanes along z per block of the strided sweeps (power of two)     "lt"  lines per block of the z sweeps
+ *   "m"     chunk length 16 | 32                                             "wide" 1: 512-thread blocks for lines <= 512 cells
+ *   "fuse"  1: explicit stage fused into the x sweep instead of its own pass
+ *   "profile" 1: record per-kernel CUDA events (adi_profile_read)            "sync_check" 1: synchronise after every step */
 int adi_set_option(adi_ctx *ctx, const char *name, long value);
 long adi_launch_count(adi_ctx *ctx);
 /* Per-kernel device timing (the `[time]` prints of quick_compare_neumann_robin_backend.py:

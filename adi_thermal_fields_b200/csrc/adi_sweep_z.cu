@@ -21,6 +21,14 @@ static int launch_sweep_z_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
     const size_t budget = s.var == VAR_32L ? 220 * 1024 : 28 * 1024;  // one 1024-cell line is 25.6 KB  // small blocks overlap best (measured)
     int LT = s.W;
     while (LT > 1 && LT * line_bytes > budget) LT >>= 1;
+    if (s.var == VAR_16) {
+        // measured on B200 (dense operands, 512 x 512 lines): one-warp tiles win for short lines -- many
+        // resident blocks keep the loads, solves and stores of different tiles overlapped:
+        // nz 32: 0.31 -> 0.22 ms (LT 8), 64: 0.17 -> 0.135 (8), 128: 0.22 -> 0.18 (4), 256: 0.35 -> 0.31 (2),
+        // 384: 0.61 -> 0.57 (4)
+        if (s.P <= 16) LT = std::min(8, std::max(1, 32 / s.P));
+        else if (s.P <= 24) LT = 4;
+    }
     if (ctx->opt_lt > 0) LT = (int)std::min<long>(ctx->opt_lt, s.W);
     const size_t smem = LT * line_bytes;
     if (smem > 227 * 1024) {

@@ -505,3 +505,45 @@ int emu_cyl_step_slab(const double *Tin, double *Tout, int nr, int nphi, int nz,
 }
 
 }  // extern "C"
+
+// ---- ASCII output path: adi_fmt_core.h on the CPU ---------------------------------------------
+#include "adi_fmt_core.h"
+
+static const double h_pow10[][2] = {ADI_POW10_TABLE};
+
+extern "C" {
+
+// formats n values; out has 16 bytes per value (NUL padded), lens[i] = text length
+void emu_format_values(const double *v, long n, int fmt, char *out, int *lens)
+{
+    for (long i = 0; i < n; ++i) {
+        char *o = out + 16 * i;
+        memset(o, 0, 16);
+        lens[i] = fmt == adifmt::FMT_E6 ? adifmt::format_value<adifmt::FMT_E6>(v[i], &h_pow10[0][0], o)
+                                        : adifmt::format_value<adifmt::FMT_G6>(v[i], &h_pow10[0][0], o);
+    }
+}
+
+// exact comparison on its own (tests drive it over the full exponent range)
+int emu_exact_cmp_half(double a, unsigned n, int q) { return adifmt::exact_cmp_half(a, n, q); }
+
+// the whole data section of a field, in the kernel's order; returns the byte count
+long emu_text_field(const void *src, int dtype, int nx, int ny, int nz, int fmt, char *out)
+{
+    const uint64_t N = (uint64_t)nx * ny * nz;
+    char *p = out;
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const size_t c = ((size_t)i * ny + j) * nz + k;
+                const double v = dtype == 0 ? ((const double *)src)[c]
+                                 : dtype == 1 ? (double)((const float *)src)[c]
+                                              : (double)((const uint8_t *)src)[c];
+                p += fmt == adifmt::FMT_E6 ? adifmt::format_value<adifmt::FMT_E6>(v, &h_pow10[0][0], p)
+                                           : adifmt::format_value<adifmt::FMT_G6>(v, &h_pow10[0][0], p);
+                *p++ = adifmt::separator(fmt, ((uint64_t)k * ny + j) * nx + i, i, nx, N);
+            }
+    return (long)(p - out);
+}
+
+}  // extern "C"

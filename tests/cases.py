@@ -331,3 +331,29 @@ def build_voxel_bc_case(name="ellipsoid"):
     base_h = {"x-": 40.0, "x+": 55.0, "y-": 40.0, "y+": 0.0, "z-": 25.0, "z+": 80.0}
     return dict(name=name, shape=shape, dx=dx, origin=origin, mask=mask, mesh=mesh, base_h=base_h,
                 max_subdiv=6 if name != "coarse" else 4)
+
+
+# ---- ASCII VTK output (vtk_writer.py, waam_from_stl_v7_mm.py:186-215) -------------------------
+def vtk_text_cases():
+    """name -> dict(T, dx, origin, mask, field_name): small seeded fields that exercise every
+    branch of '.6e' / '.6g' formatting (negative values, exact ties, zeros, tiny and huge
+    magnitudes, 3-digit exponents, non-finite entries) and ragged line ends (N % 9 != 0)."""
+    out = {}
+    rng = np.random.default_rng(2024)
+    T = 20.0 + 1380.0 * rng.random((7, 5, 4))
+    m = rng.random((7, 5, 4)) < 0.7
+    out["plate"] = dict(T=T, dx=1e-3, origin=(0.0, 0.0, 0.0), mask=m, field_name="Temperature")
+    T = (rng.random((6, 3, 5)) - 0.4) * 10.0 ** rng.integers(-12, 13, size=(6, 3, 5))
+    T[0, 0, 0] = 0.0; T[1, 0, 0] = -0.0; T[2, 0, 0] = 1234567.5; T[3, 0, 0] = 123456.5
+    T[4, 0, 0] = 9.9999995; T[5, 0, 0] = 999999.5; T[0, 1, 0] = 1e-100; T[1, 1, 0] = -3.5e120
+    T[2, 1, 0] = 1e5; T[3, 1, 0] = 1e-5; T[4, 1, 0] = 100.0; T[5, 1, 0] = 0.0001
+    out["wide_range"] = dict(T=T, dx=0.25, origin=(-1.5, 2.0, 1e-7), mask=None, field_name="Temperature")
+    T = rng.normal(0.0, 50.0, (10, 1, 1))
+    out["line10"] = dict(T=T, dx=2.0, origin=(1.0, 2.0, 3.0), mask=np.ones((10, 1, 1), bool), field_name="T_C")
+    T = rng.random((3, 4, 3)) * 1e3
+    T[1, 1, 1] = np.nan; T[2, 2, 2] = np.inf; T[0, 3, 1] = -np.inf
+    out["nonfinite"] = dict(T=T, dx=0.5, origin=(0.0, 0.0, 0.0), mask=None, field_name="Temperature")
+    T = np.round(rng.random((9, 9, 2)) * 4096.0) / 16.0            # short dyadic values
+    out["dyadic"] = dict(T=T.astype(np.float32), dx=1.0, origin=(0.0, 0.0, 0.0), mask=rng.random((9, 9, 2)) < 0.5,
+                         field_name="Temperature")
+    return out

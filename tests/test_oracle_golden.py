@@ -195,3 +195,14 @@ def test_voxel_bc_oracle_bit_exact(name, golden_dir):
         assert np.array_equal(robin[f], g["robin_" + f])
         assert np.array_equal(scale[f], g["scale_" + f])
         assert np.array_equal(nofb[f], g["robin_nofallback_" + f])
+
+
+# ---- ASCII VTK writers (oracle/vtk_text.py vs the reference's files) --------------------------
+@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("name", sorted(cases.vtk_text_cases()))
+def test_vtk_text_oracle_byte_exact(name, fmt, golden_dir):
+    from oracle import vtk_text
+    g = np.load(os.path.join(golden_dir, "vtk_text.npz"))
+    c = cases.vtk_text_cases()[name]
+    got = vtk_text.vtk_bytes(fmt, c["T"], c["dx"], c["origin"], c["field_name"], c["mask"])
+    assert got == g[f"{name}__{fmt}"].tobytes()

@@ -18,6 +18,8 @@ What is pinned:
                     or quick_spiral_deposition_gif_v5.adi_step_masked (:31) when masked
   spiral_sim.npz    tests/test_spiral_vs_analytic.py:_run_numeric_simulation snapshots,
                     with GridCyl accepting (and ignoring) R_in -- see SURVEY.md F2
+  vtk_text.npz      the files written by vtk_writer.write_vtk_structured_points (vtk_writer.py:12) and
+                    waam_from_stl_v7_mm.write_vtk_structured_points (:186) for small seeded fields
   cyl_birth.npz     the nz-growth event loop of quick_compare_layer_birth_robin_cyl_v3.py:171-204
 """
 from __future__ import annotations
@@ -229,19 +231,42 @@ def gen_voxel_bc(ref, outdir):
               f"{int(sum((robin[f] > 0).sum() for f in robin))} corrected face entries")
 
 
+def gen_vtk_text(ref, outdir):
+    """Files written by the reference's two ASCII VTK writers (vtk_writer.py:12,
+    waam_from_stl_v7_mm.py:186) for tests/cases.py:vtk_text_cases -> vtk_text.npz (raw bytes)."""
+    import vtk_writer
+    _stub_matplotlib()
+    import waam_from_stl_v7_mm as waam
+    out = {}
+    tmp = tempfile.mkdtemp(prefix="vtk_golden_")
+    for name, c in cases.vtk_text_cases().items():
+        for fl, fn in ((0, vtk_writer.write_vtk_structured_points), (1, waam.write_vtk_structured_points)):
+            path = os.path.join(tmp, f"{name}_{fl}.vtk")
+            fn(path, c["T"], c["dx"], c["origin"], c["field_name"], c["mask"])
+            with open(path, "rb") as f:
+                out[f"{name}__{fl}"] = np.frombuffer(f.read(), dtype=np.uint8)
+            print(f"[vtk] {name} flavour {fl}: {out[f'{name}__{fl}'].size} bytes")
+    np.savez_compressed(os.path.join(outdir, "vtk_text.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="", help="generate one family only (e.g. vtk)")
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
     a = ap.parse_args()
     sys.path.insert(0, a.ref)
     os.makedirs(a.out, exist_ok=True)
+    if a.only == "vtk":
+        gen_vtk_text(a.ref, a.out)
+        return
     gen_cart(a.ref, a.out)
     gen_cart_gpu_algo(a.ref, a.out)
     gen_cyl(a.ref, a.out)
     gen_spiral_sim(a.ref, a.out)
     gen_cyl_birth(a.ref, a.out)
     gen_voxel_bc(a.ref, a.out)
+    gen_vtk_text(a.ref, a.out)
 
 
 if __name__ == "__main__":

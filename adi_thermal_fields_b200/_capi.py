@@ -22,6 +22,8 @@ SYMBOLS = (
     "adi_cart_zsweep_reduce", "adi_cart_zsweep_finish",
     "adi_voxel_project", "adi_voxel_correct", "adi_cart_step_host_async",
     "adi_cyl_set_slab", "adi_cyl_step_rphi", "adi_cyl_zsweep_reduce", "adi_cyl_zsweep_finish",
+    "adi_text_capacity", "adi_text_format", "adi_text_write",
+    "adi_probe_open", "adi_probe_record", "adi_probe_fetch",
 )
 
 
@@ -95,6 +97,16 @@ def load():
     L.adi_cyl_zsweep_reduce.argtypes = [vp, dp, C.POINTER(CylParams), dp, vp]
     L.adi_cyl_zsweep_finish.argtypes = [vp, dp, C.POINTER(CylParams), dp, bp, vp]
     L.adi_cyl_step_host.argtypes = [vp, vp, vp, C.c_int, C.POINTER(CylParams), vp, vp, vp]
+    ull = C.c_ulonglong
+    L.adi_text_capacity.argtypes = [C.c_size_t]
+    L.adi_text_capacity.restype = C.c_size_t
+    L.adi_text_format.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp,
+                                  C.c_size_t, C.POINTER(ull), vp]
+    L.adi_text_write.argtypes = [vp, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t, vp, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.POINTER(ull), vp]
+    L.adi_probe_open.argtypes = [vp, C.c_int, C.c_size_t]
+    L.adi_probe_record.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, vp]
+    L.adi_probe_fetch.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]
     _lib = L
     return L
 

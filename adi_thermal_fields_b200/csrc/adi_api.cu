@@ -82,6 +82,7 @@ int adi_ctx_destroy(adi_ctx *ctx)
     if (ctx->stage_mask) cudaFree(ctx->stage_mask);
     if (ctx->stage_src) cudaFree(ctx->stage_src);
     adi::cyl_release(ctx);
+    adi::text_release(ctx);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     delete ctx;
     return ADI_OK;
@@ -141,7 +142,7 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
     return ADI_OK;
 }
 
-long adi_launch_count(adi_ctx *ctx) { return ctx ? ctx->launches : -1; }
+long adi_launch_count(adi_ctx *ctx) { return ctx ? ctx->launches + adi::text_launches(ctx) : -1; }
 
 int adi_profile_reset(adi_ctx *ctx)
 {

@@ -27,6 +27,9 @@ struct Pack {
 };
 
 struct CylTables;  // adi_cyl.cu
+struct TextState;  // adi_text.cu: scratch of the ASCII output path and the probe slots
+void text_release(adi_ctx *ctx);
+long text_launches(adi_ctx *ctx);
 
 // profile helpers (adi_api.cu): record event #slot (0..4) of the current step:
 // 0 start, 1 after the explicit stage, 2 after the x|r sweep, 3 after y|phi, 4 after z
@@ -75,4 +78,7 @@ struct adi_ctx {
     uint8_t *stage_mask = nullptr;
     double *stage_src = nullptr;
     size_t stage_aux_cells = 0;
+
+    // ---- output path (own streams and buffers; may run beside the stepping thread) ----
+    adi::TextState *text = nullptr;
 };

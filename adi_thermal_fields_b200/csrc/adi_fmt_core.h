@@ -188,10 +188,11 @@ FMT_HD Dec round_sig(double v, const double *tab)
     const double lim_hi = P == 7 ? 1e7 : 1e6;   // 10^P
     const double lim_lo = P == 7 ? 1e6 : 1e5;   // 10^(P-1)
     Dec d;
+    // classify from the raw bits: the compiler may turn a sign-masked copy into abs.f64, whose
+    // result for a NaN input is unspecified in PTX (a negative NaN kept its sign on sm_100a)
     const uint64_t b = bits_of(v);
-    const uint64_t ab = b & ~(1ull << 63);
-    const int ef = (int)(ab >> 52);
-    const uint64_t frac = ab & ((1ull << 52) - 1);
+    const int ef = (int)(b >> 52) & 0x7ff;
+    const uint64_t frac = b & ((1ull << 52) - 1);
     d.neg = (int)(b >> 63);
     d.n = 0;
     d.k = 0;
@@ -199,7 +200,7 @@ FMT_HD Dec round_sig(double v, const double *tab)
         d.cls = frac ? CLS_NAN : CLS_INF;
         return d;
     }
-    if (ab == 0) {
+    if ((b << 1) == 0) {
         d.cls = CLS_ZERO;
         return d;
     }

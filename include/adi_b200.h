@@ -208,6 +208,39 @@ int adi_cyl_zsweep_reduce(adi_ctx *ctx, double *d_T, const adi_cyl_params *p, do
 int adi_cyl_zsweep_finish(adi_ctx *ctx, double *d_T, const adi_cyl_params *p, const double *d_y_all,
                           const uint8_t *d_active, void *stream);
 
+/* ---- output path ------------------------------------------------------------
+ * The reference writes its fields with per-value Python formatting:
+ *   fmt 0  vtk_writer.py:4-30  write_vtk_structured_points: "{float(v):.6e}", values in Fortran
+ *          order of the C-order array (x fastest), nine per line;
+ *   fmt 1  waam_from_stl_v7_mm.py:186-215 write_vtk_structured_points: "{float(T[i,j,k]):.6g}",
+ *          one line per (k, j) row of nx values.
+ * Here the device produces exactly those bytes (correctly rounded, ties to even, "nan"/"inf"
+ * spelled as Python does).  dtype: 0 = fp64, 1 = fp32, 2 = 1-byte mask (0/1).
+ * The output path keeps its own streams and buffers: these calls may be issued from a second
+ * host thread while the first one keeps stepping. */
+size_t adi_text_capacity(size_t nvalues);  /* bytes that always hold the text of nvalues values */
+/* Text of planes [k0, k0+kc) of the field into d_text (device, 16-byte aligned); *nbytes = its
+ * size.  Returns when the text is complete. */
+int adi_text_format(adi_ctx *ctx, const void *d_field, int dtype, int nx, int ny, int nz, int k0, int kc,
+                    int fmt, char *d_text, size_t capacity, unsigned long long *nbytes, void *stream);
+/* Opens `path` (truncate, or append when `append` != 0), writes `prefix` (the caller's header
+ * lines) and then the value lines of the whole field, formatted on the device in plane chunks
+ * and copied through pinned double buffers while the previous chunk is being written.  The
+ * field is read after everything queued on `stream` so far.  Returns when the file is closed. */
+int adi_text_write(adi_ctx *ctx, const char *path, int append, const void *prefix, size_t prefix_len,
+                   const void *d_field, int dtype, int nx, int ny, int nz, int fmt,
+                   unsigned long long *bytes_written, void *stream);
+/* Probe lines / slices / boxes (T[i0,j0,:], T[:,j0,:] ... in the drivers,
+ * quick_compare_neumann_robin_backend.py:147-150, waam_from_stl_v7_mm.py:497-513) without stalling
+ * the stepping stream: adi_probe_record packs the box [lo, hi) of a C-order (nx,ny,nz) array of
+ * elem_bytes (8/4/1) items on `stream` and hands the PCIe copy to a copy stream; adi_probe_fetch
+ * copies the landed record out (wait != 0 blocks until it is there; with wait == 0 it returns 1
+ * while the copy is still in flight).  A slot holds one record until it is fetched. */
+int adi_probe_open(adi_ctx *ctx, int nslots, size_t slot_bytes);
+int adi_probe_record(adi_ctx *ctx, int slot, const void *d_field, int elem_bytes, int nx, int ny, int nz,
+                     const int lo[3], const int hi[3], void *stream);
+int adi_probe_fetch(adi_ctx *ctx, int slot, void *h_dst, size_t capacity, size_t *nbytes, int wait);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,3 +88,18 @@ def cyl_step(c, M=16, nslab=1):
                              _ptr(act, C.c_uint8), _ptr(S, C.c_double), int(M), int(nslab))
     assert rc == 0
     return out
+
+
+def text_field(T, fmt):
+    """Value lines of a whole (nx,ny,nz) field, formatted by csrc/adi_fmt_core.h on the CPU."""
+    L = lib()
+    a = np.ascontiguousarray(T)
+    if a.dtype == np.bool_:
+        a = a.view(np.uint8)
+    code = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.uint8): 2}[a.dtype]
+    nx, ny, nz = a.shape
+    out = np.zeros(a.size * 15 + 16, dtype=np.uint8)
+    L.emu_text_field.restype = C.c_long
+    n = L.emu_text_field(a.ctypes.data_as(C.c_void_p), C.c_int(code), C.c_int(nx), C.c_int(ny), C.c_int(nz),
+                         C.c_int(fmt), out.ctypes.data_as(C.c_void_p))
+    return out[:n].tobytes()

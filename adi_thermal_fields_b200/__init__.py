@@ -7,6 +7,8 @@ and host-side mirrors of the reference's module interfaces:
 
   adi3d_gpu_coeff     Cartesian step, same names as the reference's adi3d_gpu_coeff.py
   adi3d_cyl_phi_v3    cylindrical (r, phi, z) backward-Euler step
+  vtk_writer          the reference's ASCII VTK writers (same bytes, formatted on the GPU), async frame
+                      writer and probe recorder
   dropin/             directory to put on sys.path in front of the reference tree:
                       `cupy` shim + the two module names above
 

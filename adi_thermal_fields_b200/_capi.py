@@ -16,7 +16,7 @@ SYMBOLS = (
     "adi_malloc", "adi_free", "adi_h2d", "adi_d2h",
     "adi_cart_bind", "adi_cart_set_mask", "adi_cart_set_pack", "adi_cart_set_robin_scalar",
     "adi_cart_step", "adi_cart_step_host", "adi_cart_build_packs", "adi_cart_exposed_mask",
-    "adi_set_option", "adi_launch_count", "adi_profile_reset", "adi_profile_read",
+    "adi_set_option", "adi_get_option", "adi_launch_count", "adi_profile_reset", "adi_profile_read",
     "adi_cyl_bind", "adi_cyl_step", "adi_cyl_step_host",
     "adi_cart_set_slab", "adi_cart_set_mask_halo", "adi_cart_pack_zplanes", "adi_cart_step_xy",
     "adi_cart_zsweep_reduce", "adi_cart_zsweep_finish",
@@ -76,6 +76,8 @@ def load():
                                        ip, C.POINTER(dbl), C.POINTER(vp)] + [dp] * 6 + [vp]
     L.adi_cart_exposed_mask.argtypes = [vp, C.c_int, bp, vp]
     L.adi_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    L.adi_get_option.argtypes = [vp, C.c_char_p]
+    L.adi_get_option.restype = C.c_long
     L.adi_launch_count.argtypes = [vp]
     L.adi_launch_count.restype = C.c_long
     L.adi_profile_reset.argtypes = [vp]

@@ -76,6 +76,8 @@ int adi_ctx_destroy(adi_ctx *ctx)
     for (int a = 0; a < 2; ++a)
         if (ctx->stage[a]) cudaFree(ctx->stage[a]);
     if (ctx->d_ghost) cudaFree(ctx->d_ghost);
+    if (ctx->d_viol) cudaFree(ctx->d_viol);
+    if (ctx->h_viol) cudaFreeHost(ctx->h_viol);
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 2; ++j)
             if (ctx->pipe[i][j]) cudaFree(ctx->pipe[i][j]);
@@ -134,12 +136,33 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
     else if (!strcmp(name, "sync_check")) ctx->opt_sync_check = value;
     else if (!strcmp(name, "profile")) ctx->opt_profile = value;
     else if (!strcmp(name, "wide")) ctx->opt_wide = value;  // 1: 512-thread blocks for lines <= 512 cells too
+    else if (!strcmp(name, "sparse_coeff")) {  // 1 (default): read verified surface-only coefficient fields at exposed cells only
+        ctx->opt_sparse = value;
+        ctx->sparse_dirty = true;
+    }
     else if (!strcmp(name, "fuse")) ctx->opt_fuse = value;  // 1: explicit stage fused into the x sweep
     else {
         adi::set_error(std::string("adi_set_option: unknown option ") + name);
         return ADI_EINVAL;
     }
     return ADI_OK;
+}
+
+long adi_get_option(adi_ctx *ctx, const char *name)
+{
+    if (!ctx || !name) return -1;
+    if (!strcmp(name, "kt")) return ctx->opt_kt;
+    if (!strcmp(name, "lt")) return ctx->opt_lt;
+    if (!strcmp(name, "m")) return ctx->opt_m;
+    if (!strcmp(name, "sync_check")) return ctx->opt_sync_check;
+    if (!strcmp(name, "profile")) return ctx->opt_profile;
+    if (!strcmp(name, "wide")) return ctx->opt_wide;
+    if (!strcmp(name, "fuse")) return ctx->opt_fuse;
+    if (!strcmp(name, "sparse_coeff")) return ctx->opt_sparse;
+    if (!strcmp(name, "sparse_active"))  // bit a: the sweep along axis a currently skips interior coefficient reads
+        return ctx->sparse_dirty ? 0 : ((ctx->sparse[0] ? 1 : 0) | (ctx->sparse[1] ? 2 : 0) | (ctx->sparse[2] ? 4 : 0));
+    adi::set_error(std::string("adi_get_option: unknown option ") + name);
+    return -1;
 }
 
 long adi_launch_count(adi_ctx *ctx) { return ctx ? ctx->launches + adi::text_launches(ctx) : -1; }

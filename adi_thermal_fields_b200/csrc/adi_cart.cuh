@@ -26,6 +26,8 @@ struct SweepArgs {
     double *out;
     const uint8_t *__restrict__ code;
     const double *__restrict__ coeff;  // CMODE 2
+    int sparse;                        // CMODE 2, x / y sweeps: coeff is +0.0 wherever the cell has both neighbours
+                                       // along the sweep axis (verified by k_check_sparse): read it at exposed cells only
     const double *__restrict__ q;      // EXTRA, may be null
     const double *__restrict__ dirv;   // EXTRA, may be null
     int nx, ny, nz;
@@ -321,8 +323,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
         const unsigned nth8 = (unsigned)NTH * 8u;
         if (CMODE == 2) {
             const char *cf = reinterpret_cast<const char *>(a.coeff + idx0);
+            if (!a.sparse) {
 #pragma unroll
-            for (int e = 0; e < M; ++e) cp_async8(scol + e * nth8, cf + (size_t)((unsigned)min(e, nvm1) * sl8));
+                for (int e = 0; e < M; ++e) cp_async8(scol + e * nth8, cf + (size_t)((unsigned)min(e, nvm1) * sl8));
+            } else {
+                // surface-only coefficient field: the two ends of the line (always exposed when active) are
+                // requested now, cells next to an interior void once the codes have arrived (below)
+#pragma unroll
+                for (int e = 0; e < M; ++e) {
+                    const int cell = t0 + e;
+                    if (e < nv && (cell == 0 || cell == n - 1)) cp_async8(scol + e * nth8, cf + (size_t)((unsigned)e * sl8));
+                }
+            }
         }
         if (EXPL) {
             // AXIS 0: blockIdx.y is the y index
@@ -379,6 +391,21 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
 #pragma unroll
         for (int e = 0; e < M; ++e) ch.T[e] = ch.active(e) ? ch.T[e] : 0.0;  // load rule (adi_core.h)
     }
+    const bool ends_only = STAGED && CMODE == 2 && a.sparse && solid;
+    if (STAGED && CMODE == 2 && a.sparse) {
+        // the codes are in: coefficient slots of the cells with an exposed face along this axis are fetched
+        // now, the others zeroed; a solid chunk can only be exposed at its two end cells
+        const char *cf = reinterpret_cast<const char *>(a.coeff + idx0);
+        const unsigned sl8 = sl * 8u;
+#pragma unroll
+        for (int e = 0; e < M; ++e) {
+            if (solid && e != 0 && e != M - 1) continue;
+            const unsigned c = ch.code(e);  // 0 beyond the chunk's valid cells
+            const int cell = t0 + e;
+            if (e < nv && (cell == 0 || cell == n - 1)) continue;  // staged above
+            col[e * NTH] = ((c & CB_SELF) && (c & (LO | HI)) != (LO | HI)) ? ldg_f64(cf + (size_t)((unsigned)e * sl8)) : 0.0;
+        }
+    }
 
     if (EXPL && STAGED) {
         double prev = (ch.code(0) & CB_XM) ? xprev : 0.0;
@@ -434,7 +461,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
     ops.NTH = NTH;
 
     First f;
-    if (solid) f = chunk_forward<M, CMODE, EXTRA, NS, true>(ch, ops, LO, HI, a.k);
+    if (ends_only) f = chunk_forward<M, CMODE, EXTRA, NS, true, CMODE == 2>(ch, ops, LO, HI, a.k);
+    else if (solid) f = chunk_forward<M, CMODE, EXTRA, NS, true>(ch, ops, LO, HI, a.k);
     else f = chunk_forward<M, CMODE, EXTRA, NS, false>(ch, ops, LO, HI, a.k);
     if (EXPL && STAGED) __syncthreads();  // slot 2 (other threads' y+ values) becomes the exchange buffer
     double Sl;
@@ -994,6 +1022,35 @@ __global__ void k_exposed_mask(const uint8_t *__restrict__ mask, uint8_t *__rest
         const int i = (int)(ij / ny);
         out[idx] = (uint8_t)((exposed_bits(mask, idx, i, j, k, nx, ny, nz, mlo, mhi) >> face) & 1u);
     }
+}
+
+// K8: is a bound dense coefficient field "surface-only"?  viol[ax] counts the active, non-Dirichlet cells
+// with both neighbours along axis ax whose coefficient is not +0.0 (bit pattern): when it is 0 the sweep
+// may read the field at exposed cells only and take +0.0 elsewhere -- bit-identical rows.
+struct SparseCheckArgs {
+    const double *coeff[3];
+    const uint8_t *code[3];
+    unsigned long long *viol;  // [3]
+};
+
+__global__ void k_check_sparse(const SparseCheckArgs a, size_t n)
+{
+    unsigned long long bad[3] = {0ull, 0ull, 0ull};
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+            if (!a.coeff[ax]) continue;
+            const unsigned c = a.code[ax][idx];
+            const unsigned both = (CB_XM | CB_XP) << (2 * ax);
+            if ((c & CB_SELF) && !(c & CB_DIR) && (c & both) == both &&
+                __double_as_longlong(a.coeff[ax][idx]) != 0ll)
+                bad[ax]++;
+        }
+    }
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax)
+        if (bad[ax]) atomicAdd(a.viol + ax, bad[ax]);
 }
 #endif  // ADI_CART_MISC_KERNELS (K7)
 

@@ -202,7 +202,9 @@ ADI_HD unsigned solid_code(const Chunk<M> &ch, int e, unsigned lo, unsigned hi)
 }
 
 // Phase 1.  SOLID: the chunk passed chunk_solid (same arithmetic, selects folded away).
-template <int M, int CMODE, bool EXTRA, int NS, bool SOLID = false, class OPS>
+// ENDS_ONLY (with SOLID, CMODE 2): the coefficient field is known to vanish on cells that have both
+// neighbours, i.e. everywhere in a solid chunk except possibly its two end cells.
+template <int M, int CMODE, bool EXTRA, int NS, bool SOLID = false, bool ENDS_ONLY = false, class OPS>
 ADI_HD First chunk_forward(Chunk<M> &ch, OPS &ops, unsigned lo, unsigned hi, const SweepConst &k)
 {
     double uprev = 0.0, dprev = 0.0, vprev = 1.0, alpha = 1.0;
@@ -211,7 +213,7 @@ ADI_HD First chunk_forward(Chunk<M> &ch, OPS &ops, unsigned lo, unsigned hi, con
 #pragma unroll
     for (int e = 0; e < M - 1; ++e) {
         const Row r = make_row<CMODE, EXTRA>(SOLID ? solid_code<M>(ch, e, lo, hi) : ch.code(e), lo, hi, ch.T[e],
-                                             CMODE == 2 ? ops.coef(e) : 0.0,
+                                             CMODE == 2 ? ((ENDS_ONLY && e != 0) ? 0.0 : ops.coef(e)) : 0.0,
                                              EXTRA ? ops.q(e) : 0.0, EXTRA ? ops.dirv(e) : 0.0, k);
         // e == 0: the coupling aa to S_{p-1} stays symbolic (uprev = dprev = 0, vprev = 1)
         const double den = fma(-r.aa, uprev, r.b);      // b - a*c'_{e-1}

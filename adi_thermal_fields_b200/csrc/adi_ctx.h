@@ -41,7 +41,7 @@ struct adi_ctx {
     int device = 0;
     long launches = 0;
     // options (adi_set_option)
-    long opt_kt = 0, opt_lt = 0, opt_m = 0, opt_sync_check = 0, opt_profile = 0, opt_fuse = 0, opt_wide = 0;
+    long opt_kt = 0, opt_lt = 0, opt_m = 0, opt_sync_check = 0, opt_profile = 0, opt_fuse = 0, opt_wide = 0, opt_sparse = 1;
     // per-kernel timing (adi_profile_*): 5 events per step, read lazily
     std::vector<cudaEvent_t> prof_ev;
     long prof_steps = 0;
@@ -58,6 +58,10 @@ struct adi_ctx {
     uint8_t *code_buf[3] = {nullptr, nullptr, nullptr};
     size_t code_cells = 0;
     bool code_dirty = true;
+    // surface-only coefficient fields (k_check_sparse): re-examined after a pack or mask change
+    bool sparse[3] = {false, false, false};
+    bool sparse_dirty = true;
+    unsigned long long *d_viol = nullptr, *h_viol = nullptr;  // [3] each
     // z-slab decomposition: mask planes of the adjacent slabs (borrowed), scratch for the ghosts
     int slab_rank = 0, slab_nranks = 1;
     const uint8_t *d_mask_lo = nullptr, *d_mask_hi = nullptr;

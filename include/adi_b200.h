@@ -140,8 +140,15 @@ int adi_cart_zsweep_finish(adi_ctx *ctx, double *d_T, const double *d_dyn_all, c
  *   "kt"    lanes along z per block of the strided sweeps (power of two)     "lt"  lines per block of the z sweeps
  *   "m"     chunk length 16 | 32                                             "wide" 1: 512-thread blocks for lines <= 512 cells
  *   "fuse"  1: explicit stage fused into the x sweep instead of its own pass
+ *   "sparse_coeff" 1 (default): after every pack / mask change the dense coefficient fields of the x and y packs are
+ *           examined (one pass, one small read-back); a field that is +0.0 on every active cell with both neighbours
+ *           along its axis -- as everything precompute_coeff_packs_unified builds is -- is then read at exposed cells
+ *           only.  Same bits as the dense reads; 0 switches the examination off
  *   "profile" 1: record per-kernel CUDA events (adi_profile_read)            "sync_check" 1: synchronise after every step */
 int adi_set_option(adi_ctx *ctx, const char *name, long value);
+long adi_get_option(adi_ctx *ctx, const char *name);  /* value of an option; "sparse_active": bit a set when the
+                                                          sweep along axis a reads its coefficient field at exposed
+                                                          cells only (state after the last step); -1 = unknown name */
 long adi_launch_count(adi_ctx *ctx);
 /* Per-kernel device timing (the `[time]` prints of quick_compare_neumann_robin_backend.py:
  * 173-186 are the reference's only profiling hook).  After adi_set_option(ctx,"profile",1)

@@ -382,3 +382,74 @@ def test_pipelined_host_fields(g, golden_dir):
     for f, o in zip(fields, outs):
         ref = g.adi_step_host(f, grid, mat, prm, packs, Tinf=c["Tinf"])
         assert np.array_equal(o, ref, equal_nan=True)
+
+
+# ---- surface-only coefficient fields: the sweeps read them at exposed cells only -----------------
+@pytest.mark.parametrize("shape", [(40, 67, 130), (96, 33, 64), (600, 7, 48), (5, 1024, 24), (33, 18, 37), (20, 20, 515)])
+def test_sparse_coefficient_reads_are_bit_identical(shape, g, cp):
+    """Packs from precompute_coeff_packs_unified vanish away from the surface (adi3d_numba_coeff.py:93-99);
+    the engine verifies that (k_check_sparse) and skips the interior coefficient reads.  Same bits as
+    with the dense reads (option sparse_coeff=0), and parity with the oracle either way."""
+    c = _oracle_case(shape, seed=7000 + shape[0])
+    nx, ny, nz = shape
+    gd = g.Grid3D(nx, ny, nz, cases.DX, c["mask"])
+    md = g.Material(cases.RHO, cases.CP, cases.K)
+    pd = g.precompute_coeff_packs_unified(gd, md, **c["bcs"])
+    outs = []
+    try:
+        for sparse in (1, 0):
+            g.set_option("sparse_coeff", sparse)
+            T = cp.asarray(c["T0"])
+            for _ in range(2):
+                T = g.adi_step_gpu_coeff(T, gd, md, g.Params(c["dt"], c["theta"]), pd, Tinf=20.0)
+            outs.append(cp.asnumpy(T))
+    finally:
+        g.set_option("sparse_coeff", 1)
+    assert np.array_equal(outs[0], outs[1], equal_nan=True)
+    _both(g, cp, c)
+
+
+def test_coefficient_fields_dense_on_one_axis_only(g, cp):
+    """A caller-made x pack with non-zero coefficients in the interior next to surface-only y / z packs:
+    the x sweep must keep its dense reads."""
+    from oracle import cart
+    shape = (37, 29, 48)
+    nx, ny, nz = shape
+    c = _oracle_case(shape, seed=7100)
+    gh = cart.Grid3D(nx, ny, nz, cases.DX, c["mask"])
+    mh = cart.Material(cases.RHO, cases.CP, cases.K)
+    ph = list(cart.precompute_coeff_packs_unified(gh, mh, **c["bcs"]))
+    dense = 3.0 * cases.splitmix_uniform(7101, shape)
+    ph[0] = cart.AxisCoeffPack(dense, ph[0].dir_mask, ph[0].dir_val, ph[0].qflux)
+    gd = g.Grid3D(nx, ny, nz, cases.DX, c["mask"])
+    md = g.Material(cases.RHO, cases.CP, cases.K)
+    pd = list(g.precompute_coeff_packs_unified(gd, md, **c["bcs"]))
+    pd[0] = g.AxisCoeffPack(cp.asarray(dense), pd[0].dir_mask, pd[0].dir_val, pd[0].qflux)
+    Th = cart.adi_step_numba_coeff(c["T0"], gh, mh, cart.Params(c["dt"], 0.5), ph, Tinf=20.0)
+    Td = cp.asnumpy(g.adi_step_gpu_coeff(cp.asarray(c["T0"]), gd, md, g.Params(c["dt"], 0.5), pd, Tinf=20.0))
+    assert cases.rel_l2(Td, Th, c["mask"]) <= TOL
+
+
+def test_coefficient_edited_in_place_is_reexamined(g, cp):
+    """After a step, the caller writes a coefficient into an interior cell of the bound z pack: the
+    next step must use it (the pack is re-bound and re-examined, not assumed surface-only)."""
+    from oracle import cart
+    shape = (24, 25, 40)
+    nx, ny, nz = shape
+    c = _oracle_case(shape, seed=7200, holes=False)
+    c["bcs"] = dict(robin_h=c["bcs"]["robin_h"])
+    gh = cart.Grid3D(nx, ny, nz, cases.DX, c["mask"])
+    mh = cart.Material(cases.RHO, cases.CP, cases.K)
+    ph = cart.precompute_coeff_packs_unified(gh, mh, **c["bcs"])
+    gd = g.Grid3D(nx, ny, nz, cases.DX, c["mask"])
+    md = g.Material(cases.RHO, cases.CP, cases.K)
+    pd = g.precompute_coeff_packs_unified(gd, md, **c["bcs"])
+    prm_h, prm_d = cart.Params(c["dt"], 0.5), g.Params(c["dt"], 0.5)
+    Th = cart.adi_step_numba_coeff(c["T0"], gh, mh, prm_h, ph, Tinf=20.0)
+    Td = g.adi_step_gpu_coeff(cp.asarray(c["T0"]), gd, md, prm_d, pd, Tinf=20.0)
+    ph[2].coeff[10:14, 11, 17:23] = 7.5
+    pd[2].coeff[10:14, 11, 17:23] = 7.5
+    Th = cart.adi_step_numba_coeff(Th, gh, mh, prm_h, ph, Tinf=20.0)
+    Td = g.adi_step_gpu_coeff(Td, gd, md, prm_d, pd, Tinf=20.0)
+    assert cases.rel_l2(cp.asnumpy(Td), Th, c["mask"]) <= TOL
+    assert abs(cp.asnumpy(Td)[12, 11, 20] - Th[12, 11, 20]) <= 1e-9 * abs(Th[12, 11, 20])

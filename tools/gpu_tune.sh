@@ -13,5 +13,5 @@ for o in "$@"; do
   timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --e2e-steps 1 $o 2>>gpurun_out/${tag}_tune.err | tee -a gpurun_out/${tag}_tune.jsonl | python -c "
 import sys,json
 for l in sys.stdin:
-    d=json.loads(l); r=d['roofline']; print('ms/step %.3f  value %.3e  sweeps %s  step_frac %.3f' % (d['ms_per_step'], d['value'], {k: round(v,3) for k,v in r['sweep_ms'].items()}, r['step_frac']))"
+    d=json.loads(l); r=d['roofline']; print('ms/step %.3f  value %.3e  sweeps %s  step_frac %.3f' % (d['ms_per_step'], d['value'], {k: round(v,3) for k,v in r.get('kernel_ms', r.get('sweep_ms', {})).items()}, r['step_frac']))"
 done

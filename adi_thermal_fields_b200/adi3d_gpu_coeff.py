@@ -126,6 +126,8 @@ class _Engine:
         self.pack_keys = [None, None, None]
         self.scalar_key = None
         self.hold = []
+        self.trust = 0
+        self.mask_epoch = 0          # counts adi_cart_set_mask calls: identifies the bound mask state
 
     def context(self):
         if self.ctx is None:
@@ -163,6 +165,8 @@ class _Engine:
             _capi.check(self.lib().adi_cart_set_mask(self.context(), m._t.data_ptr()), "adi_cart_set_mask")
             self.mask_key = key
             self.mask_hold = m
+            self.mask_epoch += 1
+            self.trust = -1          # the engine dropped its trust bits: set_packs re-asserts them
 
     def set_packs(self, packs):
         """Bind the three packs.  The arrays are kept alive in self.hold until replaced, so a
@@ -186,6 +190,19 @@ class _Engine:
                 _capi.check(L.adi_cart_set_pack(ctx, a, ptr[0], ptr[1], ptr[2], ptr[3]), "adi_cart_set_pack")
                 self.pack_keys[a] = key
                 touched = True
+        # packs straight from the device builder, for the mask that is bound now and untouched since, are
+        # surface-only by construction: the engine may skip its examination pass (option sparse_trust)
+        trust = 0
+        if not scalar:
+            for a, p in enumerate(packs[:2]):
+                b = getattr(p, "_built", None)
+                c = hold[a][0]
+                if b is not None and c is not None and b == (c._t.data_ptr(), c._t._version, self.mask_epoch):
+                    trust |= 1 << a
+        if touched or trust != self.trust:
+            # set_pack clears the engine's trust bits, so they are re-asserted after every rebind
+            _capi.check(L.adi_set_option(ctx, b"sparse_trust", trust), "adi_set_option")
+            self.trust = trust
         if scalar:
             fc = tuple(float(v) for p in packs for v in p._face_coeff)
             if touched or fc != self.scalar_key:
@@ -309,7 +326,10 @@ def precompute_coeff_packs_unified(grid, mat, dir_mask=None, dir_value=None, neu
                 e.bind(grid)
                 e.set_mask(grid)
                 return run_build(True, False)[0][a]
-        packs.append(AxisCoeffPack._symbolic(shape, coeffs[a], dm, dv, qouts[a], face_coeff=fc, builder=builder))
+        pk = AxisCoeffPack._symbolic(shape, coeffs[a], dm, dv, qouts[a], face_coeff=fc, builder=builder)
+        if coeffs[a] is not None:
+            pk._built = (coeffs[a]._t.data_ptr(), coeffs[a]._t._version, e.mask_epoch)
+        packs.append(pk)
     return tuple(packs)
 
 

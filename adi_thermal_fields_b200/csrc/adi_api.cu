@@ -140,6 +140,10 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
         ctx->opt_sparse = value;
         ctx->sparse_dirty = true;
     }
+    else if (!strcmp(name, "sparse_trust")) {
+        ctx->sparse_trust = value;
+        ctx->sparse_dirty = true;
+    }
     else if (!strcmp(name, "fuse")) ctx->opt_fuse = value;  // 1: explicit stage fused into the x sweep
     else {
         adi::set_error(std::string("adi_set_option: unknown option ") + name);

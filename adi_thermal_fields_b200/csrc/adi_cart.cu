@@ -79,12 +79,17 @@ int ensure_sparse(adi_ctx *ctx, cudaStream_t st)
         ADI_CUDA(cudaMallocHost(&ctx->h_viol, 3 * sizeof(unsigned long long)));
     }
     SparseCheckArgs c;
+    bool work = false;
     for (int a = 0; a < 3; ++a) {
         // x and y only: the z sweep stages whole contiguous lines and gained nothing from skipping
         // coefficient reads (0.65 -> 0.66 ms at 512^3; 0.88 ms with per-chunk fetches)
-        c.coeff[a] = a < 2 ? ctx->pack[a].coeff : nullptr;
+        const bool trusted = (ctx->sparse_trust >> a) & 1;
+        c.coeff[a] = (a < 2 && !trusted) ? ctx->pack[a].coeff : nullptr;
         c.code[a] = ctx->code[a];
+        if (a < 2 && trusted && ctx->pack[a].coeff) ctx->sparse[a] = true;
+        work = work || c.coeff[a] != nullptr;
     }
+    if (!work) return ADI_OK;
     c.viol = ctx->d_viol;
     ADI_CUDA(cudaMemsetAsync(ctx->d_viol, 0, 3 * sizeof(unsigned long long), st));
     const int threads = 256;
@@ -94,7 +99,8 @@ int ensure_sparse(adi_ctx *ctx, cudaStream_t st)
     ADI_CUDA(cudaGetLastError());
     ADI_CUDA(cudaMemcpyAsync(ctx->h_viol, ctx->d_viol, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     ADI_CUDA(cudaStreamSynchronize(st));
-    for (int a = 0; a < 2; ++a) ctx->sparse[a] = ctx->pack[a].coeff != nullptr && ctx->h_viol[a] == 0ull;
+    for (int a = 0; a < 2; ++a)
+        if (c.coeff[a]) ctx->sparse[a] = ctx->h_viol[a] == 0ull;
     return ADI_OK;
 }
 
@@ -142,6 +148,7 @@ int adi_cart_bind(adi_ctx *ctx, int nx, int ny, int nz, double dx)
     for (int a = 0; a < 3; ++a) ctx->pack[a] = Pack();
     ctx->scalar_robin = false;
     ctx->code_dirty = true;
+    ctx->sparse_trust = 0;
     return ADI_OK;
 }
 
@@ -151,6 +158,7 @@ int adi_cart_set_mask(adi_ctx *ctx, const uint8_t *d_mask)
     if (rc) return rc;
     ctx->d_mask = d_mask;
     ctx->code_dirty = true;
+    ctx->sparse_trust = 0;
     return ADI_OK;
 }
 
@@ -172,6 +180,7 @@ int adi_cart_set_pack(adi_ctx *ctx, int axis, const double *d_coeff, const uint8
     p.coeff = d_coeff; p.dirm = d_dir_mask; p.dirv = d_dir_mask ? d_dir_val : nullptr; p.q = d_qflux;
     ctx->scalar_robin = false;
     ctx->sparse_dirty = true;
+    ctx->sparse_trust = 0;
     return ADI_OK;
 }
 
@@ -184,6 +193,7 @@ int adi_cart_set_robin_scalar(adi_ctx *ctx, const double face_coeff[6])
     for (int a = 0; a < 3; ++a) ctx->pack[a].coeff = nullptr;
     ctx->scalar_robin = true;
     ctx->sparse_dirty = true;
+    ctx->sparse_trust = 0;
     return ADI_OK;
 }
 
@@ -299,6 +309,7 @@ int adi_cart_set_mask_halo(adi_ctx *ctx, const uint8_t *d_mask_lo, const uint8_t
     if (rc) return rc;
     ctx->d_mask_lo = d_mask_lo; ctx->d_mask_hi = d_mask_hi;
     ctx->code_dirty = true;
+    ctx->sparse_trust = 0;
     return ADI_OK;
 }
 

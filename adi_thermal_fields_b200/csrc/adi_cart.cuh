@@ -375,15 +375,27 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_strided(const SweepArgs a)
             xnext = ldg_f64(tb + ((nv == M && t0 + M < n) ? (long long)M * sl8 : 0ll));
         }
         // The barrier keeps every load above it (the compiler would otherwise sink them next
-        // to their uses, one memory round trip per batch); the wait comes after it.
-        __syncthreads();
+        // to their uses, one memory round trip per batch); the wait comes after it.  It also tells
+        // whether the tile holds an active cell at all: in place, a tile of void cells (the space around
+        // a part that is still being built) has nothing to solve and nothing to write.
+        bool any = false;
+#pragma unroll
+        for (int w = 0; w < (M + 3) / 4; ++w) any = any || (ch.cw[w] & 0x01010101u) != 0u;
+        const bool live = __syncthreads_or(any);
         cp_async_wait_all();
+        if (!EXPL && a.in == a.out && !live) return;
     } else {
         const uint8_t *cp = a.code + idx0;
 #pragma unroll
         for (int e = 0; e < M; ++e) ch.set_code(e, e < nv ? (unsigned)cp[e * sl] : 0u);
 #pragma unroll
         for (int e = 0; e < M; ++e) ch.T[e] = e < nv ? tp[e * sl] : 0.0;
+    }
+    if (!STAGED && !EXPL && a.in == a.out) {
+        bool any = false;
+#pragma unroll
+        for (int w = 0; w < (M + 3) / 4; ++w) any = any || (ch.cw[w] & 0x01010101u) != 0u;
+        if (!__syncthreads_or(any)) return;
     }
     // solid tile rows (all chunks of the warp full and without void / Dirichlet cells): the bulk of a part
     const bool solid = !EXPL && NS == 2 && __all_sync(0xffffffffu, nv == M && chunk_solid<M>(ch, LO, HI));
@@ -739,7 +751,16 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
     const bool warp_lines = P <= 32 && (P & (P - 1)) == 0;
     // warps whose chunks are all solid (adi_core.h) take the row arithmetic with the code folded away
     const bool solid = NS == 2 && __all_sync(0xffffffffu, chunk_solid<M>(ch, CB_ZM, CB_ZP));
-    __syncthreads();  // sT is reused as the reduced-system exchange buffer from here on
+    if ((ZMODE == 0 || ZMODE == 2) && a.in == a.out) {
+        // lines without an active cell (the void around a part that is still being built): nothing to
+        // solve, nothing to write (the sweep is in place); this barrier also frees sT for the exchange buffer
+        bool any = false;
+#pragma unroll
+        for (int w = 0; w < M / 4; ++w) any = any || (ch.cw[w] & 0x01010101u) != 0u;
+        if (!__syncthreads_or(any)) return;
+    } else {
+        __syncthreads();  // sT is reused as the reduced-system exchange buffer from here on
+    }
 
     TileOps<M> ops;
     ops.c = sC + (size_t)ln * RL + p * M;

@@ -61,6 +61,8 @@ struct adi_ctx {
     // surface-only coefficient fields (k_check_sparse): re-examined after a pack or mask change
     bool sparse[3] = {false, false, false};
     bool sparse_dirty = true;
+    long sparse_trust = 0;  // bit a: the caller vouches for pack a (built by adi_cart_build_packs for the bound
+                            // mask and untouched since); cleared by every pack / mask call
     unsigned long long *d_viol = nullptr, *h_viol = nullptr;  // [3] each
     // z-slab decomposition: mask planes of the adjacent slabs (borrowed), scratch for the ghosts
     int slab_rank = 0, slab_nranks = 1;

@@ -24,3 +24,6 @@ ncu --set full --clock-control none --import-source on -k regex:k_cyl -s 9 -c 3 
     python tools/cyl_probe.py 256 1024 512 --steps 2 > gpurun_out/${tag}_ncu3.log 2>&1
 tail -3 gpurun_out/${tag}_ncu3.log
 fi
+if [ "${C4:-0}" = "1" ]; then
+timeout 600 python bench.py --workload c4 --steps 8 --warmup 3 > gpurun_out/${tag}_c4.json 2> gpurun_out/${tag}_c4.err; cat gpurun_out/${tag}_c4.json; tail -2 gpurun_out/${tag}_c4.err
+fi

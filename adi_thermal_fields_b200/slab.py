@@ -156,6 +156,7 @@ class CudaBackend:
         _capi.check(self.L.adi_ctx_create(self.dev.index, C.byref(h)), "adi_ctx_create")
         self.ctx = h
         self.hold = None
+        self.pack_key = None
 
     def _st(self):
         return torch.cuda.current_stream().cuda_stream
@@ -172,6 +173,7 @@ class CudaBackend:
         _capi.check(L.adi_cart_bind(self.ctx, nx, ny, nz, dx), "adi_cart_bind")
         _capi.check(L.adi_cart_set_slab(self.ctx, rank, world), "adi_cart_set_slab")
         _capi.check(L.adi_cart_set_mask(self.ctx, mask.data_ptr()), "adi_cart_set_mask")
+        self.pack_key = None
 
     def pack_planes(self, field, lo, hi):
         _capi.check(self.L.adi_cart_pack_zplanes(self.ctx, field.data_ptr(), field.element_size(),
@@ -203,13 +205,20 @@ class CudaBackend:
 
     def set_packs(self, packs, face_coeff):
         """packs: 3 x (coeff|None, dir_mask|None, dir_val|None, q|None) device arrays."""
-        self.hold = packs
+        # re-bound only when an array was replaced or written (tensor version): every adi_cart_set_pack makes
+        # the engine re-examine the coefficient fields (option sparse_coeff), one pass and one read-back
+        key = (tuple(None if x is None else (x.data_ptr(), x._version) for p in packs for x in p),
+               None if face_coeff is None else tuple(face_coeff))
+        if key == self.pack_key:
+            return
+        self.hold = packs            # keeps the keyed tensors alive
         for a, (c, dm, dv, q) in enumerate(packs):
             p = [None if x is None else x.data_ptr() for x in (c, dm, dv, q)]
             _capi.check(self.L.adi_cart_set_pack(self.ctx, a, *p), "adi_cart_set_pack")
         if face_coeff is not None:
             _capi.check(self.L.adi_cart_set_robin_scalar(self.ctx, (C.c_double * 6)(*face_coeff)),
                         "adi_cart_set_robin_scalar")
+        self.pack_key = key
 
     def step_xy(self, Tin, Tout, Tlo, Thi, dt, theta, kappa, Tinf):
         _capi.check(self.L.adi_cart_step_xy(self.ctx, Tin.data_ptr(), Tout.data_ptr(),

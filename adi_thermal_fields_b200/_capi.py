@@ -20,6 +20,7 @@ SYMBOLS = (
     "adi_cyl_bind", "adi_cyl_step", "adi_cyl_step_host",
     "adi_cart_set_slab", "adi_cart_set_mask_halo", "adi_cart_pack_zplanes", "adi_cart_step_xy",
     "adi_cart_zsweep_reduce", "adi_cart_zsweep_finish",
+    "adi_cart_zsweep_spike", "adi_cart_zsweep_solve0", "adi_cart_zsweep_apply",
     "adi_voxel_project", "adi_voxel_correct", "adi_cart_step_host_async",
     "adi_cyl_set_slab", "adi_cyl_step_rphi", "adi_cyl_zsweep_reduce", "adi_cyl_zsweep_finish",
     "adi_text_capacity", "adi_text_format", "adi_text_write",
@@ -88,6 +89,9 @@ def load():
     L.adi_cart_step_xy.argtypes = [vp, dp, dp, dp, dp, dbl, dbl, dbl, dbl, vp]
     L.adi_cart_zsweep_reduce.argtypes = [vp, dp, dp, dp, dbl, dbl, dbl, dbl, vp]
     L.adi_cart_zsweep_finish.argtypes = [vp, dp, dp, dp, dbl, dbl, dbl, dbl, vp]
+    L.adi_cart_zsweep_spike.argtypes = [vp, dp, C.c_int, C.c_int, dbl, dp, vp, ip, dbl, dbl, dbl, vp]
+    L.adi_cart_zsweep_solve0.argtypes = [vp, dp, dp, dbl, dbl, dbl, dbl, vp]
+    L.adi_cart_zsweep_apply.argtypes = [vp, dp, dp, dp, dp, dp, vp, vp, C.c_int, vp]
     L.adi_voxel_project.argtypes = [vp, dp, dp, dp, C.c_int, C.POINTER(dbl), dbl, C.c_int, dbl, bp, C.c_int, C.c_int,
                                     C.c_int, C.POINTER(vp), vp]
     L.adi_voxel_correct.argtypes = [vp, bp, C.c_int, C.c_int, C.c_int, dbl, C.POINTER(vp), ip, C.POINTER(dbl), C.c_int,

@@ -76,6 +76,7 @@ int adi_ctx_destroy(adi_ctx *ctx)
     for (int a = 0; a < 2; ++a)
         if (ctx->stage[a]) cudaFree(ctx->stage[a]);
     if (ctx->d_ghost) cudaFree(ctx->d_ghost);
+    if (ctx->d_maxk) cudaFree(ctx->d_maxk);
     if (ctx->d_viol) cudaFree(ctx->d_viol);
     if (ctx->h_viol) cudaFreeHost(ctx->h_viol);
     for (int i = 0; i < 2; ++i)

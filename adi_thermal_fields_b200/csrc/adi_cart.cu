@@ -251,17 +251,17 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
         a.code = ctx->code[axis];
         a.coeff = p.coeff;
         a.sparse = ctx->sparse[axis] ? 1 : 0;
-        a.q = p.q;
-        a.dirv = p.dirv;
+        a.q = zmode == 5 ? nullptr : p.q;        // 5: homogeneous system (unit-ghost response)
+        a.dirv = zmode == 5 ? nullptr : p.dirv;
         a.k.h_lo = ctx->scalar_robin ? ctx->face_coeff[2 * axis] : 0.0;
         a.k.h_hi = ctx->scalar_robin ? ctx->face_coeff[2 * axis + 1] : 0.0;
         const bool dense = p.coeff != nullptr;
         const bool extra = p.q != nullptr || p.dirm != nullptr;
         if (axis == 0) rc = launch_sweep_x(ctx, a, dense, extra, expl, st);
         else if (axis == 1) rc = launch_sweep_y(ctx, a, dense, extra, st);
-        else rc = launch_sweep_z(ctx, a, dense, extra, zmode, st);
+        else rc = launch_sweep_z(ctx, a, dense, extra, zmode == 5 ? 2 : zmode, st);
         if (rc) return rc;
-        if (zmode != 1 && zmode != 3) {
+        if (zmode == 0 || zmode == 2) {
             rc = prof_mark(ctx, axis + 2, st);
             if (rc) return rc;
         }
@@ -394,6 +394,92 @@ int adi_cart_zsweep_finish(adi_ctx *ctx, double *d_T, const double *d_dyn_all, c
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
     return run_sweeps(ctx, d_T, d_T, dt, theta, kappa, Tinf, 2, 2, 2, nullptr, nullptr, nullptr, nullptr, ctx->d_ghost, st);
+}
+
+static int ensure_ghost(adi_ctx *ctx, size_t nlines, cudaStream_t st)
+{
+    if (ctx->ghost_lines < nlines) {
+        if (ctx->d_ghost) { ADI_CUDA(cudaStreamSynchronize(st)); ADI_CUDA(cudaFree(ctx->d_ghost)); }
+        ctx->d_ghost = nullptr;
+        ADI_CUDA(cudaMalloc(&ctx->d_ghost, 2 * nlines * sizeof(double)));
+        ctx->ghost_lines = nlines;
+    }
+    return ADI_OK;
+}
+
+int adi_cart_zsweep_solve0(adi_ctx *ctx, double *d_T, double *d_iface_dyn, double dt, double theta, double kappa,
+                           double Tinf, void *stream)
+{
+    int rc = check_cart(ctx, "adi_cart_zsweep_solve0");
+    if (rc) return rc;
+    if (!d_T || !d_iface_dyn) {
+        set_error("adi_cart_zsweep_solve0: NULL argument");
+        return ADI_EINVAL;
+    }
+    return run_sweeps(ctx, d_T, d_T, dt, theta, kappa, Tinf, 2, 2, 4, nullptr, nullptr, d_iface_dyn, nullptr, nullptr,
+                      (cudaStream_t)stream);
+}
+
+int adi_cart_zsweep_spike(adi_ctx *ctx, double *d_scratch, int end, int kmax, double threshold, double *d_compact,
+                          int *d_K, int *h_maxK, double dt, double theta, double kappa, void *stream)
+{
+    int rc = check_cart(ctx, "adi_cart_zsweep_spike");
+    if (rc) return rc;
+    if (!d_scratch || !d_compact || !d_K || !h_maxK || (end != 0 && end != 1) || kmax < 1 || kmax > ctx->nz) {
+        set_error("adi_cart_zsweep_spike: bad argument");
+        return ADI_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nlines = (size_t)ctx->nx * ctx->ny;
+    *h_maxK = 0;
+    if (!nlines || !ctx->nz) return ADI_OK;
+    if ((rc = ensure_ghost(ctx, nlines, st))) return rc;
+    if (!ctx->d_maxk) ADI_CUDA(cudaMalloc(&ctx->d_maxk, sizeof(int)));
+    ADI_CUDA(cudaMemsetAsync(d_scratch, 0, nlines * ctx->nz * sizeof(double), st));
+    ADI_CUDA(cudaMemsetAsync(ctx->d_maxk, 0, sizeof(int), st));
+    const int threads = 256;
+    const int blocks = (int)std::min<size_t>((nlines + threads - 1) / threads, 148 * 16);
+    k_fill_ghost<<<blocks, threads, 0, st>>>(ctx->d_ghost, nlines, end == 0 ? 1.0 : 0.0, end == 0 ? 0.0 : 1.0);
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
+    // homogeneous system: zero field, no flux, Dirichlet rows with value 0, ambient 0
+    rc = run_sweeps(ctx, d_scratch, d_scratch, dt, theta, kappa, 0.0, 2, 2, 5, nullptr, nullptr, nullptr, nullptr,
+                    ctx->d_ghost, st);
+    if (rc) return rc;
+    const int wblocks = (int)std::min<size_t>((nlines * 32 + threads - 1) / threads, 148 * 32);
+    k_spike_pack<<<wblocks, threads, 0, st>>>(d_scratch, nlines, ctx->nz, end, kmax, threshold, d_compact, d_K,
+                                              ctx->d_maxk);
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
+    ADI_CUDA(cudaMemcpyAsync(h_maxK, ctx->d_maxk, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ADI_CUDA(cudaStreamSynchronize(st));
+    return ADI_OK;
+}
+
+int adi_cart_zsweep_apply(adi_ctx *ctx, double *d_T, const double *d_dyn_all, const double *d_stat_all,
+                          const double *d_vC, const double *d_wC, const int *d_Kv, const int *d_Kw, int kmax,
+                          void *stream)
+{
+    int rc = check_cart(ctx, "adi_cart_zsweep_apply");
+    if (rc) return rc;
+    if (!d_T || !d_dyn_all || !d_stat_all || !d_vC || !d_wC || !d_Kv || !d_Kw || kmax < 1 || kmax > ctx->nz) {
+        set_error("adi_cart_zsweep_apply: bad argument");
+        return ADI_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nlines = (size_t)ctx->nx * ctx->ny;
+    if (!nlines || !ctx->nz) return ADI_OK;
+    if ((rc = ensure_ghost(ctx, nlines, st))) return rc;
+    const int threads = 128;
+    const int blocks = (int)std::min<size_t>((nlines + threads - 1) / threads, 148 * 32);
+    k_iface_solve<<<blocks, threads, 0, st>>>(d_dyn_all, d_stat_all, ctx->d_ghost, nlines, ctx->slab_nranks, ctx->slab_rank);
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
+    const int ablocks = (int)std::min<size_t>((nlines * 8 + 255) / 256, 148 * 32);
+    k_spike_apply<<<ablocks, 256, 0, st>>>(d_T, ctx->d_ghost, d_vC, d_wC, d_Kv, d_Kw, nlines, ctx->nz, kmax);
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
+    return prof_mark(ctx, 4, st);
 }
 
 int adi_cart_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int nsteps, double dt,

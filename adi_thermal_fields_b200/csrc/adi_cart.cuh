@@ -660,6 +660,9 @@ struct TileOps {
 };
 
 // smem: sT[LT][RL] | sC[LT][RL] | (NS 2: sU[LT][RL]) | sCode[LT][RL bytes]
+// ZMODE 4: z-slab "solve first" pass -- the segment is solved in place with both ghosts at zero and the
+// right-hand-side part of its interface relation (its first and last value) goes to a.iface_dyn; the
+// ghost terms are added afterwards by k_spike_apply from the cached unit-ghost responses.
 // ZMODE 0: whole line on this GPU.  1: z-slab pass 1 -- writes the interface relation of each
 // local line segment to a.iface_dyn / a.iface_stat and leaves the field untouched (3: the
 // right-hand-side part a.iface_dyn only).  2: z-slab pass 2 -- finishes the
@@ -751,7 +754,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
     const bool warp_lines = P <= 32 && (P & (P - 1)) == 0;
     // warps whose chunks are all solid (adi_core.h) take the row arithmetic with the code folded away
     const bool solid = NS == 2 && __all_sync(0xffffffffu, chunk_solid<M>(ch, CB_ZM, CB_ZP));
-    if ((ZMODE == 0 || ZMODE == 2) && a.in == a.out) {
+    if ((ZMODE == 0 || ZMODE == 2) && a.in == a.out) {  // (ZMODE 4 must still emit its relation)
         // lines without an active cell (the void around a part that is still being built): nothing to
         // solve, nothing to write (the sweep is in place); this barrier also frees sT for the exchange buffer
         bool any = false;
@@ -816,9 +819,17 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
         if (p == P - 1) Rg = a.ghost[nlines + line];
     }
     double S;
-    if (warp_lines) S = solve_reduced_warp<M, ZMODE == 2>(ch, f, p, P, &Sl, Lg, Rg);
-    else S = solve_reduced<M, ZMODE == 2>(ch, f, red, NTH, tid, 1, p, P, &Sl, Lg, Rg);
+    constexpr bool GHOSTS = (ZMODE == 2 || ZMODE == 4);  // 4: both ghosts at zero, as in ZMODE 3
+    if (warp_lines) S = solve_reduced_warp<M, GHOSTS>(ch, f, p, P, &Sl, Lg, Rg);
+    else S = solve_reduced<M, GHOSTS>(ch, f, red, NTH, tid, 1, p, P, &Sl, Lg, Rg);
     chunk_backward<M, EXTRA, NS>(ch, ops, CB_ZM, CB_ZP, a.k.g, Sl, S);
+    if (ZMODE == 4) {
+        const size_t line = L0 + ln;
+        if (line < nlines) {  // void cells hold 0 (load rule), as in the relation of ZMODE 3
+            if (p == 0) a.iface_dyn[line] = ch.T[0];
+            if (p == P - 1) a.iface_dyn[nlines + line] = ch.T[M - 1];
+        }
+    }
     __syncthreads();  // everybody is done reading the exchange buffer
 
     // ---- results back through shared memory (each thread owns its slots) ----
@@ -957,6 +968,73 @@ __global__ void k_iface_solve(const double *__restrict__ dyn, const double *__re
         }, nranks, rank, &Lg, &Rg);
         ghost[l] = Lg;
         ghost[nlines + l] = Rg;
+    }
+}
+
+__global__ void k_fill_ghost(double *__restrict__ ghost, size_t nlines, double lo, double hi)
+{
+    for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < nlines; l += (size_t)gridDim.x * blockDim.x) {
+        ghost[l] = lo;
+        ghost[nlines + l] = hi;
+    }
+}
+
+// Unit-ghost response ("spike") of every local line segment, as left in `field` by a ZMODE 2 solve of the
+// homogeneous system with ghost 1 at one end: it decays geometrically away from that end.  One warp per
+// line: K[line] = number of cells, counted from the end, up to the last one with |value| > thr;
+// compact[line][kmax] = the kmax cells next to the end (end 0: cells 0.., end 1: cells nz-kmax..).
+__global__ void k_spike_pack(const double *__restrict__ field, size_t nlines, int nz, int end, int kmax, double thr,
+                             double *__restrict__ compact, int *__restrict__ K, int *__restrict__ maxK)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t l = warp; l < nlines; l += nwarps) {
+        const double *f = field + l * (size_t)nz;
+        int far = 0;  // extent of the cells above the threshold, counted from the end
+        for (int k0 = 0; k0 < nz; k0 += 32) {
+            const int k = k0 + lane;
+            const bool big = k < nz && fabs(f[k]) > thr;
+            const unsigned m = __ballot_sync(0xffffffffu, big);
+            if (m) {
+                if (end == 0) far = max(far, k0 + 32 - __clz((int)m));          // last set lane + 1
+                else far = max(far, nz - (k0 + __ffs((int)m) - 1));             // nz - first set index
+            }
+        }
+        for (int j = lane; j < kmax; j += 32) {
+            const int k = end == 0 ? j : nz - kmax + j;
+            compact[l * (size_t)kmax + j] = (k >= 0 && k < nz) ? f[k] : 0.0;
+        }
+        if (lane == 0) {
+            K[l] = min(far, kmax);
+            if (far > 0) atomicMax(maxK, far);
+        }
+    }
+}
+
+// x = y + L*v + R*w on the cells within reach of the two ends of every local line segment (8 lanes per line).
+// Cells where the response is exactly 0 (void cells, cells behind a void gap) are not touched.
+__global__ void k_spike_apply(double *__restrict__ T, const double *__restrict__ ghost, const double *__restrict__ vC,
+                              const double *__restrict__ wC, const int *__restrict__ Kv, const int *__restrict__ Kw,
+                              size_t nlines, int nz, int kmax)
+{
+    const int sub = threadIdx.x & 7;
+    for (size_t l = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; l < nlines;
+         l += ((size_t)gridDim.x * blockDim.x) >> 3) {
+        const double L = ghost[l], R = ghost[nlines + l];
+        const int kv = Kv[l], kw = Kw[l];
+        double *t = T + l * (size_t)nz;
+        const double *v = vC + l * (size_t)kmax, *w = wC + l * (size_t)kmax;
+        const int hi0 = nz - kw;  // first cell within reach of the upper end
+        for (int k = sub; k < kv; k += 8) {
+            double c = L * v[k];
+            if (k >= hi0) c = fma(R, w[k - (nz - kmax)], c);
+            if (c != 0.0) t[k] += c;
+        }
+        for (int k = max(kv, hi0) + sub; k < nz; k += 8) {
+            const double c = R * w[k - (nz - kmax)];
+            if (c != 0.0) t[k] += c;
+        }
     }
 }
 

@@ -69,6 +69,7 @@ struct adi_ctx {
     const uint8_t *d_mask_lo = nullptr, *d_mask_hi = nullptr;
     double *d_ghost = nullptr;
     size_t ghost_lines = 0;
+    int *d_maxk = nullptr;  // k_spike_pack: longest reach of a unit-ghost response
     // host-array convenience path
     double *stage[2] = {nullptr, nullptr};
     size_t stage_cells = 0;

@@ -58,6 +58,7 @@ int launch_sweep_z(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, int
     if (zmode == 1) return launch_sweep_z_mode<1>(ctx, a, dense, extra, st);
     if (zmode == 2) return launch_sweep_z_mode<2>(ctx, a, dense, extra, st);
     if (zmode == 3) return launch_sweep_z_mode<3>(ctx, a, dense, extra, st);
+    if (zmode == 4) return launch_sweep_z_mode<4>(ctx, a, dense, extra, st);
     return launch_sweep_z_mode<0>(ctx, a, dense, extra, st);
 }
 

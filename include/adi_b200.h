@@ -136,6 +136,24 @@ int adi_cart_zsweep_reduce(adi_ctx *ctx, double *d_T, double *d_iface_dyn, doubl
  * ranks; solves the inter-rank system per line and finishes the local segments in place. */
 int adi_cart_zsweep_finish(adi_ctx *ctx, double *d_T, const double *d_dyn_all, const double *d_stat_all,
                            double dt, double theta, double kappa, double Tinf, void *stream);
+/* "Solve first" form of the same split, for steady stepping (mask, packs, dt, theta unchanged for many steps).
+ * x = y + L*v + R*w per local line segment: y = the segment solved with both ghosts at zero, v / w = its
+ * responses to a unit ghost at the lower / upper end (matrix only), L / R = the ghost values from the
+ * gathered relations.  v and w decay geometrically away from their end (ratio ~ theta*gamma / (1 + 2 theta*gamma)),
+ * so only the `kmax` cells next to each end are kept and corrected: the second full pass over the slab goes away.
+ *   adi_cart_zsweep_spike   once per (mask, packs, dt, theta): computes the response of end 0 / 1 in the zeroed
+ *                           scratch field (size of T), keeps compact[nx*ny][kmax] and K[nx*ny] (cells above
+ *                           `threshold`, clipped to kmax); *h_maxK = longest reach found -- if it exceeds kmax the
+ *                           caller stays with adi_cart_zsweep_reduce / _finish.  Synchronises.
+ *   adi_cart_zsweep_solve0  every step: solves T in place with zero ghosts, writes d_iface_dyn[2][nx*ny]
+ *   adi_cart_zsweep_apply   every step, after the all-gather: ghosts from the relations, then the corrections */
+int adi_cart_zsweep_spike(adi_ctx *ctx, double *d_scratch, int end, int kmax, double threshold, double *d_compact,
+                          int *d_K, int *h_maxK, double dt, double theta, double kappa, void *stream);
+int adi_cart_zsweep_solve0(adi_ctx *ctx, double *d_T, double *d_iface_dyn, double dt, double theta, double kappa,
+                           double Tinf, void *stream);
+int adi_cart_zsweep_apply(adi_ctx *ctx, double *d_T, const double *d_dyn_all, const double *d_stat_all,
+                          const double *d_vC, const double *d_wC, const int *d_Kv, const int *d_Kw, int kmax,
+                          void *stream);
 /* Tuning / introspection: kernel variant selection (0 = default) and launch counter.  Options:
  *   "kt"    lanes along z per block of the strided sweeps (power of two)     "lt"  lines per block of the z sweeps
  *   "m"     chunk length 16 | 32                                             "wide" 1: 512-thread blocks for lines <= 512 cells

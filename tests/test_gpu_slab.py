@@ -84,3 +84,44 @@ def test_cyl_slab_cuda_matches_reference(name, world, golden_dir):
         out[:, :, z0:z1] = t
         assert nl == 5      # r, phi, z pass 1, ghost map, z pass 2
     assert cases.rel_l2(out, g["T_out"]) <= TOL
+
+
+# ---- steady stepping: solve-first z pass with unit-ghost response corrections ---------------------
+@pytest.mark.parametrize("world,shape,mk,bk,theta,cfl,kmax,expect", [
+    (2, (9, 11, 64),  "full",        "robin6",       0.5, 0.128, 32, True),
+    (3, (10, 7, 96),  "cyl_holes",   "combined",     0.5, 0.128, 32, True),    # voids and Dirichlet cells at slab faces
+    (4, (6, 9, 128),  "random",      "robin_dict3d", 0.5, 0.3,   32, True),
+    (2, (12, 8, 32),  "plate_track", "robin_mixed",  1.0, 0.128, 32, True),    # 16-cell segments: both ends reach every cell
+    (2, (8, 8, 256),  "cyl_holes",   "robin_dict3d", 0.5, 2.0,   64, True),    # slower decay, longer reach
+    (2, (8, 8, 128),  "full",        "robin6",       0.5, 50.0,  32, False),   # reach > kmax: stays with the two-pass form
+])
+def test_slab_solve_first_z_pass(world, shape, mk, bk, theta, cfl, kmax, expect):
+    """After `spike_after` steps with unchanged (mask, packs, dt, theta) the z sweep becomes: solve the local
+    segment with zero ghosts in place -> all-gather (yf, yl) -> ghosts -> add L*v + R*w on the cells within
+    reach of the slab faces.  Same answer as the undivided grid, void cells untouched."""
+    import torch
+    from adi_thermal_fields_b200 import slab
+    from slab_cases import Mat, slice_bcs
+    nsteps = 5
+    pb = make_problem(shape, mk, bk, theta, cfl, seed=31)
+    ref = oracle_steps(pb, nsteps)
+
+    def rank_fn(comm):
+        class Prm:
+            dt, theta = pb["dt"], pb["theta"]
+        nx, ny, nz = pb["shape"]
+        z0, z1 = slab.split_z(nz, comm.world)[comm.rank]
+        grid = slab.SlabGrid3D(nx, ny, z1 - z0, cases.DX, pb["mask"][:, :, z0:z1], comm)
+        grid.spike_after, grid.spike_kmax = 1, kmax
+        packs = slab.precompute_coeff_packs_unified(grid, Mat, **slice_bcs(pb["bcs"], z0, z1))
+        T = grid.be.asarray(pb["T0"][:, :, z0:z1], torch.float64)
+        for _ in range(nsteps):
+            T = slab.adi_step_gpu_coeff(T, grid, Mat, Prm, packs, Tinf=pb["Tinf"])
+        return (z0, z1, T.cpu().numpy(), bool(grid._spikes))
+
+    parts = slab.LocalComm(world).run(rank_fn)
+    out = assemble(shape, parts)
+    m = pb["mask"]
+    assert [p[3] for p in parts] == [expect] * world
+    assert cases.rel_l2(out, ref, m) <= TOL * nsteps
+    assert np.array_equal(out[~m], pb["T0"][~m], equal_nan=True)

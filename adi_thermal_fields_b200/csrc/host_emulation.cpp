@@ -170,6 +170,11 @@ void emu_build_code_halo(const uint8_t *mask, const uint8_t *dirm, uint8_t *code
 // phase 1: interface relations of the z lines of Tout -> iface_dyn[2][nx*ny], iface_stat[4][nx*ny];
 // phase 3: the right-hand-side part iface_dyn only;
 // phase 2: inter-rank solve from dyn_all[nranks][2][nx*ny], stat_all[nranks][4][nx*ny] + local finish in place.
+// Solve-first form (adi_cart_zsweep_solve0 / _spike / _apply):
+// phase 4: local finish in place with both ghosts at zero; iface_dyn = (first, last) value of every segment;
+// phase 5 / 6: the homogeneous system (no flux, Dirichlet value 0, ambient 0) with ghost 1 at the lower /
+//              upper end, in place on the caller's zeroed field: the unit-ghost response;
+// phase 7: inter-rank solve only: iface_dyn[2][nx*ny] = (L, R) ghosts of this rank.
 int emu_cart_slab(const double *Tin, double *Tout, const uint8_t *mask, int nx, int ny, int nz,
                   double dx, double dt, double theta, double kappa, double Tinf,
                   const double *const coeff[3], const uint8_t *const dirm[3],
@@ -207,6 +212,23 @@ int emu_cart_slab(const double *Tin, double *Tout, const uint8_t *mask, int nx, 
                             : Tin[idx];
         }
     }
+    if (phase == 7) {
+        for (size_t line = 0; line < nlines; ++line) {
+            double Lg = 0.0, Rg = 0.0;
+            iface_solve([&](int r) {
+                const double *dd = dyn_all + (size_t)r * 2 * nlines + line;
+                const double *qq = stat_all + (size_t)r * 4 * nlines + line;
+                Iface w;
+                w.yf = dd[0]; w.yl = dd[nlines];
+                w.vf = qq[0]; w.wf = qq[nlines]; w.vl = qq[2 * nlines]; w.wl = qq[3 * nlines];
+                return w;
+            }, nranks, rank, &Lg, &Rg);
+            iface_dyn[line] = Lg; iface_dyn[nlines + line] = Rg;
+        }
+        return 0;
+    }
+    const bool homogeneous = phase == 5 || phase == 6;
+    if (homogeneous) k.Tinf = 0.0;
     const int a0 = phase == 0 ? 0 : 2, a1 = phase == 0 ? 1 : 2;
     for (int axis = a0; axis <= a1; ++axis) {
         if (axis > 0 || phase != 0) emu_build_code_halo(mask, dirm[axis], code.data(), nx, ny, nz, mlo, mhi);
@@ -231,7 +253,9 @@ int emu_cart_slab(const double *Tin, double *Tout, const uint8_t *mask, int nx, 
                 double Lg = 0.0, Rg = 0.0;
                 const size_t line = (size_t)u * ny + v;
                 if (axis == 2) {
-                    zmode = phase;
+                    zmode = phase >= 4 ? 2 : phase;
+                    if (phase == 5) Lg = 1.0;
+                    if (phase == 6) Rg = 1.0;
                     if (phase == 2)
                         iface_solve([&](int r) {
                             const double *dd = dyn_all + (size_t)r * 2 * nlines + line;
@@ -242,12 +266,17 @@ int emu_cart_slab(const double *Tin, double *Tout, const uint8_t *mask, int nx, 
                             return w;
                         }, nranks, rank, &Lg, &Rg);
                 }
+                const double *qa = homogeneous ? nullptr : q[axis], *dva = homogeneous ? nullptr : dirv[axis];
                 if (variant == 0)
-                    sweep_line_any<16, 2>(dense, extra, Tout, code.data(), coeff[axis], q[axis], dirv[axis], base,
+                    sweep_line_any<16, 2>(dense, extra, Tout, code.data(), coeff[axis], qa, dva, base,
                                           stride, len, LO, HI, k, zmode, &f, Lg, Rg);
                 else
-                    sweep_line_any<32, 1>(dense, extra, Tout, code.data(), coeff[axis], q[axis], dirv[axis], base,
+                    sweep_line_any<32, 1>(dense, extra, Tout, code.data(), coeff[axis], qa, dva, base,
                                           stride, len, LO, HI, k, zmode, &f, Lg, Rg);
+                if (axis == 2 && phase == 4) {  // void end cells count as 0 (load rule of the kernels)
+                    iface_dyn[line] = (code[base] & CB_SELF) ? Tout[base] : 0.0;
+                    iface_dyn[nlines + line] = (code[base + nz - 1] & CB_SELF) ? Tout[base + nz - 1] : 0.0;
+                }
                 if (axis == 2 && (phase == 1 || phase == 3)) {
                     iface_dyn[line] = f.yf; iface_dyn[nlines + line] = f.yl;
                     if (phase == 1) {

@@ -108,5 +108,41 @@ class HostBackend:
     def zsweep_finish(self, T, dyn_all, stat_all, dt, theta, kappa, Tinf):
         self._call(T, T, None, None, 2, None, None, dyn_all, stat_all, dt, theta, kappa, Tinf)
 
+    # solve-first z pass (adi_cart_zsweep_spike / _solve0 / _apply): the kernels' per-thread code for the
+    # solves (emu_cart_slab phases 4-7), NumPy for k_spike_pack / k_spike_apply
+    def zsweep_spikes(self, shape, kmax, threshold, dt, theta, kappa):
+        nz = shape[2]
+        out = []
+        for end in (0, 1):
+            F = torch.zeros(shape, dtype=torch.float64)
+            self._call(F, F, None, None, 5 + end, None, None, None, None, dt, theta, kappa, 0.0)
+            f = F.numpy().reshape(-1, nz)
+            big = np.abs(f) > threshold
+            first, last = np.argmax(big, axis=1), nz - 1 - np.argmax(big[:, ::-1], axis=1)
+            far = np.where(big.any(axis=1), (last + 1) if end == 0 else (nz - first), 0)
+            if far.size and far.max() > kmax:
+                return None
+            comp = f[:, :kmax] if end == 0 else f[:, nz - kmax:]
+            out += [torch.from_numpy(np.ascontiguousarray(comp)), torch.from_numpy(np.minimum(far, kmax).astype(np.int32))]
+        return out[0], out[2], out[1], out[3]
+
+    def zsweep_solve0(self, T, dyn, dt, theta, kappa, Tinf):
+        self._call(T, T, None, None, 4, dyn, None, None, None, dt, theta, kappa, Tinf)
+
+    def zsweep_apply(self, T, dyn_all, stat_all, spikes, kmax):
+        vC, wC, Kv, Kw = (x.numpy() for x in spikes)
+        nl, nz = self.nx * self.ny, self.nz
+        ghosts = torch.zeros((2, nl), dtype=torch.float64)
+        self._call(T, T, None, None, 7, ghosts, None, dyn_all, stat_all, 0.0, 0.0, 0.0, 0.0)
+        L, R = ghosts.numpy()
+        j = np.arange(kmax)
+        corr = np.zeros((nl, nz))
+        corr[:, :kmax] += np.where(j[None, :] < Kv[:, None], L[:, None] * vC, 0.0)
+        corr[:, nz - kmax:] += np.where(j[None, :] >= kmax - Kw[:, None], R[:, None] * wC, 0.0)
+        t = T.numpy().reshape(nl, nz)           # a view: the update lands in T
+        hit = corr != 0.0
+        t[hit] += corr[hit]
+        self.launches += 1
+
     def launch_count(self):
         return self.launches

@@ -14,6 +14,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <cstring>
 #include <mutex>
@@ -162,8 +163,10 @@ struct ProbeSlot {
 };
 
 struct TextState {
-    std::mutex mu;
-    long launches = 0;
+    std::mutex mu;   // the text pipeline (buffers, stream, events)
+    std::mutex pmu;  // the probe slots: a probe recorded by the stepping thread must not wait for a frame
+                     // that a second thread is writing
+    std::atomic<long> launches{0};
     uint32_t *d_len = nullptr, *d_off = nullptr;
     size_t pieces_cap = 0;
     unsigned long long *d_total = nullptr, *h_total = nullptr;  // two entries each
@@ -177,11 +180,14 @@ struct TextState {
     cudaStream_t copy_stream = nullptr;
 };
 
+static std::mutex g_text_create_mu;
+
 static int text_state(adi_ctx *ctx, TextState **out)
 {
+    std::lock_guard<std::mutex> create_lock(g_text_create_mu);
     if (!ctx->text) {
         TextState *ts = new TextState();
-        ctx->text = ts;
+        ctx->text = ts;  // released by text_release() even if one of the calls below fails
         ADI_CUDA(cudaSetDevice(ctx->device));
         ADI_CUDA(cudaStreamCreateWithFlags(&ts->stream, cudaStreamNonBlocking));
         ADI_CUDA(cudaStreamCreateWithFlags(&ts->copy_stream, cudaStreamNonBlocking));
@@ -224,7 +230,7 @@ void text_release(adi_ctx *ctx)
     ctx->text = nullptr;
 }
 
-long text_launches(adi_ctx *ctx) { return ctx->text ? ctx->text->launches : 0; }
+long text_launches(adi_ctx *ctx) { return ctx->text ? ctx->text->launches.load() : 0; }
 
 static int ensure_pieces(TextState *ts, size_t pieces)
 {
@@ -469,7 +475,7 @@ int adi_probe_open(adi_ctx *ctx, int nslots, size_t slot_bytes)
     adi::TextState *ts;
     int rc = adi::text_state(ctx, &ts);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lock(ts->mu);
+    std::lock_guard<std::mutex> lock(ts->pmu);
     ADI_CUDA(cudaSetDevice(ctx->device));
     for (adi::ProbeSlot &s : ts->slots) {
         if (s.busy) {
@@ -497,7 +503,7 @@ int adi_probe_record(adi_ctx *ctx, int slot, const void *d_field, int elem_bytes
 {
     if (!ctx || !ctx->text || !d_field || !lo || !hi) return ADI_EINVAL;
     adi::TextState *ts = ctx->text;
-    std::lock_guard<std::mutex> lock(ts->mu);
+    std::lock_guard<std::mutex> lock(ts->pmu);
     if (slot < 0 || (size_t)slot >= ts->slots.size()) {
         adi::set_error("adi_probe_record: no such slot (adi_probe_open first)");
         return ADI_EINVAL;
@@ -551,7 +557,7 @@ int adi_probe_fetch(adi_ctx *ctx, int slot, void *h_dst, size_t capacity, size_t
 {
     if (!ctx || !ctx->text || !h_dst) return ADI_EINVAL;
     adi::TextState *ts = ctx->text;
-    std::lock_guard<std::mutex> lock(ts->mu);
+    std::lock_guard<std::mutex> lock(ts->pmu);
     if (slot < 0 || (size_t)slot >= ts->slots.size() || !ts->slots[(size_t)slot].busy) {
         adi::set_error("adi_probe_fetch: nothing recorded in this slot");
         return ADI_ESTATE;

@@ -135,3 +135,22 @@ def test_field_layout_matches_writer_loops(fmt, shape):
                          out.ctypes.data_as(C.c_void_p))
     want = ov.data_section(T, fmt)
     assert bytes(out[:n]) == want
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_writer_headers_match_the_reference_files(fmt, golden_dir):
+    """Host side of the writers (adi_thermal_fields_b200/vtk_writer.py): the header and section lines it
+    hands to adi_text_write as `prefix` are the reference's, byte for byte (no device needed)."""
+    import os
+    import cases
+    from adi_thermal_fields_b200 import vtk_writer as vw
+    g = np.load(os.path.join(golden_dir, "vtk_text.npz"))
+    for name, c in cases.vtk_text_cases().items():
+        want = g[f"{name}__{fmt}"].tobytes()
+        head = vw._header(fmt, c["T"].shape, c["dx"], c["origin"], c["field_name"]).encode("utf-8")
+        assert want.startswith(head)
+        if c["mask"] is not None:
+            assert vw._section("mask" if fmt == 0 else "Mask").encode() in want[len(head):]
+        # data section by the host build of the device formatter completes the file
+        body = emu.text_field(np.asarray(c["T"]), fmt)
+        assert want[len(head):len(head) + len(body)] == body

@@ -693,7 +693,11 @@ def run_ours_c4(args, local):
                      "achieved": 75.0 * cells / (ts / nsteps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": 75.0 * cells / (ts / nsteps * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                      "steady_ms_per_step": ts / nsteps, "birth_ms": tb / len(mid),
-                     "birth_note": "mask update + k_build_packs (6 dense h fields -> 3 coeff fields) + neighbour code rebuild"},
+                     "birth_note": "mask update + k_build_packs (6 dense h fields -> 3 coeff fields) + neighbour code rebuild",
+                     "note": "achieved/frac restate the metric (all cells of the box, void included, at SURVEY 8(d)'s "
+                             "75 B/cell-step) in GB/s; they are not DRAM utilisation: sweep tiles without an active "
+                             "cell are skipped and coefficient fields are read at exposed cells only, so the bytes "
+                             "moved per step are well below 75 B x cells while the part is being built"},
         "cpu_baseline": None, "clocks": clocks,
         "e2e": {"value": cells * nsteps / wall, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "api": "adi3d_gpu_coeff.precompute_coeff_packs_unified + adi_step_gpu_coeff (device arrays, host wall clock)"},

@@ -45,7 +45,9 @@ def main():
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for d in data:
         name = d[hdr.index("Kernel Name")]
-        key = re.sub(r"^void ", "", name).split("(")[0]
+        # "void <unnamed>::k_text<double, 0, 1>(...)" -> "k_text<double, 0, 1>"
+        key = re.sub(r"^void ", "", name)
+        key = re.sub(r"<unnamed>::|\(anonymous namespace\)::|adi::", "", key).split("(")[0]
         tot = 0.0
         for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = hdr.index(m)

@@ -357,3 +357,14 @@ def vtk_text_cases():
     out["dyadic"] = dict(T=T.astype(np.float32), dx=1.0, origin=(0.0, 0.0, 0.0), mask=rng.random((9, 9, 2)) < 0.5,
                          field_name="Temperature")
     return out
+
+
+def vtk_text_big_case():
+    """A seeded field with multi-piece rows (nx > 256) whose reference files are pinned by digest only."""
+    rng = np.random.default_rng(777)
+    T = 20.0 + 1380.0 * rng.random((300, 5, 7))
+    T[::7, :, 1] *= -1.0
+    T[5:9, 2, 3] = 0.0
+    T[::11, 1, :] = np.round(T[::11, 1, :] * 8.0) / 8.0
+    m = rng.random((300, 5, 7)) < 0.6
+    return dict(T=T, dx=2.5e-4, origin=(0.1, -0.2, 0.3), mask=m, field_name="Temperature")

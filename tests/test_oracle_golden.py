@@ -206,3 +206,21 @@ def test_vtk_text_oracle_byte_exact(name, fmt, golden_dir):
     c = cases.vtk_text_cases()[name]
     got = vtk_text.vtk_bytes(fmt, c["T"], c["dx"], c["origin"], c["field_name"], c["mask"])
     assert got == g[f"{name}__{fmt}"].tobytes()
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_vtk_text_big_case_digest(fmt, golden_dir):
+    """Rows longer than one 256-value piece: oracle and the host build of the device formatter against the
+    digest of the reference's own file."""
+    import hashlib
+    import emu
+    from oracle import vtk_text
+    g = np.load(os.path.join(golden_dir, "vtk_text.npz"))
+    c = cases.vtk_text_big_case()
+    data = vtk_text.vtk_bytes(fmt, c["T"], c["dx"], c["origin"], c["field_name"], c["mask"])
+    assert len(data) == int(g[f"big_size__{fmt}"][0])
+    assert hashlib.sha256(data).digest() == g[f"big_sha256__{fmt}"].tobytes()
+    head = vtk_text.header(fmt, c["T"].shape, c["dx"], c["origin"], c["field_name"]).encode()
+    sec = vtk_text.section_header("mask" if fmt == 0 else "Mask").encode()
+    dev = head + emu.text_field(c["T"], fmt) + sec + emu.text_field(c["mask"], fmt)
+    assert dev == data

@@ -246,6 +246,16 @@ def gen_vtk_text(ref, outdir):
             with open(path, "rb") as f:
                 out[f"{name}__{fl}"] = np.frombuffer(f.read(), dtype=np.uint8)
             print(f"[vtk] {name} flavour {fl}: {out[f'{name}__{fl}'].size} bytes")
+    import hashlib
+    c = cases.vtk_text_big_case()
+    for fl, fn in ((0, vtk_writer.write_vtk_structured_points), (1, waam.write_vtk_structured_points)):
+        path = os.path.join(tmp, f"big_{fl}.vtk")
+        fn(path, c["T"], c["dx"], c["origin"], c["field_name"], c["mask"])
+        with open(path, "rb") as f:
+            data = f.read()
+        out[f"big_sha256__{fl}"] = np.frombuffer(hashlib.sha256(data).digest(), dtype=np.uint8)
+        out[f"big_size__{fl}"] = np.array([len(data)], dtype=np.int64)
+        print(f"[vtk] big flavour {fl}: {len(data)} bytes, sha256 {hashlib.sha256(data).hexdigest()[:16]}...")
     np.savez_compressed(os.path.join(outdir, "vtk_text.npz"), **out)
 
 

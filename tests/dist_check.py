@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Multi-GPU parity check of the z-slab path over NCCL (run under torchrun on the GPU box):
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-      --master-port 29511 tools/dist_check.py
+      --master-port 29511 tests/dist_check.py
 Every rank steps its slab of a seeded problem; rank 0 gathers the slabs and compares with the
-oracle on the undivided grid (rel-L2 <= 1e-12 per step, void cells bit-identical)."""
+oracle on the undivided grid (rel-L2 <= 1e-12 per step, void cells bit-identical).
+A parity checker: it lives in tests/ because it imports oracle/ (test infrastructure); it is not collected by pytest
+(no test_ prefix) -- tools/gpu_scale.sh launches it."""
 import os
 import sys
 

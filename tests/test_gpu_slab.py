@@ -3,7 +3,7 @@
 cuda:0 and run the CUDA kernels of the N>1 path -- halo-aware neighbour code and packs, explicit
 stage with T halo planes, z sweep pass 1 (interface relations) / inter-rank solve / pass 2 --
 against the oracle on the undivided grid.  rel-L2 <= 1e-12 per step, void cells bit-identical.
-(The NCCL transport itself is exercised by tools/dist_check.py under torchrun.)"""
+(The NCCL transport itself is exercised by tests/dist_check.py under torchrun.)"""
 import numpy as np
 import pytest
 

@@ -5,7 +5,7 @@ tag=${1:-s}; weak=${2:-"8 4"}; c5=${3:-"8 4 2"}
 mkdir -p gpurun_out
 T="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 nmax=$(nvidia-smi -L | wc -l)
-timeout 300 $T --nproc-per-node $nmax --master-port 29520 tools/dist_check.py 2>&1 | grep dist_check | tee gpurun_out/${tag}_dist_check.txt
+timeout 300 $T --nproc-per-node $nmax --master-port 29520 tests/dist_check.py 2>&1 | grep dist_check | tee gpurun_out/${tag}_dist_check.txt
 : > gpurun_out/${tag}_scale.jsonl
 port=29530
 for n in $weak; do

@@ -62,10 +62,15 @@ def main():
                                "file_GB_per_s": nbytes / dt / 1e9, "dir": tmp}
         os.remove(path)
         # the reference's loops (oracle restatement) on a bounded sample of the same field
-        from oracle import vtk_text
+        # (vtk_writer.py:4-9 / waam_from_stl_v7_mm.py:203-206: one Python format call per value)
         sample = T[:64, :64, :32].cpu().numpy()
         t0 = time.perf_counter()
-        vtk_text.data_section(sample, fmt)
+        if fmt == 0:
+            flat = sample.reshape(-1, order="F")
+            "".join(" ".join(f"{float(v):.6e}" for v in flat[i:i + 9]) + "\n" for i in range(0, flat.size, 9))
+        else:
+            "".join(" ".join(f"{float(sample[i, j, k]):.6g}" for i in range(sample.shape[0])) + "\n"
+                    for k in range(sample.shape[2]) for j in range(sample.shape[1]))
         dt = time.perf_counter() - t0
         res[f"reference_python_{name}"] = {"sample_values": sample.size, "seconds": dt,
                                            "Mvalues_per_s": sample.size / dt / 1e6, "cores": 1}

@@ -55,6 +55,28 @@ def test_null_context_is_rejected(lib):
     assert lib.adi_cart_step(None, None, None, 0.1, 0.5, 1.0, 0.0, None) != 0
 
 
+def test_null_context_is_rejected_by_the_newer_entry_points(lib):
+    """Output path, solve-first z pass, options: argument checks come before any CUDA call."""
+    n = C.c_ulonglong(0)
+    assert lib.adi_text_capacity(10) >= 10 * 15
+    assert lib.adi_text_format(None, None, 0, 4, 4, 4, 0, 4, 0, None, 0, C.byref(n), None) != 0
+    assert lib.adi_text_write(None, b"/nonexistent/x.vtk", 0, b"", 0, None, 0, 4, 4, 4, 0, C.byref(n), None) != 0
+    assert lib.adi_probe_open(None, 4, 1024) != 0
+    assert lib.adi_probe_fetch(None, 0, None, 0, None, 1) != 0
+    assert lib.adi_cart_zsweep_solve0(None, None, None, 0.1, 0.5, 1.0, 0.0, None) != 0
+    assert lib.adi_cart_zsweep_apply(None, None, None, None, None, None, None, None, 32, None) != 0
+    assert lib.adi_get_option(None, b"sparse_coeff") == -1
+    assert lib.adi_set_option(None, b"sparse_coeff", 0) != 0
+
+
+def test_tools_do_not_import_oracle():
+    """Developer tools measure and drive; anything that checks against the oracle lives under tests/."""
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py") and f != "gen_golden.py":
+            txt = open(os.path.join(ROOT, "tools", f)).read()
+            assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
 def test_product_does_not_import_oracle():
     """Only tests/, smoke() and bench.py's CPU legs may touch oracle/ (checker, never shipped)."""
     pkg = os.path.join(ROOT, "adi_thermal_fields_b200")

@@ -415,5 +415,10 @@ def set_option(name, value):
                 "adi_set_option")
 
 
+def get_option(name):
+    """Current value of an engine option (adi_get_option)."""
+    return int(_engine.lib().adi_get_option(_engine.context(), str(name).encode()))
+
+
 def launch_count():
     return int(_engine.lib().adi_launch_count(_engine.context()))

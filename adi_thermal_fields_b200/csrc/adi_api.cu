@@ -74,6 +74,8 @@ int adi_ctx_destroy(adi_ctx *ctx)
     for (int a = 0; a < 3; ++a)
         if (ctx->code_buf[a]) cudaFree(ctx->code_buf[a]);
     for (int a = 0; a < 2; ++a)
+        if (ctx->codeT[a]) cudaFree(ctx->codeT[a]);
+    for (int a = 0; a < 2; ++a)
         if (ctx->stage[a]) cudaFree(ctx->stage[a]);
     if (ctx->d_ghost) cudaFree(ctx->d_ghost);
     if (ctx->d_maxk) cudaFree(ctx->d_maxk);
@@ -145,6 +147,12 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
         ctx->sparse_trust = value;
         ctx->sparse_dirty = true;
     }
+    else if (!strcmp(name, "xy2")) {   // 1 (default): second-generation x / y sweeps (adi_sweep_xy.cuh)
+        ctx->opt_xy2 = value;
+        ctx->code_dirty = true;
+    }
+    else if (!strcmp(name, "uni")) ctx->opt_uni = value;    // 1 (default): tabulated factors for uniform chunks
+    else if (!strcmp(name, "tw")) ctx->opt_tw = value;      // 1 (default): reduced system solved by warps
     else if (!strcmp(name, "fuse")) ctx->opt_fuse = value;  // 1: explicit stage fused into the x sweep
     else {
         adi::set_error(std::string("adi_set_option: unknown option ") + name);
@@ -163,6 +171,9 @@ long adi_get_option(adi_ctx *ctx, const char *name)
     if (!strcmp(name, "profile")) return ctx->opt_profile;
     if (!strcmp(name, "wide")) return ctx->opt_wide;
     if (!strcmp(name, "fuse")) return ctx->opt_fuse;
+    if (!strcmp(name, "xy2")) return ctx->opt_xy2;
+    if (!strcmp(name, "uni")) return ctx->opt_uni;
+    if (!strcmp(name, "tw")) return ctx->opt_tw;
     if (!strcmp(name, "sparse_coeff")) return ctx->opt_sparse;
     if (!strcmp(name, "sparse_active"))  // bit a: the sweep along axis a currently skips interior coefficient reads
         return ctx->sparse_dirty ? 0 : ((ctx->sparse[0] ? 1 : 0) | (ctx->sparse[1] ? 2 : 0) | (ctx->sparse[2] ? 4 : 0));

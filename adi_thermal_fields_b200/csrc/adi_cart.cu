@@ -58,6 +58,25 @@ int ensure_code(adi_ctx *ctx, cudaStream_t st)
         ADI_CUDA(cudaGetLastError());
     }
     for (int a = 0; a < 3; ++a) ctx->code[a] = ctx->code_buf[shared ? 0 : a];
+    // transposed copies for the x / y sweeps: line axis fastest, lines padded to a multiple of 32
+    for (int a = 0; a < 2; ++a) {
+        const int len = a == 0 ? ctx->nx : ctx->ny, batch = a == 0 ? ctx->ny : ctx->nx;
+        const int npad = (len + 31) / 32 * 32;
+        const size_t bytes = (size_t)batch * ctx->nz * npad;
+        if (!ctx->opt_xy2 || !n || len > 2048) { ctx->npadT[a] = 0; continue; }
+        if (ctx->codeT_bytes[a] != bytes || ctx->npadT[a] != npad) {
+            if (ctx->codeT[a]) { ADI_CUDA(cudaFree(ctx->codeT[a])); ctx->codeT[a] = nullptr; }
+            ADI_CUDA(cudaMalloc(&ctx->codeT[a], bytes));
+            ADI_CUDA(cudaMemsetAsync(ctx->codeT[a], 0, bytes, st));
+            ctx->codeT_bytes[a] = bytes; ctx->npadT[a] = npad;
+        }
+        const size_t snx = (size_t)ctx->ny * ctx->nz;
+        dim3 tgrid((unsigned)((ctx->nz + 31) / 32), (unsigned)((len + 31) / 32), (unsigned)std::min(batch, 65535));
+        k_transpose_code<<<tgrid, dim3(32, 8), 0, st>>>(ctx->code[a], ctx->codeT[a], len, ctx->nz, npad, batch,
+                                                        a == 0 ? (size_t)ctx->nz : snx, a == 0 ? snx : (size_t)ctx->nz);
+        ctx->launches++;
+        ADI_CUDA(cudaGetLastError());
+    }
     ctx->code_dirty = false;
     ctx->sparse_dirty = true;
     return ADI_OK;

@@ -38,6 +38,12 @@ struct SweepArgs {
     double *iface_dyn;                 // z sweep pass 1 out: [2][nx*ny] (yf, yl): right-hand-side part
     double *iface_stat;                // z sweep pass 1 out: [4][nx*ny] (vf, wf, vl, wl): matrix part (ZMODE 1)
     const double *__restrict__ ghost;  // z sweep pass 2 in:  [2][nx*ny] (L, R per line)
+    // second-generation x / y sweeps (adi_sweep_xy.cuh)
+    const uint8_t *__restrict__ codeT; // code transposed for this axis: [other][nz][npad], line axis fastest
+    int npad;                          // padded line length of codeT (multiple of 32, padding = code 0)
+    int uni;                           // uniform chunks may take the tabulated factors of `uc`
+    int tw;                            // reduced system by warps (transposed exchange)
+    UniConst uc;
 };
 
 #ifdef ADI_CART_MISC_KERNELS  // defined by adi_cart.cu, the one unit that launches K0/K7
@@ -69,6 +75,31 @@ __global__ void k_build_code(const uint8_t *__restrict__ mask, const uint8_t *__
             if (k + 1 < nz ? mask[idx + 1] : (mhi && mhi[ij])) c |= CB_ZP;
         }
         code[idx] = (uint8_t)c;
+    }
+}
+
+// K0t: per-axis transposed copy of the code array for the x / y sweeps (adi_sweep_xy.cuh):
+// dst[(b*nz + c)*npad + r] = src[b*sb + r*sr + c],  r < n (line axis), c < nz, b < batch.
+// 32 x 32 byte tiles through shared memory; padding columns (r >= n) keep the zeros of the allocation.
+__global__ void __launch_bounds__(256) k_transpose_code(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                        int n, int nz, int npad, int batch, size_t sb, size_t sr)
+{
+    __shared__ uint8_t tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int b = blockIdx.z; b < batch; b += gridDim.z) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + ty + 8 * i, c = c0 + tx;
+            tile[ty + 8 * i][tx] = (r < n && c < nz) ? src[(size_t)b * sb + (size_t)r * sr + c] : (uint8_t)0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = c0 + ty + 8 * i, r = r0 + tx;
+            if (c < nz && r < n) dst[((size_t)b * nz + c) * npad + r] = tile[tx][ty + 8 * i];
+        }
+        __syncthreads();
     }
 }
 

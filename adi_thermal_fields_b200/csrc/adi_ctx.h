@@ -41,7 +41,8 @@ struct adi_ctx {
     int device = 0;
     long launches = 0;
     // options (adi_set_option)
-    long opt_kt = 0, opt_lt = 0, opt_m = 0, opt_sync_check = 0, opt_profile = 0, opt_fuse = 0, opt_wide = 0, opt_sparse = 1;
+    long opt_kt = 0, opt_lt = 0, opt_m = 0, opt_sync_check = 0, opt_profile = 0, opt_fuse = 0, opt_wide = 0, opt_sparse = 1,
+         opt_xy2 = 1, opt_uni = 1, opt_tw = 1;
     // per-kernel timing (adi_profile_*): 5 events per step, read lazily
     std::vector<cudaEvent_t> prof_ev;
     long prof_steps = 0;
@@ -58,6 +59,10 @@ struct adi_ctx {
     uint8_t *code_buf[3] = {nullptr, nullptr, nullptr};
     size_t code_cells = 0;
     bool code_dirty = true;
+    // transposed copies for the x / y sweeps (line axis fastest, padded to npadT[a]); option xy2
+    uint8_t *codeT[2] = {nullptr, nullptr};
+    size_t codeT_bytes[2] = {0, 0};
+    int npadT[2] = {0, 0};
     // surface-only coefficient fields (k_check_sparse): re-examined after a pack or mask change
     bool sparse[3] = {false, false, false};
     bool sparse_dirty = true;

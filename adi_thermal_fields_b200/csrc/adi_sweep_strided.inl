@@ -1,6 +1,7 @@
 // adi_sweep_strided.inl -- launcher body of the strided sweeps; included by adi_sweep_x.cu
 // (ADI_AXIS 0, with the fused explicit stage) and adi_sweep_y.cu (ADI_AXIS 1).
 #include "adi_launch.h"
+#include "adi_sweep_xy.cuh"
 
 namespace adi {
 
@@ -10,6 +11,50 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
     constexpr int AXIS = ADI_AXIS;
     const int n = AXIS == 0 ? a.nx : a.ny;
     const int other = AXIS == 0 ? a.ny : a.nx;
+    if (ctx->opt_xy2 && ctx->npadT[AXIS] > 0 && n <= 2048 && !(AXIS == 0 && expl) && other <= 65535) {
+        // second-generation sweeps (adi_sweep_xy.cuh).  Shapes:
+        //   n <= 512          M 16 (two factors per cell), <= 32 chunks, 256 threads, 2 blocks / SM   (option m=32: as below)
+        //   512 < n <= 1024   M 32 (one factor per cell),  <= 32 chunks, 256 threads, 2 blocks / SM
+        //   1024 < n <= 2048  M 32, <= 64 chunks (two reduced rows per lane), 512 threads, 1 block / SM
+        const int M = (n <= 512 && ctx->opt_m != 32) ? 16 : 32;
+        const int P = (n + M - 1) / M;
+        const int PR = P > 32 ? 2 : 1, maxt = P > 32 ? 512 : 256;
+        int KT = 32;
+        while (KT > 1 && KT * P > maxt) KT >>= 1;
+        if (ctx->opt_kt > 0) {
+            int w = 1;
+            while (2 * w <= ctx->opt_kt && 2 * w <= 32 && 2 * w * P <= maxt) w <<= 1;
+            KT = w;
+        }
+        const int NTH = KT * P;
+        SweepArgs b = a;
+        b.codeT = ctx->codeT[AXIS];
+        b.npad = ctx->npadT[AXIS];
+        b.tw = (ctx->opt_tw && NTH >= 32) ? 1 : 0;
+        b.uni = (ctx->opt_uni && !extra && (!dense || a.sparse)) ? 1 : 0;
+        uni_const_build(b.uc, M, a.k.g);
+        const int NS = M == 16 ? 2 : 1;
+        const size_t xch = std::max<size_t>((size_t)7 * P * (KT + 1), (size_t)6 * NTH);
+        const size_t smem = ((size_t)NS * M * NTH + xch) * sizeof(double);
+        if ((unsigned long long)M * 8ull * (AXIS == 0 ? (unsigned long long)a.ny * a.nz : (unsigned long long)a.nz) >= (1ull << 32)) {
+            set_error("adi_cart_step: grid too large for 32-bit in-chunk byte offsets (chunk length x line stride x 8 >= 4 GiB)");
+            return ADI_EINVAL;
+        }
+        dim3 block(KT, P), grid((a.nz + KT - 1) / KT, other);
+#define ADI_GO2(M_, NS_, PR_, MAXT, MINB)                                                                            \
+        {                                                                                                        \
+            if (dense) {                                                                                         \
+                if (extra) return launch(k_sweep_xy<AXIS, M_, NS_, 2, true, PR_, MAXT, MINB>, grid, block, smem, st, ctx, b);  \
+                return launch(k_sweep_xy<AXIS, M_, NS_, 2, false, PR_, MAXT, MINB>, grid, block, smem, st, ctx, b);            \
+            }                                                                                                    \
+            if (extra) return launch(k_sweep_xy<AXIS, M_, NS_, 1, true, PR_, MAXT, MINB>, grid, block, smem, st, ctx, b);      \
+            return launch(k_sweep_xy<AXIS, M_, NS_, 1, false, PR_, MAXT, MINB>, grid, block, smem, st, ctx, b);                \
+        }
+        if (M == 16) ADI_GO2(16, 2, 1, 256, 2)
+        else if (PR == 1) ADI_GO2(32, 1, 1, 256, 2)
+        else ADI_GO2(32, 1, 2, 512, 1)
+#undef ADI_GO2
+    }
     if (n > 1024 && n <= 4096 && !(AXIS == 0 && expl) && ctx->opt_m != 32) {
         // long lines: a cluster of 2 or 4 CTAs shares each line (K1c)
         // 2 or 4 CTAs of <= 64 chunks x 8 lanes (512 threads, one CTA per SM); measured against 4 / 8 CTAs

@@ -15,6 +15,8 @@ using namespace adi;
 
 namespace {
 
+int g_uniform = 1;   // take the tabulated uniform-chunk path (adi_core.h) where it applies, as the kernels do
+
 template <int M>
 struct HostOps {
     const double *coeff, *qp, *dvp;  // offset to the chunk's first cell; may be null
@@ -41,6 +43,9 @@ void sweep_line(double *T, const uint8_t *code, const double *coeff, const doubl
     std::vector<HostOps<M>> ops(P);
     std::vector<First> fi(P);
     std::vector<Red> red(P), nxt(P);
+    std::vector<char> uni(P, 0);
+    UniConst uc;
+    uni_const_build(uc, M, k.g);
     for (int p = 0; p < P; ++p) {
         const size_t idx0 = base + (size_t)p * M * stride;
         ops[p].coeff = coeff ? coeff + idx0 : nullptr;
@@ -54,7 +59,13 @@ void sweep_line(double *T, const uint8_t *code, const double *coeff, const doubl
             ch[p].set_code(e, ok ? code[idx] : 0u);
             ch[p].T[e] = (ok && (code[idx] & CB_SELF)) ? T[idx] : 0.0;   // load rule
         }
-        fi[p] = chunk_forward<M, CMODE, EXTRA, NS>(ch[p], ops[p], LO, HI, k);
+        // the kernels take the uniform path when the coefficient field is known to vanish away from the
+        // surface (CMODE 1 by construction; CMODE 2 after k_check_sparse): here the values themselves are checked
+        bool u = g_uniform && !EXTRA && ops[p].nv == M && chunk_uniform<M>(ch[p], LO, HI);
+        if (u && CMODE == 2)
+            for (int e = 0; e < M; ++e) u = u && ops[p].coef(e) == 0.0;
+        uni[p] = u;
+        fi[p] = u ? chunk_forward_uniform<M>(ch[p], uc) : chunk_forward<M, CMODE, EXTRA, NS>(ch[p], ops[p], LO, HI, k);
     }
     if (zmode == 1) {  // z-slab pass 1: separators as affine functions of the ghosts (solve_reduced3)
         std::vector<Red3> r3(P), n3(P);
@@ -105,7 +116,9 @@ void sweep_line(double *T, const uint8_t *code, const double *coeff, const doubl
         return;
     }
     for (int p = 0; p < P; ++p) {
-        chunk_backward<M, EXTRA, NS>(ch[p], ops[p], LO, HI, k.g, p > 0 ? red[p - 1].D : (zmode == 2 ? Lg : 0.0), red[p].D);
+        const double Slp = p > 0 ? red[p - 1].D : (zmode == 2 ? Lg : 0.0);
+        if (uni[p]) chunk_backward_uniform<M>(ch[p], uc, Slp, red[p].D);
+        else chunk_backward<M, EXTRA, NS>(ch[p], ops[p], LO, HI, k.g, Slp, red[p].D);
         for (int e = 0; e < ops[p].nv; ++e)
             if (ch[p].active(e)) T[base + ((size_t)p * M + e) * stride] = ch[p].T[e];
     }
@@ -129,6 +142,8 @@ void sweep_line_any(bool dense, bool extra, double *T, const uint8_t *code, cons
 }  // namespace
 
 extern "C" {
+
+void emu_set_uniform(int on) { g_uniform = on; }
 
 // code as built by k_build_code (adi_cart.cuh)
 void emu_build_code(const uint8_t *mask, const uint8_t *dirm, uint8_t *code, int nx, int ny, int nz)

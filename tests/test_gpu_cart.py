@@ -453,3 +453,34 @@ def test_coefficient_edited_in_place_is_reexamined(g, cp):
     Td = g.adi_step_gpu_coeff(Td, gd, md, prm_d, pd, Tinf=20.0)
     assert cases.rel_l2(cp.asnumpy(Td), Th, c["mask"]) <= TOL
     assert abs(cp.asnumpy(Td)[12, 11, 20] - Th[12, 11, 20]) <= 1e-9 * abs(Th[12, 11, 20])
+
+
+# ---- second-generation x / y sweeps: uniform chunks, transposed codes, warp-level reduced solve ------------
+def _uniform_case(shape, mask_kind, bk, theta, cfl, seed):
+    mask = cases.make_mask(mask_kind, shape, seed)
+    bcs = cases.make_bcs(bk, shape, mask, seed, 20.0)
+    T0 = 20.0 + 1380.0 * cases.splitmix_uniform(seed + 1, shape)
+    T0[~mask] = np.nan
+    kappa = cases.K / (cases.RHO * cases.CP)
+    return dict(shape=shape, mask=mask, T0=T0, dt=cfl * cases.DX ** 2 / kappa, theta=theta, bcs=bcs, kappa=kappa)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(uni=0), dict(tw=0), dict(xy2=0), dict(m=32), dict(kt=4), dict(m=32, kt=2)],
+                         ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
+@pytest.mark.parametrize("shape,mask_kind", [((70, 40, 37), "full"), ((40, 70, 130), "plate_track"), ((96, 50, 64), "cyl_holes"),
+                                             ((600, 7, 48), "full"), ((5, 1100, 24), "full"), ((2050, 3, 10), "full"),
+                                             ((1030, 2, 9), "random")],
+                         ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else v)
+def test_uniform_chunk_paths(shape, mask_kind, opts, g, cp):
+    """Chunks whose cells all have both neighbours along the swept axis take tabulated elimination factors
+    (adi_core.h UniConst); every launch shape / option gives the oracle's answer: dense per-face h and scalar h,
+    theta 0.5 and 1, cfl from 0.128 to 3000 (slowly decaying couplings)."""
+    restore = {k: int(g.get_option(k)) for k in opts}
+    for k, v in opts.items():
+        g.set_option(k, v)
+    try:
+        for bk, theta, cfl in [("robin_dict3d", 0.5, 0.128), ("robin6", 0.5, 3000.0), ("robin_dict3d", 1.0, 40.0)]:
+            _both(g, cp, _uniform_case(shape, mask_kind, bk, theta, cfl, seed=8000 + shape[0]), nsteps=2)
+    finally:
+        for k, v in restore.items():
+            g.set_option(k, v)

@@ -153,6 +153,9 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
     }
     else if (!strcmp(name, "uni")) ctx->opt_uni = value;    // 1 (default): tabulated factors for uniform chunks
     else if (!strcmp(name, "tw")) ctx->opt_tw = value;      // 1 (default): reduced system solved by warps
+    else if (!strcmp(name, "occ")) ctx->opt_occ = value;    // x / y sweeps, 16-cell chunks: resident blocks per SM (2, 3, 4)
+    else if (!strcmp(name, "remap")) ctx->opt_remap = value;  // 1 (default): both ends of a line in one warp
+    else if (!strcmp(name, "dbg")) ctx->opt_dbg = value;    // tuning aid (1: x / y sweeps move data only -- wrong results)
     else if (!strcmp(name, "fuse")) ctx->opt_fuse = value;  // 1: explicit stage fused into the x sweep
     else {
         adi::set_error(std::string("adi_set_option: unknown option ") + name);
@@ -174,6 +177,9 @@ long adi_get_option(adi_ctx *ctx, const char *name)
     if (!strcmp(name, "xy2")) return ctx->opt_xy2;
     if (!strcmp(name, "uni")) return ctx->opt_uni;
     if (!strcmp(name, "tw")) return ctx->opt_tw;
+    if (!strcmp(name, "remap")) return ctx->opt_remap;
+    if (!strcmp(name, "occ")) return ctx->opt_occ;
+    if (!strcmp(name, "dbg")) return ctx->opt_dbg;
     if (!strcmp(name, "sparse_coeff")) return ctx->opt_sparse;
     if (!strcmp(name, "sparse_active"))  // bit a: the sweep along axis a currently skips interior coefficient reads
         return ctx->sparse_dirty ? 0 : ((ctx->sparse[0] ? 1 : 0) | (ctx->sparse[1] ? 2 : 0) | (ctx->sparse[2] ? 4 : 0));

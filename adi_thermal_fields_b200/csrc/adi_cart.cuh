@@ -43,6 +43,8 @@ struct SweepArgs {
     int npad;                          // padded line length of codeT (multiple of 32, padding = code 0)
     int uni;                           // uniform chunks may take the tabulated factors of `uc`
     int tw;                            // reduced system by warps (transposed exchange)
+    int remap;                         // chunk order inside a block: ends of the line in the same warp
+    int dbg;                           // tuning aid: 1 = loads and stores only
     UniConst uc;
 };
 

@@ -31,9 +31,14 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
         b.codeT = ctx->codeT[AXIS];
         b.npad = ctx->npadT[AXIS];
         b.tw = (ctx->opt_tw && NTH >= 32) ? 1 : 0;
+        b.remap = ctx->opt_remap ? 1 : 0;
+        b.dbg = (int)ctx->opt_dbg;
         b.uni = (ctx->opt_uni && !extra && (!dense || a.sparse)) ? 1 : 0;
         uni_const_build(b.uc, M, a.k.g);
-        const int NS = M == 16 ? 2 : 1;
+        // blocks per SM (M 16 only): 2 = 128 registers, two factors per cell in shared memory; 3 / 4 = 80 / 64
+        // registers with one factor per cell (the general path recomputes the couplings from the code)
+        const int occ = (M == 16 && (ctx->opt_occ == 3 || ctx->opt_occ == 4)) ? (int)ctx->opt_occ : 2;
+        const int NS = (M == 16 && occ == 2) ? 2 : 1;
         const size_t xch = std::max<size_t>((size_t)7 * P * (KT + 1), (size_t)6 * NTH);
         const size_t smem = ((size_t)NS * M * NTH + xch) * sizeof(double);
         if ((unsigned long long)M * 8ull * (AXIS == 0 ? (unsigned long long)a.ny * a.nz : (unsigned long long)a.nz) >= (1ull << 32)) {
@@ -50,7 +55,9 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
             if (extra) return launch(k_sweep_xy<AXIS, M_, NS_, 1, true, PR_, MAXT, MINB>, grid, block, smem, st, ctx, b);      \
             return launch(k_sweep_xy<AXIS, M_, NS_, 1, false, PR_, MAXT, MINB>, grid, block, smem, st, ctx, b);                \
         }
-        if (M == 16) ADI_GO2(16, 2, 1, 256, 2)
+        if (M == 16 && occ == 2) ADI_GO2(16, 2, 1, 256, 2)
+        else if (M == 16 && occ == 3) ADI_GO2(16, 1, 1, 256, 3)
+        else if (M == 16) ADI_GO2(16, 1, 1, 256, 4)
         else if (PR == 1) ADI_GO2(32, 1, 1, 256, 2)
         else ADI_GO2(32, 1, 2, 512, 1)
 #undef ADI_GO2

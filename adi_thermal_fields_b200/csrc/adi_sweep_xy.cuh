@@ -174,9 +174,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_xy(const SweepArgs a)
     static_assert(M % 16 == 0, "codes are loaded sixteen at a time");
     extern __shared__ double smem[];
     const int KT = blockDim.x, P = blockDim.y;
-    const int kk = threadIdx.x, p = threadIdx.y;
+    const int kk = threadIdx.x;
+    // chunk of this thread: with `remap` the two ends of the line share a warp (threadIdx.y = 0, 1, 2, 3 ->
+    // chunks 0, P-1, 1, P-2, ...), so that a part spanning the whole line has ONE warp per block on the
+    // general path (its end chunks are exposed) instead of two
+    const int p = a.remap ? ((threadIdx.y & 1) ? P - 1 - (int)(threadIdx.y >> 1) : (int)(threadIdx.y >> 1)) : (int)threadIdx.y;
     const int NTH = KT * P;
-    const int tid = p * KT + kk;
+    const int tid = threadIdx.y * KT + kk;
     const int k = blockIdx.x * KT + kk;
     const int n = (AXIS == 0) ? a.nx : a.ny;
     const unsigned sl = (AXIS == 0) ? (unsigned)a.ny * (unsigned)a.nz : (unsigned)a.nz;
@@ -231,7 +235,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_xy(const SweepArgs a)
     ops.coeff = nullptr; ops.qp = nullptr; ops.dvp = nullptr;
     ops.sl = sl; ops.nv = nv; ops.col = col; ops.NTH = NTH;
     First f;
-    if (uni) {
+    f.Y = f.V = f.W = 0.0;
+    if (a.dbg == 1) {
+    } else if (uni) {
         f = chunk_forward_uniform<M>(ch, a.uc);
     } else {
         solid = NS == 2 && __all_sync(0xffffffffu, nv == M && chunk_solid<M>(ch, LO, HI));
@@ -256,11 +262,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_xy(const SweepArgs a)
         else if (solid) f = chunk_forward<M, CMODE, EXTRA, NS, true>(ch, ops, LO, HI, a.k);
         else f = chunk_forward<M, CMODE, EXTRA, NS, false>(ch, ops, LO, HI, a.k);
     }
-    double Sl, S;
-    if (a.tw) S = solve_reduced_tw<M, PR>(ch, f, xch, KT, P, kk, p, tid, NTH, &Sl);
-    else S = solve_reduced<M>(ch, f, xch, NTH, tid, KT, p, P, &Sl);
-    if (uni) chunk_backward_uniform<M>(ch, a.uc, Sl, S);
-    else chunk_backward<M, EXTRA, NS>(ch, ops, LO, HI, a.k.g, Sl, S);
+    if (a.dbg != 1) {   // dbg 1: data movement only (tuning aid; wrong results)
+        double Sl, S;
+        if (a.tw) S = solve_reduced_tw<M, PR>(ch, f, xch, KT, P, kk, p, tid, NTH, &Sl);
+        else S = solve_reduced<M>(ch, f, xch, NTH, p * KT + kk, KT, p, P, &Sl);
+        if (uni) chunk_backward_uniform<M>(ch, a.uc, Sl, S);
+        else chunk_backward<M, EXTRA, NS>(ch, ops, LO, HI, a.k.g, Sl, S);
+    }
 
     double *op = a.out + idx0;
     if (solid) {

@@ -243,30 +243,33 @@ ADI_HD First chunk_forward(Chunk<M> &ch, OPS &ops, unsigned lo, unsigned hi, con
 }
 
 // ---- uniform chunks ---------------------------------------------------------------------
-// A chunk is "uniform" when every one of its M cells is active, has BOTH neighbours along the swept
-// axis (so it is exposed on neither face of this axis: the Robin coefficient is zero, :93-99), is no
-// Dirichlet cell and carries no flux term: all M rows are (-g, 1+2g, -g | T).  This is the bulk of
-// every part.  The elimination factors of such a chunk do not depend on the data or on where the
-// chunk sits -- only on g -- so they are tabulated once per launch on the host (UniConst, passed
-// in the kernel parameters = constant bank operands) and phase 1 / phase 3 shrink to three / two
-// fused multiply-adds per cell with no reciprocal, no code decoding and no factor store.
+// A cell is "uniform" when it is active, has BOTH neighbours along the swept axis (so it is exposed on
+// neither face of this axis: the Robin coefficient is zero, :93-99), is no Dirichlet cell and carries no
+// flux term: its row is (-g, 1+2g, -g | T).  This is the bulk of every part.  The elimination factors of a
+// run of uniform cells do not depend on the data or on where the run sits -- only on g -- so they are
+// tabulated once per launch on the host (UniConst, passed in the kernel parameters = constant bank
+// operands) and phase 1 / phase 3 shrink to three / two fused multiply-adds per cell with no reciprocal,
+// no code decoding and no factor store.  Two chunk shapes take this path:
+//   OFF 0   interior cells 0..M-2 uniform;
+//   OFF 1   cell 0 any active, non-Dirichlet cell coupled to cell 1 (typically the exposed first cell of a
+//           line), cells 1..M-2 uniform: cell 0 is eliminated by hand against the tabulated run.
+// The separator (cell M-1) is a general row in both (typically the exposed last cell of a line).
 constexpr int UNI_MAX = 32;
 struct UniConst {
     double rinv[UNI_MAX];  // 1/den_e
-    double u[UNI_MAX];     // cc/den_e = aa/den_e  (la == u for a uniform chunk)
-    double vp[UNI_MAX];    // coefficient of S_{p-1} in x_e after the forward pass
-    double al[UNI_MAX];    // u_0 ... u_{e-1}: weight of d'_e in the First relation
-    double V, W, Vl, Wl;   // the matrix part of First and of the last-interior relation
-    double g, b;           // off-diagonal (as the non-negative number -a = -c) and diagonal of the rows
+    double u[UNI_MAX];     // cc/den_e = aa/den_e  (la == u in a uniform run)
+    double vp[UNI_MAX];    // coefficient of the value left of the run in x_e after the forward pass
+    double al[UNI_MAX];    // u_0 ... u_{e-1}: weight of d'_e in the relation of the run's first cell
+    double Vn[UNI_MAX];    // sum_{e<n} al_e*vp_e: coefficient of the left value in the first cell of a run of n cells
 };
 
-// Host side: the table for chunk length M (same recurrences as chunk_forward on uniform rows).
-inline void uni_const_build(UniConst &uc, int M, double g)
+// Host side (same recurrences as chunk_forward on uniform rows).
+inline void uni_const_build(UniConst &uc, double g)
 {
     const double b = (1.0 + (g + g)) + 0.0;      // make_row: (1 + nn) + dt*c with c = 0
     double uprev = 0.0, vprev = 1.0, alpha = 1.0, V = 0.0;
-    for (int e = 0; e < UNI_MAX; ++e) uc.rinv[e] = uc.u[e] = uc.vp[e] = uc.al[e] = 0.0;
-    for (int e = 0; e < M - 1; ++e) {
+    for (int e = 0; e < UNI_MAX; ++e) {
+        uc.Vn[e] = V;
         const double den = fma(-g, uprev, b);
         const double rinv = 1.0 / den;
         const double u = g * rinv;
@@ -276,52 +279,85 @@ inline void uni_const_build(UniConst &uc, int M, double g)
         alpha = alpha * u;
         uprev = u; vprev = vp;
     }
-    uc.V = V; uc.W = alpha; uc.Vl = vprev; uc.Wl = uprev;
-    uc.g = g; uc.b = b;
 }
 
-template <int M>
+// Cells OFF..M-2 uniform (and, OFF 1, cell 0 active, not Dirichlet, coupled to cell 1).
+template <int M, int OFF>
 ADI_HD bool chunk_uniform(const Chunk<M> &ch, unsigned lo, unsigned hi)
 {
-    static_assert(M % 4 == 0, "codes are packed four per word");
-    const unsigned need = (CB_SELF | lo | hi) * 0x01010101u, care = (CB_SELF | lo | hi | CB_DIR) * 0x01010101u;
+    static_assert(M % 4 == 0 && M >= 8, "codes are packed four per word");
+    const unsigned need1 = CB_SELF | lo | hi, care1 = CB_SELF | lo | hi | CB_DIR;
     bool ok = true;
 #pragma unroll
-    for (int w = 0; w < M / 4; ++w) ok = ok && ((ch.cw[w] & care) == need);
+    for (int w = 0; w < M / 4; ++w) {
+        unsigned need = 0u, care = 0u;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int cell = 4 * w + b;
+            if (cell >= OFF && cell <= M - 2) { need |= need1 << (8 * b); care |= care1 << (8 * b); }
+        }
+        ok = ok && ((ch.cw[w] & care) == need);
+    }
+    if (OFF == 1) ok = ok && ((ch.cw[0] & (CB_SELF | hi | CB_DIR)) == (CB_SELF | hi));
     return ok;
 }
 
-// Phase 1 of a uniform chunk.  Leaves d'_e (forward-eliminated right-hand side with S_{p-1} = 0) in
-// ch.T[e]; chunk_backward_uniform adds the S_{p-1} term from the tabulated vp.
-template <int M>
-ADI_HD First chunk_forward_uniform(Chunk<M> &ch, const UniConst &uc)
+// Relation of the hand-eliminated first cell (OFF 1): x_0 = al + bl*S_{p-1} + br*S_p.
+struct UniHead {
+    double al, bl, br;
+};
+
+// Phase 1.  sep: row of the separator (cell M-1); head: row of cell 0 (OFF 1 only).  Leaves d'_e
+// (forward-eliminated right-hand side with the value left of the run = 0) in ch.T[e] of the run.
+template <int M, int OFF>
+ADI_HD First chunk_forward_uniform(Chunk<M> &ch, const UniConst &uc, const Row &sep, const Row &head, UniHead &hd)
 {
-    static_assert(M <= UNI_MAX, "UniConst is too short for this chunk length");
+    static_assert(M - 1 <= UNI_MAX, "UniConst is too short for this chunk length");
+    constexpr int N = M - 1 - OFF;               // cells in the run
     double dprev = 0.0, Y = 0.0;
 #pragma unroll
-    for (int e = 0; e < M - 1; ++e) {
-        const double dp = fma(uc.u[e], dprev, ch.T[e] * uc.rinv[e]);
-        ch.T[e] = dp;
-        Y = fma(uc.al[e], dp, Y);
+    for (int j = 0; j < N; ++j) {
+        const double dp = fma(uc.u[j], dprev, ch.T[OFF + j] * uc.rinv[j]);
+        ch.T[OFF + j] = dp;
+        Y = fma(uc.al[j], dp, Y);
         dprev = dp;
     }
+    // run: x_first = Y + V*left + W*S_p,  x_last = dprev + Vl*left + Wl*S_p
+    const double V = uc.Vn[N], W = uc.al[N], Vl = uc.vp[N - 1], Wl = uc.u[N - 1];
     First f;
-    f.Y = Y; f.V = uc.V; f.W = uc.W;
-    ch.Yl = dprev; ch.Vl = uc.Vl; ch.Wl = uc.Wl;
-    ch.s_aa = uc.g; ch.s_cc = uc.g; ch.s_b = uc.b; ch.s_d = ch.T[M - 1];
+    if (OFF == 0) {
+        f.Y = Y; f.V = V; f.W = W;
+        ch.Yl = dprev; ch.Vl = Vl; ch.Wl = Wl;
+        hd.al = hd.bl = hd.br = 0.0;
+    } else {
+        // -aa0*S_{p-1} + b0*x0 - cc0*x_first = d0
+        const double r = frcp(fma(-head.cc, V, head.b));
+        hd.al = fma(head.cc, Y, head.d) * r;
+        hd.bl = head.aa * r;
+        hd.br = (head.cc * W) * r;
+        f.Y = hd.al; f.V = hd.bl; f.W = hd.br;
+        ch.Yl = fma(Vl, hd.al, dprev); ch.Vl = Vl * hd.bl; ch.Wl = fma(Vl, hd.br, Wl);
+    }
+    ch.s_aa = sep.aa; ch.s_cc = sep.cc; ch.s_b = sep.b; ch.s_d = sep.d;
     return f;
 }
 
-// Phase 3 of a uniform chunk.
-template <int M>
-ADI_HD void chunk_backward_uniform(Chunk<M> &ch, const UniConst &uc, double Sl, double S)
+// Phase 3.
+template <int M, int OFF>
+ADI_HD void chunk_backward_uniform(Chunk<M> &ch, const UniConst &uc, const UniHead &hd, double Sl, double S)
 {
+    constexpr int N = M - 1 - OFF;
+    double left = Sl;
+    if (OFF == 1) {
+        left = fma(hd.br, S, fma(hd.bl, Sl, hd.al));
+        ch.T[0] = left;
+    }
     double xn = S;
     ch.T[M - 1] = S;
 #pragma unroll
-    for (int e = M - 2; e >= 0; --e) {
-        const double x = fma(uc.u[e], xn, fma(uc.vp[e], Sl, ch.T[e]));
-        ch.T[e] = x;
+    for (int j = N - 1; j >= 0; --j) {
+        const double x = fma(uc.u[j], xn, fma(uc.vp[j], left, ch.T[OFF + j]));
+        ch.T[OFF + j] = x;
         xn = x;
     }
 }

@@ -18,7 +18,8 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
         //   1024 < n <= 2048  M 32, <= 64 chunks (two reduced rows per lane), 512 threads, 1 block / SM
         const int M = (n <= 512 && ctx->opt_m != 32) ? 16 : 32;
         const int P = (n + M - 1) / M;
-        const int PR = P > 32 ? 2 : 1, maxt = P > 32 ? 512 : 256;
+        const bool wide = M == 16 && ctx->opt_wide;   // 16-cell chunks in 512-thread blocks: twice the lanes per row
+        const int PR = P > 32 ? 2 : 1, maxt = (P > 32 || wide) ? 512 : 256;
         int KT = 32;
         while (KT > 1 && KT * P > maxt) KT >>= 1;
         if (ctx->opt_kt > 0) {
@@ -34,11 +35,11 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
         b.remap = ctx->opt_remap ? 1 : 0;
         b.dbg = (int)ctx->opt_dbg;
         b.uni = (ctx->opt_uni && !extra && (!dense || a.sparse)) ? 1 : 0;
-        uni_const_build(b.uc, M, a.k.g);
+        uni_const_build(b.uc, a.k.g);
         // blocks per SM (M 16 only): 2 = 128 registers, two factors per cell in shared memory; 3 / 4 = 80 / 64
         // registers with one factor per cell (the general path recomputes the couplings from the code)
         const int occ = (M == 16 && (ctx->opt_occ == 3 || ctx->opt_occ == 4)) ? (int)ctx->opt_occ : 2;
-        const int NS = (M == 16 && occ == 2) ? 2 : 1;
+        const int NS = (M == 16 && occ == 2 && !wide) ? 2 : 1;
         const size_t xch = std::max<size_t>((size_t)7 * P * (KT + 1), (size_t)6 * NTH);
         const size_t smem = ((size_t)NS * M * NTH + xch) * sizeof(double);
         if ((unsigned long long)M * 8ull * (AXIS == 0 ? (unsigned long long)a.ny * a.nz : (unsigned long long)a.nz) >= (1ull << 32)) {
@@ -55,7 +56,8 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
             if (extra) return launch(k_sweep_xy<AXIS, M_, NS_, 1, true, PR_, MAXT, MINB>, grid, block, smem, st, ctx, b);      \
             return launch(k_sweep_xy<AXIS, M_, NS_, 1, false, PR_, MAXT, MINB>, grid, block, smem, st, ctx, b);                \
         }
-        if (M == 16 && occ == 2) ADI_GO2(16, 2, 1, 256, 2)
+        if (wide) ADI_GO2(16, 1, 1, 512, 2)
+        else if (M == 16 && occ == 2) ADI_GO2(16, 2, 1, 256, 2)
         else if (M == 16 && occ == 3) ADI_GO2(16, 1, 1, 256, 3)
         else if (M == 16) ADI_GO2(16, 1, 1, 256, 4)
         else if (PR == 1) ADI_GO2(32, 1, 1, 256, 2)

@@ -213,11 +213,17 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_xy(const SweepArgs a)
     for (int e = 0; e < M; ++e) ch.T[e] = ldg_f64(tb + (size_t)((unsigned)min(e, nvm1) * sl8));
     const unsigned scol = smem_u32(col);
     const unsigned nth8 = (unsigned)NTH * 8u;
+    const char *cf = reinterpret_cast<const char *>(a.coeff + (CMODE == 2 ? idx0 : 0));
+    const int el = n - 1 - t0;                              // slot of the line's last cell, if it is in this chunk
     if (CMODE == 2) {
-        const char *cf = reinterpret_cast<const char *>(a.coeff + idx0);
         if (!a.sparse) {
 #pragma unroll
             for (int e = 0; e < M; ++e) cp_async8(scol + e * nth8, cf + (size_t)((unsigned)min(e, nvm1) * sl8));
+        } else if (nv > 0) {
+            // surface-only coefficient field: the two ends of the line (always exposed when active) are requested
+            // now, cells next to an interior void once the codes have arrived
+            if (t0 == 0) cp_async8(scol, cf);
+            if (el < M) cp_async8(scol + (unsigned)el * nth8, cf + (size_t)((unsigned)el * sl8));
         }
     }
     // The barrier keeps every load above it in flight together (one memory round trip per thread) and tells
@@ -229,16 +235,40 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_xy(const SweepArgs a)
     cp_async_wait_all();
     if (a.in == a.out && !live) return;
 
-    const bool uni = a.uni && __all_sync(0xffffffffu, chunk_uniform<M>(ch, LO, HI));
-    bool solid = uni;
+    // coefficient of an ACTIVE cell e of this chunk when only exposed cells carry one (CMODE 1 / sparse CMODE 2 are
+    // the modes of the uniform paths; make_row derives the CMODE 1 value from the code itself)
+    auto exposed_coef = [&](int e, unsigned c) -> double {
+        if (CMODE != 2) return 0.0;
+        if ((c & (LO | HI)) == (LO | HI)) return 0.0;
+        const int cell = t0 + e;
+        if (cell == 0 || cell == n - 1) return col[e * NTH];
+        return ldg_f64(cf + (size_t)((unsigned)e * sl8));
+    };
+
+    // 0: general rows; 1: cells 0..M-2 uniform; 2: cell 0 general, cells 1..M-2 uniform (adi_core.h)
+    int path = 0;
+    if (a.uni) {
+        if (__all_sync(0xffffffffu, chunk_uniform<M, 1>(ch, LO, HI)))
+            path = __all_sync(0xffffffffu, chunk_uniform<M, 0>(ch, LO, HI)) ? 1 : 2;
+    }
+    bool solid = path != 0;
     StridedOps<M, true> ops;
     ops.coeff = nullptr; ops.qp = nullptr; ops.dvp = nullptr;
     ops.sl = sl; ops.nv = nv; ops.col = col; ops.NTH = NTH;
     First f;
     f.Y = f.V = f.W = 0.0;
+    UniHead hd;
+    hd.al = hd.bl = hd.br = 0.0;
     if (a.dbg == 1) {
-    } else if (uni) {
-        f = chunk_forward_uniform<M>(ch, a.uc);
+    } else if (path != 0) {
+        const unsigned cs = ch.code(M - 1), c0 = ch.code(0);
+        const Row sep = make_row<CMODE, EXTRA>(cs, LO, HI, ch.T[M - 1], exposed_coef(M - 1, cs), 0.0, 0.0, a.k);
+        if (path == 1) {
+            f = chunk_forward_uniform<M, 0>(ch, a.uc, sep, sep, hd);
+        } else {
+            const Row head = make_row<CMODE, EXTRA>(c0, LO, HI, ch.T[0], exposed_coef(0, c0), 0.0, 0.0, a.k);
+            f = chunk_forward_uniform<M, 1>(ch, a.uc, sep, head, hd);
+        }
     } else {
         solid = NS == 2 && __all_sync(0xffffffffu, nv == M && chunk_solid<M>(ch, LO, HI));
         if (!solid) {
@@ -247,12 +277,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_xy(const SweepArgs a)
         }
         const bool ends_only = CMODE == 2 && a.sparse && solid;
         if (CMODE == 2 && a.sparse) {
-            // surface-only coefficient field: fetched where the cell has an exposed face along this axis, zero elsewhere
-            const char *cf = reinterpret_cast<const char *>(a.coeff + idx0);
 #pragma unroll
             for (int e = 0; e < M; ++e) {
                 if (solid && e != 0 && e != M - 1) continue;
                 const unsigned c = ch.code(e);  // 0 beyond the chunk's valid cells
+                const int cell = t0 + e;
+                if (e < nv && (cell == 0 || cell == n - 1)) continue;  // staged above
                 col[e * NTH] = ((c & CB_SELF) && (c & (LO | HI)) != (LO | HI)) ? ldg_f64(cf + (size_t)((unsigned)e * sl8)) : 0.0;
             }
         }
@@ -266,7 +296,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_xy(const SweepArgs a)
         double Sl, S;
         if (a.tw) S = solve_reduced_tw<M, PR>(ch, f, xch, KT, P, kk, p, tid, NTH, &Sl);
         else S = solve_reduced<M>(ch, f, xch, NTH, p * KT + kk, KT, p, P, &Sl);
-        if (uni) chunk_backward_uniform<M>(ch, a.uc, Sl, S);
+        if (path == 1) chunk_backward_uniform<M, 0>(ch, a.uc, hd, Sl, S);
+        else if (path == 2) chunk_backward_uniform<M, 1>(ch, a.uc, hd, Sl, S);
         else chunk_backward<M, EXTRA, NS>(ch, ops, LO, HI, a.k.g, Sl, S);
     }
 

@@ -44,8 +44,9 @@ void sweep_line(double *T, const uint8_t *code, const double *coeff, const doubl
     std::vector<First> fi(P);
     std::vector<Red> red(P), nxt(P);
     std::vector<char> uni(P, 0);
+    std::vector<UniHead> hd(P);
     UniConst uc;
-    uni_const_build(uc, M, k.g);
+    uni_const_build(uc, k.g);
     for (int p = 0; p < P; ++p) {
         const size_t idx0 = base + (size_t)p * M * stride;
         ops[p].coeff = coeff ? coeff + idx0 : nullptr;
@@ -59,13 +60,27 @@ void sweep_line(double *T, const uint8_t *code, const double *coeff, const doubl
             ch[p].set_code(e, ok ? code[idx] : 0u);
             ch[p].T[e] = (ok && (code[idx] & CB_SELF)) ? T[idx] : 0.0;   // load rule
         }
-        // the kernels take the uniform path when the coefficient field is known to vanish away from the
+        // the kernels take the uniform paths when the coefficient field is known to vanish away from the
         // surface (CMODE 1 by construction; CMODE 2 after k_check_sparse): here the values themselves are checked
-        bool u = g_uniform && !EXTRA && ops[p].nv == M && chunk_uniform<M>(ch[p], LO, HI);
-        if (u && CMODE == 2)
-            for (int e = 0; e < M; ++e) u = u && ops[p].coef(e) == 0.0;
-        uni[p] = u;
-        fi[p] = u ? chunk_forward_uniform<M>(ch[p], uc) : chunk_forward<M, CMODE, EXTRA, NS>(ch[p], ops[p], LO, HI, k);
+        int v = 0;   // 0: general, 1: OFF 0, 2: OFF 1
+        if (g_uniform && !EXTRA && ops[p].nv == M) {
+            if (chunk_uniform<M, 0>(ch[p], LO, HI)) v = 1;
+            else if (chunk_uniform<M, 1>(ch[p], LO, HI)) v = 2;
+            if (v && CMODE == 2)
+                for (int e = v - 1; e < M - 1; ++e)
+                    if (ops[p].coef(e) != 0.0) v = 0;
+        }
+        uni[p] = (char)v;
+        if (v) {
+            const Row sep = make_row<CMODE, EXTRA>(ch[p].code(M - 1), LO, HI, ch[p].T[M - 1], CMODE == 2 ? ops[p].coef(M - 1) : 0.0,
+                                                   0.0, 0.0, k);
+            const Row head = make_row<CMODE, EXTRA>(ch[p].code(0), LO, HI, ch[p].T[0], CMODE == 2 ? ops[p].coef(0) : 0.0,
+                                                    0.0, 0.0, k);
+            fi[p] = v == 1 ? chunk_forward_uniform<M, 0>(ch[p], uc, sep, head, hd[p])
+                           : chunk_forward_uniform<M, 1>(ch[p], uc, sep, head, hd[p]);
+        } else {
+            fi[p] = chunk_forward<M, CMODE, EXTRA, NS>(ch[p], ops[p], LO, HI, k);
+        }
     }
     if (zmode == 1) {  // z-slab pass 1: separators as affine functions of the ghosts (solve_reduced3)
         std::vector<Red3> r3(P), n3(P);
@@ -117,7 +132,8 @@ void sweep_line(double *T, const uint8_t *code, const double *coeff, const doubl
     }
     for (int p = 0; p < P; ++p) {
         const double Slp = p > 0 ? red[p - 1].D : (zmode == 2 ? Lg : 0.0);
-        if (uni[p]) chunk_backward_uniform<M>(ch[p], uc, Slp, red[p].D);
+        if (uni[p] == 1) chunk_backward_uniform<M, 0>(ch[p], uc, hd[p], Slp, red[p].D);
+        else if (uni[p] == 2) chunk_backward_uniform<M, 1>(ch[p], uc, hd[p], Slp, red[p].D);
         else chunk_backward<M, EXTRA, NS>(ch[p], ops[p], LO, HI, k.g, Slp, red[p].D);
         for (int e = 0; e < ops[p].nv; ++e)
             if (ch[p].active(e)) T[base + ((size_t)p * M + e) * stride] = ch[p].T[e];

@@ -52,3 +52,32 @@ def test_emulated_scalar_robin_mode(name, golden_dir):
     fc = [c["bcs"]["robin_h"][f] * A / Ccell for f in cart.FACES]
     T = emu.cart_step(c["T0"], c["mask"], c["dx"], c["dt"], c["theta"], kappa, c["Tinf"], face_coeff=fc)
     assert cases.rel_l2(T, g["T_out"], c["mask"]) <= TOL
+
+
+@pytest.mark.parametrize("variant", [0, 1], ids=["M16", "M32"])
+@pytest.mark.parametrize("cfl,theta", [(0.128, 0.5), (40.0, 1.0), (3000.0, 0.5)])
+@pytest.mark.parametrize("shape,mask_kind,bk", [((70, 6, 37), "full", "robin_dict3d"), ((40, 70, 35), "plate_track", "robin_dict3d"),
+                                                ((6, 5, 133), "full", "robin6"), ((48, 51, 53), "cyl_holes", "robin_dict3d")])
+def test_uniform_chunk_paths_against_the_oracle(shape, mask_kind, bk, cfl, theta, variant):
+    """Runs of uniform cells (adi_core.h UniConst: tabulated elimination factors) with a general separator and,
+    at the start of a line, a hand-eliminated first cell -- against the oracle directly, from cfl 0.128 to 3000."""
+    mask = cases.make_mask(mask_kind, shape, 11)
+    bcs = cases.make_bcs(bk, shape, mask, 11, 20.0)
+    T0 = 20.0 + 1380.0 * cases.splitmix_uniform(12, shape)
+    T0[~mask] = np.nan
+    kappa = cases.K / (cases.RHO * cases.CP)
+    dt = cfl * cases.DX ** 2 / kappa
+    nx, ny, nz = shape
+    hg, hm = cart.Grid3D(nx, ny, nz, cases.DX, mask), cart.Material(cases.RHO, cases.CP, cases.K)
+    packs = cart.precompute_coeff_packs_unified(hg, hm, **bcs)
+    ref = cart.adi_step_numba_coeff(T0, hg, hm, cart.Params(dt, theta), packs, Tinf=20.0)
+    out = {}
+    for on in (1, 0):
+        emu.lib().emu_set_uniform(on)
+        try:
+            out[on] = emu.cart_step(T0, mask, cases.DX, dt, theta, kappa, 20.0, coeff=[p.coeff for p in packs], variant=variant)
+        finally:
+            emu.lib().emu_set_uniform(1)
+        assert cases.rel_l2(out[on], ref, mask) <= TOL
+        assert np.array_equal(out[on][~mask], T0[~mask], equal_nan=True)
+    assert not np.array_equal(out[0], out[1], equal_nan=True) or min(shape) < 4   # the tabulated path really ran

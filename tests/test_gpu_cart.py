@@ -466,7 +466,7 @@ def _uniform_case(shape, mask_kind, bk, theta, cfl, seed):
 
 
 @pytest.mark.parametrize("opts", [dict(), dict(uni=0), dict(tw=0), dict(xy2=0), dict(m=32), dict(kt=4), dict(m=32, kt=2),
-                                  dict(occ=3), dict(occ=4, tw=0), dict(remap=0), dict(remap=0, tw=0)],
+                                  dict(occ=3), dict(occ=4, tw=0), dict(remap=1), dict(remap=1, tw=0), dict(wide=1), dict(wide=1, tw=0)],
                          ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
 @pytest.mark.parametrize("shape,mask_kind", [((70, 40, 37), "full"), ((40, 70, 130), "plate_track"), ((96, 50, 64), "cyl_holes"),
                                              ((600, 7, 48), "full"), ((5, 1100, 24), "full"), ((2050, 3, 10), "full"),

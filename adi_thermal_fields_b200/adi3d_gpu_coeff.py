@@ -194,7 +194,7 @@ class _Engine:
         # surface-only by construction: the engine may skip its examination pass (option sparse_trust)
         trust = 0
         if not scalar:
-            for a, p in enumerate(packs[:2]):
+            for a, p in enumerate(packs):
                 b = getattr(p, "_built", None)
                 c = hold[a][0]
                 if b is not None and c is not None and b == (c._t.data_ptr(), c._t._version, self.mask_epoch):

@@ -152,7 +152,7 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
         ctx->code_dirty = true;
     }
     else if (!strcmp(name, "uni")) ctx->opt_uni = value;    // 1 (default): tabulated factors for uniform chunks
-    else if (!strcmp(name, "tw")) ctx->opt_tw = value;      // 1 (default): reduced system solved by warps
+    else if (!strcmp(name, "tw")) ctx->opt_tw = value;      // 1: reduced system solved by warps (default 0: shared-memory PCR, measured faster)
     else if (!strcmp(name, "occ")) ctx->opt_occ = value;    // x / y sweeps, 16-cell chunks: resident blocks per SM (2, 3, 4)
     else if (!strcmp(name, "remap")) ctx->opt_remap = value;  // 1: both ends of a line in one warp (measured slower)
     else if (!strcmp(name, "dbg")) ctx->opt_dbg = value;    // tuning aid (1: x / y sweeps move data only -- wrong results)

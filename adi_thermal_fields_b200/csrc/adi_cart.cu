@@ -92,7 +92,7 @@ int ensure_sparse(adi_ctx *ctx, cudaStream_t st)
     ctx->sparse_dirty = false;
     const size_t n = (size_t)ctx->nx * ctx->ny * ctx->nz;
     if (!ctx->opt_sparse || ctx->scalar_robin || n == 0) return ADI_OK;
-    if (!ctx->pack[0].coeff && !ctx->pack[1].coeff) return ADI_OK;
+    if (!ctx->pack[0].coeff && !ctx->pack[1].coeff && !ctx->pack[2].coeff) return ADI_OK;
     if (!ctx->d_viol) {
         ADI_CUDA(cudaMalloc(&ctx->d_viol, 3 * sizeof(unsigned long long)));
         ADI_CUDA(cudaMallocHost(&ctx->h_viol, 3 * sizeof(unsigned long long)));
@@ -100,12 +100,10 @@ int ensure_sparse(adi_ctx *ctx, cudaStream_t st)
     SparseCheckArgs c;
     bool work = false;
     for (int a = 0; a < 3; ++a) {
-        // x and y only: the z sweep stages whole contiguous lines and gained nothing from skipping
-        // coefficient reads (0.65 -> 0.66 ms at 512^3; 0.88 ms with per-chunk fetches)
         const bool trusted = (ctx->sparse_trust >> a) & 1;
-        c.coeff[a] = (a < 2 && !trusted) ? ctx->pack[a].coeff : nullptr;
+        c.coeff[a] = !trusted ? ctx->pack[a].coeff : nullptr;
         c.code[a] = ctx->code[a];
-        if (a < 2 && trusted && ctx->pack[a].coeff) ctx->sparse[a] = true;
+        if (trusted && ctx->pack[a].coeff) ctx->sparse[a] = true;
         work = work || c.coeff[a] != nullptr;
     }
     if (!work) return ADI_OK;
@@ -118,7 +116,7 @@ int ensure_sparse(adi_ctx *ctx, cudaStream_t st)
     ADI_CUDA(cudaGetLastError());
     ADI_CUDA(cudaMemcpyAsync(ctx->h_viol, ctx->d_viol, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     ADI_CUDA(cudaStreamSynchronize(st));
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 3; ++a)
         if (c.coeff[a]) ctx->sparse[a] = ctx->h_viol[a] == 0ull;
     return ADI_OK;
 }

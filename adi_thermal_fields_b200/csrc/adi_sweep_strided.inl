@@ -12,13 +12,18 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
     const int n = AXIS == 0 ? a.nx : a.ny;
     const int other = AXIS == 0 ? a.ny : a.nx;
     if (ctx->opt_xy2 && ctx->npadT[AXIS] > 0 && n <= 2048 && !(AXIS == 0 && expl) && other <= 65535) {
-        // second-generation sweeps (adi_sweep_xy.cuh).  Shapes:
-        //   n <= 512          M 16 (two factors per cell), <= 32 chunks, 256 threads, 2 blocks / SM   (option m=32: as below)
-        //   512 < n <= 1024   M 32 (one factor per cell),  <= 32 chunks, 256 threads, 2 blocks / SM
-        //   1024 < n <= 2048  M 32, <= 64 chunks (two reduced rows per lane), 512 threads, 1 block / SM
-        const int M = (n <= 512 && ctx->opt_m != 32) ? 16 : 32;
+        // second-generation sweeps (adi_sweep_xy.cuh).  Shapes (measured on B200, profiles/r02c_xy_probe.txt):
+        //   n <= 128          M 16 (two factors per cell), 256 threads, 2 blocks / SM
+        //   128 < n <= 1024   M 32 (one factor per cell), <= 32 chunks, 256 threads, 2 blocks / SM; up to 512 cells
+        //                     that is 16 lanes per row (128-byte rows: x 0.40 / y 0.40 ms at 512^3 against
+        //                     0.51 / 0.46 ms for M 16 with 64-byte rows at 3 blocks / SM)
+        //   1024 < n <= 2048  M 32, <= 64 chunks, 512 threads, 1 block / SM
+        // options: m=16 / m=32 force the chunk length (n <= 512), occ=3|4 more resident blocks (M 16), wide=1
+        // 512-thread blocks (twice the lanes per row), kt=N lanes per row
+        int M = n <= 128 ? 16 : 32;
+        if (n <= 512 && (ctx->opt_m == 16 || ctx->opt_m == 32)) M = (int)ctx->opt_m;
         const int P = (n + M - 1) / M;
-        const bool wide = M == 16 && ctx->opt_wide;   // 16-cell chunks in 512-thread blocks: twice the lanes per row
+        const bool wide = P <= 32 && ctx->opt_wide;
         const int PR = P > 32 ? 2 : 1, maxt = (P > 32 || wide) ? 512 : 256;
         int KT = 32;
         while (KT > 1 && KT * P > maxt) KT >>= 1;
@@ -40,6 +45,7 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
         // registers with one factor per cell (the general path recomputes the couplings from the code)
         const int occ = (M == 16 && (ctx->opt_occ == 3 || ctx->opt_occ == 4)) ? (int)ctx->opt_occ : 2;
         const int NS = (M == 16 && occ == 2 && !wide) ? 2 : 1;
+        const bool big = NTH > 256;   // 512-thread launch bounds
         const size_t xch = std::max<size_t>((size_t)7 * P * (KT + 1), (size_t)6 * NTH);
         const size_t smem = ((size_t)NS * M * NTH + xch) * sizeof(double);
         if ((unsigned long long)M * 8ull * (AXIS == 0 ? (unsigned long long)a.ny * a.nz : (unsigned long long)a.nz) >= (1ull << 32)) {
@@ -56,11 +62,12 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
             if (extra) return launch(k_sweep_xy<AXIS, M_, NS_, 1, true, PR_, MAXT, MINB>, grid, block, smem, st, ctx, b);      \
             return launch(k_sweep_xy<AXIS, M_, NS_, 1, false, PR_, MAXT, MINB>, grid, block, smem, st, ctx, b);                \
         }
-        if (wide) ADI_GO2(16, 1, 1, 512, 2)
+        if (M == 16 && wide) ADI_GO2(16, 1, 1, 512, 2)
         else if (M == 16 && occ == 2) ADI_GO2(16, 2, 1, 256, 2)
         else if (M == 16 && occ == 3) ADI_GO2(16, 1, 1, 256, 3)
         else if (M == 16) ADI_GO2(16, 1, 1, 256, 4)
-        else if (PR == 1) ADI_GO2(32, 1, 1, 256, 2)
+        else if (PR == 1 && !big) ADI_GO2(32, 1, 1, 256, 2)
+        else if (PR == 1) ADI_GO2(32, 1, 1, 512, 1)
         else ADI_GO2(32, 1, 2, 512, 1)
 #undef ADI_GO2
     }

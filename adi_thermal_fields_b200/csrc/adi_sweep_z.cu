@@ -30,23 +30,26 @@ static int launch_sweep_z_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
         else if (s.P <= 24) LT = 4;
     }
     if (ctx->opt_lt > 0) LT = (int)std::min<long>(ctx->opt_lt, s.W);
-    const size_t smem = LT * line_bytes;
+    const size_t smem = LT * line_bytes + 2 * LT * sizeof(double);   // + the coefficients of the lines' end cells
     if (smem > 227 * 1024) {
         set_error("adi_cart_step: z tile does not fit shared memory");
         return ADI_EINVAL;
     }
     const size_t nlines = (size_t)a.nx * a.ny;
     dim3 block(s.P, LT), grid((unsigned)((nlines + LT - 1) / LT));
+    SweepArgs b = a;
+    b.uni = (ctx->opt_uni && !extra && (!dense || a.sparse) && s.M <= UNI_MAX) ? 1 : 0;
+    uni_const_build(b.uc, a.k.g);
     const int vec = ((a.nz & 1) == 0 && (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.coeff |
                                           (uintptr_t)a.code) & 15) == 0) ? 1 : 0;
 #define ADI_GO(M, NS, MAXT, MINB)                                                                          \
     {                                                                                                  \
         if (dense) {                                                                                   \
-            if (extra) return launch(k_sweep_z<M, NS, 2, true, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, a, vec);  \
-            return launch(k_sweep_z<M, NS, 2, false, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, a, vec);            \
+            if (extra) return launch(k_sweep_z<M, NS, 2, true, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, b, vec);  \
+            return launch(k_sweep_z<M, NS, 2, false, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, b, vec);            \
         }                                                                                              \
-        if (extra) return launch(k_sweep_z<M, NS, 1, true, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, a, vec);      \
-        return launch(k_sweep_z<M, NS, 1, false, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, a, vec);                \
+        if (extra) return launch(k_sweep_z<M, NS, 1, true, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, b, vec);      \
+        return launch(k_sweep_z<M, NS, 1, false, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, b, vec);                \
     }
     ADI_FOR_VARIANT(s.var, ADI_GO)
 #undef ADI_GO

@@ -465,12 +465,14 @@ def _uniform_case(shape, mask_kind, bk, theta, cfl, seed):
     return dict(shape=shape, mask=mask, T0=T0, dt=cfl * cases.DX ** 2 / kappa, theta=theta, bcs=bcs, kappa=kappa)
 
 
-@pytest.mark.parametrize("opts", [dict(), dict(uni=0), dict(tw=0), dict(xy2=0), dict(m=32), dict(kt=4), dict(m=32, kt=2),
-                                  dict(occ=3), dict(occ=4, tw=0), dict(remap=1), dict(remap=1, tw=0), dict(wide=1), dict(wide=1, tw=0)],
+@pytest.mark.parametrize("opts", [dict(), dict(uni=0), dict(tw=1), dict(xy2=0), dict(m=16), dict(m=32), dict(kt=4), dict(m=16, kt=2),
+                                  dict(m=16, occ=3), dict(m=16, occ=4, tw=1), dict(remap=1), dict(remap=1, tw=1), dict(wide=1),
+                                  dict(m=16, wide=1, tw=1), dict(lt=1), dict(sparse_coeff=0)],
                          ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
 @pytest.mark.parametrize("shape,mask_kind", [((70, 40, 37), "full"), ((40, 70, 130), "plate_track"), ((96, 50, 64), "cyl_holes"),
                                              ((600, 7, 48), "full"), ((5, 1100, 24), "full"), ((2050, 3, 10), "full"),
-                                             ((1030, 2, 9), "random")],
+                                             ((1030, 2, 9), "random"), ((6, 5, 1000), "full"), ((3, 4, 1500), "full"),
+                                             ((20, 9, 515), "plate_track")],
                          ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else v)
 def test_uniform_chunk_paths(shape, mask_kind, opts, g, cp):
     """Chunks whose cells all have both neighbours along the swept axis take tabulated elimination factors

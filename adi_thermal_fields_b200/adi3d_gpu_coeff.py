@@ -61,6 +61,10 @@ class AxisCoeffPack:
         self._dir_mask = cp.asarray(dir_mask, dtype=cp.bool_)
         self._dir_val = cp.asarray(dir_val, dtype=cp.float64)
         self._qflux = None if qflux is None else cp.asarray(qflux, dtype=cp.float64)
+        for name, arr in (("dir_mask", self._dir_mask), ("dir_val", self._dir_val), ("qflux", self._qflux)):
+            if arr is not None and tuple(arr.shape) != self._shape:
+                # the kernels index every operand with the grid's strides: a mis-shaped array would be read out of bounds
+                raise ValueError(f"AxisCoeffPack: {name} has shape {tuple(arr.shape)}, coeff has {self._shape}")
         self._face_coeff = None     # (lo, hi) scalars when coeff is symbolic
         self._scalar_src = None     # (engine build args) to materialise coeff lazily
         self._dir_any = None        # cached "dir_mask has a True" keyed by tensor version
@@ -75,6 +79,7 @@ class AxisCoeffPack:
         self._scalar_src = builder
         self._dir_any = None
         self._q_zero = qflux is None
+        self._mask_epoch = None     # scalar Robin: the engine's mask state the symbolic coefficients stand for
         return self
 
     # dense views, as the reference exposes them
@@ -173,6 +178,16 @@ class _Engine:
         (pointer, version) key can never be reused by a different tensor while it is cached."""
         L, ctx = self.lib(), self.context()
         scalar = all(p._coeff is None and p._face_coeff is not None for p in packs)
+        if scalar:
+            # Symbolic scalar-Robin packs stand for coefficients frozen from the mask they were precomputed for
+            # (adi3d_gpu_coeff.py:86-92); the kernels derive them from the mask bound NOW.  When the mask has
+            # moved on since, freeze them for real: the dense arrays are built from a snapshot the pack keeps.
+            for p in packs:
+                ep = getattr(p, "_mask_epoch", None)
+                if ep is not None and ep != (self.mask_epoch, id(self)):
+                    raise RuntimeError("adi_step_gpu_coeff: these scalar-Robin packs were precomputed for an earlier "
+                                       "state of grid.mask; call precompute_coeff_packs_unified again after changing "
+                                       "the mask (the reference would keep stepping with the stale coefficients)")
         hold = []
         touched = False
         for a, p in enumerate(packs):
@@ -266,6 +281,12 @@ def precompute_coeff_packs_unified(grid, mat, dir_mask=None, dir_value=None, neu
         dv = cp.asarray(dir_value, dtype=cp.float64)
     if dm is not None and dv is None:
         dv = cp.zeros(shape, cp.float64)
+    for name, arr in (("dir_mask", dm), ("dir_value", dv)):
+        if arr is not None and tuple(arr.shape) != shape:
+            raise ValueError(f"{name} has shape {tuple(arr.shape)}, the grid is {shape}")
+    # one Dirichlet mask / value array shared by the three packs, as in the reference (adi3d_gpu_coeff.py:73-78,108-110)
+    if dm is None and dv is not None:
+        dm = cp.zeros(shape, cp.bool_)
 
     def classify(v):
         if v is None:
@@ -327,6 +348,8 @@ def precompute_coeff_packs_unified(grid, mat, dir_mask=None, dir_value=None, neu
                 e.set_mask(grid)
                 return run_build(True, False)[0][a]
         pk = AxisCoeffPack._symbolic(shape, coeffs[a], dm, dv, qouts[a], face_coeff=fc, builder=builder)
+        if fc is not None:
+            pk._mask_epoch = (e.mask_epoch, id(e))
         if coeffs[a] is not None:
             pk._built = (coeffs[a]._t.data_ptr(), coeffs[a]._t._version, e.mask_epoch)
         packs.append(pk)
@@ -341,7 +364,9 @@ def adi_step_gpu_coeff(Tn, grid, mat, params, packs, Tinf=0.0):
     kappa = mat.k / (mat.rho * mat.cp)
     T = Tn if isinstance(Tn, cp.ndarray) else cp.asarray(Tn, dtype=cp.float64)
     if T.dtype != np.float64:
-        raise TypeError("adi_step_gpu_coeff: fp64 fields only")
+        # the reference promotes a float32 field on its first step (waam_from_stl_v7_mm.py --precision float32
+        # builds T with cp.full(..., dtype=float32)); the arithmetic and the result are float64
+        T = cp.asarray(T, dtype=cp.float64)
     if not T._t.is_contiguous():
         T = cp.asarray(T)
     if T.shape != (grid.nx, grid.ny, grid.nz):

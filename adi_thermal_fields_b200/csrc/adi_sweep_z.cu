@@ -12,7 +12,7 @@ static int launch_sweep_z_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
     int rc = pick_shape(ctx, a.nz, -1, &s);  // -1: z sweep (no lane-count option)
     if (rc) return rc;
     if (ZMODE != 0 && a.nz % s.M != 0) {
-        set_error("adi_cart_zsweep_*: the local z extent must be a multiple of the chunk length (16; 32 for nz > 512)");
+        set_error("adi_cart_zsweep_*: the local z extent must be a multiple of the chunk length (16; 32 for local nz > 1024)");
         return ADI_EINVAL;
     }
     // lines per block: fill the block, but keep the staged tiles small enough for two

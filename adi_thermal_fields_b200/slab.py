@@ -32,8 +32,19 @@ from . import _capi
 FACES = ("x-", "x+", "y-", "y+", "z-", "z+")
 
 
-def split_z(nz, world):
-    """Balanced slab extents: list of (z0, z1)."""
+def split_z(nz, world, multiple=1):
+    """Balanced slab extents: list of (z0, z1).  With `multiple` every extent but the last is a multiple of
+    it (the Cartesian z-sweep kernels of the slab path need local nz % 16 == 0, 32 for local nz > 1024; the last
+    rank takes the remainder and must then satisfy it too -- i.e. nz itself must be a multiple)."""
+    if multiple > 1:
+        units, rem = divmod(nz, multiple)
+        q, r = divmod(units, world)
+        out, z = [], 0
+        for i in range(world):
+            n = (q + (1 if i < r else 0)) * multiple + (rem if i == world - 1 else 0)
+            out.append((z, z + n))
+            z += n
+        return out
     q, r = divmod(nz, world)
     out, z = [], 0
     for i in range(world):
@@ -332,6 +343,7 @@ class SlabGrid3D:
         self.comm.exchange_planes(self._m_lo, self._m_hi, self.mask_lo, self.mask_hi)
         be.set_mask_halo(self.mask_lo if self.rank > 0 else None,
                          self.mask_hi if self.rank + 1 < self.world else None)
+        self._mask_synced = (self.mask.data_ptr(), self.mask._version)
 
 
 class SlabPacks:
@@ -408,7 +420,13 @@ def adi_step_gpu_coeff(Tn, grid, mat, params, packs, Tinf=0.0, out=None):
     be.step_xy(T, out, grid.T_lo if lo_ok else None, grid.T_hi if hi_ok else None, dt, theta, kappa, float(Tinf))
     # the matrix part of the interface relations (4 of the 6 numbers per line) only changes with
     # mask, packs, dt or theta: it is computed and gathered once and reused while those stay the same
-    key = (dt, theta, kappa, id(packs), grid.mask_version)
+    # ... keyed on the operands' identity AND content version (set_packs' key: data_ptr + tensor version of every
+    # bound array) and on the mask tensor itself, so that in-place edits of coeff / dir_mask / mask are seen
+    mk = (grid.mask.data_ptr(), grid.mask._version)
+    if mk != grid._mask_synced:
+        raise RuntimeError("slab.adi_step_gpu_coeff: grid.mask was edited (or rebound) without sync_mask(); the adjacent "
+                           "ranks' view of it and the neighbour code are stale")
+    key = (dt, theta, kappa, id(packs), getattr(be, "pack_key", None), grid.mask_version, mk)
     fresh = key != grid._stat_key
     if fresh:
         grid._spikes, grid._stat_uses = None, 0

@@ -166,6 +166,9 @@ class _Engine:
             key = (m._t.data_ptr(), m._t._version)
         if m.shape != (grid.nx, grid.ny, grid.nz):
             raise AssertionError("mask shape does not match the grid")
+        if key is None and self.mask_hold is not None and self.mask_key is None \
+                and self.mask_hold.shape == m.shape and bool(torch.equal(m._t, self.mask_hold._t)):
+            return   # a host mask with the same content as the one bound: nothing to rebuild
         if key is None or key != self.mask_key:
             _capi.check(self.lib().adi_cart_set_mask(self.context(), m._t.data_ptr()), "adi_cart_set_mask")
             self.mask_key = key

@@ -92,7 +92,7 @@ int ensure_sparse(adi_ctx *ctx, cudaStream_t st)
     ctx->sparse_dirty = false;
     const size_t n = (size_t)ctx->nx * ctx->ny * ctx->nz;
     if (!ctx->opt_sparse || ctx->scalar_robin || n == 0) return ADI_OK;
-    if (!ctx->pack[0].coeff && !ctx->pack[1].coeff) return ADI_OK;
+    if (!ctx->pack[0].coeff && !ctx->pack[1].coeff && !ctx->pack[2].coeff) return ADI_OK;
     if (!ctx->d_viol) {
         ADI_CUDA(cudaMalloc(&ctx->d_viol, 3 * sizeof(unsigned long long)));
         ADI_CUDA(cudaMallocHost(&ctx->h_viol, 3 * sizeof(unsigned long long)));
@@ -100,14 +100,13 @@ int ensure_sparse(adi_ctx *ctx, cudaStream_t st)
     SparseCheckArgs c;
     bool work = false;
     for (int a = 0; a < 3; ++a) {
-        // x and y only.  The z sweep stages whole contiguous lines; a warp there is ONE line, so a single exposed
-        // cell inside the line (the top of a plate) sends the whole line down the general path, where fetching the
-        // coefficients of exposed cells costs a second memory round trip: 0.63 -> 0.76 ms at 512^3 (r02d), so the
-        // z sweep keeps its dense coefficient reads
+        // x, y and (second-generation z sweep, option zt) z; the first-generation z sweep gives a line to one warp,
+        // where fetching the coefficients of exposed cells costs a second memory round trip (0.63 -> 0.76 ms at 512^3)
+        const bool want = a < 2 || ctx->opt_zt;
         const bool trusted = (ctx->sparse_trust >> a) & 1;
-        c.coeff[a] = (a < 2 && !trusted) ? ctx->pack[a].coeff : nullptr;
+        c.coeff[a] = (want && !trusted) ? ctx->pack[a].coeff : nullptr;
         c.code[a] = ctx->code[a];
-        if (a < 2 && trusted && ctx->pack[a].coeff) ctx->sparse[a] = true;
+        if (want && trusted && ctx->pack[a].coeff) ctx->sparse[a] = true;
         work = work || c.coeff[a] != nullptr;
     }
     if (!work) return ADI_OK;
@@ -120,7 +119,7 @@ int ensure_sparse(adi_ctx *ctx, cudaStream_t st)
     ADI_CUDA(cudaGetLastError());
     ADI_CUDA(cudaMemcpyAsync(ctx->h_viol, ctx->d_viol, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     ADI_CUDA(cudaStreamSynchronize(st));
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 3; ++a)
         if (c.coeff[a]) ctx->sparse[a] = ctx->h_viol[a] == 0ull;
     return ADI_OK;
 }

@@ -717,8 +717,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
     double *sC = sT + (size_t)LT * RL;
     double *sU = sC + (size_t)LT * RL;
     uint8_t *sCode = reinterpret_cast<uint8_t *>(sU + (NS == 2 ? (size_t)LT * RL : 0));
-    double *sEnd = reinterpret_cast<double *>(sCode + (size_t)LT * RL);   // [LT][2]: coefficient of a line's two end cells
-    const bool sparse = CMODE == 2 && a.sparse;   // surface-only coefficient field: read at exposed cells only
     double *red = sT;
     constexpr int SW = (M / 2 >= 8) ? 7 : (M / 2 - 1);
 
@@ -735,7 +733,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
                 const int z = 2 * pl;
                 const bool ok = lok && z < nz;
                 cp_async16(sT + dst, srcT + (ok ? z : 0), ok ? 16 : 0);
-                if (CMODE == 2 && !sparse) cp_async16(sC + dst, srcC + (ok ? z : 0), ok ? 16 : 0);
+                if (CMODE == 2) cp_async16(sC + dst, srcC + (ok ? z : 0), ok ? 16 : 0);
             }
         }
     } else {
@@ -746,7 +744,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
                 const int dst = l * RL + zslot<M>(z / M, (z % M) >> 1) + (z & 1);
                 const bool ok = lok && z < nz;
                 sT[dst] = ok ? a.in[line * (size_t)nz + z] : 0.0;
-                if (CMODE == 2 && !sparse) sC[dst] = ok ? a.coeff[line * (size_t)nz + z] : 0.0;
+                if (CMODE == 2) sC[dst] = ok ? a.coeff[line * (size_t)nz + z] : 0.0;
             }
         }
     }
@@ -767,11 +765,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
             for (int z = tid; z < RL; z += NTH)
                 sCode[(size_t)l * RL + z] = (lok && z < nz) ? a.code[line * (size_t)nz + z] : (uint8_t)0;
         }
-    }
-    if (sparse && tid < 2 * LT) {
-        // the two ends of every line (always exposed when active) are requested with the tile
-        const size_t line = min(L0 + (size_t)(tid >> 1), nlines - 1);
-        sEnd[tid] = a.coeff[line * (size_t)nz + ((tid & 1) ? nz - 1 : 0)];
     }
     cp_async_wait_all();
     __syncthreads();
@@ -817,43 +810,26 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
         ops.nv = (L0 + ln < nlines) ? min(max(nz - p * M, 0), M) : 0;
     }
 
-    // coefficient of ACTIVE cell e of this chunk when only exposed cells carry one (sparse mode)
-    const size_t gline = min(L0 + (size_t)ln, nlines - 1) * (size_t)nz;
-    auto exposed_coef = [&](int e, unsigned c) -> double {
-        if (CMODE != 2) return 0.0;
-        if ((c & (CB_ZM | CB_ZP)) == (CB_ZM | CB_ZP)) return 0.0;
-        const int cell = p * M + e;
-        if (cell == 0) return sEnd[2 * ln];
-        if (cell == nz - 1) return sEnd[2 * ln + 1];
-        return a.coeff[gline + cell];
-    };
-    // 0: general rows; 1: cells 0..M-2 uniform; 2: cell 0 general, cells 1..M-2 uniform (adi_core.h)
+    // 0: general rows; 1: cells 0..M-2 uniform; 2: cell 0 general, cells 1..M-2 uniform (adi_core.h).  Only without
+    // a dense coefficient field (scalar Robin / no Robin term): a warp here is ONE line, and a dense field read at
+    // exposed cells only would cost the general path a second memory round trip (see ensure_sparse)
     int path = 0;
-    if (a.uni && (CMODE != 2 || sparse)) {
+    if (CMODE != 2 && a.uni) {
         if (__all_sync(0xffffffffu, chunk_uniform<M, 1>(ch, CB_ZM, CB_ZP)))
             path = __all_sync(0xffffffffu, chunk_uniform<M, 0>(ch, CB_ZM, CB_ZP)) ? 1 : 2;
     }
     First f;
     UniHead hd;
     hd.al = hd.bl = hd.br = 0.0;
-    if (path != 0) {
-        const unsigned cs = ch.code(M - 1), c0 = ch.code(0);
-        const Row sep = make_row<CMODE, EXTRA>(cs, CB_ZM, CB_ZP, ch.T[M - 1], exposed_coef(M - 1, cs), 0.0, 0.0, a.k);
+    if (CMODE != 2 && path != 0) {
+        const Row sep = make_row<CMODE, EXTRA>(ch.code(M - 1), CB_ZM, CB_ZP, ch.T[M - 1], 0.0, 0.0, 0.0, a.k);
         if (path == 1) {
             f = chunk_forward_uniform<M, 0>(ch, a.uc, sep, sep, hd);
         } else {
-            const Row head = make_row<CMODE, EXTRA>(c0, CB_ZM, CB_ZP, ch.T[0], exposed_coef(0, c0), 0.0, 0.0, a.k);
+            const Row head = make_row<CMODE, EXTRA>(ch.code(0), CB_ZM, CB_ZP, ch.T[0], 0.0, 0.0, 0.0, a.k);
             f = chunk_forward_uniform<M, 1>(ch, a.uc, sep, head, hd);
         }
     } else {
-        if (sparse) {
-            // the coefficient slots of this chunk: fetched where the cell is exposed along z, zero elsewhere
-#pragma unroll
-            for (int e = 0; e < M; ++e) {
-                const unsigned c = ch.code(e);   // 0 beyond the line's end
-                ops.c[ops.at(e)] = (c & CB_SELF) ? exposed_coef(e, c) : 0.0;
-            }
-        }
         if (solid) f = chunk_forward<M, CMODE, EXTRA, NS, true>(ch, ops, CB_ZM, CB_ZP, a.k);
         else f = chunk_forward<M, CMODE, EXTRA, NS, false>(ch, ops, CB_ZM, CB_ZP, a.k);
     }
@@ -899,8 +875,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
     constexpr bool GHOSTS = (ZMODE == 2 || ZMODE == 4);  // 4: both ghosts at zero, as in ZMODE 3
     if (warp_lines) S = solve_reduced_warp<M, GHOSTS>(ch, f, p, P, &Sl, Lg, Rg);
     else S = solve_reduced<M, GHOSTS>(ch, f, red, NTH, tid, 1, p, P, &Sl, Lg, Rg);
-    if (path == 1) chunk_backward_uniform<M, 0>(ch, a.uc, hd, Sl, S);
-    else if (path == 2) chunk_backward_uniform<M, 1>(ch, a.uc, hd, Sl, S);
+    if (CMODE != 2 && path == 1) chunk_backward_uniform<M, 0>(ch, a.uc, hd, Sl, S);
+    else if (CMODE != 2 && path == 2) chunk_backward_uniform<M, 1>(ch, a.uc, hd, Sl, S);
     else chunk_backward<M, EXTRA, NS>(ch, ops, CB_ZM, CB_ZP, a.k.g, Sl, S);
     if (ZMODE == 4) {
         const size_t line = L0 + ln;

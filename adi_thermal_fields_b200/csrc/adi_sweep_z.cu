@@ -30,7 +30,7 @@ static int launch_sweep_z_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
         else if (s.P <= 24) LT = 4;
     }
     if (ctx->opt_lt > 0) LT = (int)std::min<long>(ctx->opt_lt, s.W);
-    const size_t smem = LT * line_bytes + 2 * LT * sizeof(double);   // + the coefficients of the lines' end cells
+    const size_t smem = LT * line_bytes;
     if (smem > 227 * 1024) {
         set_error("adi_cart_step: z tile does not fit shared memory");
         return ADI_EINVAL;
@@ -38,7 +38,7 @@ static int launch_sweep_z_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
     const size_t nlines = (size_t)a.nx * a.ny;
     dim3 block(s.P, LT), grid((unsigned)((nlines + LT - 1) / LT));
     SweepArgs b = a;
-    b.uni = (ctx->opt_uni && !extra && (!dense || a.sparse) && s.M <= UNI_MAX) ? 1 : 0;
+    b.uni = (ctx->opt_uni && !extra && !dense && s.M <= UNI_MAX) ? 1 : 0;
     uni_const_build(b.uc, a.k.g);
     const int vec = ((a.nz & 1) == 0 && (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.coeff |
                                           (uintptr_t)a.code) & 15) == 0) ? 1 : 0;
@@ -56,8 +56,13 @@ static int launch_sweep_z_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
     return ADI_OK;
 }
 
+int launch_sweep_zt(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, int zmode, cudaStream_t st, int *used);
+
 int launch_sweep_z(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, int zmode, cudaStream_t st)
 {
+    int used = 0;
+    const int rc = launch_sweep_zt(ctx, a, dense, extra, zmode, st, &used);   // second generation (adi_sweep_zt.cuh)
+    if (rc || used) return rc;
     if (zmode == 1) return launch_sweep_z_mode<1>(ctx, a, dense, extra, st);
     if (zmode == 2) return launch_sweep_z_mode<2>(ctx, a, dense, extra, st);
     if (zmode == 3) return launch_sweep_z_mode<3>(ctx, a, dense, extra, st);

@@ -1,0 +1,73 @@
+// adi_sweep_zt.cu -- launcher of the second-generation z sweep (adi_sweep_zt.cuh).
+#include <stdint.h>
+
+#include "adi_launch.h"
+#include "adi_sweep_zt.cuh"
+
+namespace adi {
+
+template <int ZMODE>
+static int launch_zt_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, int M, int P, int KT, size_t smem,
+                          cudaStream_t st)
+{
+    SweepArgs b = a;
+    b.uni = (ctx->opt_uni && !extra) ? 1 : 0;
+    uni_const_build(b.uc, a.k.g);
+    const size_t nlines = (size_t)a.nx * a.ny;
+    dim3 block(KT, P), grid((unsigned)((nlines + KT - 1) / KT));
+    const int vec = ((a.nz & 1) == 0 && (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.code) & 15) == 0) ? 1 : 0;
+    const bool big = KT * P > 256;
+#define ADI_GOZ(M_, MAXT, MINB)                                                                                    \
+    {                                                                                                              \
+        if (dense) {                                                                                               \
+            if (extra) return launch(k_sweep_zt<M_, 2, true, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, b, vec);  \
+            return launch(k_sweep_zt<M_, 2, false, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, b, vec);            \
+        }                                                                                                          \
+        if (extra) return launch(k_sweep_zt<M_, 1, true, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, b, vec);      \
+        return launch(k_sweep_zt<M_, 1, false, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, b, vec);                \
+    }
+    if (M == 16) { if (big) ADI_GOZ(16, 512, 1) else ADI_GOZ(16, 256, 2) }
+    else { if (big) ADI_GOZ(32, 512, 1) else ADI_GOZ(32, 256, 2) }
+#undef ADI_GOZ
+    return ADI_OK;
+}
+
+// *used = 0: this sweep is not one for k_sweep_zt (the caller falls back to k_sweep_z).
+// Shapes: nz <= 128: 16-cell chunks; longer lines: 32-cell chunks (the z-slab modes need nz % chunk == 0 and take
+// 16-cell chunks when nz is no multiple of 32); up to 32 chunks per line in 256-thread blocks (2 per SM), up to 64
+// in 512-thread blocks; KT lines per tile = threads / chunks, halved until the tile fits.
+int launch_sweep_zt(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, int zmode, cudaStream_t st, int *used)
+{
+    *used = 0;
+    if (!ctx->opt_zt || a.nz > 2048 || a.nz < 1) return ADI_OK;
+    if (dense && !a.sparse) return ADI_OK;     // a dense coefficient field that must be read everywhere: k_sweep_z stages it
+    int M = a.nz <= 128 ? 16 : 32;
+    if (ctx->opt_m == 16 || (zmode != 0 && a.nz % 32 != 0)) M = 16;
+    if (zmode != 0 && a.nz % M != 0) return ADI_OK;   // (k_sweep_z reports the error)
+    const int P = (a.nz + M - 1) / M;
+    if (P > 64) return ADI_OK;
+    const int maxt = P > 32 ? 512 : 256;
+    int KT = 32;
+    while (KT > 1 && KT * P > maxt) KT >>= 1;
+    if (ctx->opt_lt > 0) {
+        int w = 1;
+        while (2 * w <= ctx->opt_lt && 2 * w <= 32 && 2 * w * P <= maxt) w <<= 1;
+        KT = w;
+    }
+    const size_t RL = (size_t)P * M;
+    auto bytes = [&](int kt) {
+        return ((size_t)kt * (RL + 2) + (size_t)(zmode == 1 ? 10 : 6) * kt * P + 2 * (size_t)kt) * sizeof(double) + (size_t)kt * (RL + 16);
+    };
+    const size_t limit = maxt == 256 ? 113 * 1024 : 226 * 1024;
+    while (KT > 1 && bytes(KT) > limit) KT >>= 1;
+    if (bytes(KT) > 226 * 1024) return ADI_OK;
+    *used = 1;
+    const size_t smem = bytes(KT);
+    if (zmode == 1) return launch_zt_mode<1>(ctx, a, dense, extra, M, P, KT, smem, st);
+    if (zmode == 2) return launch_zt_mode<2>(ctx, a, dense, extra, M, P, KT, smem, st);
+    if (zmode == 3) return launch_zt_mode<3>(ctx, a, dense, extra, M, P, KT, smem, st);
+    if (zmode == 4) return launch_zt_mode<4>(ctx, a, dense, extra, M, P, KT, smem, st);
+    return launch_zt_mode<0>(ctx, a, dense, extra, M, P, KT, smem, st);
+}
+
+}  // namespace adi

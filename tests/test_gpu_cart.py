@@ -207,6 +207,12 @@ def test_mask_mutation_and_rebinding_are_seen(g, cp):
             Th = cart.adi_step_numba_coeff(Th, grid_h, mat_h, cart.Params(dt, 0.5), ph, Tinf=20.0)
             Td = g.adi_step_gpu_coeff(Td, grid_d, mat_d, g.Params(dt, 0.5), pd, Tinf=20.0)
         assert cases.rel_l2(cp.asnumpy(Td), Th, mh) <= TOL
+    # scalar-Robin packs are symbolic (the kernel derives the coefficients from the mask bound at step time); the
+    # reference freezes them at precompute time, so stepping with packs older than the mask is refused
+    grid_d.mask = cp.asarray(mh)
+    grid_d.mask[:, :, 36:38] = True
+    with pytest.raises(RuntimeError):
+        g.adi_step_gpu_coeff(Td, grid_d, mat_d, g.Params(dt, 0.5), pd, Tinf=20.0)
 
 
 def test_shape_errors(g, cp):
@@ -217,8 +223,15 @@ def test_shape_errors(g, cp):
     packs = g.precompute_coeff_packs_unified(grid, mat)
     with pytest.raises(ValueError):
         g.adi_step_gpu_coeff(cp.zeros((4, 4, 5)), grid, mat, g.Params(1e-3), packs)
-    with pytest.raises(TypeError):
-        g.adi_step_gpu_coeff(cp.zeros((4, 4, 4), dtype=cp.float32), grid, mat, g.Params(1e-3), packs)
+    # a float32 field is promoted, as the reference does on its first step (waam_from_stl_v7_mm.py --precision float32)
+    T32 = cp.asarray(np.linspace(20.0, 900.0, 64, dtype=np.float32).reshape(4, 4, 4))
+    o32 = g.adi_step_gpu_coeff(T32, grid, mat, g.Params(1e-3), packs)
+    o64 = g.adi_step_gpu_coeff(cp.asarray(cp.asnumpy(T32).astype(np.float64)), grid, mat, g.Params(1e-3), packs)
+    assert o32.dtype == np.float64 and np.array_equal(cp.asnumpy(o32), cp.asnumpy(o64))
+    with pytest.raises(ValueError):
+        g.AxisCoeffPack(np.zeros((4, 4, 4)), np.zeros((4, 4, 5), bool), np.zeros((4, 4, 4)))
+    with pytest.raises(ValueError):
+        g.precompute_coeff_packs_unified(grid, mat, dir_mask=np.zeros((4, 4, 5), bool), dir_value=1.0)
 
 
 # ---- size-independent properties at the benchmark's full size (512^3) -------------------
@@ -467,7 +480,7 @@ def _uniform_case(shape, mask_kind, bk, theta, cfl, seed):
 
 @pytest.mark.parametrize("opts", [dict(), dict(uni=0), dict(tw=1), dict(xy2=0), dict(m=16), dict(m=32), dict(kt=4), dict(m=16, kt=2),
                                   dict(m=16, occ=3), dict(m=16, occ=4, tw=1), dict(remap=1), dict(remap=1, tw=1), dict(wide=1),
-                                  dict(m=16, wide=1, tw=1), dict(lt=1), dict(sparse_coeff=0)],
+                                  dict(m=16, wide=1, tw=1), dict(lt=1), dict(lt=4), dict(sparse_coeff=0), dict(zt=0), dict(zt=0, uni=0)],
                          ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
 @pytest.mark.parametrize("shape,mask_kind", [((70, 40, 37), "full"), ((40, 70, 130), "plate_track"), ((96, 50, 64), "cyl_holes"),
                                              ((600, 7, 48), "full"), ((5, 1100, 24), "full"), ((2050, 3, 10), "full"),

@@ -10,10 +10,14 @@ out=gpurun_out/${tag}_probe.txt
 : > $out
 run() { echo "== $*" >> $out; timeout 300 python tools/sweep_probe.py "$@" >> $out 2>&1; tail -1 $out; }
 run 512 512 512
+run 512 512 512 --opt zt=0
+run 512 512 512 --opt lt=8
+run 512 512 512 --opt m=16
 run 512 512 512 --scalar
 run 512 512 512 --scalar --full
 run 1024 1024 128
 run 512 512 1024 --scalar --full
+run 512 512 1024
 run 2048 2048 128 --scalar --full
 if [ "$2" = "ncu" ]; then
     ncu --set full --clock-control none --import-source on -k regex:"k_sweep|k_explicit" -s 12 -c 4 -f -o /tmp/${tag}_prof \

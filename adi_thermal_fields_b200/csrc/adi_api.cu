@@ -157,6 +157,7 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
         ctx->opt_zt = value;
         ctx->sparse_dirty = true;
     }
+    else if (!strcmp(name, "bulk")) ctx->opt_bulk = value;  // 1 (default): z sweep tiles as bulk asynchronous copies
     else if (!strcmp(name, "occ")) ctx->opt_occ = value;    // x / y sweeps, 16-cell chunks: resident blocks per SM (2, 3, 4)
     else if (!strcmp(name, "remap")) ctx->opt_remap = value;  // 1: both ends of a line in one warp (measured slower)
     else if (!strcmp(name, "dbg")) ctx->opt_dbg = value;    // tuning aid (1: x / y sweeps move data only -- wrong results)
@@ -184,6 +185,7 @@ long adi_get_option(adi_ctx *ctx, const char *name)
     if (!strcmp(name, "remap")) return ctx->opt_remap;
     if (!strcmp(name, "occ")) return ctx->opt_occ;
     if (!strcmp(name, "zt")) return ctx->opt_zt;
+    if (!strcmp(name, "bulk")) return ctx->opt_bulk;
     if (!strcmp(name, "dbg")) return ctx->opt_dbg;
     if (!strcmp(name, "sparse_coeff")) return ctx->opt_sparse;
     if (!strcmp(name, "sparse_active"))  // bit a: the sweep along axis a currently skips interior coefficient reads

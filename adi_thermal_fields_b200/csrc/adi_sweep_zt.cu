@@ -15,7 +15,8 @@ static int launch_zt_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, bool ext
     uni_const_build(b.uc, a.k.g);
     const size_t nlines = (size_t)a.nx * a.ny;
     dim3 block(KT, P), grid((unsigned)((nlines + KT - 1) / KT));
-    const int vec = ((a.nz & 1) == 0 && (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.code) & 15) == 0) ? 1 : 0;
+    int vec = ((a.nz & 1) == 0 && (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.code) & 15) == 0) ? 1 : 0;
+    if (vec && (a.nz & 15) == 0 && a.in == a.out && ctx->opt_bulk) vec = 2;   // whole lines as bulk asynchronous copies
     const bool big = KT * P > 256;
 #define ADI_GOZ(M_, MAXT, MINB)                                                                                    \
     {                                                                                                              \
@@ -56,7 +57,7 @@ int launch_sweep_zt(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, in
     }
     const size_t RL = (size_t)P * M;
     auto bytes = [&](int kt) {
-        return ((size_t)kt * (RL + 2) + (size_t)(zmode == 1 ? 10 : 6) * kt * P + 2 * (size_t)kt) * sizeof(double) + (size_t)kt * (RL + 16);
+        return ((size_t)kt * (RL + 2) + (size_t)(zmode == 1 ? 10 : 6) * kt * P + 2 * (size_t)kt + 2) * sizeof(double) + (size_t)kt * (RL + 16);
     };
     const size_t limit = maxt == 256 ? 113 * 1024 : 226 * 1024;
     while (KT > 1 && bytes(KT) > limit) KT >>= 1;

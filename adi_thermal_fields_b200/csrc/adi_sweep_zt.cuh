@@ -7,9 +7,13 @@
 // in the x / y sweeps (adi_sweep_xy.cuh): neighbouring lines look alike, so the warps holding the bulk of a
 // part are uniform and only the warps that hold the surface chunks assemble general rows.
 //
-//  * the tile (KT lines of nz contiguous cells) is staged with 16-byte cp.async copies into shared memory,
-//    pitch RL+2 doubles: the per-thread 16-byte chunk reads of a quarter warp then fall into eight different
-//    bank groups; results go back through the same slots and leave with coalesced 16-byte stores;
+//  * the tile (KT lines of nz contiguous cells) travels as BULK ASYNCHRONOUS COPIES (cp.async.bulk, the TMA
+//    engine's 1-D form, SASS UBLKCP): one instruction per line and direction, completion on an mbarrier on the
+//    way in, bulk-group wait on the way out -- the per-16-byte staging loops of k_sweep_z cost more instructions
+//    than the solve (measured: 347 M warp instructions per 512^3 sweep with cp.async pieces against 134 M of the
+//    x / y sweeps).  Lines whose length is no multiple of 16 fall back to cp.async pieces / scalar copies.
+//    Shared-memory pitch RL+2 doubles: the per-thread 16-byte chunk reads of a quarter warp fall into eight
+//    different bank groups;
 //  * a dense coefficient field is read at exposed cells only (the field must have been verified surface-only,
 //    k_check_sparse; otherwise the launcher keeps k_sweep_z): the two end cells of every line with the tile,
 //    cells next to an interior void once the codes have arrived;
@@ -22,6 +26,48 @@
 #include "adi_cart.cuh"
 
 namespace adi {
+
+// ---- bulk asynchronous copies (the TMA engine's 1-D form: SASS UBLKCP) and the mbarrier they complete on ----
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
 template <int M>
 struct ZtOps {
@@ -39,7 +85,7 @@ struct ZtOps {
     __device__ __forceinline__ double u(int) const { return 0.0; }
 };
 
-// smem: sT[KT][RL+2] doubles | xch[(ZMODE 1 ? 10 : 6) * NTH] | sEnd[KT][2] | sCode[KT][RL+16] bytes
+// smem: sT[KT][RL+2] doubles | xch[(ZMODE 1 ? 10 : 6) * NTH] | sEnd[KT][2] | mbarrier (16 B) | sCode[KT][RL+16] bytes
 template <int M, int CMODE, bool EXTRA, int MAXT, int MINB, int ZMODE>
 __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, const int vec)
 {
@@ -58,11 +104,42 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
     double *sT = smem;
     double *xch = sT + (size_t)KT * pitch;
     double *sEnd = xch + (size_t)(ZMODE == 1 ? 10 : 6) * NTH;
-    uint8_t *sCode = reinterpret_cast<uint8_t *>(sEnd + 2 * KT);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sEnd + 2 * KT);       // one mbarrier (+ 8 bytes of padding)
+    uint8_t *sCode = reinterpret_cast<uint8_t *>(sEnd + 2 * KT + 2);
     const bool sparse = CMODE == 2;       // this kernel reads a dense coefficient field at exposed cells only
+    const int nval = (int)min((size_t)KT, nlines - L0);                // lines of this tile that exist
+    // vec 2: whole lines travel as bulk asynchronous copies (one instruction per line and direction);
+    // vec 1: 16-byte cp.async pieces / vector stores; vec 0: scalar loads and stores
+    const bool bulk = vec == 2;
 
     // ---- stage in ----
-    if (vec) {
+    if (bulk) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        // cells beyond the line's end and lines beyond the grid: code 0, T 0 (generic stores, disjoint from the copies)
+        for (int i = tid; i < KT * (RL - nz); i += NTH) {
+            const int l = i / (RL - nz), z = nz + (i - l * (RL - nz));
+            sT[(size_t)l * pitch + z] = 0.0;
+            sCode[(size_t)l * cpitch + z] = 0;
+        }
+        for (int i = tid; i < (KT - nval) * nz; i += NTH) {
+            const int l = nval + i / nz, z = i % nz;
+            sT[(size_t)l * pitch + z] = 0.0;
+            sCode[(size_t)l * cpitch + z] = 0;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            if (tid == 0) mbar_expect_tx(bar, (unsigned)nval * (unsigned)nz * 9u);
+            __syncwarp();
+            for (int l = tid; l < nval; l += 32) {
+                const size_t g = (L0 + l) * (size_t)nz;
+                bulk_g2s(sT + (size_t)l * pitch, a.in + g, (unsigned)nz * 8u, bar);
+                bulk_g2s(sCode + (size_t)l * cpitch, a.code + g, (unsigned)nz, bar);
+            }
+        }
+    } else if (vec) {
         const int ppl = RL / 2;
         for (int l = 0; l < KT; ++l) {
             const size_t line = L0 + l;
@@ -82,7 +159,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
                 sT[(size_t)l * pitch + z] = (lok && z < nz) ? a.in[line * (size_t)nz + z] : 0.0;
         }
     }
-    if (vec && (nz & 15) == 0) {
+    if (bulk) {
+    } else if (vec && (nz & 15) == 0) {
         const int cpl = RL / 16;
         for (int i = tid; i < KT * cpl; i += NTH) {
             const int l = i / cpl, c16 = i - l * cpl;
@@ -98,12 +176,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
                 sCode[(size_t)l * cpitch + z] = (lok && z < nz) ? a.code[line * (size_t)nz + z] : (uint8_t)0;
         }
     }
-    if (sparse && tid < 2 * KT) {
+    if (sparse) {
         // the two ends of every line (always exposed when active) are requested with the tile
-        const size_t line = min(L0 + (size_t)(tid >> 1), nlines - 1);
-        cp_async8(smem_u32(sEnd + tid), a.coeff + line * (size_t)nz + ((tid & 1) ? nz - 1 : 0));
+        for (int i = tid; i < 2 * KT; i += NTH) {
+            const size_t line = min(L0 + (size_t)(i >> 1), nlines - 1);
+            cp_async8(smem_u32(sEnd + i), a.coeff + line * (size_t)nz + ((i & 1) ? nz - 1 : 0));
+        }
     }
     cp_async_wait_all();
+    if (bulk) mbar_wait(bar, 0);
     __syncthreads();
 
     // ---- chunk to registers ----
@@ -223,11 +304,27 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
     }
 
     // ---- results back through the thread's own slots, then coalesced copy-out ----
-    // The sweep runs in place, so void cells must keep the bits they have in global memory: the copy-out
-    // only writes cells whose staged code is active.
+    // The sweep runs in place, so void cells must keep the bits they have in global memory.  Bulk mode stores whole
+    // lines: uniform chunks hold no void cell; the general path has used the slots of its void cells for factors
+    // and puts the original bits back (void cells are written by nobody, so re-reading them is safe).
+    if (bulk && path == 0) {
+#pragma unroll
+        for (int e = 0; e < M; ++e)
+            if (e < nv && !ch.active(e)) ch.T[e] = a.in[gline + p * M + e];
+    }
 #pragma unroll
     for (int j = 0; j < M / 2; ++j)
         *reinterpret_cast<double2 *>(slot + 2 * j) = make_double2(ch.T[2 * j], ch.T[2 * j + 1]);
+    if (bulk) {
+        fence_proxy_async();       // generic-proxy writes above -> visible to the bulk copy engine
+        __syncthreads();
+        if (tid < 32) {
+            for (int l = tid; l < nval; l += 32)
+                bulk_s2g(a.out + (L0 + l) * (size_t)nz, sT + (size_t)l * pitch, (unsigned)nz * 8u);
+            bulk_commit_wait_read();   // shared memory must outlive the reads of the copy engine
+        }
+        return;
+    }
     __syncthreads();
     const bool inplace = (a.in == a.out);
     if (vec) {

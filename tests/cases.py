@@ -245,9 +245,23 @@ CYL_CASES = {
 }
 
 
+# round-2 additions (own seeds: the seeds of CYL_CASES depend on that dict's sorted order, which must not move):
+# r lines at BASELINE configs[2] length (nr = 256: P = 16 chunks, Robin row at the far end), cfl 1 and 50
+CYL_CASES_R2 = {
+    "long_r":          ((256, 8, 6,  0.02,  1.0,  "neumann0", "robin",     500.0, False, False), 9001),
+    "long_r_cfl50":    ((256, 8, 6,  0.02,  50.0, "robin",    "robin",     500.0, True,  False), 9014),
+}
+ALL_CYL_CASES = sorted(CYL_CASES) + sorted(CYL_CASES_R2)
+# a slab of BASELINE configs[2] itself: 256 x 1024 x 16 (golden stored as a sub-sample + SHA-256 of the full array)
+CYL_C3_SLICE = ((256, 1024, 16, 0.02, 1.0, "neumann0", "robin", 500.0, False, False), 9027)
+
+
 def build_cyl_case(name: str) -> dict:
-    nr, nphi, nz, R, cfl, kb, kt, h_r, source, masked = CYL_CASES[name]
-    seed = 5000 + sorted(CYL_CASES).index(name) * 13
+    if name in CYL_CASES_R2 or name == "c3_slice":
+        (nr, nphi, nz, R, cfl, kb, kt, h_r, source, masked), seed = CYL_CASES_R2[name] if name in CYL_CASES_R2 else CYL_C3_SLICE
+    else:
+        nr, nphi, nz, R, cfl, kb, kt, h_r, source, masked = CYL_CASES[name]
+        seed = 5000 + sorted(CYL_CASES).index(name) * 13
     dr = R / nr
     dz = dr
     dphi = (2.0 * math.pi) / max(nphi, 1)

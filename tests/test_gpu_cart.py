@@ -399,7 +399,7 @@ def test_pipelined_host_fields(g, golden_dir):
 
 # ---- surface-only coefficient fields: the sweeps read them at exposed cells only -----------------
 @pytest.mark.parametrize("shape", [(40, 67, 130), (96, 33, 64), (600, 7, 48), (5, 1024, 24), (33, 18, 37), (20, 20, 515)])
-def test_sparse_coefficient_reads_are_bit_identical(shape, g, cp):
+def test_sparse_coefficient_reads_agree(shape, g, cp):
     """Packs from precompute_coeff_packs_unified vanish away from the surface (adi3d_numba_coeff.py:93-99);
     the engine verifies that (k_check_sparse) and skips the interior coefficient reads.  Same bits as
     with the dense reads (option sparse_coeff=0), and parity with the oracle either way."""
@@ -418,7 +418,10 @@ def test_sparse_coefficient_reads_are_bit_identical(shape, g, cp):
             outs.append(cp.asnumpy(T))
     finally:
         g.set_option("sparse_coeff", 1)
-    assert np.array_equal(outs[0], outs[1], equal_nan=True)
+    # same rows either way; the sweeps that skip the interior coefficient reads may also take the tabulated
+    # uniform-run factors, so the two agree to rounding, not bit for bit
+    assert cases.rel_l2(outs[0], outs[1], c["mask"]) <= 1e-13
+    assert np.array_equal(outs[0][~c["mask"]], outs[1][~c["mask"]], equal_nan=True)
     _both(g, cp, c)
 
 
@@ -480,7 +483,7 @@ def _uniform_case(shape, mask_kind, bk, theta, cfl, seed):
 
 @pytest.mark.parametrize("opts", [dict(), dict(uni=0), dict(tw=1), dict(xy2=0), dict(m=16), dict(m=32), dict(kt=4), dict(m=16, kt=2),
                                   dict(m=16, occ=3), dict(m=16, occ=4, tw=1), dict(remap=1), dict(remap=1, tw=1), dict(wide=1),
-                                  dict(m=16, wide=1, tw=1), dict(lt=1), dict(lt=4), dict(sparse_coeff=0), dict(zt=0), dict(zt=0, uni=0)],
+                                  dict(m=16, wide=1, tw=1), dict(lt=1), dict(lt=4), dict(sparse_coeff=0), dict(zt=0), dict(zt=0, uni=0), dict(bulk=0), dict(bulk=0, uni=0)],
                          ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
 @pytest.mark.parametrize("shape,mask_kind", [((70, 40, 37), "full"), ((40, 70, 130), "plate_track"), ((96, 50, 64), "cyl_holes"),
                                              ((600, 7, 48), "full"), ((5, 1100, 24), "full"), ((2050, 3, 10), "full"),

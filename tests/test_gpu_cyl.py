@@ -36,7 +36,7 @@ def _run(m, c):
     return m.adi_step(c["T0"], grid, mat, prm, rob, zbc, S=c["S"])
 
 
-@pytest.mark.parametrize("name", sorted(cases.CYL_CASES))
+@pytest.mark.parametrize("name", cases.ALL_CYL_CASES)
 def test_cyl_step_matches_reference(name, gc, golden_dir):
     c = cases.build_cyl_case(name)
     g = np.load(os.path.join(golden_dir, f"cyl_{name}.npz"))
@@ -197,3 +197,23 @@ def test_spiral_simulation_snapshots(gc, golden_dir):
     assert np.array_equal(np.array(act), g["active"])
     for s, r in zip(snaps, g["snapshots"]):
         assert cases.rel_l2(s, r) <= 1e-11      # up to 72 steps accumulated
+    # per step the bar is 1e-12 (north_star): snapshot 0 is the initial state, snapshot 1 (t = 1 s) has 18 steps behind
+    # it and still meets the one-step bar
+    assert cases.rel_l2(snaps[1], g["snapshots"][1]) <= 1e-12
+
+
+def test_c3_slice_matches_reference_and_oracle(gc, golden_dir):
+    """256 x 1024 x 16: lines of BASELINE configs[2]'s own length along r (256 cells, Robin row at the far end) and phi
+    (1024-cell rings) -- against the reference's golden sub-sample and, cell for cell, against the oracle (which
+    reproduces the reference's whole array bit for bit, tests/test_oracle_golden.py)."""
+    c = cases.build_cyl_case("c3_slice")
+    g = np.load(os.path.join(golden_dir, "cyl_c3_slice.npz"))
+    out = _run(gc, c)
+    assert cases.rel_l2(out[:, ::32, :], g["T_sub"]) <= TOL
+    ref = cyl.adi_step(c["T0"], cyl.GridCyl(c["nr"], c["nphi"], c["nz"], c["dr"], c["dphi"], c["dz"], c["R"]),
+                       cyl.Material(c["rho"], c["cp"], c["k"]), cyl.Params(c["dt"], 1.0, "be"),
+                       cyl.RobinR(c["h_r"], c["Tinf_r"]), cyl.ZBC(**c["zbc"]))
+    assert cases.rel_l2(out, ref) <= TOL
+    # worst single r line / phi ring, not only the global norm
+    num = np.sqrt(((out - ref) ** 2).sum(axis=0)); den = np.sqrt((ref ** 2).sum(axis=0))
+    assert float((num / den).max()) <= 10 * TOL

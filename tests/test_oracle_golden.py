@@ -104,19 +104,30 @@ def _cyl_run(c, solver):
     return cyl.adi_step(c["T0"], grid, mat, prm, rob, zbc, S=c["S"], phi_solver=solver)
 
 
-@pytest.mark.parametrize("name", sorted(cases.CYL_CASES))
+@pytest.mark.parametrize("name", cases.ALL_CYL_CASES)
 def test_cyl_oracle_bit_exact(name, golden_dir):
     c = cases.build_cyl_case(name)
     g = np.load(os.path.join(golden_dir, f"cyl_{name}.npz"))
     assert np.array_equal(_cyl_run(c, cyl.phi_solve_spectral), g["T_out"])
 
 
-@pytest.mark.parametrize("name", sorted(cases.CYL_CASES))
+@pytest.mark.parametrize("name", cases.ALL_CYL_CASES)
 def test_cyclic_sherman_morrison_matches_spectral(name, golden_dir):
     """The direct cyclic solve the CUDA kernel implements vs the reference's FFT solve."""
     c = cases.build_cyl_case(name)
     g = np.load(os.path.join(golden_dir, f"cyl_{name}.npz"))
     assert cases.rel_l2(_cyl_run(c, cyl.phi_solve_cyclic), g["T_out"]) < 1e-13
+
+
+def test_cyl_c3_slice_bit_exact(golden_dir):
+    """A 256 x 1024 x 16 slab of BASELINE configs[2] itself (r lines of 256 cells, phi rings of 1024): the golden
+    file holds every 32nd phi row and the SHA-256 of the reference's whole output."""
+    import hashlib
+    c = cases.build_cyl_case("c3_slice")
+    g = np.load(os.path.join(golden_dir, "cyl_c3_slice.npz"))
+    out = _cyl_run(c, cyl.phi_solve_spectral)
+    assert np.array_equal(out[:, ::32, :], g["T_sub"])
+    assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).digest() == g["sha256"].tobytes()
 
 
 def test_cyl_bad_kind_raises():

@@ -138,7 +138,7 @@ def _host_step(Tn, grid, p, active=None, S=None, nsteps=1):
         src = np.ascontiguousarray(np.broadcast_to(np.asarray(S, dtype=np.float64), shape))
     e = _engine
     e.bind(grid)
-    out = np.empty(shape, dtype=np.float64)
+    out = cp.pinned_empty(shape, np.float64)     # page-locked: PCIe-speed download, and upload when it comes back as Tn
     _capi.check(_capi.load().adi_cyl_step_host(
         e.context(), T.ctypes.data, out.ctypes.data, int(nsteps), C.byref(p),
         None if act is None else act.ctypes.data, None if src is None else src.ctypes.data,

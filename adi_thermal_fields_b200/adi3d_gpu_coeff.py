@@ -395,7 +395,7 @@ def adi_step_host(Tn, grid, mat, params, packs, Tinf=0.0, nsteps=1):
     e.bind(grid)
     e.set_mask(grid)
     e.set_packs(packs)
-    out = np.empty_like(T)
+    out = cp.pinned_empty(T.shape, np.float64)   # page-locked: PCIe-speed download, and upload when it comes back as Tn
     _capi.check(e.lib().adi_cart_step_host(e.context(), T.ctypes.data, out.ctypes.data, int(nsteps),
                                            params.dt, params.theta, kappa, float(Tinf), _stream_ptr()),
                 "adi_cart_step_host")

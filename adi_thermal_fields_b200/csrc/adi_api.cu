@@ -1,7 +1,10 @@
 // adi_api.cu -- context, memory and error plumbing of the C ABI (include/adi_b200.h).
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "adi_ctx.h"
 
@@ -31,6 +34,108 @@ int prof_mark(adi_ctx *ctx, int slot, cudaStream_t st)
     ADI_CUDA(cudaEventRecord(ctx->prof_ev[(size_t)ctx->prof_steps * 5 + slot], st));
     if (slot == 4) ctx->prof_steps++;
     return ADI_OK;
+}
+
+// ---- staged copies of pageable host arrays ------------------------------------------------------------
+static const size_t PIN_CHUNK = (size_t)32 << 20;
+
+static bool host_is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+static int ensure_pin(adi_ctx *ctx)
+{
+    for (int i = 0; i < 2; ++i) {
+        if (!ctx->pin[i]) ADI_CUDA(cudaHostAlloc(&ctx->pin[i], PIN_CHUNK, cudaHostAllocDefault));
+        if (!ctx->pin_ev[i]) ADI_CUDA(cudaEventCreateWithFlags(&ctx->pin_ev[i], cudaEventDisableTiming));
+    }
+    return ADI_OK;
+}
+
+static void par_memcpy(void *dst, const void *src, size_t n)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = std::min<size_t>(std::max(1u, std::min(hw, 8u)), (n + ((size_t)4 << 20) - 1) / ((size_t)4 << 20));
+    if (nt <= 1) {
+        memcpy(dst, src, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((n + nt - 1) / nt + 63) & ~(size_t)63;
+    for (size_t t = 0; t < nt; ++t) {
+        const size_t o = t * per;
+        if (o >= n) break;
+        const size_t m = std::min(per, n - o);
+        th.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, m); });
+    }
+    for (auto &t : th) t.join();
+}
+
+int stage_h2d(adi_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st)
+{
+    if (!bytes) return ADI_OK;
+    if (bytes < ((size_t)1 << 20) || host_is_pinned(h_src)) {
+        ADI_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+        return ADI_OK;
+    }
+    int rc = ensure_pin(ctx);
+    if (rc) return rc;
+    size_t off = 0;
+    for (int i = 0; off < bytes; ++i, off += PIN_CHUNK) {
+        const int b = i & 1;
+        const size_t n = std::min(PIN_CHUNK, bytes - off);
+        if (i >= 2) ADI_CUDA(cudaEventSynchronize(ctx->pin_ev[b]));   // the transfer out of this buffer is done
+        par_memcpy(ctx->pin[b], (const char *)h_src + off, n);
+        ADI_CUDA(cudaMemcpyAsync((char *)d_dst + off, ctx->pin[b], n, cudaMemcpyHostToDevice, st));
+        ADI_CUDA(cudaEventRecord(ctx->pin_ev[b], st));
+    }
+    // the staging buffers may be reused by the next call straight away: wait for the last two transfers
+    ADI_CUDA(cudaEventSynchronize(ctx->pin_ev[0]));
+    ADI_CUDA(cudaEventSynchronize(ctx->pin_ev[1]));
+    return ADI_OK;
+}
+
+int stage_d2h(adi_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, cudaStream_t st)
+{
+    if (!bytes) return ADI_OK;
+    if (bytes < ((size_t)1 << 20) || host_is_pinned(h_dst)) {
+        ADI_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+        ADI_CUDA(cudaStreamSynchronize(st));
+        return ADI_OK;
+    }
+    int rc = ensure_pin(ctx);
+    if (rc) return rc;
+    const size_t nchunk = (bytes + PIN_CHUNK - 1) / PIN_CHUNK;
+    for (size_t i = 0; i <= nchunk; ++i) {
+        if (i < nchunk) {
+            const int b = (int)(i & 1);
+            const size_t off = i * PIN_CHUNK, n = std::min(PIN_CHUNK, bytes - off);
+            ADI_CUDA(cudaMemcpyAsync(ctx->pin[b], (const char *)d_src + off, n, cudaMemcpyDeviceToHost, st));
+            ADI_CUDA(cudaEventRecord(ctx->pin_ev[b], st));
+        }
+        if (i >= 1) {   // piece i-1 has had the time of one transfer to arrive
+            const int b = (int)((i - 1) & 1);
+            const size_t off = (i - 1) * PIN_CHUNK, n = std::min(PIN_CHUNK, bytes - off);
+            ADI_CUDA(cudaEventSynchronize(ctx->pin_ev[b]));
+            par_memcpy((char *)h_dst + off, ctx->pin[b], n);
+        }
+    }
+    return ADI_OK;
+}
+
+void stage_release(adi_ctx *ctx)
+{
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
+        if (ctx->pin_ev[i]) cudaEventDestroy(ctx->pin_ev[i]);
+        ctx->pin[i] = nullptr; ctx->pin_ev[i] = nullptr;
+    }
 }
 
 }  // namespace adi
@@ -88,6 +193,7 @@ int adi_ctx_destroy(adi_ctx *ctx)
     if (ctx->stage_src) cudaFree(ctx->stage_src);
     adi::cyl_release(ctx);
     adi::text_release(ctx);
+    adi::stage_release(ctx);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     delete ctx;
     return ADI_OK;

@@ -515,16 +515,14 @@ int adi_cart_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int ns
     const size_t ncell = (size_t)ctx->nx * ctx->ny * ctx->nz;
     rc = ensure_stage(ctx, ncell);
     if (rc) return rc;
-    ADI_CUDA(cudaMemcpyAsync(ctx->stage[0], h_Tin, ncell * sizeof(double), cudaMemcpyHostToDevice, st));
+    if ((rc = stage_h2d(ctx, ctx->stage[0], h_Tin, ncell * sizeof(double), st))) return rc;
     int cur = 0;
     for (int s = 0; s < nsteps; ++s) {
         rc = adi_cart_step(ctx, ctx->stage[cur], ctx->stage[cur ^ 1], dt, theta, kappa, Tinf, stream);
         if (rc) return rc;
         cur ^= 1;
     }
-    ADI_CUDA(cudaMemcpyAsync(h_Tout, ctx->stage[cur], ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
-    ADI_CUDA(cudaStreamSynchronize(st));
-    return ADI_OK;
+    return stage_d2h(ctx, h_Tout, ctx->stage[cur], ncell * sizeof(double), st);
 }
 
 int adi_cart_step_host_async(adi_ctx *ctx, int slot, const double *h_Tin, double *h_Tout, double dt,

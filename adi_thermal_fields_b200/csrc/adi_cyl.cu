@@ -790,9 +790,9 @@ int adi_cyl_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int nst
     }
     int rc = ensure_aux(ctx, ncell);
     if (rc) return rc;
-    ADI_CUDA(cudaMemcpyAsync(ctx->stage[0], h_Tin, ncell * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (h_active) ADI_CUDA(cudaMemcpyAsync(ctx->stage_mask, h_active, ncell, cudaMemcpyHostToDevice, st));
-    if (h_S) ADI_CUDA(cudaMemcpyAsync(ctx->stage_src, h_S, ncell * sizeof(double), cudaMemcpyHostToDevice, st));
+    if ((rc = stage_h2d(ctx, ctx->stage[0], h_Tin, ncell * sizeof(double), st))) return rc;
+    if (h_active && (rc = stage_h2d(ctx, ctx->stage_mask, h_active, ncell, st))) return rc;
+    if (h_S && (rc = stage_h2d(ctx, ctx->stage_src, h_S, ncell * sizeof(double), st))) return rc;
     int cur = 0;
     for (int s = 0; s < nsteps; ++s) {
         rc = adi_cyl_step(ctx, ctx->stage[cur], ctx->stage[cur ^ 1], p, h_active ? ctx->stage_mask : nullptr,
@@ -800,9 +800,7 @@ int adi_cyl_step_host(adi_ctx *ctx, const double *h_Tin, double *h_Tout, int nst
         if (rc) return rc;
         cur ^= 1;
     }
-    ADI_CUDA(cudaMemcpyAsync(h_Tout, ctx->stage[cur], ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
-    ADI_CUDA(cudaStreamSynchronize(st));
-    return ADI_OK;
+    return stage_d2h(ctx, h_Tout, ctx->stage[cur], ncell * sizeof(double), st);
 }
 
 }  // extern "C"

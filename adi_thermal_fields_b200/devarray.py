@@ -453,3 +453,15 @@ class cuda:  # namespace
     @staticmethod
     def is_available():
         return torch.cuda.is_available()
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """A host NumPy array in page-locked memory (from torch's caching host allocator: reuse after the first allocation
+    is free).  The host-array entry points return their results in such arrays: the download runs at PCIe speed, and
+    in a time loop T = step(T) the next upload does too.  Small arrays come from the ordinary heap."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if n < (1 << 20) or not torch.cuda.is_available():
+        return np.empty(shape, dtype=dtype)
+    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32, np.dtype(np.bool_): torch.bool,
+           np.dtype(np.uint8): torch.uint8}[np.dtype(dtype)]
+    return torch.empty(tuple(int(v) for v in shape), dtype=tdt, pin_memory=True).numpy()

@@ -206,6 +206,7 @@ def test_c3_slice_matches_reference_and_oracle(gc, golden_dir):
     """256 x 1024 x 16: lines of BASELINE configs[2]'s own length along r (256 cells, Robin row at the far end) and phi
     (1024-cell rings) -- against the reference's golden sub-sample and, cell for cell, against the oracle (which
     reproduces the reference's whole array bit for bit, tests/test_oracle_golden.py)."""
+    from oracle import cyl
     c = cases.build_cyl_case("c3_slice")
     g = np.load(os.path.join(golden_dir, "cyl_c3_slice.npz"))
     out = _run(gc, c)

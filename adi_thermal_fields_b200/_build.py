@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libadi_b200.so")
-SOURCES = ["adi_api.cu", "adi_cart.cu", "adi_sweep_x.cu", "adi_sweep_y.cu", "adi_sweep_z.cu", "adi_sweep_zt.cu", "adi_cyl.cu", "adi_voxel.cu", "adi_text.cu"]
+SOURCES = ["adi_api.cu", "adi_cart.cu", "adi_sweep_x.cu", "adi_sweep_y.cu", "adi_sweep_z.cu", "adi_sweep_zt.cu", "adi_dist.cu", "adi_cyl.cu", "adi_voxel.cu", "adi_text.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--threads", "0"]
 

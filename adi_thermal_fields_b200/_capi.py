@@ -25,6 +25,8 @@ SYMBOLS = (
     "adi_cyl_set_slab", "adi_cyl_step_rphi", "adi_cyl_zsweep_reduce", "adi_cyl_zsweep_finish",
     "adi_text_capacity", "adi_text_format", "adi_text_write",
     "adi_probe_open", "adi_probe_record", "adi_probe_fetch",
+    "adi_dist_unique_id", "adi_dist_init", "adi_dist_init_comm", "adi_dist_comm", "adi_dist_destroy", "adi_dist_set_option",
+    "adi_dist_info", "adi_cart_slab_sync_mask", "adi_cart_slab_step",
 )
 
 
@@ -113,6 +115,15 @@ def load():
     L.adi_probe_open.argtypes = [vp, C.c_int, C.c_size_t]
     L.adi_probe_record.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, vp]
     L.adi_probe_fetch.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]
+    L.adi_dist_unique_id.argtypes = [vp]
+    L.adi_dist_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.adi_dist_init_comm.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.adi_dist_comm.argtypes = [vp, C.POINTER(vp)]
+    L.adi_dist_destroy.argtypes = [vp]
+    L.adi_dist_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    L.adi_dist_info.argtypes = [vp, ip, ip, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+    L.adi_cart_slab_sync_mask.argtypes = [vp, vp]
+    L.adi_cart_slab_step.argtypes = [vp, dp, dp, dbl, dbl, dbl, dbl, vp]
     _lib = L
     return L
 

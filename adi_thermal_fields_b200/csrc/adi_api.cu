@@ -194,6 +194,7 @@ int adi_ctx_destroy(adi_ctx *ctx)
     adi::cyl_release(ctx);
     adi::text_release(ctx);
     adi::stage_release(ctx);
+    adi::dist_release(ctx);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     delete ctx;
     return ADI_OK;

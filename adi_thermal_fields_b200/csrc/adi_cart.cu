@@ -179,6 +179,7 @@ int adi_cart_set_mask(adi_ctx *ctx, const uint8_t *d_mask)
     ctx->d_mask = d_mask;
     ctx->code_dirty = true;
     ctx->sparse_trust = 0;
+    ctx->operand_epoch++;
     return ADI_OK;
 }
 
@@ -201,6 +202,7 @@ int adi_cart_set_pack(adi_ctx *ctx, int axis, const double *d_coeff, const uint8
     ctx->scalar_robin = false;
     ctx->sparse_dirty = true;
     ctx->sparse_trust = 0;
+    ctx->operand_epoch++;
     return ADI_OK;
 }
 
@@ -214,15 +216,18 @@ int adi_cart_set_robin_scalar(adi_ctx *ctx, const double face_coeff[6])
     ctx->scalar_robin = true;
     ctx->sparse_dirty = true;
     ctx->sparse_trust = 0;
+    ctx->operand_epoch++;
     return ADI_OK;
 }
 
 // Sweeps `first`..`last` (0 = explicit stage + x, 1 = y, 2 = z) of one step.
 // zmode: 0 whole z lines, 1 z-slab pass 1 (interface relations -> d_iface), 2 z-slab pass 2.
+// line0 / nlb: (z sweep only) restrict the sweep to the z lines [line0, line0 + nlb) -- the batches of the
+// overlapped multi-GPU z solve; nlb == 0: all lines.  d_iface_* / d_ghost are then the BATCH's arrays ([2][nlb] ...).
 static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, double theta,
                       double kappa, double Tinf, int first, int last, int zmode, const double *d_Tlo,
                       const double *d_Thi, double *d_iface_dyn, double *d_iface_stat, const double *d_ghost,
-                      cudaStream_t st)
+                      cudaStream_t st, size_t line0 = 0, size_t nlb = 0)
 {
     const size_t ncell = (size_t)ctx->nx * ctx->ny * ctx->nz;
     if (ncell == 0) return ADI_OK;
@@ -279,7 +284,17 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
         const bool extra = p.q != nullptr || p.dirm != nullptr;
         if (axis == 0) rc = launch_sweep_x(ctx, a, dense, extra, expl, st);
         else if (axis == 1) rc = launch_sweep_y(ctx, a, dense, extra, st);
-        else rc = launch_sweep_z(ctx, a, dense, extra, zmode == 5 ? 2 : zmode, st);
+        else if (nlb == 0) rc = launch_sweep_z(ctx, a, dense, extra, zmode == 5 ? 2 : zmode, st);
+        else {
+            SweepArgs b = a;   // the z kernels see a grid of nlb lines
+            const size_t off = line0 * (size_t)a.nz;
+            b.in += off; b.out += off; b.code += off;
+            if (b.coeff) b.coeff += off;
+            if (b.q) b.q += off;
+            if (b.dirv) b.dirv += off;
+            b.nx = 1; b.ny = (int)nlb;
+            rc = launch_sweep_z(ctx, b, dense, extra, zmode == 5 ? 2 : zmode, st);
+        }
         if (rc) return rc;
         if (zmode == 0 || zmode == 2) {
             rc = prof_mark(ctx, axis + 2, st);
@@ -330,6 +345,7 @@ int adi_cart_set_mask_halo(adi_ctx *ctx, const uint8_t *d_mask_lo, const uint8_t
     ctx->d_mask_lo = d_mask_lo; ctx->d_mask_hi = d_mask_hi;
     ctx->code_dirty = true;
     ctx->sparse_trust = 0;
+    ctx->operand_epoch++;
     return ADI_OK;
 }
 
@@ -410,7 +426,7 @@ int adi_cart_zsweep_finish(adi_ctx *ctx, double *d_T, const double *d_dyn_all, c
     }
     const int threads = 128;
     const int blocks = (int)std::min<size_t>((nlines + threads - 1) / threads, 148 * 32);
-    k_iface_solve<<<blocks, threads, 0, st>>>(d_dyn_all, d_stat_all, ctx->d_ghost, nlines, ctx->slab_nranks, ctx->slab_rank);
+    k_iface_solve<<<blocks, threads, 0, st>>>(d_dyn_all, d_stat_all, nlines, ctx->d_ghost, nlines, ctx->slab_nranks, ctx->slab_rank);
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
     return run_sweeps(ctx, d_T, d_T, dt, theta, kappa, Tinf, 2, 2, 2, nullptr, nullptr, nullptr, nullptr, ctx->d_ghost, st);
@@ -492,7 +508,7 @@ int adi_cart_zsweep_apply(adi_ctx *ctx, double *d_T, const double *d_dyn_all, co
     if ((rc = ensure_ghost(ctx, nlines, st))) return rc;
     const int threads = 128;
     const int blocks = (int)std::min<size_t>((nlines + threads - 1) / threads, 148 * 32);
-    k_iface_solve<<<blocks, threads, 0, st>>>(d_dyn_all, d_stat_all, ctx->d_ghost, nlines, ctx->slab_nranks, ctx->slab_rank);
+    k_iface_solve<<<blocks, threads, 0, st>>>(d_dyn_all, d_stat_all, nlines, ctx->d_ghost, nlines, ctx->slab_nranks, ctx->slab_rank);
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
     const int ablocks = (int)std::min<size_t>((nlines * 8 + 255) / 256, 148 * 32);
@@ -621,3 +637,40 @@ int adi_cart_exposed_mask(adi_ctx *ctx, int face, uint8_t *d_out, void *stream)
 }
 
 }  // extern "C"
+
+// ---- internal entry points of the in-library multi-GPU sequencing (adi_dist.cu) ---------------------------
+namespace adi {
+
+int cart_ensure_ghost(adi_ctx *ctx, size_t nlines, cudaStream_t st) { return ensure_ghost(ctx, nlines, st); }
+
+// "solve first" z pass of the lines [line0, line0 + nlb): in place with zero ghosts, (y_first, y_last) -> d_dyn[2][nlb]
+int cart_zsolve0_range(adi_ctx *ctx, double *d_T, double *d_dyn, double dt, double theta, double kappa, double Tinf,
+                       size_t line0, size_t nlb, cudaStream_t st)
+{
+    return run_sweeps(ctx, d_T, d_T, dt, theta, kappa, Tinf, 2, 2, 4, nullptr, nullptr, d_dyn, nullptr, nullptr, st, line0, nlb);
+}
+
+// inter-rank solve + ghost corrections of the lines [line0, line0 + nlb): d_dyn_all[R][2][nlb] is the batch's gathered
+// right-hand-side part, d_stat_all[R][4][nl] the matrix part of all lines
+int cart_zapply_range(adi_ctx *ctx, double *d_T, const double *d_dyn_all, const double *d_stat_all, const double *d_vC,
+                      const double *d_wC, const int *d_Kv, const int *d_Kw, int kmax, size_t line0, size_t nlb,
+                      cudaStream_t st)
+{
+    const size_t nl = (size_t)ctx->nx * ctx->ny;
+    double *ghost = ctx->d_ghost + 2 * line0;
+    const int threads = 128;
+    const int blocks = (int)std::min<size_t>((nlb + threads - 1) / threads, 148 * 32);
+    k_iface_solve<<<blocks, threads, 0, st>>>(d_dyn_all, d_stat_all + line0, nl, ghost, nlb, ctx->slab_nranks, ctx->slab_rank);
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
+    const int ablocks = (int)std::min<size_t>((nlb * 8 + 255) / 256, 148 * 32);
+    k_spike_apply<<<ablocks, 256, 0, st>>>(d_T + line0 * (size_t)ctx->nz, ghost, d_vC + line0 * (size_t)kmax,
+                                           d_wC + line0 * (size_t)kmax, d_Kv + line0, d_Kw + line0, nlb, ctx->nz, kmax);
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
+    return ADI_OK;
+}
+
+int cart_prof_mark(adi_ctx *ctx, int slot, cudaStream_t st) { return prof_mark(ctx, slot, st); }
+
+}  // namespace adi

@@ -1007,18 +1007,19 @@ __global__ void k_pack_zplanes(const T *__restrict__ f, T *__restrict__ lo, T *_
     }
 }
 
-__global__ void k_iface_solve(const double *__restrict__ dyn, const double *__restrict__ stat,
+__global__ void k_iface_solve(const double *__restrict__ dyn, const double *__restrict__ stat, size_t sstride,
                               double *__restrict__ ghost, size_t nlines, int nranks, int rank)
 {
-    // dyn[rank][2][nlines] = (yf, yl), stat[rank][4][nlines] = (vf, wf, vl, wl)
+    // dyn[rank][2][nlines] = (yf, yl), stat[rank][4][sstride] = (vf, wf, vl, wl) (sstride >= nlines: a batch of
+    // lines out of a longer array; `stat` already points at the batch's first line)
     for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < nlines; l += (size_t)gridDim.x * blockDim.x) {
         double Lg, Rg;
         iface_solve([&](int r) {
             const double *d = dyn + (size_t)r * 2 * nlines + l;
-            const double *q = stat + (size_t)r * 4 * nlines + l;
+            const double *q = stat + (size_t)r * 4 * sstride + l;
             Iface v;
             v.yf = d[0]; v.yl = d[nlines];
-            v.vf = q[0]; v.wf = q[nlines]; v.vl = q[2 * nlines]; v.wl = q[3 * nlines];
+            v.vf = q[0]; v.wf = q[sstride]; v.vl = q[2 * sstride]; v.wl = q[3 * sstride];
             return v;
         }, nranks, rank, &Lg, &Rg);
         ghost[l] = Lg;

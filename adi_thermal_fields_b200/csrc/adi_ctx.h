@@ -27,6 +27,8 @@ struct Pack {
 };
 
 struct CylTables;  // adi_cyl.cu
+struct DistState;  // adi_dist.cu: NCCL communicator, exchange buffers and caches of the in-library z-slab step
+void dist_release(adi_ctx *ctx);
 struct TextState;  // adi_text.cu: scratch of the ASCII output path and the probe slots
 void text_release(adi_ctx *ctx);
 long text_launches(adi_ctx *ctx);
@@ -77,6 +79,8 @@ struct adi_ctx {
     long sparse_trust = 0;  // bit a: the caller vouches for pack a (built by adi_cart_build_packs for the bound
                             // mask and untouched since); cleared by every pack / mask call
     unsigned long long *d_viol = nullptr, *h_viol = nullptr;  // [3] each
+    long operand_epoch = 0;  // counts mask / pack / halo (re)bindings: keys the caches of the multi-GPU z solve
+    adi::DistState *dist = nullptr;
     // z-slab decomposition: mask planes of the adjacent slabs (borrowed), scratch for the ghosts
     int slab_rank = 0, slab_nranks = 1;
     const uint8_t *d_mask_lo = nullptr, *d_mask_hi = nullptr;

@@ -30,6 +30,7 @@ import torch
 from . import _capi
 
 FACES = ("x-", "x+", "y-", "y+", "z-", "z+")
+USE_LIBRARY_SEQUENCING = True   # NCCL ranks: adi_cart_slab_step (False: the call-by-call sequencing of this module)
 
 
 def split_z(nz, world, multiple=1):
@@ -168,6 +169,7 @@ class CudaBackend:
         self.ctx = h
         self.hold = None
         self.pack_key = None
+        self.dist = False     # True: the library sequences the slab step over its own NCCL communicator
 
     def _st(self):
         return torch.cuda.current_stream().cuda_stream
@@ -283,7 +285,46 @@ class CudaBackend:
         return int(self.L.adi_launch_count(self.ctx))
 
     def set_option(self, name, value):
+        if str(name) in ("batches", "spike_after", "spike_kmax"):
+            _capi.check(self.L.adi_dist_set_option(self.ctx, str(name).encode(), int(value)), "adi_dist_set_option")
+            return
         _capi.check(self.L.adi_set_option(self.ctx, str(name).encode(), int(value)), "adi_set_option")
+
+    # ---- sequencing inside the library over its own NCCL communicator (csrc/adi_dist.cu) ----
+    _owners = {}     # (device, rank, world) -> context that owns the process's communicator
+
+    def dist_init(self, comm):
+        """Join the library's NCCL communicator for `comm`'s ranks (created once per process and shared by later
+        contexts).  Collective the first time.  The 128-byte id travels over torch.distributed."""
+        key = (self.dev.index, comm.rank, comm.world)
+        owner = CudaBackend._owners.get(key)
+        if owner is None:
+            buf = (C.c_ubyte * 128)()
+            if comm.rank == 0:
+                _capi.check(self.L.adi_dist_unique_id(buf), "adi_dist_unique_id")
+            t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=self.dev)
+            comm.dist.broadcast(t, src=comm._peer(0), group=comm.group)
+            raw = bytes(t.cpu().tolist())
+            _capi.check(self.L.adi_dist_init(self.ctx, raw, comm.rank, comm.world), "adi_dist_init")
+            CudaBackend._owners[key] = self.ctx
+            self._keep_owner = None
+        else:
+            h = C.c_void_p()
+            _capi.check(self.L.adi_dist_comm(owner, C.byref(h)), "adi_dist_comm")
+            _capi.check(self.L.adi_dist_init_comm(self.ctx, h, comm.rank, comm.world), "adi_dist_init_comm")
+        self.dist = True
+
+    def slab_sync_mask(self):
+        _capi.check(self.L.adi_cart_slab_sync_mask(self.ctx, self._st()), "adi_cart_slab_sync_mask")
+
+    def slab_step(self, Tin, Tout, dt, theta, kappa, Tinf):
+        _capi.check(self.L.adi_cart_slab_step(self.ctx, Tin.data_ptr(), Tout.data_ptr(), dt, theta, kappa, Tinf,
+                                              self._st()), "adi_cart_slab_step")
+
+    def dist_info(self):
+        r, n, a, b = C.c_int(), C.c_int(), C.c_long(), C.c_long()
+        _capi.check(self.L.adi_dist_info(self.ctx, C.byref(r), C.byref(n), C.byref(a), C.byref(b)), "adi_dist_info")
+        return dict(rank=r.value, nranks=n.value, steps_two_pass=a.value, steps_solve_first=b.value)
 
     def profile(self, on):
         self.L.adi_set_option(self.ctx, b"profile", 1 if on else 0)
@@ -296,7 +337,7 @@ class CudaBackend:
         return [ms[i] for i in range(4)], n.value
 
     def close(self):
-        if self.ctx is not None:
+        if self.ctx is not None and self.ctx not in CudaBackend._owners.values():
             self.L.adi_ctx_destroy(self.ctx)
             self.ctx = None
 
@@ -316,14 +357,6 @@ class SlabGrid3D:
         be = self.be
         self.mask = be.asarray(mask_local, torch.bool)
         assert tuple(self.mask.shape) == (self.nx, self.ny, self.nz)
-        pl = (self.nx, self.ny)
-        self._m_lo, self._m_hi = be.empty(pl, torch.bool), be.empty(pl, torch.bool)      # to send
-        self.mask_lo, self.mask_hi = be.empty(pl, torch.bool), be.empty(pl, torch.bool)  # received
-        self._t_lo, self._t_hi = be.empty(pl, torch.float64), be.empty(pl, torch.float64)
-        self.T_lo, self.T_hi = be.empty(pl, torch.float64), be.empty(pl, torch.float64)
-        nl = self.nx * self.ny
-        self.iface_dyn, self.iface_stat = be.empty((2, nl), torch.float64), be.empty((4, nl), torch.float64)
-        self.dyn_all, self.stat_all = be.empty((self.world, 2, nl), torch.float64), be.empty((self.world, 4, nl), torch.float64)
         self.mask_version = 0
         self._stat_key = None   # (dt, theta, kappa, packs, mask version) the gathered matrix part belongs to
         # steady stepping: after `spike_after` steps with the same key the z sweep switches to the solve-first
@@ -331,7 +364,32 @@ class SlabGrid3D:
         self.spike_after, self.spike_kmax, self.spike_threshold = 2, 32, 2.0 ** -80
         self._spikes, self._stat_uses = None, 0
         be.bind(self.nx, self.ny, self.nz, self.dx, self.mask, self.rank, self.world)
+        # NCCL ranks (one process per GPU): the whole step is sequenced inside the library (csrc/adi_dist.cu: its own
+        # communicator and communication stream, batched / overlapped z solve).  LocalComm (virtual ranks on one
+        # device) and the CPU test backend keep the sequencing below, which is the same algorithm call by call.
+        if (USE_LIBRARY_SEQUENCING and backend is None and isinstance(comm, TorchDistComm) and self.world > 1
+                and comm.dist.get_backend(comm.group) == "nccl"):
+            be.dist_init(comm)
+        else:
+            pl = (self.nx, self.ny)
+            self._m_lo, self._m_hi = be.empty(pl, torch.bool), be.empty(pl, torch.bool)      # to send
+            self.mask_lo, self.mask_hi = be.empty(pl, torch.bool), be.empty(pl, torch.bool)  # received
+            self._t_lo, self._t_hi = be.empty(pl, torch.float64), be.empty(pl, torch.float64)
+            self.T_lo, self.T_hi = be.empty(pl, torch.float64), be.empty(pl, torch.float64)
+            nl = self.nx * self.ny
+            self.iface_dyn, self.iface_stat = be.empty((2, nl), torch.float64), be.empty((4, nl), torch.float64)
+            self.dyn_all = be.empty((self.world, 2, nl), torch.float64)
+            self.stat_all = be.empty((self.world, 4, nl), torch.float64)
         self.sync_mask()
+
+    def z_form(self):
+        """'solve-first' / 'two-pass' / 'single GPU': the form the last steps' z sweep took."""
+        if self.world == 1:
+            return "single GPU"
+        if getattr(self.be, "dist", False):
+            i = self.be.dist_info()
+            return "solve-first" if i["steps_solve_first"] > 0 else "two-pass"
+        return "solve-first" if self._spikes else "two-pass"
 
     def sync_mask(self):
         """Call after the local mask changed (layer births): refreshes the adjacent ranks' view of
@@ -339,6 +397,10 @@ class SlabGrid3D:
         be = self.be
         self.mask_version += 1
         be.mark_mask_changed(self.mask)
+        if getattr(be, "dist", False):
+            be.slab_sync_mask()
+            self._mask_synced = (self.mask.data_ptr(), self.mask._version)
+            return
         be.pack_planes(self.mask, self._m_lo, self._m_hi)
         self.comm.exchange_planes(self._m_lo, self._m_hi, self.mask_lo, self.mask_hi)
         be.set_mask_halo(self.mask_lo if self.rank > 0 else None,
@@ -412,6 +474,13 @@ def adi_step_gpu_coeff(Tn, grid, mat, params, packs, Tinf=0.0, out=None):
     be.set_packs(packs.packs, packs.face_coeff)
     if grid.world == 1 and hasattr(be, "step_plain"):   # a single slab is the plain step
         be.step_plain(T, out, dt, theta, kappa, float(Tinf))
+        return out
+    if getattr(be, "dist", False):   # sequenced inside the library (adi_cart_slab_step)
+        mk = (grid.mask.data_ptr(), grid.mask._version)
+        if mk != grid._mask_synced:
+            raise RuntimeError("slab.adi_step_gpu_coeff: grid.mask was edited (or rebound) without sync_mask(); the adjacent "
+                               "ranks' view of it and the neighbour code are stale")
+        be.slab_step(T, out, dt, theta, kappa, float(Tinf))
         return out
     lo_ok, hi_ok = grid.rank > 0, grid.rank + 1 < grid.world
     if theta != 1.0:   # the explicit stage is the only consumer of the T halo (beta = 0 at theta = 1)

@@ -794,7 +794,7 @@ def bench_slab(args, rank, world, local, c5=False, sub=False):
         return None
     peak, peak_src = peaks()
     per = [ms3[i] / max(1, nst) for i in range(4)]
-    solve_first = bool(getattr(grid, "_spikes", None))
+    solve_first = grid.z_form() == "solve-first"
     names = ["k_explicit", "k_sweep_xy<x>", "k_sweep_xy<y>",
              "k_sweep_z solve-first + all-gather + k_spike_apply" if solve_first
              else ("k_sweep_z" if world == 1 else "k_sweep_z pass1 + all-gather + pass2")]
@@ -900,7 +900,9 @@ def slab_parity(rank, world, local):
     comm = slab.TorchDistComm()
     nx = ny = 256
     nz = 128
-    out = {"grid": [nx, ny, nz], "tol_per_step": 1e-12, "steps": 3}
+    out = {"grid": [nx, ny, nz], "tol_per_step": 1e-12, "steps": 4,
+           "sequencing": "adi_cart_slab_step (inside the library, own NCCL communicator)" if slab.USE_LIBRARY_SEQUENCING
+           else "adi_thermal_fields_b200/slab.py (torch.distributed collectives)"}
     ext = slab.split_z(nz, world, multiple=16)
     z0, z1 = ext[rank]
     for name in ("c5_scalar_full", "plate_dense"):
@@ -924,7 +926,7 @@ def slab_parity(rank, world, local):
         for _ in range(out["steps"]):
             T = slab.adi_step_gpu_coeff(T, grid, _Mat, _Prm, packs, Tinf=TINF)
         parts = [None] * world
-        dist.all_gather_object(parts, (z0, z1, T.cpu().numpy(), bool(getattr(grid, "_spikes", None))))
+        dist.all_gather_object(parts, (z0, z1, T.cpu().numpy(), grid.z_form() == "solve-first"))
         if rank == 0:
             full = np.empty((nx, ny, nz))
             for a, b, t, _ in parts:

@@ -177,6 +177,37 @@ long adi_launch_count(adi_ctx *ctx);
 int adi_profile_reset(adi_ctx *ctx);
 int adi_profile_read(adi_ctx *ctx, double ms[4], long *nsteps);
 
+/* ---- multi-GPU: the z-slab step sequenced inside the library over NCCL (SURVEY 8b "adi_dist_init", 8e) ----
+ * The reference is single-process; this is the multi-GPU form of adi_step_gpu_coeff (adi3d_gpu_coeff.py:213-230): one
+ * process per GPU, rank r of R holds the z planes [z0_r, z1_r) of every array and binds its LOCAL grid
+ * (adi_cart_bind with the local nz, a multiple of 16; 32 for local nz > 1024), mask and packs as on a single GPU.
+ * NCCL is bound at run time (dlopen libnccl.so.2); nothing here is needed on a single GPU.
+ *   adi_dist_unique_id   rank 0: a fresh 128-byte communicator id (ncclGetUniqueId); the host carries it to the
+ *                        other ranks by its own means (MPI, a file, torch.distributed ...)
+ *   adi_dist_init        every rank: joins the communicator (ncclCommInitRank); collective
+ *   adi_dist_init_comm   alternative: adopt an ncclComm_t the host already owns (not destroyed by the library)
+ *   adi_dist_set_option  "batches" (line batches of the overlapped z solve, default 4), "spike_after" (steps with
+ *                        unchanged operands before the solve-first z form replaces the two-pass form, default 2;
+ *                        < 0 never), "spike_kmax" (reach of the ghost corrections in cells, default 32)
+ *   adi_dist_info        rank / size and how many steps ran in either z form */
+int adi_dist_unique_id(void *id128);
+int adi_dist_init(adi_ctx *ctx, const void *id128, int rank, int nranks);
+int adi_dist_init_comm(adi_ctx *ctx, void *nccl_comm, int rank, int nranks);
+int adi_dist_comm(adi_ctx *ctx, void **nccl_comm);   /* the ncclComm_t in use (e.g. to share it with a second context) */
+int adi_dist_destroy(adi_ctx *ctx);
+int adi_dist_set_option(adi_ctx *ctx, const char *name, long value);
+int adi_dist_info(adi_ctx *ctx, int *rank, int *nranks, long *steps_two_pass, long *steps_solve_first);
+/* Collective, after adi_cart_set_mask and whenever the mask changes (layer births, waam_from_stl_v7_mm.py:487-495):
+ * the adjacent ranks' boundary mask planes are exchanged, so that faces on a slab boundary couple / are exposed
+ * exactly as in the undivided grid (adi_cart_set_slab + adi_cart_set_mask_halo are applied inside). */
+int adi_cart_slab_sync_mask(adi_ctx *ctx, void *stream);
+/* Collective: one theta-step on the local slab.  Per step the ranks exchange one T plane per side (explicit stage,
+ * adi3d_numba_coeff.py:274-288) and all-gather two doubles per z line and rank (partitioned z solve, :205-237), on
+ * the library's own communication stream; the z solve runs in line batches so that the gather of one batch overlaps
+ * the solve of the next.  Results equal adi_cart_step on the undivided grid to rounding. */
+int adi_cart_slab_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, double theta, double kappa,
+                       double Tinf, void *stream);
+
 /* ---- voxel_bc_correction (producer of the per-face dense Robin fields) ------------------
  * STLBoundaryCorrector.compute_voxel_projected_areas  voxel_bc_correction.py:53-108: triangles
  * (d_tri[ntri][3][3]), unit normals (d_nrm[ntri][3]) and areas (d_area[ntri]) of the surface mesh are

@@ -20,6 +20,8 @@ import cases  # noqa: E402
 from adi_thermal_fields_b200 import slab  # noqa: E402
 from slab_cases import make_problem, oracle_steps, rank_run  # noqa: E402
 
+if "--python-seq" in sys.argv:    # the call-by-call sequencing of slab.py instead of adi_cart_slab_step
+    slab.USE_LIBRARY_SEQUENCING = False
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -40,7 +42,7 @@ for shape, mk, bk, theta, cfl, nsteps in [((24, 20, 16 * world * 2), "cyl_holes"
         void = bool(np.array_equal(out[~pb["mask"]], pb["T0"][~pb["mask"]], equal_nan=True))
         good = err <= 1e-12 * nsteps and void
         ok &= good
-        print(f"[dist_check] world={world} shape={shape} {mk}/{bk} theta={theta}: rel_l2={err:.2e} "
+        print(f"[dist_check] world={world} seq={'library' if slab.USE_LIBRARY_SEQUENCING else 'python'} shape={shape} {mk}/{bk} theta={theta}: rel_l2={err:.2e} "
               f"void_bit_equal={void} launches/rank={parts[0][3]} {'OK' if good else 'FAIL'}", flush=True)
 # cylindrical path: z-slab decomposition against the oracle on the undivided grid
 from adi_thermal_fields_b200 import adi3d_cyl_phi_v3 as gc  # noqa: E402

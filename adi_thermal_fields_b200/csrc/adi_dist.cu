@@ -119,6 +119,7 @@ struct DistState {
     int *Kv = nullptr, *Kw = nullptr;
     // options
     int nbatch = 4, spike_after = 2, spike_kmax = 32;
+    long batch_min = 4096;    // lines: smaller batches are not worth a collective of their own
     double spike_thr = 0x1p-80;
     long steps_two_pass = 0, steps_solve_first = 0;
 };
@@ -293,6 +294,7 @@ int adi_dist_set_option(adi_ctx *ctx, const char *name, long value)
     if (!ctx || !ctx->dist || !name) { set_error("adi_dist_set_option: adi_dist_init has not been called"); return ADI_ESTATE; }
     DistState *d = ctx->dist;
     if (!strcmp(name, "batches")) d->nbatch = (int)std::min<long>(std::max<long>(value, 1), MAX_BATCH);
+    else if (!strcmp(name, "batch_min_lines")) d->batch_min = std::max<long>(value, 32);
     else if (!strcmp(name, "spike_after")) d->spike_after = (int)value;       // < 0: never leave the two-pass form
     else if (!strcmp(name, "spike_kmax")) { d->spike_kmax = (int)std::max<long>(value, 1); d->spike_state = 0; }
     else { set_error(std::string("adi_dist_set_option: unknown option ") + name); return ADI_EINVAL; }
@@ -389,7 +391,7 @@ int adi_cart_slab_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double
         if ((rc = cart_ensure_ghost(ctx, nl, st))) return rc;
         int nb = std::max(1, std::min(d->nbatch, MAX_BATCH));
         size_t per = ((nl + nb - 1) / nb + 31) & ~(size_t)31;
-        if (per < 4096) per = std::min<size_t>(nl, 4096);    // tiny grids: not worth splitting
+        if (per < (size_t)d->batch_min) per = std::min<size_t>(nl, (size_t)d->batch_min);    // tiny grids: not worth splitting
         nb = (int)((nl + per - 1) / per);
         for (int b = 0; b < nb; ++b) {
             const size_t l0 = (size_t)b * per, n = std::min(per, nl - l0);

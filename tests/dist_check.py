@@ -26,11 +26,15 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for shape, mk, bk, theta, cfl, nsteps in [((24, 20, 16 * world * 2), "cyl_holes", "combined", 0.5, 2.0, 3),
-                                           ((16, 40, 64 * world), "random", "robin_dict3d", 0.5, 3000.0, 2),
-                                           ((32, 16, 16 * world), "plate_track", "robin6", 1.0, 0.128, 2)]:
+for shape, mk, bk, theta, cfl, nsteps, opts in [
+        ((24, 20, 16 * world * 2), "cyl_holes", "combined", 0.5, 2.0, 3, None),
+        ((16, 40, 64 * world), "random", "robin_dict3d", 0.5, 3000.0, 2, None),
+        ((32, 16, 16 * world), "plate_track", "robin6", 1.0, 0.128, 2, None),
+        # steady stepping: the solve-first z form, its all-gathers in three overlapped line batches
+        ((40, 37, 32 * world), "cyl_holes", "robin_dict3d", 0.5, 0.128, 6, dict(batches=3, batch_min_lines=64)),
+        ((48, 48, 16 * world), "full", "robin6", 0.5, 0.3, 5, dict(batches=4, batch_min_lines=32))]:
     pb = make_problem(shape, mk, bk, theta, cfl)
-    z0, z1, t, nl = rank_run(slab.TorchDistComm(), pb, nsteps, None)
+    z0, z1, t, nl = rank_run(slab.TorchDistComm(), pb, nsteps, None, opts)
     parts = [None] * world
     dist.all_gather_object(parts, (z0, z1, t, nl))
     if rank == 0:

@@ -43,13 +43,16 @@ class Mat:
     rho, cp, k = cases.RHO, cases.CP, cases.K
 
 
-def rank_run(comm, pb, nsteps, backend):
+def rank_run(comm, pb, nsteps, backend, options=None):
     """What one rank does: the calls a user of the reference API would make, on its slab."""
     class Prm:
         dt, theta = pb["dt"], pb["theta"]
     nx, ny, nz = pb["shape"]
     z0, z1 = slab.split_z(nz, comm.world)[comm.rank]
     grid = slab.SlabGrid3D(nx, ny, z1 - z0, cases.DX, pb["mask"][:, :, z0:z1], comm, backend=backend)
+    for k, v in (options or {}).items():
+        if getattr(grid.be, "dist", False) or k not in ("batches", "batch_min_lines", "spike_after", "spike_kmax"):
+            grid.be.set_option(k, v)
     packs = slab.precompute_coeff_packs_unified(grid, Mat, **slice_bcs(pb["bcs"], z0, z1))
     T = grid.be.asarray(pb["T0"][:, :, z0:z1], torch.float64)
     n0 = grid.be.launch_count()

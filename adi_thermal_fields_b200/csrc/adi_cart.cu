@@ -512,7 +512,7 @@ int adi_cart_zsweep_apply(adi_ctx *ctx, double *d_T, const double *d_dyn_all, co
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
     const int ablocks = (int)std::min<size_t>((nlines * 8 + 255) / 256, 148 * 32);
-    k_spike_apply<<<ablocks, 256, 0, st>>>(d_T, ctx->d_ghost, d_vC, d_wC, d_Kv, d_Kw, nlines, ctx->nz, kmax);
+    k_spike_apply<false><<<ablocks, 256, 0, st>>>(d_T, ctx->d_ghost, d_vC, d_wC, d_Kv, d_Kw, nlines, ctx->nz, kmax);
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
     return prof_mark(ctx, 4, st);
@@ -657,15 +657,10 @@ int cart_zapply_range(adi_ctx *ctx, double *d_T, const double *d_dyn_all, const 
                       cudaStream_t st)
 {
     const size_t nl = (size_t)ctx->nx * ctx->ny;
-    double *ghost = ctx->d_ghost + 2 * line0;
-    const int threads = 128;
-    const int blocks = (int)std::min<size_t>((nlb + threads - 1) / threads, 148 * 32);
-    k_iface_solve<<<blocks, threads, 0, st>>>(d_dyn_all, d_stat_all + line0, nl, ghost, nlb, ctx->slab_nranks, ctx->slab_rank);
-    ctx->launches++;
-    ADI_CUDA(cudaGetLastError());
     const int ablocks = (int)std::min<size_t>((nlb * 8 + 255) / 256, 148 * 32);
-    k_spike_apply<<<ablocks, 256, 0, st>>>(d_T + line0 * (size_t)ctx->nz, ghost, d_vC + line0 * (size_t)kmax,
-                                           d_wC + line0 * (size_t)kmax, d_Kv + line0, d_Kw + line0, nlb, ctx->nz, kmax);
+    k_spike_apply<true><<<ablocks, 256, 0, st>>>(d_T + line0 * (size_t)ctx->nz, nullptr, d_vC + line0 * (size_t)kmax,
+                                                 d_wC + line0 * (size_t)kmax, d_Kv + line0, d_Kw + line0, nlb, ctx->nz, kmax,
+                                                 d_dyn_all, d_stat_all + line0, nl, ctx->slab_nranks, ctx->slab_rank);
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
     return ADI_OK;

@@ -1070,14 +1070,38 @@ __global__ void k_spike_pack(const double *__restrict__ field, size_t nlines, in
 
 // x = y + L*v + R*w on the cells within reach of the two ends of every local line segment (8 lanes per line).
 // Cells where the response is exactly 0 (void cells, cells behind a void gap) are not touched.
+// FUSED: the line's two ghosts (L, R) are not read from `ghost` but solved here from the gathered interface
+// relations (iface_solve by the first lane of the line's eight, shuffled to the others): one launch and one
+// round trip through memory less per batch of the overlapped multi-GPU z solve.
+template <bool FUSED>
 __global__ void k_spike_apply(double *__restrict__ T, const double *__restrict__ ghost, const double *__restrict__ vC,
                               const double *__restrict__ wC, const int *__restrict__ Kv, const int *__restrict__ Kw,
-                              size_t nlines, int nz, int kmax)
+                              size_t nlines, int nz, int kmax, const double *__restrict__ dyn = nullptr,
+                              const double *__restrict__ stat = nullptr, size_t sstride = 0, int nranks = 1, int rank = 0)
 {
     const int sub = threadIdx.x & 7;
-    for (size_t l = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; l < nlines;
-         l += ((size_t)gridDim.x * blockDim.x) >> 3) {
-        const double L = ghost[l], R = ghost[nlines + l];
+    const size_t step = ((size_t)gridDim.x * blockDim.x) >> 3;
+    const size_t lmax = (nlines + step - 1) / step * step;   // whole groups of eight stay together (shuffles below)
+    for (size_t l = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; l < lmax; l += step) {
+        const bool ok = l < nlines;
+        double L = 0.0, R = 0.0;
+        if (FUSED) {
+            if (ok && sub == 0) {
+                iface_solve([&](int r) {
+                    const double *d = dyn + (size_t)r * 2 * nlines + l;
+                    const double *q = stat + (size_t)r * 4 * sstride + l;
+                    Iface v;
+                    v.yf = d[0]; v.yl = d[nlines];
+                    v.vf = q[0]; v.wf = q[sstride]; v.vl = q[2 * sstride]; v.wl = q[3 * sstride];
+                    return v;
+                }, nranks, rank, &L, &R);
+            }
+            L = __shfl_sync(0xffffffffu, L, 0, 8);
+            R = __shfl_sync(0xffffffffu, R, 0, 8);
+        } else if (ok) {
+            L = ghost[l]; R = ghost[nlines + l];
+        }
+        if (!ok) continue;
         const int kv = Kv[l], kw = Kw[l];
         double *t = T + l * (size_t)nz;
         const double *v = vC + l * (size_t)kmax, *w = wC + l * (size_t)kmax;

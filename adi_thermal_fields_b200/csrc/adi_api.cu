@@ -180,6 +180,10 @@ int adi_ctx_destroy(adi_ctx *ctx)
         if (ctx->code_buf[a]) cudaFree(ctx->code_buf[a]);
     for (int a = 0; a < 2; ++a)
         if (ctx->codeT[a]) cudaFree(ctx->codeT[a]);
+    for (int a = 0; a < 3; ++a)
+        if (ctx->tiles[a].d) cudaFree(ctx->tiles[a].d);
+    if (ctx->d_tflags) cudaFree(ctx->d_tflags);
+    if (ctx->h_tflags) cudaFreeHost(ctx->h_tflags);
     for (int a = 0; a < 2; ++a)
         if (ctx->stage[a]) cudaFree(ctx->stage[a]);
     if (ctx->d_ghost) cudaFree(ctx->d_ghost);
@@ -264,6 +268,10 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
         ctx->opt_zt = value;
         ctx->sparse_dirty = true;
     }
+    else if (!strcmp(name, "tiles")) {  // 1 (default): sweeps launch only the tiles that hold an active cell
+        ctx->opt_tiles = value;
+        for (int a = 0; a < 3; ++a) ctx->tiles[a].valid = false;
+    }
     else if (!strcmp(name, "bulk")) ctx->opt_bulk = value;  // 1 (default): z sweep tiles as bulk asynchronous copies
     else if (!strcmp(name, "occ")) ctx->opt_occ = value;    // x / y sweeps, 16-cell chunks: resident blocks per SM (2, 3, 4)
     else if (!strcmp(name, "remap")) ctx->opt_remap = value;  // 1: both ends of a line in one warp (measured slower)
@@ -293,6 +301,9 @@ long adi_get_option(adi_ctx *ctx, const char *name)
     if (!strcmp(name, "occ")) return ctx->opt_occ;
     if (!strcmp(name, "zt")) return ctx->opt_zt;
     if (!strcmp(name, "bulk")) return ctx->opt_bulk;
+    if (!strcmp(name, "tiles")) return ctx->opt_tiles;
+    if (!strcmp(name, "tiles_active")) return ctx->tiles[0].n + ctx->tiles[1].n + ctx->tiles[2].n;
+    if (!strcmp(name, "tiles_total")) return ctx->tiles[0].total + ctx->tiles[1].total + ctx->tiles[2].total;
     if (!strcmp(name, "dbg")) return ctx->opt_dbg;
     if (!strcmp(name, "sparse_coeff")) return ctx->opt_sparse;
     if (!strcmp(name, "sparse_active"))  // bit a: the sweep along axis a currently skips interior coefficient reads

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <vector>
 
 #define ADI_CART_MISC_KERNELS
 #include "adi_cart.cuh"
@@ -79,6 +80,7 @@ int ensure_code(adi_ctx *ctx, cudaStream_t st)
     }
     ctx->code_dirty = false;
     ctx->sparse_dirty = true;
+    for (int a = 0; a < 3; ++a) ctx->tiles[a].valid = false;
     return ADI_OK;
 }
 
@@ -125,6 +127,60 @@ int ensure_sparse(adi_ctx *ctx, cudaStream_t st)
 }
 
 }  // namespace
+
+// Active-tile list of a sweep axis for tiles of KT rows (see k_tile_flags): flags on the device, compaction on the
+// host (one small read-back per mask change), ascending order so that neighbouring blocks keep touching
+// neighbouring memory.
+int adi::ensure_tiles(adi_ctx *ctx, int axis, int KT, cudaStream_t st, const int **list, int *nactive, int *tiles_nx)
+{
+    *list = nullptr; *nactive = 0; *tiles_nx = 0;
+    if (!ctx->opt_tiles || KT < 1) return ADI_OK;
+    const uint8_t *base;
+    size_t unit;
+    int inner, outer;
+    if (axis == 2) {
+        base = ctx->code[2]; unit = (size_t)ctx->nz; inner = (int)std::min<size_t>((size_t)ctx->nx * ctx->ny, 0x7fffffff); outer = 1;
+        if ((size_t)ctx->nx * ctx->ny > 0x7fffffffull) return ADI_OK;
+    } else {
+        if (!ctx->codeT[axis] || ctx->npadT[axis] <= 0) return ADI_OK;
+        base = ctx->codeT[axis]; unit = (size_t)ctx->npadT[axis]; inner = ctx->nz; outer = axis == 0 ? ctx->ny : ctx->nx;
+    }
+    const int nti = (inner + KT - 1) / KT;
+    const long long total = (long long)nti * outer;
+    if (total < 1 || total > 0x7fffffffll) return ADI_OK;
+    TileList &L = ctx->tiles[axis];
+    if (!(L.valid && L.kt == KT && L.total == (int)total)) {
+        const size_t n = (size_t)total;
+        if (ctx->tflags_cap < n) {
+            if (ctx->d_tflags) { ADI_CUDA(cudaFree(ctx->d_tflags)); ADI_CUDA(cudaFreeHost(ctx->h_tflags)); }
+            ctx->d_tflags = nullptr; ctx->h_tflags = nullptr;
+            ADI_CUDA(cudaMalloc(&ctx->d_tflags, n));
+            ADI_CUDA(cudaMallocHost(&ctx->h_tflags, n));
+            ctx->tflags_cap = n;
+        }
+        k_tile_flags<<<(unsigned)std::min<size_t>(n, 148 * 64), 128, 0, st>>>(base, unit, KT, inner, (int)total, ctx->d_tflags);
+        ctx->launches++;
+        ADI_CUDA(cudaGetLastError());
+        ADI_CUDA(cudaMemcpyAsync(ctx->h_tflags, ctx->d_tflags, n, cudaMemcpyDeviceToHost, st));
+        ADI_CUDA(cudaStreamSynchronize(st));
+        std::vector<int> ids;
+        ids.reserve(n);
+        for (size_t t = 0; t < n; ++t)
+            if (ctx->h_tflags[t]) ids.push_back((int)t);
+        if (L.cap < std::max<size_t>(ids.size(), 1)) {
+            if (L.d) ADI_CUDA(cudaFree(L.d));
+            L.d = nullptr;
+            L.cap = std::max<size_t>(n, 1);
+            ADI_CUDA(cudaMalloc(&L.d, L.cap * sizeof(int)));
+        }
+        if (!ids.empty()) ADI_CUDA(cudaMemcpyAsync(L.d, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        ADI_CUDA(cudaStreamSynchronize(st));   // `ids` leaves scope
+        L.n = (int)ids.size(); L.total = (int)total; L.kt = KT; L.valid = true;
+    }
+    *tiles_nx = nti;
+    if (L.n < L.total) { *list = L.d; *nactive = L.n; }
+    return ADI_OK;
+}
 
 // adi_sweep_x.cu / adi_sweep_y.cu / adi_sweep_z.cu (one translation unit per sweep so that the
 // template instantiations compile in parallel)
@@ -246,6 +302,9 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
     a.k.beta = dt * kappa * (1.0 - theta);
     a.k.invdx2 = 1.0 / (dx * dx);
     a.zlo = d_Tlo; a.zhi = d_Thi; a.iface_dyn = d_iface_dyn; a.iface_stat = d_iface_stat; a.ghost = d_ghost;
+    a.codeT = nullptr; a.npad = 0; a.uni = 0; a.tw = 0; a.remap = 0; a.dbg = 0;
+    a.tiles = nullptr; a.tiles_nx = 0;
+    a.line_batch = nlb != 0 ? 1 : 0;
     bool expl = a.k.beta != 0.0;
     bool x_in_place = false;
     if (expl && first == 0 && !ctx->opt_fuse) {
@@ -293,6 +352,7 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
             if (b.q) b.q += off;
             if (b.dirv) b.dirv += off;
             b.nx = 1; b.ny = (int)nlb;
+            b.line_batch = 1;
             rc = launch_sweep_z(ctx, b, dense, extra, zmode == 5 ? 2 : zmode, st);
         }
         if (rc) return rc;

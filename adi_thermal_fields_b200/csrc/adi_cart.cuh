@@ -45,6 +45,11 @@ struct SweepArgs {
     int tw;                            // reduced system by warps (transposed exchange)
     int remap;                         // chunk order inside a block: ends of the line in the same warp
     int dbg;                           // tuning aid: 1 = loads and stores only
+    // active-tile list (parts under construction: most of the box is void): block b works on tile tiles[b] =
+    // by * tiles_nx + bx instead of (blockIdx.x, blockIdx.y); NULL = every tile, addressed by blockIdx
+    const int *__restrict__ tiles;
+    int tiles_nx;
+    int line_batch;                    // z sweep of a batch of lines (multi-GPU): the pointers are offset, no tile list
     UniConst uc;
 };
 
@@ -102,6 +107,34 @@ __global__ void __launch_bounds__(256) k_transpose_code(const uint8_t *__restric
             if (c < nz && r < n) dst[((size_t)b * nz + c) * npad + r] = tile[tx][ty + 8 * i];
         }
         __syncthreads();
+    }
+}
+
+// K0f: which sweep tiles hold an active cell?  The rows of `base` (unit bytes each, contiguous) are grouped into
+// tiles of KT consecutive rows inside runs of `inner` rows (x / y sweeps: rows = (other index, z), runs = one `other`
+// index, base = the transposed code array; z sweep: rows = z lines, one run).  flags[t] = 1 when any byte of tile
+// t = by * ceil(inner / KT) + bx is non-zero.  One block per tile.
+__global__ void __launch_bounds__(128) k_tile_flags(const uint8_t *__restrict__ base, size_t unit, int KT, int inner,
+                                                    int ntiles, uint8_t *__restrict__ flags)
+{
+    const int nti = (inner + KT - 1) / KT;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int by = t / nti, bx = t - by * nti;
+        const size_t row0 = (size_t)by * inner + (size_t)bx * KT;
+        const size_t len = (size_t)min(KT, inner - bx * KT) * unit;
+        const uint8_t *p = base + row0 * unit;
+        bool any = false;
+        if ((((uintptr_t)p | len) & 15) == 0) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(p);
+            for (size_t i = threadIdx.x; i < len / 16 && !any; i += blockDim.x) {
+                const uint4 v = q[i];
+                any = (v.x | v.y | v.z | v.w) != 0u;
+            }
+        } else {
+            for (size_t i = threadIdx.x; i < len && !any; i += blockDim.x) any = p[i] != 0;
+        }
+        any = __syncthreads_or(any);
+        if (threadIdx.x == 0) flags[t] = any ? 1 : 0;
     }
 }
 

@@ -26,6 +26,17 @@ struct Pack {
     const double *q = nullptr;
 };
 
+// Active-tile list of one sweep axis (adi_cart.cu ensure_tiles): built lazily for the tile height the launcher
+// uses, dropped whenever the neighbour code is rebuilt.
+struct TileList {
+    int *d = nullptr;        // device: ids of the tiles with an active cell, ascending
+    size_t cap = 0;
+    int n = 0, total = 0, kt = 0;
+    bool valid = false;
+};
+// -> *list = device list (NULL when every tile is active or the option is off), *nactive = tiles to launch
+int ensure_tiles(adi_ctx *ctx, int axis, int KT, cudaStream_t st, const int **list, int *nactive, int *tiles_nx);
+
 struct CylTables;  // adi_cyl.cu
 struct DistState;  // adi_dist.cu: NCCL communicator, exchange buffers and caches of the in-library z-slab step
 void dist_release(adi_ctx *ctx);
@@ -52,7 +63,7 @@ struct adi_ctx {
     long launches = 0;
     // options (adi_set_option)
     long opt_kt = 0, opt_lt = 0, opt_m = 0, opt_sync_check = 0, opt_profile = 0, opt_fuse = 0, opt_wide = 0, opt_sparse = 1,
-         opt_xy2 = 1, opt_uni = 1, opt_tw = 0, opt_remap = 0, opt_dbg = 0, opt_occ = 0, opt_zt = 1, opt_bulk = 1;
+         opt_xy2 = 1, opt_uni = 1, opt_tw = 0, opt_remap = 0, opt_dbg = 0, opt_occ = 0, opt_zt = 1, opt_bulk = 1, opt_tiles = 1;
     // per-kernel timing (adi_profile_*): 5 events per step, read lazily
     std::vector<cudaEvent_t> prof_ev;
     long prof_steps = 0;
@@ -69,6 +80,9 @@ struct adi_ctx {
     uint8_t *code_buf[3] = {nullptr, nullptr, nullptr};
     size_t code_cells = 0;
     bool code_dirty = true;
+    adi::TileList tiles[3];
+    uint8_t *d_tflags = nullptr, *h_tflags = nullptr;
+    size_t tflags_cap = 0;
     // transposed copies for the x / y sweeps (line axis fastest, padded to npadT[a]); option xy2
     uint8_t *codeT[2] = {nullptr, nullptr};
     size_t codeT_bytes[2] = {0, 0};

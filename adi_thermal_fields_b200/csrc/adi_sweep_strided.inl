@@ -53,6 +53,18 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
             return ADI_EINVAL;
         }
         dim3 block(KT, P), grid((a.nz + KT - 1) / KT, other);
+        if (a.in == a.out) {
+            // in place, nothing to do for void tiles: launch only the tiles that hold an active cell
+            const int *list = nullptr;
+            int nact = 0, tnx = 0;
+            int rc = ensure_tiles(ctx, AXIS, KT, st, &list, &nact, &tnx);
+            if (rc) return rc;
+            if (list) {
+                if (nact == 0) return ADI_OK;
+                b.tiles = list; b.tiles_nx = tnx;
+                grid = dim3((unsigned)nact, 1);
+            }
+        }
 #define ADI_GO2(M_, NS_, PR_, MAXT, MINB)                                                                            \
         {                                                                                                        \
             if (dense) {                                                                                         \

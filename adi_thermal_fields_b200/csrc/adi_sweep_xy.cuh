@@ -181,7 +181,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_xy(const SweepArgs a)
     const int p = a.remap ? ((threadIdx.y & 1) ? P - 1 - (int)(threadIdx.y >> 1) : (int)(threadIdx.y >> 1)) : (int)threadIdx.y;
     const int NTH = KT * P;
     const int tid = threadIdx.y * KT + kk;
-    const int k = blockIdx.x * KT + kk;
+    unsigned bx = blockIdx.x, by = blockIdx.y;
+    if (a.tiles) {   // active-tile list: the block's tile comes from the list
+        const unsigned t = (unsigned)a.tiles[blockIdx.x];
+        by = t / (unsigned)a.tiles_nx; bx = t - by * (unsigned)a.tiles_nx;
+    }
+    const int k = bx * KT + kk;
     const int n = (AXIS == 0) ? a.nx : a.ny;
     const unsigned sl = (AXIS == 0) ? (unsigned)a.ny * (unsigned)a.nz : (unsigned)a.nz;
     constexpr unsigned LO = (AXIS == 0) ? CB_XM : CB_YM;
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_xy(const SweepArgs a)
     const bool lane_ok = k < a.nz;
     const int nv = lane_ok ? min(n - t0, M) : 0;
     const int kc = min(k, a.nz - 1);
-    const size_t idx0 = ((AXIS == 0) ? (size_t)blockIdx.y * a.nz : (size_t)blockIdx.y * a.ny * a.nz) +
+    const size_t idx0 = ((AXIS == 0) ? (size_t)by * a.nz : (size_t)by * a.ny * a.nz) +
                         (size_t)kc + (size_t)t0 * sl;
     double *col = smem + tid;
     double *xch = smem + (size_t)NS * M * NTH;              // behind the factor slots
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_xy(const SweepArgs a)
     const unsigned sl8 = sl * 8u;
     const char *tb = reinterpret_cast<const char *>(tp);
     {
-        const uint8_t *cb = a.codeT + ((size_t)blockIdx.y * a.nz + kc) * (size_t)a.npad + t0;
+        const uint8_t *cb = a.codeT + ((size_t)by * a.nz + kc) * (size_t)a.npad + t0;
 #pragma unroll
         for (int w = 0; w < M / 16; ++w) {
             const uint4 v = ldg_u128(cb + 16 * w);

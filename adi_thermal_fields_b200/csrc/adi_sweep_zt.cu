@@ -15,6 +15,18 @@ static int launch_zt_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, bool ext
     uni_const_build(b.uc, a.k.g);
     const size_t nlines = (size_t)a.nx * a.ny;
     dim3 block(KT, P), grid((unsigned)((nlines + KT - 1) / KT));
+    if (!a.line_batch && (ZMODE == 0 || ZMODE == 2) && a.in == a.out) {
+        // in place, nothing to emit for void lines: launch only the tiles that hold an active cell
+        const int *list = nullptr;
+        int nact = 0, tnx = 0;
+        int rc = ensure_tiles(ctx, 2, KT, st, &list, &nact, &tnx);
+        if (rc) return rc;
+        if (list) {
+            if (nact == 0) return ADI_OK;
+            b.tiles = list; b.tiles_nx = tnx;
+            grid = dim3((unsigned)nact);
+        }
+    }
     int vec = ((a.nz & 1) == 0 && (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.code) & 15) == 0) ? 1 : 0;
     if (vec && (a.nz & 15) == 0 && a.in == a.out && ctx->opt_bulk) vec = 2;   // whole lines as bulk asynchronous copies
     const bool big = KT * P > 256;

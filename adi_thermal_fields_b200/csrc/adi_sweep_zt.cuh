@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
     const int NTH = KT * P, tid = p * KT + kk;
     const int nz = a.nz;
     const size_t nlines = (size_t)a.nx * a.ny;
-    const size_t L0 = (size_t)blockIdx.x * KT;
+    const size_t L0 = (size_t)(a.tiles ? a.tiles[blockIdx.x] : (int)blockIdx.x) * KT;   // active-tile list, if any
     const int RL = P * M;                 // padded line length
     const int pitch = RL + 2;             // doubles
     const int cpitch = RL + 16;           // bytes

@@ -187,7 +187,7 @@ int adi_profile_read(adi_ctx *ctx, double ms[4], long *nsteps);
  *   adi_dist_init        every rank: joins the communicator (ncclCommInitRank); collective
  *   adi_dist_init_comm   alternative: adopt an ncclComm_t the host already owns (not destroyed by the library)
  *   adi_dist_set_option  "batches" (line batches of the overlapped z solve, default 4; "batch_min_lines": no batch smaller than
- *                        this, default 4096), "spike_after" (steps with
+ *                        this, default 1048576), "spike_after" (steps with
  *                        unchanged operands before the solve-first z form replaces the two-pass form, default 2;
  *                        < 0 never), "spike_kmax" (reach of the ghost corrections in cells, default 32)
  *   adi_dist_info        rank / size and how many steps ran in either z form */

@@ -483,7 +483,7 @@ def _uniform_case(shape, mask_kind, bk, theta, cfl, seed):
 
 @pytest.mark.parametrize("opts", [dict(), dict(uni=0), dict(tw=1), dict(xy2=0), dict(m=16), dict(m=32), dict(kt=4), dict(m=16, kt=2),
                                   dict(m=16, occ=3), dict(m=16, occ=4, tw=1), dict(remap=1), dict(remap=1, tw=1), dict(wide=1),
-                                  dict(m=16, wide=1, tw=1), dict(lt=1), dict(lt=4), dict(sparse_coeff=0), dict(zt=0), dict(zt=0, uni=0), dict(bulk=0), dict(bulk=0, uni=0)],
+                                  dict(m=16, wide=1, tw=1), dict(lt=1), dict(lt=4), dict(sparse_coeff=0), dict(zt=0), dict(zt=0, uni=0), dict(bulk=0), dict(bulk=0, uni=0), dict(tiles=0)],
                          ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
 @pytest.mark.parametrize("shape,mask_kind", [((70, 40, 37), "full"), ((40, 70, 130), "plate_track"), ((96, 50, 64), "cyl_holes"),
                                              ((600, 7, 48), "full"), ((5, 1100, 24), "full"), ((2050, 3, 10), "full"),
@@ -503,3 +503,49 @@ def test_uniform_chunk_paths(shape, mask_kind, opts, g, cp):
     finally:
         for k, v in restore.items():
             g.set_option(k, v)
+
+
+def test_active_tile_lists(g, cp):
+    """A part under construction: most sweep tiles hold no active cell and are not launched at all (option tiles);
+    births move the boundary.  Same answer as the oracle, void cells untouched, and the lists really are short."""
+    from oracle import cart
+    shape = (160, 144, 200)
+    nx, ny, nz = shape
+    ax = [(np.arange(n) + 0.5) / n - 0.5 for n in shape]
+    X, Y, Z = np.meshgrid(*ax, indexing="ij")
+    full = (X / 0.3) ** 2 + (Y / 0.35) ** 2 + (Z / 0.4) ** 2 <= 1.0
+    h = {f: 40.0 * (0.3 + cases.splitmix_uniform(90 + i, shape)) for i, f in enumerate(cart.FACES)}
+    kappa = cases.K / (cases.RHO * cases.CP)
+    dt = 50.0 * cases.DX ** 2 / kappa
+    act = np.zeros(shape, bool)
+    Th = np.full(shape, 20.0)
+    Td = cp.asarray(Th)
+    grid = g.Grid3D(nx, ny, nz, cases.DX, act)
+    mat, hm = g.Material(cases.RHO, cases.CP, cases.K), cart.Material(cases.RHO, cases.CP, cases.K)
+    hd = {f: cp.asarray(v) for f, v in h.items()}
+    for opt in (1, 0):
+        g.set_option("tiles", opt)
+        try:
+            for k0 in (20, 36, 52):
+                born = np.zeros(shape, bool)
+                born[:, :, k0:k0 + 16] = full[:, :, k0:k0 + 16] & ~act[:, :, k0:k0 + 16]
+                act |= born
+                Th[born] = 1000.0
+                Td[cp.asarray(born)] = 1000.0
+                grid.mask = act.copy()
+                pd = g.precompute_coeff_packs_unified(grid, mat, robin_h=hd)
+                hg = cart.Grid3D(nx, ny, nz, cases.DX, act)
+                ph = cart.precompute_coeff_packs_unified(hg, hm, robin_h=h)
+                for _ in range(2):
+                    Th = cart.adi_step_numba_coeff(Th, hg, hm, cart.Params(dt, 0.5), ph, Tinf=20.0)
+                    Td = g.adi_step_gpu_coeff(Td, grid, mat, g.Params(dt, 0.5), pd, Tinf=20.0)
+                out = cp.asnumpy(Td)
+                assert cases.rel_l2(out, Th, act) <= 6 * TOL
+                assert np.array_equal(out[~act], Th[~act])
+                if opt:
+                    assert 0 < g.get_option("tiles_active") < 0.5 * g.get_option("tiles_total")
+        finally:
+            g.set_option("tiles", 1)
+        act[:] = False
+        Th[:] = 20.0
+        Td = cp.asarray(Th)

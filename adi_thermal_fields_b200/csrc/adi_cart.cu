@@ -314,10 +314,13 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
         const bool vec = (a.nz % 2 == 0) && ((((uintptr_t)d_Tin | (uintptr_t)d_Tout) & 15) == 0) &&
                          (((uintptr_t)a.code & 1) == 0);
         const int VEC = vec ? 2 : 1, threads = 128, JT = 16;
-        dim3 grid((unsigned)(((a.nz + VEC - 1) / VEC + threads - 1) / threads), (unsigned)((a.ny + JT - 1) / JT),
-                  (unsigned)a.nx);
-        if (vec) k_explicit<2><<<grid, threads, 0, st>>>(a, JT);
-        else k_explicit<1><<<grid, threads, 0, st>>>(a, JT);
+        // block order (option eorder): 0 = z chunks fastest, x slowest; 1 = x fastest -- the blocks of neighbouring x
+        // planes then run together and find each other's rows (their x-1 / x+1 neighbours) in L2
+        const unsigned gz = (unsigned)(((a.nz + VEC - 1) / VEC + threads - 1) / threads), gy = (unsigned)((a.ny + JT - 1) / JT);
+        const int xfast = (ctx->opt_eorder && gz <= 65535u) ? 1 : 0;
+        dim3 grid = xfast ? dim3((unsigned)a.nx, gy, gz) : dim3(gz, gy, (unsigned)a.nx);
+        if (vec) k_explicit<2><<<grid, threads, 0, st>>>(a, JT, xfast);
+        else k_explicit<1><<<grid, threads, 0, st>>>(a, JT, xfast);
         ctx->launches++;
         ADI_CUDA(cudaGetLastError());
         expl = false;

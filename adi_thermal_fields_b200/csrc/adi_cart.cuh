@@ -976,11 +976,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_z(const SweepArgs a, const
 // grid = (ceil(nz/VEC/blockDim.x), ceil(ny/JT), nx).
 // ------------------------------------------------------------------------------------
 template <int VEC>
-__global__ void __launch_bounds__(128) k_explicit(const SweepArgs a, const int JT)
+__global__ void __launch_bounds__(128) k_explicit(const SweepArgs a, const int JT, const int xfast)
 {
-    const int z = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    const int z = ((xfast ? blockIdx.z : blockIdx.x) * blockDim.x + threadIdx.x) * VEC;
     if (z >= a.nz) return;
-    const int i = blockIdx.z;
+    const int i = xfast ? blockIdx.x : blockIdx.z;
     const int j0 = blockIdx.y * JT, j1 = min(j0 + JT, a.ny);
     const size_t snx = (size_t)a.ny * a.nz;
     size_t idx = ((size_t)i * a.ny + j0) * a.nz + z;
@@ -995,13 +995,21 @@ __global__ void __launch_bounds__(128) k_explicit(const SweepArgs a, const int J
     for (int v = 0; v < VEC; ++v) prev[v] = next[v] = xm[v] = xp[v] = 0.0;
     if (j0 > 0) ldv(idx - a.nz, prev);
     ldv(idx, cur);
+    // the code of a row is fetched one row ahead: rows without an active cell (the space around a part under
+    // construction) are plain copies and skip the loads of their x neighbours
+    auto ldc = [&](size_t g) -> unsigned {
+        if (VEC == 2) return *reinterpret_cast<const unsigned short *>(a.code + g);
+        return a.code[g];
+    };
+    unsigned cw_next = ldc(idx);
     for (int j = j0; j < j1; ++j) {
+        const unsigned cw = cw_next;
         if (j + 1 < a.ny) ldv(idx + a.nz, next);
-        if (i > 0) ldv(idx - snx, xm);
-        if (i + 1 < a.nx) ldv(idx + snx, xp);
-        unsigned cw;
-        if (VEC == 2) cw = *reinterpret_cast<const unsigned short *>(a.code + idx);
-        else cw = a.code[idx];
+        if (j + 1 < j1) cw_next = ldc(idx + a.nz);
+        if (cw != 0u) {
+            if (i > 0) ldv(idx - snx, xm);
+            if (i + 1 < a.nx) ldv(idx + snx, xp);
+        }
         const unsigned c0 = cw & 0xffu, cl = (cw >> (8 * (VEC - 1))) & 0xffu;
         double zlo_v = 0.0, zhi_v = 0.0;
         if (c0 & CB_ZM) zlo_v = z > 0 ? a.in[idx - 1] : a.zlo[(size_t)i * a.ny + j];

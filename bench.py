@@ -1027,12 +1027,25 @@ def bench_c4(args, local, sub=False):
     sampler = ClockSampler(local)
     sampler.start()
     l0 = g.launch_count()
+    from adi_thermal_fields_b200 import _capi
+    Lc, cctx = _capi.load(), g._engine.context()
+    for o in args.opt:
+        name, _, val = o.partition("=")
+        _capi.check(Lc.adi_set_option(cctx, name.encode(), int(val)), "adi_set_option")
+    Lc.adi_set_option(cctx, b"profile", 1)
+    Lc.adi_profile_reset(cctx)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     nsteps, tb, ts = run(mid)
     wall = time.perf_counter() - t0
     launches = g.launch_count() - l0
     clocks = sampler.stop()
+    ms4 = (C.c_double * 4)()
+    nst = C.c_long()
+    Lc.adi_profile_read(cctx, ms4, C.byref(nst))
+    Lc.adi_set_option(cctx, b"profile", 0)
+    kernel_ms = {k: ms4[i] / max(1, nst.value) for i, k in enumerate(("explicit", "x", "y", "z"))}
+    tiles = {"active": int(Lc.adi_get_option(cctx, b"tiles_active")), "total": int(Lc.adi_get_option(cctx, b"tiles_total"))}
     cells = n ** 3
     active_frac = float(act.sum().item()) / cells
     peak, peak_src = peaks()
@@ -1054,7 +1067,8 @@ def bench_c4(args, local, sub=False):
         "roofline": {"bound": "hbm", "kernel": "whole step (explicit + x + y + z), steady state between births",
                      "achieved": 75.0 * cells / (ts / nsteps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": 75.0 * cells / (ts / nsteps * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                     "steady_ms_per_step": ts / nsteps, "birth_ms": tb / len(mid),
+                     "steady_ms_per_step": ts / nsteps, "birth_ms": tb / len(mid), "kernel_ms": kernel_ms,
+                     "sweep_tiles": tiles,
                      "active_cell_steps_per_s": active_frac * cells / (ts / nsteps * 1e-3),
                      "birth_note": "mask update + k_build_packs (6 dense h fields -> 3 coeff fields) + neighbour code rebuild",
                      "note": "achieved/frac restate the metric (all cells of the box, void included, at SURVEY 8(d)'s "

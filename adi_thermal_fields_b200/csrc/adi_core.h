@@ -362,6 +362,124 @@ ADI_HD void chunk_backward_uniform(Chunk<M> &ch, const UniConst &uc, const UniHe
     }
 }
 
+// ---- hybrid chunks ----------------------------------------------------------------------
+// A chunk whose first R4 cells (R4 a multiple of four, 4 <= R4 <= M-4, the same for every lane of the warp) are
+// uniform and whose remaining cells are anything: the chunk that holds the top surface of a part in a z sweep
+// (uniform bulk below the surface, the exposed cell, void above).  The run takes the tabulated factors, the
+// tail the general row assembly; the hand-over carries the run's last elimination state (all tabulated).
+// Storage convention: T[e] = d'_e for e < R4 (as in chunk_forward_uniform), T[e] = d_e and ops.put1(e, 1/den_e)
+// for e >= R4 (as in chunk_forward with NS = 1).  The branch per group of four cells is warp-uniform.
+
+// Number of leading uniform cells of a chunk, rounded down to a multiple of four (0 .. M-4).
+template <int M>
+ADI_HD int chunk_uniform_lead4(const Chunk<M> &ch, unsigned lo, unsigned hi)
+{
+    const unsigned need = (CB_SELF | lo | hi) * 0x01010101u, care = (CB_SELF | lo | hi | CB_DIR) * 0x01010101u;
+    int r = 0;
+    bool run = true;
+#pragma unroll
+    for (int w = 0; w < M / 4 - 1; ++w) {
+        run = run && ((ch.cw[w] & care) == need);
+        r += run ? 4 : 0;
+    }
+    return r;
+}
+
+template <int M, int CMODE, bool EXTRA, class OPS>
+ADI_HD First chunk_forward_hybrid(Chunk<M> &ch, const UniConst &uc, OPS &ops, int R4, unsigned lo, unsigned hi,
+                                  const SweepConst &k)
+{
+    static_assert(M % 4 == 0 && M <= UNI_MAX, "groups of four cells; tables hold UNI_MAX entries");
+    double uprev = 0.0, dprev = 0.0, vprev = 1.0, alpha = 1.0;
+    First f;
+    f.Y = 0.0; f.V = 0.0; f.W = 0.0;
+#pragma unroll
+    for (int g4 = 0; g4 < M / 4; ++g4) {
+        if (4 * g4 < R4) {               // warp-uniform; R4 <= M-4, so never the group of the separator
+#pragma unroll
+            for (int e = 4 * g4; e < 4 * g4 + 4; ++e) {
+                const double dp = fma(uc.u[e], dprev, ch.T[e] * uc.rinv[e]);
+                ch.T[e] = dp;
+                f.Y = fma(uc.al[e], dp, f.Y);
+                dprev = dp;
+            }
+            uprev = uc.u[4 * g4 + 3]; vprev = uc.vp[4 * g4 + 3];
+            alpha = uc.al[(4 * g4 + 4) & (UNI_MAX - 1)]; f.V = uc.Vn[(4 * g4 + 4) & (UNI_MAX - 1)];
+        } else {
+#pragma unroll
+            for (int e = 4 * g4; e < 4 * g4 + 4; ++e) {
+                if (e == M - 1) break;
+                const Row r = make_row<CMODE, EXTRA>(ch.code(e), lo, hi, ch.T[e], CMODE == 2 ? ops.coef(e) : 0.0,
+                                                     EXTRA ? ops.q(e) : 0.0, EXTRA ? ops.dirv(e) : 0.0, k);
+                const double den = fma(-r.aa, uprev, r.b);
+                const double rinv = frcp(den);
+                const double u = r.cc * rinv;
+                const double la = r.aa * rinv;
+                const double dp = fma(la, dprev, r.d * rinv);
+                const double vp = la * vprev;
+                ops.put1(e, rinv); ch.T[e] = r.d;
+                f.Y = fma(alpha, dp, f.Y);
+                f.V = fma(alpha, vp, f.V);
+                alpha = alpha * u;
+                uprev = u; dprev = dp; vprev = vp;
+            }
+        }
+    }
+    f.W = alpha;
+    ch.Yl = dprev; ch.Vl = vprev; ch.Wl = uprev;
+    {
+        const int e = M - 1;
+        const Row r = make_row<CMODE, EXTRA>(ch.code(e), lo, hi, ch.T[e], CMODE == 2 ? ops.coef(e) : 0.0,
+                                             EXTRA ? ops.q(e) : 0.0, EXTRA ? ops.dirv(e) : 0.0, k);
+        ch.s_aa = r.aa; ch.s_cc = r.cc; ch.s_b = r.b; ch.s_d = r.d;
+    }
+    return f;
+}
+
+template <int M, bool EXTRA, class OPS>
+ADI_HD void chunk_backward_hybrid(Chunk<M> &ch, const UniConst &uc, OPS &ops, int R4, unsigned lo, unsigned hi,
+                                  double g, double Sl, double S)
+{
+    // tail: forward elimination once more with the true value left of it, d'_{R4-1} + vp_{R4-1}*S_{p-1}
+    double dprev = Sl;
+#pragma unroll
+    for (int g4 = 1; g4 < M / 4; ++g4) {
+        if (4 * g4 == R4) dprev = fma(uc.vp[4 * g4 - 1], Sl, ch.T[4 * g4 - 1]);
+        if (4 * g4 >= R4) {
+#pragma unroll
+            for (int e = 4 * g4; e < 4 * g4 + 4; ++e) {
+                if (e == M - 1) break;
+                const double aa = sel(couples<EXTRA>(ch.code(e), lo), g, 0.0);
+                const double dp = fma(aa, dprev, ch.T[e]) * ops.rinv(e);
+                ch.T[e] = dp;
+                dprev = dp;
+            }
+        }
+    }
+    double xn = S;
+    ch.T[M - 1] = S;
+#pragma unroll
+    for (int g4 = M / 4 - 1; g4 >= 0; --g4) {
+        if (4 * g4 >= R4) {
+#pragma unroll
+            for (int e = 4 * g4 + 3; e >= 4 * g4; --e) {
+                if (e == M - 1) continue;
+                const double u = sel(couples<EXTRA>(ch.code(e), hi), g, 0.0) * ops.rinv(e);
+                const double x = fma(u, xn, ch.T[e]);
+                ch.T[e] = x;
+                xn = x;
+            }
+        } else {
+#pragma unroll
+            for (int e = 4 * g4 + 3; e >= 4 * g4; --e) {
+                const double x = fma(uc.u[e], xn, fma(uc.vp[e], Sl, ch.T[e]));
+                ch.T[e] = x;
+                xn = x;
+            }
+        }
+    }
+}
+
 // Phase 2a: the separator row of this chunk given the next chunk's First relation
 // (zeros when there is no next chunk).  Returns the normalised reduced row.
 template <int M>

@@ -24,7 +24,8 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
         if (n <= 512 && (ctx->opt_m == 16 || ctx->opt_m == 32)) M = (int)ctx->opt_m;
         const int P = (n + M - 1) / M;
         const bool wide = P <= 32 && ctx->opt_wide;
-        const int PR = P > 32 ? 2 : 1, maxt = (P > 32 || wide) ? 512 : 256;
+        const bool half = P > 32 && ctx->opt_lb == 256;   // long lines in 256-thread blocks (4 lanes per row), 2 blocks / SM
+        const int PR = P > 32 ? 2 : 1, maxt = ((P > 32 && !half) || wide) ? 512 : 256;
         int KT = 32;
         while (KT > 1 && KT * P > maxt) KT >>= 1;
         if (ctx->opt_kt > 0) {
@@ -80,6 +81,7 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
         else if (M == 16) ADI_GO2(16, 1, 1, 256, 4)
         else if (PR == 1 && !big) ADI_GO2(32, 1, 1, 256, 2)
         else if (PR == 1) ADI_GO2(32, 1, 1, 512, 1)
+        else if (half) ADI_GO2(32, 1, 2, 256, 2)
         else ADI_GO2(32, 1, 2, 512, 1)
 #undef ADI_GO2
     }

@@ -273,6 +273,8 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
         for (int a = 0; a < 3; ++a) ctx->tiles[a].valid = false;
     }
     else if (!strcmp(name, "eorder")) ctx->opt_eorder = value;  // explicit stage: 1 = blocks of neighbouring x planes run together
+    else if (!strcmp(name, "hyb")) ctx->opt_hyb = value;    // 1 (default): z sweep, uniform lead + general tail in one chunk (the chunk under a surface)
+    else if (!strcmp(name, "xyp")) ctx->opt_xyp = value;    // 1: x / y lines of 1025..2048 cells on persistent blocks with a one-tile prefetch (default 0: measured slower, r02m)
     else if (!strcmp(name, "lb")) ctx->opt_lb = value;      // 256: x / y lines of 1025..2048 cells in 256-thread blocks
     else if (!strcmp(name, "bulk")) ctx->opt_bulk = value;  // 1 (default): z sweep tiles as bulk asynchronous copies
     else if (!strcmp(name, "occ")) ctx->opt_occ = value;    // x / y sweeps, 16-cell chunks: resident blocks per SM (2, 3, 4)
@@ -302,6 +304,8 @@ long adi_get_option(adi_ctx *ctx, const char *name)
     if (!strcmp(name, "remap")) return ctx->opt_remap;
     if (!strcmp(name, "occ")) return ctx->opt_occ;
     if (!strcmp(name, "zt")) return ctx->opt_zt;
+    if (!strcmp(name, "hyb")) return ctx->opt_hyb;
+    if (!strcmp(name, "xyp")) return ctx->opt_xyp;
     if (!strcmp(name, "lb")) return ctx->opt_lb;
     if (!strcmp(name, "bulk")) return ctx->opt_bulk;
     if (!strcmp(name, "eorder")) return ctx->opt_eorder;

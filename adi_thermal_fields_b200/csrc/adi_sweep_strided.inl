@@ -1,7 +1,7 @@
 // adi_sweep_strided.inl -- launcher body of the strided sweeps; included by adi_sweep_x.cu
 // (ADI_AXIS 0, with the fused explicit stage) and adi_sweep_y.cu (ADI_AXIS 1).
 #include "adi_launch.h"
-#include "adi_sweep_xy.cuh"
+#include "adi_sweep_xyp.cuh"
 
 namespace adi {
 
@@ -64,6 +64,21 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
                 if (nact == 0) return ADI_OK;
                 b.tiles = list; b.tiles_nx = tnx;
                 grid = dim3((unsigned)nact, 1);
+            }
+        }
+        if (P > 32 && !half && b.uni && ctx->opt_xyp && !ctx->opt_kt && KT == 8) {
+            // long lines, uniform paths allowed: persistent blocks with a one-tile prefetch (adi_sweep_xyp.cuh)
+            if (ctx->sm_count <= 0) {
+                int sms = 0;
+                ADI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+                ctx->sm_count = sms > 0 ? sms : 148;
+            }
+            const long long nt = b.tiles ? (long long)grid.x : (long long)grid.x * grid.y;
+            if (nt <= 0x7fffffffll) {
+                const size_t smp = ((size_t)M * NTH + (size_t)6 * NTH) * sizeof(double) + (size_t)2 * NTH * 16 + (size_t)2 * NTH * sizeof(double);
+                const dim3 pgrid((unsigned)std::min<long long>(nt, ctx->sm_count));
+                if (dense) return launch(k_sweep_xyp<AXIS, 2>, pgrid, block, smp, st, ctx, b, (int)nt);
+                return launch(k_sweep_xyp<AXIS, 1>, pgrid, block, smp, st, ctx, b, (int)nt);
             }
         }
 #define ADI_GO2(M_, NS_, PR_, MAXT, MINB)                                                                            \

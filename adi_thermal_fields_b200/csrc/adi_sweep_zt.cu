@@ -11,7 +11,7 @@ static int launch_zt_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, bool ext
                           cudaStream_t st)
 {
     SweepArgs b = a;
-    b.uni = (ctx->opt_uni && !extra) ? 1 : 0;
+    b.uni = (ctx->opt_uni && !extra) ? (ctx->opt_hyb ? 2 : 1) : 0;   // 2: chunks with a uniform lead take the hybrid path
     uni_const_build(b.uc, a.k.g);
     const size_t nlines = (size_t)a.nx * a.ny;
     dim3 block(KT, P), grid((unsigned)((nlines + KT - 1) / KT));

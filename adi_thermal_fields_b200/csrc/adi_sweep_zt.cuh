@@ -69,16 +69,19 @@ __device__ __forceinline__ void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// The slots of VOID cells are never written: they keep the bits the cell has in global memory, so that a whole
+// line can be copied out again (void rows are identity rows: 1/den = 1).
 template <int M>
 struct ZtOps {
-    double *slot;            // this chunk's M slots of the staged tile: coefficient, then 1/den
+    double *slot;            // this chunk's M slots of the staged tile: coefficient, then 1/den (active cells)
     const double *qp, *dvp;  // global, contiguous along the line; may be null
+    const Chunk<M> *ch;
     int nv;
-    __device__ __forceinline__ double coef(int e) const { return slot[e]; }
+    __device__ __forceinline__ double coef(int e) const { return slot[e]; }   // make_row ignores it for void cells
     __device__ __forceinline__ double q(int e) const { return (qp && e < nv) ? qp[e] : 0.0; }
     __device__ __forceinline__ double dirv(int e) const { return (dvp && e < nv) ? dvp[e] : 0.0; }
-    __device__ __forceinline__ void put1(int e, double v) { slot[e] = v; }
-    __device__ __forceinline__ double rinv(int e) const { return slot[e]; }
+    __device__ __forceinline__ void put1(int e, double v) { if (ch->active(e)) slot[e] = v; }
+    __device__ __forceinline__ double rinv(int e) const { return ch->active(e) ? slot[e] : 1.0; }
     // two-factor interface (unused: NS = 1)
     __device__ __forceinline__ void put2(int, double, double) {}
     __device__ __forceinline__ double la(int) const { return 0.0; }
@@ -224,19 +227,35 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
         if (cell == nz - 1) return sEnd[2 * kk + 1];
         return ldg_f64(a.coeff + gline + cell);
     };
+    // coefficient of cell e into its slot (CMODE 2; active cells only: void slots keep the cell's bits).
+    // Exposed interior cells are fetched asynchronously (cp.async, 8 bytes) -- the caller waits before reading.
+    auto stage_coef = [&](int e) {
+        const unsigned c = ch.code(e);   // 0 beyond the line's end
+        if (!(c & CB_SELF)) return;
+        const int cell = p * M + e;
+        if ((c & (CB_ZM | CB_ZP)) == (CB_ZM | CB_ZP)) slot[e] = 0.0;
+        else if (cell == 0) slot[e] = sEnd[2 * kk];
+        else if (cell == nz - 1) slot[e] = sEnd[2 * kk + 1];
+        else cp_async8(smem_u32(slot + e), a.coeff + gline + cell);
+    };
 
-    // 0: general rows; 1: cells 0..M-2 uniform; 2: cell 0 general, cells 1..M-2 uniform (adi_core.h)
-    int path = 0;
+    // 0: general rows; 1: cells 0..M-2 uniform; 2: cell 0 general, cells 1..M-2 uniform; 3: the first R4 cells
+    // uniform, general rows behind them (adi_core.h)
+    int path = 0, R4 = 0;
     if (a.uni) {
-        if (__all_sync(0xffffffffu, chunk_uniform<M, 1>(ch, CB_ZM, CB_ZP)))
+        if (__all_sync(0xffffffffu, chunk_uniform<M, 1>(ch, CB_ZM, CB_ZP))) {
             path = __all_sync(0xffffffffu, chunk_uniform<M, 0>(ch, CB_ZM, CB_ZP)) ? 1 : 2;
+        } else if (a.uni > 1) {
+            R4 = __reduce_min_sync(0xffffffffu, chunk_uniform_lead4<M>(ch, CB_ZM, CB_ZP));
+            if (R4 >= 8) path = 3;
+        }
     }
     ZtOps<M> ops;
-    ops.slot = slot; ops.qp = nullptr; ops.dvp = nullptr; ops.nv = nv;
+    ops.slot = slot; ops.qp = nullptr; ops.dvp = nullptr; ops.nv = nv; ops.ch = &ch;
     First f;
     UniHead hd;
     hd.al = hd.bl = hd.br = 0.0;
-    if (path != 0) {
+    if (path == 1 || path == 2) {
         const unsigned cs = ch.code(M - 1), c0 = ch.code(0);
         const Row sep = make_row<CMODE, EXTRA>(cs, CB_ZM, CB_ZP, ch.T[M - 1], exposed_coef(M - 1, cs), 0.0, 0.0, a.k);
         if (path == 1) {
@@ -245,18 +264,38 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
             const Row head = make_row<CMODE, EXTRA>(c0, CB_ZM, CB_ZP, ch.T[0], exposed_coef(0, c0), 0.0, 0.0, a.k);
             f = chunk_forward_uniform<M, 1>(ch, a.uc, sep, head, hd);
         }
-    } else {
-#pragma unroll
-        for (int e = 0; e < M; ++e) ch.T[e] = ch.active(e) ? ch.T[e] : 0.0;  // load rule (adi_core.h)
+    } else if (path == 3) {
+        // the coefficients of the tail are requested first and arrive while the run is eliminated
         if (CMODE == 2) {
 #pragma unroll
-            for (int e = 0; e < M; ++e) {
-                const unsigned c = ch.code(e);   // 0 beyond the line's end
-                slot[e] = (c & CB_SELF) ? exposed_coef(e, c) : 0.0;
+            for (int g4 = 2; g4 < M / 4; ++g4) {
+                if (4 * g4 >= R4) {
+#pragma unroll
+                    for (int e = 4 * g4; e < 4 * g4 + 4; ++e) stage_coef(e);
+                }
+            }
+        }
+#pragma unroll
+        for (int g4 = 2; g4 < M / 4; ++g4) {
+            if (4 * g4 >= R4) {
+#pragma unroll
+                for (int e = 4 * g4; e < 4 * g4 + 4; ++e) ch.T[e] = ch.active(e) ? ch.T[e] : 0.0;  // load rule
             }
         }
         ops.qp = (EXTRA && a.q) ? a.q + gline + min(p * M, nz - 1) : nullptr;
         ops.dvp = (EXTRA && a.dirv) ? a.dirv + gline + min(p * M, nz - 1) : nullptr;
+        if (CMODE == 2) cp_async_wait_all();
+        f = chunk_forward_hybrid<M, CMODE, EXTRA>(ch, a.uc, ops, R4, CB_ZM, CB_ZP, a.k);
+    } else {
+        if (CMODE == 2) {
+#pragma unroll
+            for (int e = 0; e < M; ++e) stage_coef(e);
+        }
+#pragma unroll
+        for (int e = 0; e < M; ++e) ch.T[e] = ch.active(e) ? ch.T[e] : 0.0;  // load rule (adi_core.h)
+        ops.qp = (EXTRA && a.q) ? a.q + gline + min(p * M, nz - 1) : nullptr;
+        ops.dvp = (EXTRA && a.dirv) ? a.dirv + gline + min(p * M, nz - 1) : nullptr;
+        if (CMODE == 2) cp_async_wait_all();
         f = chunk_forward<M, CMODE, EXTRA, NS, false>(ch, ops, CB_ZM, CB_ZP, a.k);
     }
     if (ZMODE == 1) {
@@ -295,6 +334,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
     const double S = solve_reduced<M, GHOSTS>(ch, f, xch, NTH, tid, KT, p, P, &Sl, Lg, Rg);
     if (path == 1) chunk_backward_uniform<M, 0>(ch, a.uc, hd, Sl, S);
     else if (path == 2) chunk_backward_uniform<M, 1>(ch, a.uc, hd, Sl, S);
+    else if (path == 3) chunk_backward_hybrid<M, EXTRA>(ch, a.uc, ops, R4, CB_ZM, CB_ZP, a.k.g, Sl, S);
     else chunk_backward<M, EXTRA, NS>(ch, ops, CB_ZM, CB_ZP, a.k.g, Sl, S);
     if (ZMODE == 4) {
         if (line < nlines) {  // void cells hold 0 (load rule), as in the relation of ZMODE 3
@@ -305,16 +345,17 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
 
     // ---- results back through the thread's own slots, then coalesced copy-out ----
     // The sweep runs in place, so void cells must keep the bits they have in global memory.  Bulk mode stores whole
-    // lines: uniform chunks hold no void cell; the general path has used the slots of its void cells for factors
-    // and puts the original bits back (void cells are written by nobody, so re-reading them is safe).
-    if (bulk && path == 0) {
+    // lines: uniform chunks hold no void cell, and the general paths never write the slot of a void cell.
+    if (path == 1 || path == 2) {
+#pragma unroll
+        for (int j = 0; j < M / 2; ++j)
+            *reinterpret_cast<double2 *>(slot + 2 * j) = make_double2(ch.T[2 * j], ch.T[2 * j + 1]);
+    } else {
+        // the slots of void cells still hold the cells' own bits
 #pragma unroll
         for (int e = 0; e < M; ++e)
-            if (e < nv && !ch.active(e)) ch.T[e] = a.in[gline + p * M + e];
+            if (ch.active(e)) slot[e] = ch.T[e];
     }
-#pragma unroll
-    for (int j = 0; j < M / 2; ++j)
-        *reinterpret_cast<double2 *>(slot + 2 * j) = make_double2(ch.T[2 * j], ch.T[2 * j + 1]);
     if (bulk) {
         fence_proxy_async();       // generic-proxy writes above -> visible to the bulk copy engine
         __syncthreads();

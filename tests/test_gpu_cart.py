@@ -483,7 +483,7 @@ def _uniform_case(shape, mask_kind, bk, theta, cfl, seed):
 
 @pytest.mark.parametrize("opts", [dict(), dict(uni=0), dict(tw=1), dict(xy2=0), dict(m=16), dict(m=32), dict(kt=4), dict(m=16, kt=2),
                                   dict(m=16, occ=3), dict(m=16, occ=4, tw=1), dict(remap=1), dict(remap=1, tw=1), dict(wide=1),
-                                  dict(m=16, wide=1, tw=1), dict(lt=1), dict(lt=4), dict(sparse_coeff=0), dict(zt=0), dict(zt=0, uni=0), dict(bulk=0), dict(bulk=0, uni=0), dict(tiles=0)],
+                                  dict(m=16, wide=1, tw=1), dict(lt=1), dict(lt=4), dict(sparse_coeff=0), dict(zt=0), dict(zt=0, uni=0), dict(bulk=0), dict(bulk=0, uni=0), dict(tiles=0), dict(hyb=0), dict(xyp=0)],
                          ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
 @pytest.mark.parametrize("shape,mask_kind", [((70, 40, 37), "full"), ((40, 70, 130), "plate_track"), ((96, 50, 64), "cyl_holes"),
                                              ((600, 7, 48), "full"), ((5, 1100, 24), "full"), ((2050, 3, 10), "full"),
@@ -549,3 +549,54 @@ def test_active_tile_lists(g, cp):
         act[:] = False
         Th[:] = 20.0
         Td = cp.asarray(Th)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(hyb=0), dict(lt=2), dict(lt=16), dict(m=16), dict(bulk=0)],
+                         ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
+@pytest.mark.parametrize("shape", [(24, 40, 256), (16, 12, 515), (9, 33, 160)], ids=lambda s: "x".join(map(str, s)))
+def test_z_sweep_surface_chunks(shape, opts, g, cp):
+    """z lines that cross the top surface of a part: the chunk under the surface has a uniform lead and a general tail
+    (adi_core.h chunk_forward_hybrid).  Terraced surface heights (every lead length occurs, different ones inside one
+    warp), a floating block above a gap, NaN in the void; dense per-face h, scalar h, and a Neumann + Dirichlet set
+    (which keeps the general rows) -- against the oracle; void cells keep their bits."""
+    nx, ny, nz = shape
+    k = np.arange(nz)[None, None, :]
+    height = (nz // 3 + (7 * np.arange(nx)[:, None] + 3 * (np.arange(ny)[None, :] // 5)) % (nz - nz // 3 - 1))[:, :, None]
+    mask = k < height
+    mask |= (k >= height + 3) & (k < height + 9) & ((np.arange(nx) % 4 == 1)[:, None, None])   # floating blocks
+    mask[0, :, :] = True
+    mask[:, 1, 5:11] = False                                                                   # a gap low in the line
+    restore = {kk: int(g.get_option(kk)) for kk in opts}
+    for kk, v in opts.items():
+        g.set_option(kk, v)
+    try:
+        for bk, theta, cfl in [("robin_dict3d", 0.5, 0.9), ("robin6", 1.0, 300.0), ("combined", 0.5, 5.0)]:
+            bcs = cases.make_bcs(bk, shape, mask, 31, 20.0)
+            T0 = 20.0 + 1380.0 * cases.splitmix_uniform(32, shape)
+            T0[~mask] = np.nan
+            kappa = cases.K / (cases.RHO * cases.CP)
+            _both(g, cp, dict(shape=shape, mask=mask, T0=T0, dt=cfl * cases.DX ** 2 / kappa, theta=theta, bcs=bcs,
+                              kappa=kappa), nsteps=2)
+    finally:
+        for kk, v in restore.items():
+            g.set_option(kk, v)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(xyp=0), dict(tiles=0)],
+                         ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
+@pytest.mark.parametrize("shape,mask_kind", [((1100, 40, 37), "plate_track"), ((40, 1100, 37), "cyl_holes"), ((2048, 21, 20), "full"),
+                                             ((6, 2048, 70), "plate_track"), ((1500, 30, 9), "random")],
+                         ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else v)
+def test_long_lines_persistent_blocks(shape, mask_kind, opts, g, cp):
+    """x / y lines of 1025..2048 cells run on persistent blocks that prefetch the next tile (adi_sweep_xyp.cuh): more
+    tiles than blocks (every block walks over several tiles, uniform and general warps mixed), ragged z tiles, void
+    tiles (in place: skipped, with and without the active-tile list), dense per-face h and scalar h."""
+    restore = {k: int(g.get_option(k)) for k in opts}
+    for k, v in opts.items():
+        g.set_option(k, v)
+    try:
+        for bk, theta, cfl in [("robin_dict3d", 0.5, 0.7), ("robin6", 1.0, 500.0)]:
+            _both(g, cp, _uniform_case(shape, mask_kind, bk, theta, cfl, seed=9000 + shape[0]), nsteps=2)
+    finally:
+        for k, v in restore.items():
+            g.set_option(k, v)

@@ -483,7 +483,7 @@ def _uniform_case(shape, mask_kind, bk, theta, cfl, seed):
 
 @pytest.mark.parametrize("opts", [dict(), dict(uni=0), dict(tw=1), dict(xy2=0), dict(m=16), dict(m=32), dict(kt=4), dict(m=16, kt=2),
                                   dict(m=16, occ=3), dict(m=16, occ=4, tw=1), dict(remap=1), dict(remap=1, tw=1), dict(wide=1),
-                                  dict(m=16, wide=1, tw=1), dict(lt=1), dict(lt=4), dict(sparse_coeff=0), dict(zt=0), dict(zt=0, uni=0), dict(bulk=0), dict(bulk=0, uni=0), dict(tiles=0), dict(hyb=0), dict(xyp=0)],
+                                  dict(m=16, wide=1, tw=1), dict(lt=1), dict(lt=4), dict(sparse_coeff=0), dict(zt=0), dict(zt=0, uni=0), dict(bulk=0), dict(bulk=0, uni=0), dict(tiles=0), dict(hyb=0), dict(xyp=1)],
                          ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
 @pytest.mark.parametrize("shape,mask_kind", [((70, 40, 37), "full"), ((40, 70, 130), "plate_track"), ((96, 50, 64), "cyl_holes"),
                                              ((600, 7, 48), "full"), ((5, 1100, 24), "full"), ((2050, 3, 10), "full"),
@@ -582,7 +582,7 @@ def test_z_sweep_surface_chunks(shape, opts, g, cp):
             g.set_option(kk, v)
 
 
-@pytest.mark.parametrize("opts", [dict(), dict(xyp=0), dict(tiles=0)],
+@pytest.mark.parametrize("opts", [dict(xyp=1), dict(xyp=0), dict(xyp=1, tiles=0)],
                          ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
 @pytest.mark.parametrize("shape,mask_kind", [((1100, 40, 37), "plate_track"), ((40, 1100, 37), "cyl_holes"), ((2048, 21, 20), "full"),
                                              ((6, 2048, 70), "plate_track"), ((1500, 30, 9), "random")],

@@ -274,7 +274,9 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
     }
     else if (!strcmp(name, "eorder")) ctx->opt_eorder = value;  // explicit stage: 1 = blocks of neighbouring x planes run together
     else if (!strcmp(name, "hyb")) ctx->opt_hyb = value;    // 1 (default): z sweep, uniform lead + general tail in one chunk (the chunk under a surface)
-    else if (!strcmp(name, "xyp")) ctx->opt_xyp = value;    // 1: x / y lines of 1025..2048 cells on persistent blocks with a one-tile prefetch (default 0: measured slower, r02m)
+    else if (!strcmp(name, "xyp")) ctx->opt_xyp = value;    // 1: x / y lines of 1025..2048 cells on persistent blocks, tiles prefetched by the TMA engine (default 0: no faster than k_sweep_xy, r02o-r02q)
+    else if (!strcmp(name, "seq")) ctx->opt_seq = value;    // k_sweep_xyp: 1 contiguous tile range per block, 0 (default) round-robin
+    else if (!strcmp(name, "promo")) ctx->opt_promo = value;  // k_sweep_xyp: L2 promotion of the tensor map (0 / 64 / 128 / 256 bytes)
     else if (!strcmp(name, "lb")) ctx->opt_lb = value;      // 256: x / y lines of 1025..2048 cells in 256-thread blocks
     else if (!strcmp(name, "bulk")) ctx->opt_bulk = value;  // 1 (default): z sweep tiles as bulk asynchronous copies
     else if (!strcmp(name, "occ")) ctx->opt_occ = value;    // x / y sweeps, 16-cell chunks: resident blocks per SM (2, 3, 4)
@@ -306,6 +308,10 @@ long adi_get_option(adi_ctx *ctx, const char *name)
     if (!strcmp(name, "zt")) return ctx->opt_zt;
     if (!strcmp(name, "hyb")) return ctx->opt_hyb;
     if (!strcmp(name, "xyp")) return ctx->opt_xyp;
+    if (!strcmp(name, "xyp_used")) return ctx->xyp_used;     // launches of k_sweep_xyp so far
+    if (!strcmp(name, "xyp_layout")) return ctx->xyp_state;  // tensor-map layout in use (0 / 1), -1: refused by the driver
+    if (!strcmp(name, "seq")) return ctx->opt_seq;
+    if (!strcmp(name, "promo")) return ctx->opt_promo;
     if (!strcmp(name, "lb")) return ctx->opt_lb;
     if (!strcmp(name, "bulk")) return ctx->opt_bulk;
     if (!strcmp(name, "eorder")) return ctx->opt_eorder;

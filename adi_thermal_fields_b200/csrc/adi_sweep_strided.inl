@@ -1,5 +1,7 @@
 // adi_sweep_strided.inl -- launcher body of the strided sweeps; included by adi_sweep_x.cu
 // (ADI_AXIS 0, with the fused explicit stage) and adi_sweep_y.cu (ADI_AXIS 1).
+#include <stdint.h>
+
 #include "adi_launch.h"
 #include "adi_sweep_xyp.cuh"
 
@@ -66,20 +68,28 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
                 grid = dim3((unsigned)nact, 1);
             }
         }
-        if (P > 32 && !half && b.uni && ctx->opt_xyp && !ctx->opt_kt && KT == 8) {
-            // long lines, uniform paths allowed: persistent blocks with a one-tile prefetch (adi_sweep_xyp.cuh)
+        if (P > 32 && !half && b.uni && ctx->opt_xyp && !ctx->opt_kt && KT == 8 && n % 128 == 0 && a.nz % 2 == 0 &&
+            ((uintptr_t)a.in & 15) == 0 && ctx->xyp_state >= 0) {
+            // long lines, uniform paths allowed: persistent blocks, tiles prefetched by the TMA engine (adi_sweep_xyp.cuh)
             if (ctx->sm_count <= 0) {
                 int sms = 0;
                 ADI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
                 ctx->sm_count = sms > 0 ? sms : 148;
             }
             const long long nt = b.tiles ? (long long)grid.x : (long long)grid.x * grid.y;
-            if (nt <= 0x7fffffffll) {
-                const size_t smp = ((size_t)M * NTH + (size_t)6 * NTH) * sizeof(double) + (size_t)2 * NTH * 16 + (size_t)2 * NTH * sizeof(double);
+            CUtensorMap tm;
+            int lay = ctx->xyp_state;
+            if (nt <= 0x7fffffffll && xyp_tensor_map(&tm, &lay, AXIS, a.in, a.nx, a.ny, a.nz, (int)ctx->opt_promo) == ADI_OK) {
+                ctx->xyp_state = lay;
+                ctx->xyp_used++;
+                const int NW = NTH / 32;
+                const size_t smp = (size_t)NW * 8192 + (size_t)6 * NTH * sizeof(double) + (size_t)2 * NTH * 16 +
+                                   (size_t)2 * NTH * sizeof(double) + (size_t)NW * 8;
                 const dim3 pgrid((unsigned)std::min<long long>(nt, ctx->sm_count));
-                if (dense) return launch(k_sweep_xyp<AXIS, 2>, pgrid, block, smp, st, ctx, b, (int)nt);
-                return launch(k_sweep_xyp<AXIS, 1>, pgrid, block, smp, st, ctx, b, (int)nt);
+                if (dense) return launch(k_sweep_xyp<AXIS, 2>, pgrid, block, smp, st, ctx, b, tm, (int)nt, lay, (int)ctx->opt_seq);
+                return launch(k_sweep_xyp<AXIS, 1>, pgrid, block, smp, st, ctx, b, tm, (int)nt, lay, (int)ctx->opt_seq);
             }
+            if (nt <= 0x7fffffffll) ctx->xyp_state = -1;   // the driver refused the tensor map: k_sweep_xy from now on
         }
 #define ADI_GO2(M_, NS_, PR_, MAXT, MINB)                                                                            \
         {                                                                                                        \

@@ -1,28 +1,32 @@
-// adi_sweep_xyp.cuh -- K1p: x / y sweeps of long lines (1025..2048 cells), persistent blocks with a one-tile
-// prefetch.
+// adi_sweep_xyp.cuh -- K1p: x / y sweeps of long lines (1025..2048 cells), persistent blocks, tiles prefetched
+// by the TMA engine.
 //
 // A line of up to 2048 cells needs 64 chunks of 32 cells: 64 x 8 lanes = 512 threads at 128 registers is the
-// whole register file of an SM, so k_sweep_xy runs ONE block per SM and its load, solve and store phases cannot
-// hide behind another block's (measured on 2048 x 2048 x 128: x 2.69 / y 2.18 ms against 2.08 / 1.69 ms for the
-// same loads and stores without the solve, and 1.28 ms at the copy peak).  Here the block stays on its SM and
-// walks over tiles (grid = number of SMs); while it solves tile t, the field values and neighbour codes of
-// tile t + gridDim.x travel into shared memory with cp.async:
+// whole register file of an SM, so k_sweep_xy runs ONE block per SM, and its 512 x 32 eight-byte loads per tile
+// are 2048 separate 64-byte row requests that fill the load/store unit's queue (ncu r02n: "LG throttle" 10.1 /
+// 6.7 stall cycles per issued instruction in the x / y sweep, 2.72 / 2.16 ms on 2048 x 2048 x 128 where the copy
+// peak allows 1.28 ms).  Here
 //
-//   * every thread prefetches exactly the 32 cells (+ 32 code bytes, + the line-end coefficients) it will own in
-//     the next tile, into its OWN shared-memory column (col[e * NTH], the layout of the factor slots of
-//     k_sweep_xy) -- no other thread ever touches those slots, so the hand-over needs no barrier, only the
-//     thread's own cp.async.wait_all at the top of the next tile;
-//   * warps on the tabulated uniform paths (the bulk) issue the prefetch right after reading their chunk out of
-//     the column, i.e. before the elimination; warps on the general path keep 1/den in the same column (as
-//     k_sweep_xy does) and issue it after their back substitution;
-//   * results go straight from registers to global memory (fire-and-forget stores), so the stores of tile t
-//     overlap the wait for tile t + gridDim.x.
+//   * the block stays on its SM and walks over tiles (grid = number of SMs);
+//   * the field values of a tile travel as TENSOR copies (cp.async.bulk.tensor.4d, SASS UTMALDG) described by a
+//     4-D tensor map over (z, chunk, cell in chunk, other strided axis): one instruction per WARP fetches the
+//     box (8 lanes, the warp's 4 chunks, 32 cells) = 8 KB that the warp's 32 threads own, laid out in shared
+//     memory as [cell][chunk][lane] -- the 32 values a warp reads together are 256 consecutive bytes;
+//   * every warp prefetches its own box of the NEXT tile as soon as it has pulled the current one into
+//     registers (warps on the general path keep 1/den in the same slots and prefetch after their back
+//     substitution): the hand-over is warp-local -- a proxy fence, __syncwarp and the warp's own mbarrier --
+//     and the load of tile t + gridDim.x overlaps the solve and the stores of tile t;
+//   * neighbour codes (32 bytes per thread from the transposed code array) and the line-end coefficients follow
+//     with cp.async into thread-owned slots; results go from registers to global memory (plain stores: they
+//     need no registers to come back, so the load/store unit only ever queues stores).
 //
 // Only launched for sweeps that may take the uniform paths (no flux / Dirichlet operand, coefficient field
-// scalar or verified surface-only); everything else keeps k_sweep_xy.
+// scalar or verified surface-only) on lines whose length is a multiple of 128; everything else keeps k_sweep_xy.
 //
 // Reference semantics: adi3d_numba_coeff.py:133-203 (sweep_axis0 / sweep_axis1).
 #pragma once
+#include <cuda.h>
+
 #include "adi_sweep_xy.cuh"
 
 namespace adi {
@@ -31,38 +35,79 @@ __device__ __forceinline__ void cp_async16u(unsigned dst_smem, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
+__device__ __forceinline__ void xyp_mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void xyp_mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void xyp_mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void xyp_tma_load4(unsigned dst_smem, const CUtensorMap *tm, unsigned bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst_smem), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 
-// smem: col[M][NTH] doubles | xch[6*NTH] doubles | codes [2][NTH] uint4 | cend [2][NTH] doubles (line-end coefficients)
+constexpr int XYP_BOX_BYTES = 8 * 4 * 32 * 8;   // one warp's box: 8 lanes x 4 chunks x 32 cells of fp64
+
+// smem: tile [NW][1024] doubles (8 KB per warp, 1 KB aligned) | xch[6*NTH] | codes [2][NTH] uint4 | cend [2][NTH] | mbarrier [NW]
+// lay 0: tensor dimensions (z, chunk, cell, other): shared-memory slot of cell e = e*32 + c*8 + lane   (se 32, sc 8)
+// lay 1: dimensions in memory order (host fallback when the driver refuses lay 0): slot = c*256 + e*8 + lane (se 8, sc 256)
 template <int AXIS, int CMODE>
-__global__ void __launch_bounds__(512, 1) k_sweep_xyp(const SweepArgs a, const int ntiles)
+__global__ void __launch_bounds__(512, 1) k_sweep_xyp(const SweepArgs a, const __grid_constant__ CUtensorMap tm,
+                                                      const int ntiles, const int lay, const int seq)
 {
     constexpr int M = 32, NS = 1;
     constexpr bool EXTRA = false;
-    extern __shared__ double smem[];
-    const int KT = blockDim.x, P = blockDim.y;
+    extern __shared__ __align__(1024) double smem[];
+    const int KT = 8, P = blockDim.y;
     const int kk = threadIdx.x, p = threadIdx.y;
-    const int NTH = KT * P;
+    const int NTH = KT * P, NW = NTH >> 5;
     const int tid = p * KT + kk;
+    const int warp = tid >> 5, lane = tid & 31, c = p & 3;
     const int n = (AXIS == 0) ? a.nx : a.ny;
     const unsigned sl = (AXIS == 0) ? (unsigned)a.ny * (unsigned)a.nz : (unsigned)a.nz;
     constexpr unsigned LO = (AXIS == 0) ? CB_XM : CB_YM;
     constexpr unsigned HI = (AXIS == 0) ? CB_XP : CB_YP;
-    const int t0 = p * M;                                   // < n: the launcher uses P = ceil(n / M)
+    const int t0 = p * M;
     const int nti = (a.nz + KT - 1) / KT;                   // tiles per index of the other strided axis
     const int el = n - 1 - t0;                              // slot of the line's last cell, if it is in this chunk
     const unsigned sl8 = sl * 8u;
-    const unsigned nth8 = (unsigned)NTH * 8u;
+    const int se = lay ? 8 : 32, sc = lay ? 256 : 8;
 
-    double *col = smem + tid;
-    double *xch = smem + (size_t)M * NTH;
+    double *wtile = smem + (size_t)warp * 1024;
+    double *col = wtile + c * sc + kk;                      // slot of cell e: col[e * se]
+    double *xch = smem + (size_t)NW * 1024;
     uint4 *cslot = reinterpret_cast<uint4 *>(xch + (size_t)6 * NTH) + tid;      // word w at cslot[w * NTH]
     double *cend = reinterpret_cast<double *>(reinterpret_cast<uint4 *>(xch + (size_t)6 * NTH) + (size_t)2 * NTH) + tid;
-    const unsigned scol = smem_u32(col), scode = smem_u32(cslot), send = smem_u32(cend);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(reinterpret_cast<uint4 *>(xch + (size_t)6 * NTH) + (size_t)2 * NTH) + (size_t)2 * NTH);
+    const unsigned swt = smem_u32(wtile), scode = smem_u32(cslot), send = smem_u32(cend), sbar = smem_u32(bars + warp);
+    const unsigned nth8 = (unsigned)NTH * 8u;
 
-    // position of tile t for this thread: first cell of its chunk, lane validity
+    if (tid == 0) {
+        for (int w = 0; w < NW; ++w) xyp_mbar_init(smem_u32(bars + w), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
     struct Pos {
         size_t idx0;
         size_t crow;      // offset of the chunk's codes in codeT
+        int bx, by;
         bool lane_ok;
     };
     auto locate = [&](int t) -> Pos {
@@ -71,36 +116,50 @@ __global__ void __launch_bounds__(512, 1) k_sweep_xyp(const SweepArgs a, const i
         const int k = (int)bx * KT + kk;
         const int kc = min(k, a.nz - 1);
         Pos q;
+        q.bx = (int)bx; q.by = (int)by;
         q.lane_ok = k < a.nz;
         q.idx0 = ((AXIS == 0) ? (size_t)by * a.nz : (size_t)by * a.ny * a.nz) + (size_t)kc + (size_t)t0 * sl;
         q.crow = ((size_t)by * a.nz + kc) * (size_t)a.npad + t0;
         return q;
     };
-    // cells beyond the line's end re-read the chunk's last valid cell; their codes are the padding zeros of codeT
-    const int nvl = min(n - t0, M) - 1;
+    // Called by all lanes of a warp together, after their last access to the warp's box.
     auto prefetch = [&](int t) {
         const Pos q = locate(t);
         const uint8_t *cb = a.codeT + q.crow;
         cp_async16u(scode, cb);
         cp_async16u(scode + (unsigned)NTH * 16u, cb + 16);
-        const char *tb = reinterpret_cast<const char *>(a.in + q.idx0);
-#pragma unroll
-        for (int e = 0; e < M; ++e) cp_async8(scol + e * nth8, tb + (size_t)((unsigned)min(e, nvl) * sl8));
         if (CMODE == 2) {
             // surface-only coefficient field: the two ends of the line are always exposed when active
             const char *cf = reinterpret_cast<const char *>(a.coeff + q.idx0);
             if (t0 == 0) cp_async8(send, cf);
             if (el < M) cp_async8(send + nth8, cf + (size_t)((unsigned)el * sl8));
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses to the box come first
+        __syncwarp();
+        if (lane == 0) {
+            xyp_mbar_expect_tx(sbar, (unsigned)XYP_BOX_BYTES);
+            const int z0 = q.bx * KT, ch0 = 4 * warp;
+            if (lay == 0) xyp_tma_load4(swt, &tm, sbar, z0, ch0, 0, q.by);
+            else if (AXIS == 1) xyp_tma_load4(swt, &tm, sbar, z0, 0, ch0, q.by);
+            else xyp_tma_load4(swt, &tm, sbar, z0, q.by, 0, ch0);
+        }
     };
 
-    int t = blockIdx.x;
-    if (t < ntiles) prefetch(t);
-    for (; t < ntiles; t += gridDim.x) {
+    // seq: every block walks over a CONTIGUOUS range of tiles (consecutive z tiles of the same lines: the 64-byte rows
+    // of neighbouring tiles share 128-byte lines and DRAM pages, and the tensor map asks L2 to fetch 256 bytes at a
+    // time); otherwise tiles are dealt round-robin
+    unsigned parity = 0;
+    const int per = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int tstep = seq ? 1 : (int)gridDim.x;
+    const int tend = seq ? min(ntiles, ((int)blockIdx.x + 1) * per) : ntiles;
+    int t = seq ? (int)blockIdx.x * per : (int)blockIdx.x;
+    if (t < tend) prefetch(t);
+    for (; t < tend; t += tstep, parity ^= 1u) {
         const Pos q = locate(t);
-        const int tn = t + gridDim.x;
-        const int nv = q.lane_ok ? nvl + 1 : 0;
-        cp_async_wait_all();                                // this thread's own copies of tile t have landed
+        const int tn = t + tstep;
+        const int nv = q.lane_ok ? M : 0;
+        cp_async_wait_all();                                // this thread's codes / line-end coefficients
+        xyp_mbar_wait(sbar, parity);                        // the warp's box
         Chunk<M> ch;
         {
             const uint4 v0 = cslot[0], v1 = cslot[NTH];
@@ -110,7 +169,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_xyp(const SweepArgs a, const i
             ch.cw[6] = q.lane_ok ? v1.z : 0u; ch.cw[7] = q.lane_ok ? v1.w : 0u;
         }
 #pragma unroll
-        for (int e = 0; e < M; ++e) ch.T[e] = col[e * NTH];
+        for (int e = 0; e < M; ++e) ch.T[e] = col[e * se];
         double ce0 = 0.0, ce1 = 0.0;
         if (CMODE == 2) { ce0 = cend[0]; ce1 = cend[NTH]; }
         bool any = false;
@@ -119,13 +178,13 @@ __global__ void __launch_bounds__(512, 1) k_sweep_xyp(const SweepArgs a, const i
         // (also the barrier that separates this tile's use of xch from the previous tile's)
         const bool live = __syncthreads_or(any);
         if (a.in == a.out && !live) {                       // in place, a tile of void cells: nothing to solve
-            if (tn < ntiles) prefetch(tn);
+            if (tn < tend) prefetch(tn);
             continue;
         }
         const char *cf = reinterpret_cast<const char *>(a.coeff + (CMODE == 2 ? q.idx0 : 0));
-        auto exposed_coef = [&](int e, unsigned c) -> double {
+        auto exposed_coef = [&](int e, unsigned cd) -> double {
             if (CMODE != 2) return 0.0;
-            if ((c & (LO | HI)) == (LO | HI)) return 0.0;
+            if ((cd & (LO | HI)) == (LO | HI)) return 0.0;
             const int cell = t0 + e;
             if (cell == 0) return ce0;
             if (cell == n - 1) return ce1;
@@ -140,14 +199,14 @@ __global__ void __launch_bounds__(512, 1) k_sweep_xyp(const SweepArgs a, const i
         }
         StridedOps<M, true> ops;
         ops.coeff = nullptr; ops.qp = nullptr; ops.dvp = nullptr;
-        ops.sl = sl; ops.nv = nv; ops.col = col; ops.NTH = NTH;
+        ops.sl = sl; ops.nv = nv; ops.col = col; ops.NTH = se;
         First f;
         f.Y = f.V = f.W = 0.0;
         UniHead hd;
         hd.al = hd.bl = hd.br = 0.0;
         if (path != 0) {
-            // the column is free again: the next tile starts travelling while this one is solved
-            if (tn < ntiles) prefetch(tn);
+            // the box is free again: the next tile starts travelling while this one is solved
+            if (tn < tend) prefetch(tn);
             const unsigned cs = ch.code(M - 1), c0 = ch.code(0);
             const Row sep = make_row<CMODE, EXTRA>(cs, LO, HI, ch.T[M - 1], exposed_coef(M - 1, cs), 0.0, 0.0, a.k);
             if (path == 1) {
@@ -162,8 +221,8 @@ __global__ void __launch_bounds__(512, 1) k_sweep_xyp(const SweepArgs a, const i
             if (CMODE == 2) {
 #pragma unroll
                 for (int e = 0; e < M; ++e) {
-                    const unsigned c = ch.code(e);  // 0 beyond the chunk's valid cells
-                    col[e * NTH] = (c & CB_SELF) ? exposed_coef(e, c) : 0.0;
+                    const unsigned cd = ch.code(e);
+                    col[e * se] = (cd & CB_SELF) ? exposed_coef(e, cd) : 0.0;
                 }
             }
             f = chunk_forward<M, CMODE, EXTRA, NS, false>(ch, ops, LO, HI, a.k);
@@ -174,7 +233,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_xyp(const SweepArgs a, const i
         else if (path == 2) chunk_backward_uniform<M, 1>(ch, a.uc, hd, Sl, S);
         else {
             chunk_backward<M, EXTRA, NS>(ch, ops, LO, HI, a.k.g, Sl, S);
-            if (tn < ntiles) prefetch(tn);                  // the factors are no longer needed
+            if (tn < tend) prefetch(tn);                  // the factors are no longer needed
         }
 
         double *op = a.out + q.idx0;
@@ -192,6 +251,54 @@ __global__ void __launch_bounds__(512, 1) k_sweep_xyp(const SweepArgs a, const i
                 if (e < nv) op[e * sl] = ch.active(e) ? ch.T[e] : tp[e * sl];
         }
     }
+}
+
+// Host: tensor map of the field `base` for the boxes above.  lay 0 = (z, chunk, cell, other); returns the layout
+// that the driver accepted in *lay (1 = dimensions in memory order), or an error.
+inline int xyp_tensor_map(CUtensorMap *tm, int *lay, int axis, const double *base, int nx, int ny, int nz, int promo)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            set_error("adi_cart_step: cuTensorMapEncodeTiled is not available");
+            return ADI_ESTATE;
+        }
+        encode = (encode_fn)fn;
+    }
+    const cuuint64_t n = axis == 0 ? nx : ny, other = axis == 0 ? ny : nx;
+    const cuuint64_t s_cell = (axis == 0 ? (cuuint64_t)ny * nz : (cuuint64_t)nz) * 8ull;
+    const cuuint64_t s_other = (axis == 0 ? (cuuint64_t)nz : (cuuint64_t)ny * nz) * 8ull;
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    for (int l = *lay; l < 2; ++l) {
+        cuuint64_t dim[4], str[3];
+        cuuint32_t box[4];
+        dim[0] = (cuuint64_t)nz; box[0] = 8;
+        if (l == 0) {
+            dim[1] = n / 32; str[0] = 32 * s_cell; box[1] = 4;
+            dim[2] = 32;     str[1] = s_cell;      box[2] = 32;
+            dim[3] = other;  str[2] = s_other;     box[3] = 1;
+        } else if (axis == 1) {
+            dim[1] = 32;     str[0] = s_cell;      box[1] = 32;
+            dim[2] = n / 32; str[1] = 32 * s_cell; box[2] = 4;
+            dim[3] = other;  str[2] = s_other;     box[3] = 1;
+        } else {
+            dim[1] = other;  str[0] = s_other;     box[1] = 1;
+            dim[2] = 32;     str[1] = s_cell;      box[2] = 32;
+            dim[3] = n / 32; str[2] = 32 * s_cell; box[3] = 4;
+        }
+        const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double *>(base), dim, str, box, es,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) { *lay = l; return ADI_OK; }
+    }
+    set_error("adi_cart_step: cuTensorMapEncodeTiled refused the sweep's tensor map");
+    return ADI_ESTATE;
 }
 
 }  // namespace adi

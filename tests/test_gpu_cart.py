@@ -584,19 +584,25 @@ def test_z_sweep_surface_chunks(shape, opts, g, cp):
 
 @pytest.mark.parametrize("opts", [dict(xyp=1), dict(xyp=0), dict(xyp=1, tiles=0)],
                          ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
-@pytest.mark.parametrize("shape,mask_kind", [((1100, 40, 37), "plate_track"), ((40, 1100, 37), "cyl_holes"), ((2048, 21, 20), "full"),
-                                             ((6, 2048, 70), "plate_track"), ((1500, 30, 9), "random")],
+@pytest.mark.parametrize("shape,mask_kind", [((1152, 40, 38), "plate_track"), ((40, 1152, 38), "cyl_holes"), ((2048, 21, 20), "full"),
+                                             ((6, 2048, 70), "plate_track"), ((1536, 30, 10), "random"), ((1100, 7, 9), "full")],
                          ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else v)
 def test_long_lines_persistent_blocks(shape, mask_kind, opts, g, cp):
-    """x / y lines of 1025..2048 cells run on persistent blocks that prefetch the next tile (adi_sweep_xyp.cuh): more
-    tiles than blocks (every block walks over several tiles, uniform and general warps mixed), ragged z tiles, void
-    tiles (in place: skipped, with and without the active-tile list), dense per-face h and scalar h."""
+    """x / y lines of 1025..2048 cells (a multiple of 128) run on persistent blocks whose tiles arrive as TMA tensor
+    copies (adi_sweep_xyp.cuh): more tiles than blocks (every block walks over several tiles, uniform and general
+    warps mixed), ragged z tiles, void tiles (in place: skipped, with and without the active-tile list), dense
+    per-face h and scalar h; other line lengths keep k_sweep_xy."""
     restore = {k: int(g.get_option(k)) for k in opts}
     for k, v in opts.items():
         g.set_option(k, v)
     try:
+        used0 = g.get_option("xyp_used")
         for bk, theta, cfl in [("robin_dict3d", 0.5, 0.7), ("robin6", 1.0, 500.0)]:
             _both(g, cp, _uniform_case(shape, mask_kind, bk, theta, cfl, seed=9000 + shape[0]), nsteps=2)
+        n_long = max(shape[0], shape[1])
+        if opts.get("xyp") == 1 and n_long % 128 == 0 and shape[2] % 2 == 0:
+            assert g.get_option("xyp_layout") >= 0, "the driver refused the tensor map"
+            assert g.get_option("xyp_used") > used0, "the persistent kernel did not run"
     finally:
         for k, v in restore.items():
             g.set_option(k, v)

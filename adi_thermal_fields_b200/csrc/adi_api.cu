@@ -272,6 +272,8 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
         ctx->opt_tiles = value;
         for (int a = 0; a < 3; ++a) ctx->tiles[a].valid = false;
     }
+    else if (!strcmp(name, "ejt")) ctx->opt_ejt = value;      // explicit stage: y rows per block (default 16)
+    else if (!strcmp(name, "eth")) ctx->opt_eth = value;      // explicit stage: threads per block (default 128)
     else if (!strcmp(name, "eorder")) ctx->opt_eorder = value;  // explicit stage: 1 = blocks of neighbouring x planes run together
     else if (!strcmp(name, "hyb")) ctx->opt_hyb = value;    // 1 (default): z sweep, uniform lead + general tail in one chunk (the chunk under a surface)
     else if (!strcmp(name, "xyp")) ctx->opt_xyp = value;    // 1: x / y lines of 1025..2048 cells on persistent blocks, tiles prefetched by the TMA engine (default 0: no faster than k_sweep_xy, r02o-r02q)
@@ -314,6 +316,8 @@ long adi_get_option(adi_ctx *ctx, const char *name)
     if (!strcmp(name, "promo")) return ctx->opt_promo;
     if (!strcmp(name, "lb")) return ctx->opt_lb;
     if (!strcmp(name, "bulk")) return ctx->opt_bulk;
+    if (!strcmp(name, "ejt")) return ctx->opt_ejt;
+    if (!strcmp(name, "eth")) return ctx->opt_eth;
     if (!strcmp(name, "eorder")) return ctx->opt_eorder;
     if (!strcmp(name, "tiles")) return ctx->opt_tiles;
     if (!strcmp(name, "tiles_active")) return ctx->tiles[0].n + ctx->tiles[1].n + ctx->tiles[2].n;

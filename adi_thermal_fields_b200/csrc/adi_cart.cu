@@ -283,7 +283,7 @@ int adi_cart_set_robin_scalar(adi_ctx *ctx, const double face_coeff[6])
 static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double dt, double theta,
                       double kappa, double Tinf, int first, int last, int zmode, const double *d_Tlo,
                       const double *d_Thi, double *d_iface_dyn, double *d_iface_stat, const double *d_ghost,
-                      cudaStream_t st, size_t line0 = 0, size_t nlb = 0)
+                      cudaStream_t st, size_t line0 = 0, size_t nlb = 0, cudaEvent_t halo_ready = nullptr)
 {
     const size_t ncell = (size_t)ctx->nx * ctx->ny * ctx->nz;
     if (ncell == 0) return ADI_OK;
@@ -302,27 +302,38 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
     a.k.beta = dt * kappa * (1.0 - theta);
     a.k.invdx2 = 1.0 / (dx * dx);
     a.zlo = d_Tlo; a.zhi = d_Thi; a.iface_dyn = d_iface_dyn; a.iface_stat = d_iface_stat; a.ghost = d_ghost;
-    a.codeT = nullptr; a.npad = 0; a.uni = 0; a.tw = 0; a.remap = 0; a.dbg = 0;
+    a.codeT = nullptr; a.npad = 0; a.uni = 0; a.tw = 0; a.remap = 0; a.dbg = 0; a.halo_defer = 0;
     a.tiles = nullptr; a.tiles_nx = 0;
     a.line_batch = nlb != 0 ? 1 : 0;
     bool expl = a.k.beta != 0.0;
     bool x_in_place = false;
+    // halo_ready: d_Tlo / d_Thi are still being received; the explicit stage leaves the cells that need them to
+    // k_explicit_faces, which the caller has queued behind the planes on another stream and which records the event
+    if (halo_ready && !(expl && first == 0 && !ctx->opt_fuse)) {
+        ADI_CUDA(cudaStreamWaitEvent(st, halo_ready, 0));
+        halo_ready = nullptr;
+    }
     if (expl && first == 0 && !ctx->opt_fuse) {
         // explicit stage as its own streaming pass Tin -> Tout; the x sweep then runs in place
         a.in = d_Tin; a.out = d_Tout; a.code = ctx->code[0];
         a.coeff = nullptr; a.sparse = 0; a.q = nullptr; a.dirv = nullptr;
         const bool vec = (a.nz % 2 == 0) && ((((uintptr_t)d_Tin | (uintptr_t)d_Tout) & 15) == 0) &&
                          (((uintptr_t)a.code & 1) == 0);
-        const int VEC = vec ? 2 : 1, threads = 128, JT = 16;
+        const int VEC = vec ? 2 : 1;
+        const int threads = (ctx->opt_eth == 32 || ctx->opt_eth == 64 || ctx->opt_eth == 128) ? (int)ctx->opt_eth : 128;
+        const int JT = ctx->opt_ejt > 0 ? (int)std::min<long>(ctx->opt_ejt, 1024) : 16;
         // block order (option eorder): 0 = z chunks fastest, x slowest; 1 = x fastest -- the blocks of neighbouring x
         // planes then run together and find each other's rows (their x-1 / x+1 neighbours) in L2
         const unsigned gz = (unsigned)(((a.nz + VEC - 1) / VEC + threads - 1) / threads), gy = (unsigned)((a.ny + JT - 1) / JT);
         const int xfast = (ctx->opt_eorder && gz <= 65535u) ? 1 : 0;
         dim3 grid = xfast ? dim3((unsigned)a.nx, gy, gz) : dim3(gz, gy, (unsigned)a.nx);
+        a.halo_defer = halo_ready ? 1 : 0;
         if (vec) k_explicit<2><<<grid, threads, 0, st>>>(a, JT, xfast);
         else k_explicit<1><<<grid, threads, 0, st>>>(a, JT, xfast);
         ctx->launches++;
         ADI_CUDA(cudaGetLastError());
+        a.halo_defer = 0;
+        if (halo_ready) ADI_CUDA(cudaStreamWaitEvent(st, halo_ready, 0));   // k_explicit_faces has filled in the face cells
         expl = false;
         x_in_place = true;
     }
@@ -730,5 +741,48 @@ int cart_zapply_range(adi_ctx *ctx, double *d_T, const double *d_dyn_all, const 
 }
 
 int cart_prof_mark(adi_ctx *ctx, int slot, cudaStream_t st) { return prof_mark(ctx, slot, st); }
+
+// Neighbour code and operand checks up to date (on `st`): what the deferred explicit stage needs before another
+// stream may run k_explicit_faces.
+int cart_prepare(adi_ctx *ctx, cudaStream_t st)
+{
+    int rc = ensure_code(ctx, st);
+    if (rc) return rc;
+    return ensure_sparse(ctx, st);
+}
+
+// Explicit stage of the slab-face cells whose stencil reaches into the adjacent slabs (k_explicit_faces), queued on
+// `st` (the communication stream, behind the arrival of the planes).  No-op without an explicit stage.
+int cart_explicit_faces(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const double *d_Tlo, const double *d_Thi,
+                        double dt, double theta, double kappa, cudaStream_t st)
+{
+    const size_t nlines = (size_t)ctx->nx * ctx->ny;
+    if (!nlines || !ctx->nz || theta == 1.0) return ADI_OK;
+    const double dx = ctx->dx;
+    SweepArgs a = {};
+    a.nx = ctx->nx; a.ny = ctx->ny; a.nz = ctx->nz;
+    a.k.g = theta * (kappa * dt / (dx * dx));
+    a.k.dt = dt;
+    a.k.beta = dt * kappa * (1.0 - theta);
+    a.k.invdx2 = 1.0 / (dx * dx);
+    a.in = d_Tin; a.out = d_Tout; a.code = ctx->code[0];
+    a.zlo = ctx->d_mask_lo ? d_Tlo : nullptr; a.zhi = ctx->d_mask_hi ? d_Thi : nullptr;
+    if (!a.zlo && !a.zhi) return ADI_OK;
+    k_explicit_faces<<<(unsigned)std::min<size_t>((nlines + 127) / 128, 148 * 32), 128, 0, st>>>(a);
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
+    return ADI_OK;
+}
+
+// adi_cart_step_xy with the T planes of the adjacent slabs still on their way: `halo_ready` is recorded (on another
+// stream) behind cart_explicit_faces
+int cart_step_xy_deferred(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const double *d_Tlo, const double *d_Thi,
+                          double dt, double theta, double kappa, double Tinf, cudaStream_t st, cudaEvent_t halo_ready)
+{
+    int rc = prof_mark(ctx, 0, st);
+    if (rc) return rc;
+    return run_sweeps(ctx, d_Tin, d_Tout, dt, theta, kappa, Tinf, 0, 1, 0, ctx->d_mask_lo ? d_Tlo : nullptr,
+                      ctx->d_mask_hi ? d_Thi : nullptr, nullptr, nullptr, nullptr, st, 0, 0, halo_ready);
+}
 
 }  // namespace adi

@@ -45,6 +45,8 @@ struct SweepArgs {
     int tw;                            // reduced system by warps (transposed exchange)
     int remap;                         // chunk order inside a block: ends of the line in the same warp
     int dbg;                           // tuning aid: 1 = loads and stores only
+    int halo_defer;                    // explicit stage: the adjacent slabs' T planes are still travelling -- cells that need
+                                       // them are left to k_explicit_faces (not stored here)
     // active-tile list (parts under construction: most of the box is void): block b works on tile tiles[b] =
     // by * tiles_nx + bx instead of (blockIdx.x, blockIdx.y); NULL = every tile, addressed by blockIdx
     const int *__restrict__ tiles;
@@ -1012,8 +1014,18 @@ __global__ void __launch_bounds__(128) k_explicit(const SweepArgs a, const int J
         }
         const unsigned c0 = cw & 0xffu, cl = (cw >> (8 * (VEC - 1))) & 0xffu;
         double zlo_v = 0.0, zhi_v = 0.0;
-        if (c0 & CB_ZM) zlo_v = z > 0 ? a.in[idx - 1] : a.zlo[(size_t)i * a.ny + j];
-        if (cl & CB_ZP) zhi_v = z + VEC < a.nz ? a.in[idx + VEC] : a.zhi[(size_t)i * a.ny + j];
+        // halo_defer: the planes are still on their way -- the cells that need them belong to k_explicit_faces
+        bool skip0 = false, skipl = false;
+        if (c0 & CB_ZM) {
+            if (z > 0) zlo_v = a.in[idx - 1];
+            else if (a.halo_defer) skip0 = true;
+            else zlo_v = a.zlo[(size_t)i * a.ny + j];
+        }
+        if (cl & CB_ZP) {
+            if (z + VEC < a.nz) zhi_v = a.in[idx + VEC];
+            else if (a.halo_defer) skipl = true;
+            else zhi_v = a.zhi[(size_t)i * a.ny + j];
+        }
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             const unsigned c = (cw >> (8 * v)) & 0xffu;
@@ -1024,11 +1036,46 @@ __global__ void __launch_bounds__(128) k_explicit(const SweepArgs a, const int J
                                           (c & CB_YP) ? next[v] : 0.0, zm, zp, a.k);
             r[v] = (c & CB_SELF) ? r0 : cur[v];
         }
-        if (VEC == 2) *reinterpret_cast<double2 *>(a.out + idx) = make_double2(r[0], r[VEC - 1]);
-        else a.out[idx] = r[0];
+        if (skip0 || skipl) {
+            if (!skip0) a.out[idx] = r[0];
+            if (VEC == 2 && !skipl) a.out[idx + VEC - 1] = r[VEC - 1];
+        } else if (VEC == 2) {
+            *reinterpret_cast<double2 *>(a.out + idx) = make_double2(r[0], r[VEC - 1]);
+        } else {
+            a.out[idx] = r[0];
+        }
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { prev[v] = cur[v]; cur[v] = next[v]; }
         idx += a.nz;
+    }
+}
+
+// K1f: explicit stage of the cells on the two faces of a z slab whose stencil reaches into the adjacent slab
+// (first / last z plane, neighbour across the face active): the multi-GPU step runs k_explicit (halo_defer: it leaves
+// these cells alone) while the T planes of the adjacent ranks are still travelling; this kernel follows the planes
+// on the communication stream -- same arithmetic, same operand order -- so it runs beside k_explicit.  One thread
+// per z line.
+__global__ void k_explicit_faces(const SweepArgs a)
+{
+    const size_t nlines = (size_t)a.nx * a.ny;
+    const size_t snx = (size_t)a.ny * a.nz;
+    for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < nlines; l += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(l / a.ny), j = (int)(l - (size_t)i * a.ny);
+        for (int side = 0; side < 2; ++side) {
+            const int k = side == 0 ? 0 : a.nz - 1;
+            if (side == 1 && a.nz == 1) break;                 // the single plane was done as side 0
+            const size_t idx = l * (size_t)a.nz + k;
+            const unsigned c = a.code[idx];
+            const bool lo = k == 0 && (c & CB_ZM) && a.zlo, hi = k == a.nz - 1 && (c & CB_ZP) && a.zhi;
+            if (!(c & CB_SELF) || !(lo || hi)) continue;
+            const double T = a.in[idx];
+            const double xm = (c & CB_XM) ? a.in[idx - snx] : 0.0, xp = (c & CB_XP) ? a.in[idx + snx] : 0.0;
+            const double ym = (c & CB_YM) ? a.in[idx - a.nz] : 0.0, yp = (c & CB_YP) ? a.in[idx + a.nz] : 0.0;
+            double zm = 0.0, zp = 0.0;
+            if (c & CB_ZM) zm = k > 0 ? a.in[idx - 1] : (a.zlo ? a.zlo[l] : 0.0);
+            if (c & CB_ZP) zp = k + 1 < a.nz ? a.in[idx + 1] : (a.zhi ? a.zhi[l] : 0.0);
+            a.out[idx] = explicit_r0(c, T, xm, xp, ym, yp, zm, zp, a.k);
+        }
     }
 }
 

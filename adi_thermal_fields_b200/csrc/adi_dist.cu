@@ -34,6 +34,11 @@ int cart_zapply_range(adi_ctx *ctx, double *d_T, const double *d_dyn_all, const 
                       const double *d_wC, const int *d_Kv, const int *d_Kw, int kmax, size_t line0, size_t nlb,
                       cudaStream_t st);
 int cart_prof_mark(adi_ctx *ctx, int slot, cudaStream_t st);
+int cart_prepare(adi_ctx *ctx, cudaStream_t st);
+int cart_explicit_faces(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const double *d_Tlo, const double *d_Thi,
+                        double dt, double theta, double kappa, cudaStream_t st);
+int cart_step_xy_deferred(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const double *d_Tlo, const double *d_Thi,
+                          double dt, double theta, double kappa, double Tinf, cudaStream_t st, cudaEvent_t halo_ready);
 
 // the few NCCL entry points used, by their public C signatures (nccl.h; types reduced to what the ABI needs)
 typedef struct ncclComm *nccl_comm_t;
@@ -118,7 +123,7 @@ struct DistState {
     double *vC = nullptr, *wC = nullptr;
     int *Kv = nullptr, *Kw = nullptr;
     // options
-    int nbatch = 4, spike_after = 2, spike_kmax = 32;
+    int nbatch = 4, spike_after = 2, spike_kmax = 32, overlap_halo = 0;
     long batch_min = 1 << 20; // lines: smaller batches are not worth a collective of their own (measured at 262144 lines, N = 2: one batch 1.977 ms, four 2.02 ms per step)
     double spike_thr = 0x1p-80;
     long steps_two_pass = 0, steps_solve_first = 0;
@@ -295,6 +300,8 @@ int adi_dist_set_option(adi_ctx *ctx, const char *name, long value)
     DistState *d = ctx->dist;
     if (!strcmp(name, "batches")) d->nbatch = (int)std::min<long>(std::max<long>(value, 1), MAX_BATCH);
     else if (!strcmp(name, "batch_min_lines")) d->batch_min = std::max<long>(value, 32);
+    else if (!strcmp(name, "overlap_halo")) d->overlap_halo = value ? 1 : 0;   // 1: the explicit stage runs while the T planes travel, the face cells follow them on the communication stream (default 0: measured slower at N = 2, r02t / r02u)
+    else if (!strcmp(name, "spike_thr_log2")) { d->spike_thr = std::ldexp(1.0, (int)std::min<long>(std::max<long>(value, -200), -30)); d->spike_state = 0; d->stat_valid = false; }
     else if (!strcmp(name, "spike_after")) d->spike_after = (int)value;       // < 0: never leave the two-pass form
     else if (!strcmp(name, "spike_kmax")) { d->spike_kmax = (int)std::max<long>(value, 1); d->spike_state = 0; }
     else { set_error(std::string("adi_dist_set_option: unknown option ") + name); return ADI_EINVAL; }
@@ -344,17 +351,30 @@ int adi_cart_slab_step(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double
     if (!nl || !nz) return ADI_OK;
     const bool lo_ok = d->rank > 0, hi_ok = d->rank + 1 < R;
 
-    // (1) T planes for the explicit stage (beta = 0 at theta = 1: no explicit stage, no halo)
+    // (1) T planes for the explicit stage (beta = 0 at theta = 1: no explicit stage, no halo).  The planes travel on
+    // the communication stream while the explicit stage runs; only the cells on the slab faces wait for them.
+    cudaEvent_t halo_ready = nullptr;
     if (theta != 1.0) {
+        const bool overlap = d->overlap_halo && !ctx->opt_fuse;
+        if (overlap && (rc = cart_prepare(ctx, st))) return rc;      // the neighbour code must exist before ev_c
         if ((rc = adi_cart_pack_zplanes(ctx, d_Tin, 8, d->t_send[0], d->t_send[1], stream))) return rc;
         ADI_CUDA(cudaEventRecord(d->ev_c, st));
         ADI_CUDA(cudaStreamWaitEvent(d->cs, d->ev_c, 0));
         if ((rc = exchange_planes<double>(d, d->t_send, d->t_recv, nl, NCCL_FLOAT64))) return rc;
-        ADI_CUDA(cudaEventRecord(d->ev_x, d->cs));
-        ADI_CUDA(cudaStreamWaitEvent(st, d->ev_x, 0));
+        if (overlap) {
+            // the face cells follow the planes on the communication stream, beside the explicit stage of everything else
+            if ((rc = cart_explicit_faces(ctx, d_Tin, d_Tout, lo_ok ? d->t_recv[0] : nullptr, hi_ok ? d->t_recv[1] : nullptr, dt,
+                                          theta, kappa, d->cs)))
+                return rc;
+            ADI_CUDA(cudaEventRecord(d->ev_x, d->cs));
+            halo_ready = d->ev_x;
+        } else {
+            ADI_CUDA(cudaEventRecord(d->ev_x, d->cs));
+            ADI_CUDA(cudaStreamWaitEvent(st, d->ev_x, 0));
+        }
     }
-    if ((rc = adi_cart_step_xy(ctx, d_Tin, d_Tout, lo_ok ? d->t_recv[0] : nullptr, hi_ok ? d->t_recv[1] : nullptr, dt, theta,
-                               kappa, Tinf, stream)))
+    if ((rc = cart_step_xy_deferred(ctx, d_Tin, d_Tout, lo_ok ? d->t_recv[0] : nullptr, hi_ok ? d->t_recv[1] : nullptr, dt,
+                                    theta, kappa, Tinf, st, halo_ready)))
         return rc;
 
     // (2) z sweep.  The matrix part of the interface relations only changes with mask, packs, dt or theta.

@@ -285,7 +285,7 @@ class CudaBackend:
         return int(self.L.adi_launch_count(self.ctx))
 
     def set_option(self, name, value):
-        if str(name) in ("batches", "batch_min_lines", "spike_after", "spike_kmax"):
+        if str(name) in ("batches", "batch_min_lines", "spike_after", "spike_kmax", "overlap_halo", "spike_thr_log2"):
             _capi.check(self.L.adi_dist_set_option(self.ctx, str(name).encode(), int(value)), "adi_dist_set_option")
             return
         _capi.check(self.L.adi_set_option(self.ctx, str(name).encode(), int(value)), "adi_set_option")

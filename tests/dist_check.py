@@ -28,6 +28,9 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
 for shape, mk, bk, theta, cfl, nsteps, opts in [
         ((24, 20, 16 * world * 2), "cyl_holes", "combined", 0.5, 2.0, 3, None),
+        # the explicit stage running while the T planes travel (option overlap_halo: face cells on the communication stream)
+        ((24, 20, 16 * world * 2), "cyl_holes", "combined", 0.5, 2.0, 3, dict(overlap_halo=1)),
+        ((20, 24, 16 * world), "random", "robin_dict3d", 0.5, 0.7, 3, dict(overlap_halo=1)),
         ((16, 40, 64 * world), "random", "robin_dict3d", 0.5, 3000.0, 2, None),
         ((32, 16, 16 * world), "plate_track", "robin6", 1.0, 0.128, 2, None),
         # steady stepping: the solve-first z form, its all-gathers in three overlapped line batches

@@ -51,7 +51,7 @@ def rank_run(comm, pb, nsteps, backend, options=None):
     z0, z1 = slab.split_z(nz, comm.world)[comm.rank]
     grid = slab.SlabGrid3D(nx, ny, z1 - z0, cases.DX, pb["mask"][:, :, z0:z1], comm, backend=backend)
     for k, v in (options or {}).items():
-        if getattr(grid.be, "dist", False) or k not in ("batches", "batch_min_lines", "spike_after", "spike_kmax"):
+        if getattr(grid.be, "dist", False) or k not in ("batches", "batch_min_lines", "spike_after", "spike_kmax", "overlap_halo", "spike_thr_log2"):
             grid.be.set_option(k, v)
     packs = slab.precompute_coeff_packs_unified(grid, Mat, **slice_bcs(pb["bcs"], z0, z1))
     T = grid.be.asarray(pb["T0"][:, :, z0:z1], torch.float64)

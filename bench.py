@@ -529,22 +529,30 @@ def bench_plate(args, local):
     # ---- roofline of the slowest kernel (live CUDA events inside the engine) ----
     peak, peak_src = peaks()
     per = [ms3[i] / max(1, nst.value) for i in range(4)]
-    names = ["k_explicit", "k_sweep_xy<x>", "k_sweep_xy<y>", "k_sweep_z"]
+    sparse = int(L.adi_get_option(ctx, b"sparse_active"))
+    # the z sweep of lines longer than 128 cells runs k_sweep_zt unless its coefficient field must be read densely
+    zt = bool(L.adi_get_option(ctx, b"zt")) and n > 128 and ((sparse >> 2) & 1)
+    names = ["k_explicit", "k_sweep_xy<x>", "k_sweep_xy<y>", "k_sweep_zt" if zt else "k_sweep_z"]
     # algorithmic bytes per cell: explicit stage T in 8 + code 1 + out 8; a sweep
     # in 8 + out 8 + code 1 + dense coeff 8.  The 75 B/cell-step of the metric counts the fused
     # form (3 sweeps); the separate explicit pass is extra real traffic, not extra credit.
     bpc = [17.0, 25.0, 25.0, 25.0]
     # what the kernels really fetch: a sweep whose coefficient field was verified surface-only (option
     # sparse_coeff, x / y sweeps) skips the 8 B/cell of interior coefficient reads
-    sparse = int(L.adi_get_option(ctx, b"sparse_active"))
     moved = [17.0] + [17.0 if (sparse >> a) & 1 else 25.0 for a in range(3)]
     dom = int(np.argmax(per))
     bytes_per_launch = bpc[dom] * cells
     achieved = bytes_per_launch / (per[dom] * 1e-3) / 1e9
-    kern_key = ["k_explicit", "k_sweep_xy", "k_sweep_xy", "k_sweep_z"][dom]
+    kern_key = ["k_explicit", "k_sweep_xy<0", "k_sweep_xy<1", "k_sweep_zt" if zt else "k_sweep_z"][dom]
+    traffic = traffic_of(kern_key) or traffic_of(kern_key.split("<")[0])
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic_of(kern_key), "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
+                # the same kernel against the bytes it really moves (its share of moved_bytes_per_cell_step; `traffic`
+                # is the ncu DRAM figure of the same launch shape): the DRAM-side utilisation
+                "moved_bytes_per_launch": moved[dom] * cells,
+                "achieved_moved": moved[dom] * cells / (per[dom] * 1e-3) / 1e9,
+                "frac_moved": moved[dom] * cells / (per[dom] * 1e-3) / 1e9 / peak,
                 "kernel_ms": {"explicit": per[0], "x": per[1], "y": per[2], "z": per[3]},
                 "kernel_GBs": {k: b * cells / (t * 1e-3) / 1e9 if t > 0 else None
                                for k, b, t in zip(("explicit", "x", "y", "z"), bpc, per)},

@@ -1026,31 +1026,15 @@ __global__ void __launch_bounds__(128) k_explicit(const SweepArgs a, const int J
             else if (a.halo_defer) skipl = true;
             else zhi_v = a.zhi[(size_t)i * a.ny + j];
         }
-        constexpr unsigned BULK = CB_SELF | CB_XM | CB_XP | CB_YM | CB_YP | CB_ZM | CB_ZP;
-        if ((cw & (VEC == 2 ? 0x7f7fu : 0x7fu)) == (VEC == 2 ? (BULK | (BULK << 8)) : BULK)) {
-            // bulk cells (active, all six neighbours active): the same expression with the selects and the neighbour
-            // counts (2.0 per axis) folded -- the same operations in the same order, so the same bits
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                const double zm = v == 0 ? zlo_v : cur[v - 1 < 0 ? 0 : v - 1];
-                const double zp = v == VEC - 1 ? zhi_v : cur[v + 1 < VEC ? v + 1 : v];
-                const double T = cur[v];
-                const double L0 = ((xm[v] + xp[v]) - 2.0 * T) * a.k.invdx2;
-                const double L1 = ((prev[v] + next[v]) - 2.0 * T) * a.k.invdx2;
-                const double L2 = ((zm + zp) - 2.0 * T) * a.k.invdx2;
-                r[v] = T + a.k.beta * ((L0 + L1) + L2);
-            }
-        } else {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                const unsigned c = (cw >> (8 * v)) & 0xffu;
-                const double zm = v == 0 ? zlo_v : ((c & CB_ZM) ? cur[v - 1 < 0 ? 0 : v - 1] : 0.0);
-                const double zp = v == VEC - 1 ? zhi_v : ((c & CB_ZP) ? cur[v + 1 < VEC ? v + 1 : v] : 0.0);
-                const double r0 = explicit_r0(c, (c & CB_SELF) ? cur[v] : 0.0, (c & CB_XM) ? xm[v] : 0.0,
-                                              (c & CB_XP) ? xp[v] : 0.0, (c & CB_YM) ? prev[v] : 0.0,
-                                              (c & CB_YP) ? next[v] : 0.0, zm, zp, a.k);
-                r[v] = (c & CB_SELF) ? r0 : cur[v];
-            }
+        for (int v = 0; v < VEC; ++v) {
+            const unsigned c = (cw >> (8 * v)) & 0xffu;
+            const double zm = v == 0 ? zlo_v : ((c & CB_ZM) ? cur[v - 1 < 0 ? 0 : v - 1] : 0.0);
+            const double zp = v == VEC - 1 ? zhi_v : ((c & CB_ZP) ? cur[v + 1 < VEC ? v + 1 : v] : 0.0);
+            const double r0 = explicit_r0(c, (c & CB_SELF) ? cur[v] : 0.0, (c & CB_XM) ? xm[v] : 0.0,
+                                          (c & CB_XP) ? xp[v] : 0.0, (c & CB_YM) ? prev[v] : 0.0,
+                                          (c & CB_YP) ? next[v] : 0.0, zm, zp, a.k);
+            r[v] = (c & CB_SELF) ? r0 : cur[v];
         }
         if (skip0 || skipl) {
             if (!skip0) a.out[idx] = r[0];

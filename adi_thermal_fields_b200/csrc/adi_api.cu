@@ -181,7 +181,7 @@ int adi_ctx_destroy(adi_ctx *ctx)
     for (int a = 0; a < 2; ++a)
         if (ctx->codeT[a]) cudaFree(ctx->codeT[a]);
     for (int a = 0; a < 3; ++a)
-        if (ctx->tiles[a].d) cudaFree(ctx->tiles[a].d);
+        if (ctx->tiles[a].d) { cudaFree(ctx->tiles[a].d); cudaFree(ctx->tiles[a].d_uni); cudaFree(ctx->tiles[a].d_gen); }
     if (ctx->d_tflags) cudaFree(ctx->d_tflags);
     if (ctx->h_tflags) cudaFreeHost(ctx->h_tflags);
     for (int a = 0; a < 2; ++a)
@@ -272,6 +272,9 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
         ctx->opt_tiles = value;
         for (int a = 0; a < 3; ++a) ctx->tiles[a].valid = false;
     }
+    else if (!strcmp(name, "xyu")) ctx->opt_xyu = value;      // 1 (default): all-uniform tiles of 1025..2048-cell x / y lines on k_sweep_xyu (two blocks per SM)
+    else if (!strcmp(name, "ukt")) ctx->opt_ukt = value;
+    else if (!strcmp(name, "zm")) ctx->opt_zm = value;        // k_sweep_zt: chunk length (16 / 32) whatever the line length
     else if (!strcmp(name, "ejt")) ctx->opt_ejt = value;      // explicit stage: y rows per block (default 16)
     else if (!strcmp(name, "eth")) ctx->opt_eth = value;      // explicit stage: threads per block (default 128)
     else if (!strcmp(name, "eorder")) ctx->opt_eorder = value;  // explicit stage: 1 = blocks of neighbouring x planes run together
@@ -316,6 +319,10 @@ long adi_get_option(adi_ctx *ctx, const char *name)
     if (!strcmp(name, "promo")) return ctx->opt_promo;
     if (!strcmp(name, "lb")) return ctx->opt_lb;
     if (!strcmp(name, "bulk")) return ctx->opt_bulk;
+    if (!strcmp(name, "xyu")) return ctx->opt_xyu;
+    if (!strcmp(name, "xyu_used")) return ctx->xyu_used;     // launches of k_sweep_xyu so far
+    if (!strcmp(name, "ukt")) return ctx->opt_ukt;
+    if (!strcmp(name, "zm")) return ctx->opt_zm;
     if (!strcmp(name, "ejt")) return ctx->opt_ejt;
     if (!strcmp(name, "eth")) return ctx->opt_eth;
     if (!strcmp(name, "eorder")) return ctx->opt_eorder;

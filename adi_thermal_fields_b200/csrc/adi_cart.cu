@@ -158,27 +158,54 @@ int adi::ensure_tiles(adi_ctx *ctx, int axis, int KT, cudaStream_t st, const int
             ADI_CUDA(cudaMallocHost(&ctx->h_tflags, n));
             ctx->tflags_cap = n;
         }
-        k_tile_flags<<<(unsigned)std::min<size_t>(n, 148 * 64), 128, 0, st>>>(base, unit, KT, inner, (int)total, ctx->d_tflags);
+        const unsigned ulo = axis == 0 ? CB_XM : CB_YM, uhi = axis == 0 ? CB_XP : (axis == 1 ? CB_YP : 0u);
+        k_tile_flags<<<(unsigned)std::min<size_t>(n, 148 * 64), 128, 0, st>>>(base, unit, KT, inner, (int)total, ctx->d_tflags,
+                                                                               axis == 2 ? 0u : ulo, uhi,
+                                                                               axis == 0 ? ctx->nx : ctx->ny);
         ctx->launches++;
         ADI_CUDA(cudaGetLastError());
         ADI_CUDA(cudaMemcpyAsync(ctx->h_tflags, ctx->d_tflags, n, cudaMemcpyDeviceToHost, st));
         ADI_CUDA(cudaStreamSynchronize(st));
-        std::vector<int> ids;
+        std::vector<int> ids, uni, gen;
         ids.reserve(n);
-        for (size_t t = 0; t < n; ++t)
-            if (ctx->h_tflags[t]) ids.push_back((int)t);
+        for (size_t t = 0; t < n; ++t) {
+            const uint8_t f = ctx->h_tflags[t];
+            if (f & 1) {
+                ids.push_back((int)t);
+                ((f & 2) ? uni : gen).push_back((int)t);
+            }
+        }
         if (L.cap < std::max<size_t>(ids.size(), 1)) {
-            if (L.d) ADI_CUDA(cudaFree(L.d));
-            L.d = nullptr;
+            if (L.d) { ADI_CUDA(cudaFree(L.d)); ADI_CUDA(cudaFree(L.d_uni)); ADI_CUDA(cudaFree(L.d_gen)); }
+            L.d = L.d_uni = L.d_gen = nullptr;
             L.cap = std::max<size_t>(n, 1);
             ADI_CUDA(cudaMalloc(&L.d, L.cap * sizeof(int)));
+            ADI_CUDA(cudaMalloc(&L.d_uni, L.cap * sizeof(int)));
+            ADI_CUDA(cudaMalloc(&L.d_gen, L.cap * sizeof(int)));
         }
         if (!ids.empty()) ADI_CUDA(cudaMemcpyAsync(L.d, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-        ADI_CUDA(cudaStreamSynchronize(st));   // `ids` leaves scope
-        L.n = (int)ids.size(); L.total = (int)total; L.kt = KT; L.valid = true;
+        if (!uni.empty()) ADI_CUDA(cudaMemcpyAsync(L.d_uni, uni.data(), uni.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (!gen.empty()) ADI_CUDA(cudaMemcpyAsync(L.d_gen, gen.data(), gen.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        ADI_CUDA(cudaStreamSynchronize(st));   // the vectors leave scope
+        L.n = (int)ids.size(); L.n_uni = (int)uni.size(); L.n_gen = (int)gen.size();
+        L.total = (int)total; L.kt = KT; L.valid = true;
     }
     *tiles_nx = nti;
     if (L.n < L.total) { *list = L.d; *nactive = L.n; }
+    return ADI_OK;
+}
+
+int adi::ensure_tiles_split(adi_ctx *ctx, int axis, int KT, cudaStream_t st, const int **uni, int *nuni, const int **gen,
+                            int *ngen, int *tiles_nx)
+{
+    *uni = *gen = nullptr; *nuni = *ngen = 0;
+    const int *list = nullptr;
+    int nact = 0;
+    int rc = ensure_tiles(ctx, axis, KT, st, &list, &nact, tiles_nx);
+    if (rc) return rc;
+    const TileList &L = ctx->tiles[axis];
+    if (axis > 1 || !L.valid || L.kt != KT) return ADI_OK;     // (option tiles off, or the grid is too large for lists)
+    *uni = L.d_uni; *nuni = L.n_uni; *gen = L.d_gen; *ngen = L.n_gen;
     return ADI_OK;
 }
 
@@ -303,7 +330,7 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
     a.k.invdx2 = 1.0 / (dx * dx);
     a.zlo = d_Tlo; a.zhi = d_Thi; a.iface_dyn = d_iface_dyn; a.iface_stat = d_iface_stat; a.ghost = d_ghost;
     a.codeT = nullptr; a.npad = 0; a.uni = 0; a.tw = 0; a.remap = 0; a.dbg = 0; a.halo_defer = 0;
-    a.tiles = nullptr; a.tiles_nx = 0;
+    a.tiles = nullptr; a.tiles_nx = 0; a.tsplit = 0;
     a.line_batch = nlb != 0 ? 1 : 0;
     bool expl = a.k.beta != 0.0;
     bool x_in_place = false;

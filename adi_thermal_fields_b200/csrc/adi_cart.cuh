@@ -51,6 +51,7 @@ struct SweepArgs {
     // by * tiles_nx + bx instead of (blockIdx.x, blockIdx.y); NULL = every tile, addressed by blockIdx
     const int *__restrict__ tiles;
     int tiles_nx;
+    int tsplit;                        // k_sweep_xy: 1 = the list counts tiles of twice the block's lanes (two blocks per entry)
     int line_batch;                    // z sweep of a batch of lines (multi-GPU): the pointers are offset, no tile list
     UniConst uc;
 };
@@ -116,14 +117,20 @@ __global__ void __launch_bounds__(256) k_transpose_code(const uint8_t *__restric
 // tiles of KT consecutive rows inside runs of `inner` rows (x / y sweeps: rows = (other index, z), runs = one `other`
 // index, base = the transposed code array; z sweep: rows = z lines, one run).  flags[t] = 1 when any byte of tile
 // t = by * ceil(inner / KT) + bx is non-zero.  One block per tile.
+// uni_lo / uni_hi (x / y sweeps, unit a multiple of 32 bytes, 16-byte aligned rows; 0 = not asked): bit 1 of the flag
+// is set when the tile is ALL UNIFORM -- its KT rows all exist and every 32-byte chunk of every row passes
+// chunk_uniform<32, 1> (cells 1..30 active with both neighbours along the axis and no Dirichlet bit, cell 0 active
+// and coupled to cell 1): such a tile can go to k_sweep_xyu, which has no general row assembly at all.
 __global__ void __launch_bounds__(128) k_tile_flags(const uint8_t *__restrict__ base, size_t unit, int KT, int inner,
-                                                    int ntiles, uint8_t *__restrict__ flags)
+                                                    int ntiles, uint8_t *__restrict__ flags, unsigned uni_lo = 0u,
+                                                    unsigned uni_hi = 0u, int nline = 0)
 {
     const int nti = (inner + KT - 1) / KT;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int by = t / nti, bx = t - by * nti;
         const size_t row0 = (size_t)by * inner + (size_t)bx * KT;
-        const size_t len = (size_t)min(KT, inner - bx * KT) * unit;
+        const int rows = min(KT, inner - bx * KT);
+        const size_t len = (size_t)rows * unit;
         const uint8_t *p = base + row0 * unit;
         bool any = false;
         if ((((uintptr_t)p | len) & 15) == 0) {
@@ -136,7 +143,25 @@ __global__ void __launch_bounds__(128) k_tile_flags(const uint8_t *__restrict__ 
             for (size_t i = threadIdx.x; i < len && !any; i += blockDim.x) any = p[i] != 0;
         }
         any = __syncthreads_or(any);
-        if (threadIdx.x == 0) flags[t] = any ? 1 : 0;
+        bool uni = false;
+        if (uni_hi && any && rows == KT && (nline & 31) == 0 && (unit & 31) == 0 && ((uintptr_t)p & 15) == 0) {
+            const unsigned need1 = CB_SELF | uni_lo | uni_hi, care1 = need1 | CB_DIR;
+            const unsigned need = need1 * 0x01010101u, care = care1 * 0x01010101u;
+            const unsigned care0 = (care & 0xffffff00u) | (CB_SELF | uni_hi | CB_DIR);      // cell 0 of the chunk
+            const unsigned need0 = (need & 0xffffff00u) | (CB_SELF | uni_hi);
+            const unsigned care7 = care & 0x00ffffffu, need7 = need & 0x00ffffffu;         // cell 31 (separator): any
+            const int P = nline / 32;
+            uni = true;
+            for (int c = threadIdx.x; c < rows * P && uni; c += blockDim.x) {
+                const int r = c / P, ch = c - r * P;
+                const uint4 *q = reinterpret_cast<const uint4 *>(p + (size_t)r * unit + (size_t)ch * 32);
+                const uint4 a = q[0], b = q[1];
+                uni = ((a.x & care0) == need0) && ((a.y & care) == need) && ((a.z & care) == need) && ((a.w & care) == need) &&
+                      ((b.x & care) == need) && ((b.y & care) == need) && ((b.z & care) == need) && ((b.w & care7) == need7);
+            }
+            uni = __syncthreads_and(uni);
+        }
+        if (threadIdx.x == 0) flags[t] = (any ? 1 : 0) | (uni ? 2 : 0);
     }
 }
 

@@ -33,9 +33,15 @@ struct TileList {
     size_t cap = 0;
     int n = 0, total = 0, kt = 0;
     bool valid = false;
+    // x / y sweeps: the active tiles split into ALL-UNIFORM ones (k_tile_flags bit 1: k_sweep_xyu) and the rest
+    int *d_uni = nullptr, *d_gen = nullptr;
+    int n_uni = 0, n_gen = 0;
 };
 // -> *list = device list (NULL when every tile is active or the option is off), *nactive = tiles to launch
 int ensure_tiles(adi_ctx *ctx, int axis, int KT, cudaStream_t st, const int **list, int *nactive, int *tiles_nx);
+// x / y axes: the same tiles as two lists, all-uniform tiles and the other active ones (either may be empty)
+int ensure_tiles_split(adi_ctx *ctx, int axis, int KT, cudaStream_t st, const int **uni, int *nuni, const int **gen, int *ngen,
+                       int *tiles_nx);
 
 struct CylTables;  // adi_cyl.cu
 struct DistState;  // adi_dist.cu: NCCL communicator, exchange buffers and caches of the in-library z-slab step
@@ -63,10 +69,11 @@ struct adi_ctx {
     long launches = 0;
     // options (adi_set_option)
     long opt_kt = 0, opt_lt = 0, opt_m = 0, opt_sync_check = 0, opt_profile = 0, opt_fuse = 0, opt_wide = 0, opt_sparse = 1,
-         opt_xy2 = 1, opt_uni = 1, opt_tw = 0, opt_remap = 0, opt_dbg = 0, opt_occ = 0, opt_zt = 1, opt_bulk = 1, opt_tiles = 1, opt_eorder = 0, opt_lb = 0, opt_hyb = 1, opt_xyp = 0, opt_seq = 0, opt_promo = 0, opt_ejt = 0, opt_eth = 0;
+         opt_xy2 = 1, opt_uni = 1, opt_tw = 0, opt_remap = 0, opt_dbg = 0, opt_occ = 0, opt_zt = 1, opt_bulk = 1, opt_tiles = 1, opt_eorder = 0, opt_lb = 0, opt_hyb = 1, opt_xyp = 0, opt_seq = 0, opt_promo = 0, opt_ejt = 0, opt_eth = 0, opt_zm = 0, opt_xyu = 1, opt_ukt = 0;
     int sm_count = 0;
     int xyp_state = 0;   // tensor-map layout the driver accepted for k_sweep_xyp (0 / 1), -1: refused
     long xyp_used = 0;   // launches of k_sweep_xyp
+    long xyu_used = 0;   // launches of k_sweep_xyu
     // per-kernel timing (adi_profile_*): 5 events per step, read lazily
     std::vector<cudaEvent_t> prof_ev;
     long prof_steps = 0;

@@ -183,8 +183,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_xy(const SweepArgs a)
     const int tid = threadIdx.y * KT + kk;
     unsigned bx = blockIdx.x, by = blockIdx.y;
     if (a.tiles) {   // active-tile list: the block's tile comes from the list
-        const unsigned t = (unsigned)a.tiles[blockIdx.x];
+        const unsigned t = (unsigned)a.tiles[blockIdx.x >> a.tsplit];
         by = t / (unsigned)a.tiles_nx; bx = t - by * (unsigned)a.tiles_nx;
+        if (a.tsplit) bx = 2u * bx + (blockIdx.x & 1u);     // the list counts tiles of 2*KT lanes: two blocks per entry
     }
     const int k = bx * KT + kk;
     const int n = (AXIS == 0) ? a.nx : a.ny;

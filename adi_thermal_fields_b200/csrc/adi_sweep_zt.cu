@@ -52,11 +52,14 @@ static int launch_zt_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, bool ext
 int launch_sweep_zt(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, int zmode, cudaStream_t st, int *used)
 {
     *used = 0;
-    // short lines stay with k_sweep_z (one-warp tiles, shuffle PCR): measured at nz = 128, 0.69 against 0.89 ms
-    if (!ctx->opt_zt || a.nz > 2048 || (a.nz <= 128 && ctx->opt_zt != 2)) return ADI_OK;
+    if (!ctx->opt_zt || a.nz > 2048) return ADI_OK;
     if (dense && !a.sparse) return ADI_OK;     // a dense coefficient field that must be read everywhere: k_sweep_z stages it
-    int M = a.nz <= 128 ? 16 : 32;
-    if (ctx->opt_m == 16 || (zmode != 0 && a.nz % 32 != 0)) M = 16;
+    // 32-cell chunks from 64 cells up: on 2048 x 2048 x 128 (the slab of configs[4] at N = 8) 4 chunks x 16 lines take
+    // 1.31 ms = 6.9 TB/s against 2.12 ms for k_sweep_z and 2.6 ms for 16-cell chunks (r02x)
+    int M = a.nz < 64 ? 16 : 32;
+    if (ctx->opt_m == 16 || ctx->opt_zm == 16 || (zmode != 0 && a.nz % 32 != 0)) M = 16;
+    // short lines in 16-cell chunks stay with k_sweep_z (one-warp tiles, shuffle PCR): 0.69 against 0.89 ms at nz = 128
+    if (a.nz <= 128 && M == 16 && ctx->opt_zt != 2) return ADI_OK;
     if (zmode != 0 && a.nz % M != 0) return ADI_OK;   // (k_sweep_z reports the error)
     const int P = (a.nz + M - 1) / M;
     if (P > 64) return ADI_OK;
@@ -65,6 +68,7 @@ int launch_sweep_zt(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, in
     // 256-thread ones: 0.59 against 0.66 ms at 512^3 with one general warp per tile, r02g)
     int KT = 32;
     while (KT > 1 && KT * P > (P > 32 ? 512 : 128)) KT >>= 1;
+    if (P <= 4) KT = std::min(KT, 16);     // short lines: 64-thread tiles (1.31 against 1.39 ms, r02x)
     if (ctx->opt_lt > 0) {
         int w = 1;
         while (2 * w <= ctx->opt_lt && 2 * w <= 32 && 2 * w * P <= maxt) w <<= 1;

@@ -553,7 +553,8 @@ def test_active_tile_lists(g, cp):
 
 @pytest.mark.parametrize("opts", [dict(), dict(hyb=0), dict(lt=2), dict(lt=16), dict(m=16), dict(bulk=0)],
                          ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
-@pytest.mark.parametrize("shape", [(24, 40, 256), (16, 12, 515), (9, 33, 160)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("shape", [(24, 40, 256), (16, 12, 515), (9, 33, 160), (12, 20, 96), (10, 17, 128), (7, 9, 64)],
+                         ids=lambda s: "x".join(map(str, s)))
 def test_z_sweep_surface_chunks(shape, opts, g, cp):
     """z lines that cross the top surface of a part: the chunk under the surface has a uniform lead and a general tail
     (adi_core.h chunk_forward_hybrid).  Terraced surface heights (every lead length occurs, different ones inside one
@@ -582,24 +583,29 @@ def test_z_sweep_surface_chunks(shape, opts, g, cp):
             g.set_option(kk, v)
 
 
-@pytest.mark.parametrize("opts", [dict(xyp=1), dict(xyp=0), dict(xyp=1, tiles=0)],
+@pytest.mark.parametrize("opts", [dict(), dict(ukt=16), dict(ukt=8), dict(xyu=0), dict(xyp=1), dict(xyp=1, tiles=0), dict(tiles=0)],
                          ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
 @pytest.mark.parametrize("shape,mask_kind", [((1152, 40, 38), "plate_track"), ((40, 1152, 38), "cyl_holes"), ((2048, 21, 20), "full"),
                                              ((6, 2048, 70), "plate_track"), ((1536, 30, 10), "random"), ((1100, 7, 9), "full")],
                          ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else v)
 def test_long_lines_persistent_blocks(shape, mask_kind, opts, g, cp):
-    """x / y lines of 1025..2048 cells (a multiple of 128) run on persistent blocks whose tiles arrive as TMA tensor
-    copies (adi_sweep_xyp.cuh): more tiles than blocks (every block walks over several tiles, uniform and general
-    warps mixed), ragged z tiles, void tiles (in place: skipped, with and without the active-tile list), dense
-    per-face h and scalar h; other line lengths keep k_sweep_xy."""
+    """x / y lines of 1025..2048 cells: the all-uniform tiles run on k_sweep_xyu (half of every chunk in shared
+    memory, two blocks per SM), the other active tiles on k_sweep_xy; option xyp: persistent blocks whose tiles arrive
+    as TMA tensor copies (adi_sweep_xyp.cuh).  More tiles than blocks, uniform and general warps mixed, ragged z
+    tiles, void tiles (in place: skipped, with and without the tile lists), dense per-face h and scalar h."""
     restore = {k: int(g.get_option(k)) for k in opts}
     for k, v in opts.items():
         g.set_option(k, v)
     try:
         used0 = g.get_option("xyp_used")
+        uni0 = g.get_option("xyu_used")
         for bk, theta, cfl in [("robin_dict3d", 0.5, 0.7), ("robin6", 1.0, 500.0)]:
             _both(g, cp, _uniform_case(shape, mask_kind, bk, theta, cfl, seed=9000 + shape[0]), nsteps=2)
         n_long = max(shape[0], shape[1])
+        if opts.get("xyu", 1) and not opts.get("xyp") and opts.get("tiles", 1) and n_long % 32 == 0 and mask_kind in ("full", "plate_track"):
+            assert g.get_option("xyu_used") > uni0, "the all-uniform tiles did not go to k_sweep_xyu"
+        if opts.get("xyu") == 0 or opts.get("tiles") == 0:
+            assert g.get_option("xyu_used") == uni0
         if opts.get("xyp") == 1 and n_long % 128 == 0 and shape[2] % 2 == 0:
             assert g.get_option("xyp_layout") >= 0, "the driver refused the tensor map"
             assert g.get_option("xyp_used") > used0, "the persistent kernel did not run"

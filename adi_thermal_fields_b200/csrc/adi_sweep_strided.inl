@@ -61,11 +61,17 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
         // only the other active tiles to k_sweep_xy.  16 lanes per tile (1024 threads, one block per SM, 128-byte rows)
         // where the rows of a tile lie >= 4 MB apart (x sweep of 2048 x 2048 x 1024: 17.3 against 25.2 ms; x 256: 4.09
         // against 5.11 ms), otherwise 8 lanes (512 threads, two blocks per SM: y sweep 16.0 against 19.2 ms; r02y / r02z).
-        const bool want_u = P > 32 && !half && b.uni && ctx->opt_xyu && !ctx->opt_xyp && a.in == a.out && KT == 8 && n % 32 == 0;
+        // Lines of 513..1024 cells: twice the lanes of k_sweep_xy at half the registers -- 512 threads, two blocks per SM,
+        // 128-byte rows (1024 x 1024 x 256: x 1.09 -> 0.88, y 0.92 -> 0.84 ms).  Not for 512-cell lines, where
+        // k_sweep_xy already has 128-byte rows (0.37 -> 0.41 ms; option xyu=2 forces it).
+        const bool long_u = P > 32 && !half && KT == 8;
+        const bool mid_u = P >= (ctx->opt_xyu >= 2 ? 16 : 17) && P <= 32 && M == 32 && !wide && !ctx->opt_kt && !ctx->opt_m && KT * P == 256;
+        const bool want_u = (long_u || mid_u) && b.uni && ctx->opt_xyu && !ctx->opt_xyp && a.in == a.out && n % 32 == 0;
         bool listed = false;
         if (want_u) {
             const unsigned long long row_stride = (AXIS == 0 ? (unsigned long long)a.ny * a.nz : (unsigned long long)a.nz) * 8ull;
-            const int KTU = ctx->opt_ukt == 16 ? 16 : (ctx->opt_ukt == 8 ? 8 : (row_stride >= (4ull << 20) ? 16 : 8));
+            const int KTU = mid_u ? 2 * KT
+                                  : (ctx->opt_ukt == 16 ? 16 : (ctx->opt_ukt == 8 ? 8 : (row_stride >= (4ull << 20) ? 16 : 8)));
             const int *lu = nullptr, *lg = nullptr;
             int nu = 0, ng = 0, tnx2 = 0;
             int rc = ensure_tiles_split(ctx, AXIS, KTU, st, &lu, &nu, &lg, &ng, &tnx2);
@@ -77,7 +83,7 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
                     u.tiles = lu; u.tiles_nx = tnx2;
                     const size_t smu = ((size_t)16 * KTU * P + (size_t)6 * KTU * P) * sizeof(double);
                     const dim3 ublock(KTU, P);
-                    if (KTU == 16) {
+                    if (KTU * P > 512) {
                         if (dense) rc = launch(k_sweep_xyu<AXIS, 2, 1024, 1>, dim3((unsigned)nu), ublock, smu, st, ctx, u);
                         else rc = launch(k_sweep_xyu<AXIS, 1, 1024, 1>, dim3((unsigned)nu), ublock, smu, st, ctx, u);
                     } else {
@@ -90,7 +96,7 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
                 if (ng == 0) return ADI_OK;
                 // the remaining tiles: k_sweep_xy, 8 lanes per block -- a 16-lane tile of the list is two blocks
                 b.tiles = lg; b.tiles_nx = tnx2;
-                b.tsplit = KTU == 16 ? 1 : 0;
+                b.tsplit = KTU == 2 * KT ? 1 : 0;
                 grid = dim3((unsigned)ng << b.tsplit, 1);
             }
         }

@@ -544,6 +544,9 @@ static int ensure_ghost(adi_ctx *ctx, size_t nlines, cudaStream_t st)
     return ADI_OK;
 }
 
+// the line whose unit-ghost responses stand in for every line that responds alike (k_spike_canon): mid-grid
+static size_t spike_canon_line(const adi_ctx *ctx) { return (size_t)(ctx->nx / 2) * ctx->ny + (size_t)(ctx->ny / 2); }
+
 int adi_cart_zsweep_solve0(adi_ctx *ctx, double *d_T, double *d_iface_dyn, double dt, double theta, double kappa,
                            double Tinf, void *stream)
 {
@@ -588,6 +591,9 @@ int adi_cart_zsweep_spike(adi_ctx *ctx, double *d_scratch, int end, int kmax, do
                                               ctx->d_maxk);
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
+    k_spike_canon<<<blocks, threads, 0, st>>>(d_compact, d_K, nlines, kmax, spike_canon_line(ctx));
+    ctx->launches++;
+    ADI_CUDA(cudaGetLastError());
     ADI_CUDA(cudaMemcpyAsync(h_maxK, ctx->d_maxk, sizeof(int), cudaMemcpyDeviceToHost, st));
     ADI_CUDA(cudaStreamSynchronize(st));
     return ADI_OK;
@@ -613,7 +619,9 @@ int adi_cart_zsweep_apply(adi_ctx *ctx, double *d_T, const double *d_dyn_all, co
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
     const int ablocks = (int)std::min<size_t>((nlines * 8 + 255) / 256, 148 * 32);
-    k_spike_apply<false><<<ablocks, 256, 0, st>>>(d_T, ctx->d_ghost, d_vC, d_wC, d_Kv, d_Kw, nlines, ctx->nz, kmax);
+    const size_t cl = spike_canon_line(ctx) * (size_t)kmax;
+    k_spike_apply<false><<<ablocks, 256, 0, st>>>(d_T, ctx->d_ghost, d_vC, d_wC, d_Kv, d_Kw, nlines, ctx->nz, kmax, d_vC + cl,
+                                                  d_wC + cl);
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
     return prof_mark(ctx, 4, st);
@@ -759,9 +767,11 @@ int cart_zapply_range(adi_ctx *ctx, double *d_T, const double *d_dyn_all, const 
 {
     const size_t nl = (size_t)ctx->nx * ctx->ny;
     const int ablocks = (int)std::min<size_t>((nlb * 8 + 255) / 256, 148 * 32);
+    const size_t cl = spike_canon_line(ctx) * (size_t)kmax;
     k_spike_apply<true><<<ablocks, 256, 0, st>>>(d_T + line0 * (size_t)ctx->nz, nullptr, d_vC + line0 * (size_t)kmax,
                                                  d_wC + line0 * (size_t)kmax, d_Kv + line0, d_Kw + line0, nlb, ctx->nz, kmax,
-                                                 d_dyn_all, d_stat_all + line0, nl, ctx->slab_nranks, ctx->slab_rank);
+                                                 d_vC + cl, d_wC + cl, d_dyn_all, d_stat_all + line0, nl, ctx->slab_nranks,
+                                                 ctx->slab_rank);
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
     return ADI_OK;

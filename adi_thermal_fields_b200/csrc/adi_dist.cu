@@ -125,7 +125,7 @@ struct DistState {
     // options
     int nbatch = 4, spike_after = 2, spike_kmax = 32, overlap_halo = 0;
     long batch_min = 1 << 20; // lines: smaller batches are not worth a collective of their own (measured at 262144 lines, N = 2: one batch 1.977 ms, four 2.02 ms per step)
-    double spike_thr = 0x1p-80;
+    double spike_thr = 0x1p-60;   // responses below this fraction of the ghost value are dropped: under 1/100 of an ulp of a field of the ghost's magnitude
     long steps_two_pass = 0, steps_solve_first = 0;
 };
 

@@ -361,7 +361,7 @@ class SlabGrid3D:
         self._stat_key = None   # (dt, theta, kappa, packs, mask version) the gathered matrix part belongs to
         # steady stepping: after `spike_after` steps with the same key the z sweep switches to the solve-first
         # form (one pass + corrections next to the slab faces); None = not built yet, False = responses too long
-        self.spike_after, self.spike_kmax, self.spike_threshold = 2, 32, 2.0 ** -80
+        self.spike_after, self.spike_kmax, self.spike_threshold = 2, 32, 2.0 ** -60
         self._spikes, self._stat_uses = None, 0
         be.bind(self.nx, self.ny, self.nz, self.dx, self.mask, self.rank, self.world)
         # NCCL ranks (one process per GPU): the whole step is sequenced inside the library (csrc/adi_dist.cu: its own

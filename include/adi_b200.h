@@ -144,7 +144,9 @@ int adi_cart_zsweep_finish(adi_ctx *ctx, double *d_T, const double *d_dyn_all, c
  *   adi_cart_zsweep_spike   once per (mask, packs, dt, theta): computes the response of end 0 / 1 in the zeroed
  *                           scratch field (size of T), keeps compact[nx*ny][kmax] and K[nx*ny] (cells above
  *                           `threshold`, clipped to kmax); *h_maxK = longest reach found -- if it exceeds kmax the
- *                           caller stays with adi_cart_zsweep_reduce / _finish.  Synchronises.
+ *                           caller stays with adi_cart_zsweep_reduce / _finish.  Synchronises.  Bit 30 of K[line] marks
+ *                           a line whose response equals, bit for bit, that of the mid-grid line: adi_cart_zsweep_apply
+ *                           then reads that one row for all of them (the count is K[line] & 0x3fffffff).
  *   adi_cart_zsweep_solve0  every step: solves T in place with zero ghosts, writes d_iface_dyn[2][nx*ny]
  *   adi_cart_zsweep_apply   every step, after the all-gather: ghosts from the relations, then the corrections */
 int adi_cart_zsweep_spike(adi_ctx *ctx, double *d_scratch, int end, int kmax, double threshold, double *d_compact,
@@ -189,7 +191,9 @@ int adi_profile_read(adi_ctx *ctx, double ms[4], long *nsteps);
  *   adi_dist_set_option  "batches" (line batches of the overlapped z solve, default 4; "batch_min_lines": no batch smaller than
  *                        this, default 1048576), "spike_after" (steps with
  *                        unchanged operands before the solve-first z form replaces the two-pass form, default 2;
- *                        < 0 never), "spike_kmax" (reach of the ghost corrections in cells, default 32)
+ *                        < 0 never), "spike_kmax" (reach of the ghost corrections in cells, default 32),
+ *                        "spike_thr_log2" (responses below 2^value of the ghost are dropped, default -60),
+ *                        "overlap_halo" (1: explicit stage beside the T-plane exchange, default 0)
  *   adi_dist_info        rank / size and how many steps ran in either z form */
 int adi_dist_unique_id(void *id128);
 int adi_dist_init(adi_ctx *ctx, const void *id128, int rank, int nranks);

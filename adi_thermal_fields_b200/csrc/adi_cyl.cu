@@ -96,13 +96,26 @@ __device__ __forceinline__ void cyl_cp_async_wait() { asm volatile("cp.async.wai
 // Reduced system over the P chunks of a line.  ex: 3*NTH doubles; slot(q) = index of chunk q of
 // this thread's line.  tab: this line's table blob (global, read through L1).
 // Returns S_p, *Sl = S_{p-1}.
-template <class SLOT>
+// SM: the tables have been staged in shared memory (plain loads) -- otherwise global memory through L1 (__ldg)
+template <bool SM>
+__device__ __forceinline__ double tld(const double *p) { return SM ? *p : tab_ld(p); }
+template <bool SM>
+__device__ __forceinline__ TabPair tld2(const double *p)
+{
+    if (!SM) return tab_ld2(p);
+    const double2 t = *reinterpret_cast<const double2 *>(p);
+    TabPair r;
+    r.a = t.x; r.b = t.y;
+    return r;
+}
+
+template <bool SM = false, class SLOT>
 __device__ __forceinline__ double cyl_reduced(const TabGeom &g, const double *__restrict__ tab, double *ex,
                                               int NTH, int p, double ds, double Y, double Yl, SLOT slot,
                                               double *Sl)
 {
     const int P = g.P, cyc = g.cyclic;
-    const double t0 = tab_ld(tab + g.o_t0 + p), t1 = tab_ld(tab + g.o_t1 + p), t2 = tab_ld(tab + g.o_t2 + p);
+    const double t0 = tld<SM>(tab + g.o_t0 + p), t1 = tld<SM>(tab + g.o_t1 + p), t2 = tld<SM>(tab + g.o_t2 + p);
     double *sY = ex + 2 * NTH;
     sY[slot(p)] = Y;
     __syncthreads();
@@ -112,7 +125,7 @@ __device__ __forceinline__ double cyl_reduced(const TabGeom &g, const double *__
     for (int l = 0; l < g.levels; ++l) {
         const int s = 1 << l;
         const double *R = tab + g.o_lvl + l * 3 * P;
-        const double cr = tab_ld(R + p), ca = tab_ld(R + P + p), cc = tab_ld(R + 2 * P + p);
+        const double cr = tld<SM>(R + p), ca = tld<SM>(R + P + p), cc = tld<SM>(R + 2 * P + p);
         double *b = ex + cur * NTH;
         b[slot(p)] = D;
         __syncthreads();
@@ -128,23 +141,68 @@ __device__ __forceinline__ double cyl_reduced(const TabGeom &g, const double *__
     return D;
 }
 
+// tab_forward / tab_backward (adi_tab_core.h) on tables staged in shared memory
+template <int M>
+__device__ __forceinline__ double tab_forward_sm(double (&d)[M], const double *f, const double *alpha, double *Yl)
+{
+    double dp = 0.0, Y = 0.0;
+#pragma unroll
+    for (int e = 0; e < M - 1; ++e) {
+        const TabPair t = tld2<true>(f + 2 * e);
+        dp = fma(t.b, dp, d[e] * t.a);
+        d[e] = dp;
+        Y = fma(alpha[e], dp, Y);
+    }
+    *Yl = dp;
+    return Y;
+}
+template <int M>
+__device__ __forceinline__ void tab_backward_sm(double (&d)[M], const double *b, double Sl, double S)
+{
+    double xn = S;
+    d[M - 1] = S;
+#pragma unroll
+    for (int e = M - 2; e >= 0; --e) {
+        const TabPair t = tld2<true>(b + 2 * e);
+        const double x = fma(t.a, xn, fma(t.b, Sl, d[e]));
+        d[e] = x;
+        xn = x;
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // K4: strided sweeps.  blockDim = (KT lanes along z, P chunks); grid = (ceil(nz/KT), nouter).
 // PRO: r sweep of the step -- applies the void clamp and the source term while loading.
 // BCL: the last cell of the line takes a boundary term (outer Robin row of the r sweep).
 // Shared memory: 3*NTH doubles (reduced-system exchange) only.
 // ------------------------------------------------------------------------------------
-template <int M, bool PRO, bool BCL>
-__global__ void __launch_bounds__(256, (M <= 16 ? 3 : 2)) k_cyl_strided(const CylArgs a)
+// SM: the block first copies the line's tables (everything in front of o_dl: cell tables, reduced-system assembly, PCR
+// levels -- a few KB) into shared memory and then walks over `nzt` consecutive z tiles with them: ncu (r03c) had the
+// kernel waiting on its table reads (five L1 loads per cell, long-scoreboard 10.7 / 11.4 per issued instruction, in
+// the back substitution too, where nothing else is loaded).
+template <int M, bool PRO, bool BCL, bool SM>
+__global__ void __launch_bounds__(256, (M <= 16 ? 3 : 2)) k_cyl_strided(const CylArgs a, const int nzt)
 {
     extern __shared__ double smem[];
     const int KT = blockDim.x, P = blockDim.y;
     const int kk = threadIdx.x, p = threadIdx.y;
     const int NTH = KT * P;
-    const double *__restrict__ tab = a.blob + (size_t)blockIdx.y * a.blob_stride;
+    const double *__restrict__ gtab = a.blob + (size_t)blockIdx.y * a.blob_stride;
+    const double *__restrict__ tab = gtab;
+    if (SM) {
+        double *stab = smem + 3 * NTH;
+        const int tid = p * KT + kk;
+        for (int i = tid; 2 * i < a.g.o_dl; i += NTH)           // (o_dl is even, the blob 16-byte aligned)
+            reinterpret_cast<double2 *>(stab)[i] = __ldg(reinterpret_cast<const double2 *>(gtab) + i);
+        tab = stab;
+        __syncthreads();
+    }
     const int cb = __ldg(a.geom + p), endp = __ldg(a.geom + P + p), len = __ldg(a.geom + 2 * P + p);
+    const int ntz = (a.nz + KT - 1) / KT;
+  for (int zt = blockIdx.x * nzt; zt < min((int)(blockIdx.x + 1) * nzt, ntz); ++zt) {
+    if (zt != (int)blockIdx.x * nzt) __syncthreads();           // the exchange buffer of the previous tile is free
 
-    const int k = blockIdx.x * KT + kk;
+    const int k = zt * KT + kk;
     const bool lane_ok = k < a.nz;
     // slot e holds cell i0 + e of the line; slots e < efirst are padding (never dereferenced)
     const int efirst = lane_ok ? M - len : M;
@@ -180,14 +238,17 @@ __global__ void __launch_bounds__(256, (M <= 16 ? 3 : 2)) k_cyl_strided(const Cy
         if (p == P - 1 && lane_ok) d[M - 1] = a.set_last ? a.val_last : __dadd_rn(d[M - 1], a.val_last);
     }
     double Yl;
-    const double Y = tab_forward<M>(d, tab + a.g.o_f + 2 * cb, tab + a.g.o_alpha + cb, &Yl);
+    const double Y = SM ? tab_forward_sm<M>(d, tab + a.g.o_f + 2 * cb, tab + a.g.o_alpha + cb, &Yl)
+                        : tab_forward<M>(d, tab + a.g.o_f + 2 * cb, tab + a.g.o_alpha + cb, &Yl);
     double Sl;
-    const double S = cyl_reduced(a.g, tab, smem, NTH, p, d[M - 1], Y, Yl, [=](int q) { return q * KT + kk; }, &Sl);
-    tab_backward<M>(d, tab + a.g.o_b + 2 * cb, Sl, S);
+    const double S = cyl_reduced<SM>(a.g, tab, smem, NTH, p, d[M - 1], Y, Yl, [=](int q) { return q * KT + kk; }, &Sl);
+    if (SM) tab_backward_sm<M>(d, tab + a.g.o_b + 2 * cb, Sl, S);
+    else tab_backward<M>(d, tab + a.g.o_b + 2 * cb, Sl, S);
     char *dst = reinterpret_cast<char *>(a.out + first);
 #pragma unroll
     for (int e = 0; e < M; ++e)
         if (e >= efirst) *reinterpret_cast<double *>(dst + (size_t)e * cs8) = d[e];
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -479,8 +540,9 @@ static int ensure_tables(adi_ctx *ctx, const adi_cyl_params &prm, cudaStream_t s
     return ADI_OK;
 }
 
-template <typename K>
-static int launch_cyl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, adi_ctx *ctx, const CylArgs &a)
+template <typename K, typename... Extra>
+static int launch_cyl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, adi_ctx *ctx, const CylArgs &a,
+                      Extra... extra)
 {
     if (smem > 227 * 1024) {
         set_error("adi_cyl_step: tile does not fit shared memory");
@@ -488,7 +550,7 @@ static int launch_cyl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s
     }
     if (smem > 48 * 1024)
         ADI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, block, smem, st>>>(a);
+    kern<<<grid, block, smem, st>>>(a, extra...);
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
     return ADI_OK;
@@ -522,18 +584,34 @@ static int launch_strided(adi_ctx *ctx, CylArgs &a, bool pro, int nouter, cudaSt
         set_error("adi_cyl_step: grid too large for 32-bit line strides");
         return ADI_EINVAL;
     }
-#define ADI_SGO(MM)                                                                             \
-    {                                                                                           \
-        if (pro) {                                                                              \
-            if (bcl) return launch_cyl(k_cyl_strided<MM, true, true>, grid, block, smem, st, ctx, a);   \
-            return launch_cyl(k_cyl_strided<MM, true, false>, grid, block, smem, st, ctx, a);   \
-        }                                                                                       \
-        if (bcl) return launch_cyl(k_cyl_strided<MM, false, true>, grid, block, smem, st, ctx, a);      \
-        return launch_cyl(k_cyl_strided<MM, false, false>, grid, block, smem, st, ctx, a);      \
+    // tables in shared memory, `nzt` z tiles per block (option cylsm, default on; 0 = tables through L1, one tile)
+    const bool sm = ctx->opt_cylsm != 0 && (a.g.o_dl % 2) == 0 && (nth % 2) == 0 && (size_t)a.g.o_dl * sizeof(double) <= 64 * 1024;
+    const int ntz = (int)grid.x;
+    int nzt = 1;
+    if (sm) {
+        nzt = ctx->opt_cylsm > 1 ? (int)ctx->opt_cylsm : 4;
+        while (nzt > 1 && (long long)((ntz + nzt - 1) / nzt) * nouter < 148 * 16) nzt >>= 1;   // keep the GPU full
+        grid.x = (unsigned)((ntz + nzt - 1) / nzt);
+    }
+    const size_t smem2 = smem + (sm ? (size_t)a.g.o_dl * sizeof(double) : 0);
+#define ADI_SGO2(MM, PR, BC)                                                                                   \
+    {                                                                                                          \
+        if (sm) return launch_cyl(k_cyl_strided<MM, PR, BC, true>, grid, block, smem2, st, ctx, a, nzt);      \
+        return launch_cyl(k_cyl_strided<MM, PR, BC, false>, grid, block, smem2, st, ctx, a, nzt);             \
+    }
+#define ADI_SGO(MM)                                \
+    {                                              \
+        if (pro) {                                 \
+            if (bcl) ADI_SGO2(MM, true, true)      \
+            ADI_SGO2(MM, true, false)              \
+        }                                          \
+        if (bcl) ADI_SGO2(MM, false, true)         \
+        ADI_SGO2(MM, false, false)                 \
     }
     if (a.g.M == 16) ADI_SGO(16)
     ADI_SGO(32)
 #undef ADI_SGO
+#undef ADI_SGO2
 }
 
 static int launch_z(adi_ctx *ctx, CylArgs &a, bool epi, cudaStream_t st, int zm = 0)

@@ -179,7 +179,8 @@ __device__ __forceinline__ void tab_backward_sm(double (&d)[M], const double *b,
 // SM: the block first copies the line's tables (everything in front of o_dl: cell tables, reduced-system assembly, PCR
 // levels -- a few KB) into shared memory and then walks over `nzt` consecutive z tiles with them: ncu (r03c) had the
 // kernel waiting on its table reads (five L1 loads per cell, long-scoreboard 10.7 / 11.4 per issued instruction, in
-// the back substitution too, where nothing else is loaded).
+// the back substitution too, where nothing else is loaded).  (The z sweep keeps its tables in L1: they are as large as
+// eight of its tiles, and staging them measured slower -- 0.52 against 0.48 ms.)
 template <int M, bool PRO, bool BCL, bool SM>
 __global__ void __launch_bounds__(256, (M <= 16 ? 3 : 2)) k_cyl_strided(const CylArgs a, const int nzt)
 {
@@ -558,10 +559,15 @@ static int launch_cyl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s
 
 static int lanes_for(adi_ctx *ctx, int P, int nz)
 {
-    // 64-byte rows (8 lanes) in blocks of at least 128 threads: small blocks keep more tiles in
-    // flight per SM (measured: r sweep of 256 cells 0.59 -> 0.51 ms against 16 lanes)
+    // With the tables in shared memory wide rows pay: 16 lanes (128-byte rows) in 256-thread blocks, 32 lanes for
+    // <= 8 chunks (r sweep of 256 cells: 0.474 ms with 8 lanes, 0.381 with 16; r03d).  Tables through L1 (cylsm=0):
+    // 8 lanes in blocks of at least 128 threads, small blocks keeping more tiles in flight (0.59 -> 0.51 ms then).
     int KT = 32;
-    while (KT > 8 && KT * P > 128) KT >>= 1;
+    if (ctx->opt_cylsm) {
+        if (P > 8) KT = 16;
+    } else {
+        while (KT > 8 && KT * P > 128) KT >>= 1;
+    }
     while (KT > 1 && KT * P > 256) KT >>= 1;
     if (ctx->opt_kt > 0) {
         int w = 1;

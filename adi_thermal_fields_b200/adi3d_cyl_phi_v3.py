@@ -217,3 +217,13 @@ def adi_step_device(Tn, grid, mat, prm, robin_r, zbc, S=None, active=None, robin
 
 def launch_count():
     return int(_capi.load().adi_launch_count(_engine.context()))
+
+
+def set_option(name, value):
+    """Engine tuning knob of the cylindrical path (adi_set_option): 'cylsm', 'cylzt', 'm', 'kt', 'lt' ..."""
+    _capi.check(_capi.load().adi_set_option(_engine.context(), str(name).encode(), int(value)), "adi_set_option")
+
+
+def get_option(name):
+    """Current value of an engine option (adi_get_option)."""
+    return int(_capi.load().adi_get_option(_engine.context(), str(name).encode()))

@@ -330,7 +330,7 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
     a.k.invdx2 = 1.0 / (dx * dx);
     a.zlo = d_Tlo; a.zhi = d_Thi; a.iface_dyn = d_iface_dyn; a.iface_stat = d_iface_stat; a.ghost = d_ghost;
     a.codeT = nullptr; a.npad = 0; a.uni = 0; a.tw = 0; a.remap = 0; a.dbg = 0; a.halo_defer = 0;
-    a.tiles = nullptr; a.tiles_nx = 0; a.tsplit = 0;
+    a.tiles = nullptr; a.tiles_nx = 0; a.tsplit = 0; a.zpitch = 0; a.code_line = 0;
     a.line_batch = nlb != 0 ? 1 : 0;
     bool expl = a.k.beta != 0.0;
     bool x_in_place = false;

@@ -53,6 +53,8 @@ struct SweepArgs {
     int tiles_nx;
     int tsplit;                        // k_sweep_xy: 1 = the list counts tiles of twice the block's lanes (two blocks per entry)
     int line_batch;                    // z sweep of a batch of lines (multi-GPU): the pointers are offset, no tile list
+    int zpitch;                        // k_sweep_zt: elements between consecutive z lines of in / out (0: nz)
+    int code_line;                     // k_sweep_zt: 1 = `code` holds ONE line of nz codes shared by all z lines
     UniConst uc;
 };
 

@@ -18,11 +18,14 @@
 #include <string>
 #include <vector>
 
+#include "adi_cart.cuh"
 #include "adi_core.h"
 #include "adi_ctx.h"
 #include "adi_tab_core.h"
 
 namespace adi {
+
+int launch_sweep_zt(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, int zmode, cudaStream_t st, int *used);
 
 struct CylTables {
     // cache key: everything the tables depend on
@@ -43,6 +46,12 @@ struct CylTables {
     double *d_G = nullptr;             // [2][nranks][2] ghost map
     double *d_ghost = nullptr;         // [2][nlines]
     size_t ghost_lines = 0;
+    // the z rows as a Cartesian sweep (k_sweep_zt): one line of neighbour codes shared by all z lines, the scalars of
+    // its rows; zt_ok = the boundary rows can be written that way (no Dirichlet end, one ambient temperature)
+    uint8_t *d_zcode = nullptr;
+    size_t zcode_cap = 0;
+    bool zt_ok = false;
+    SweepConst zk;
 };
 
 void cyl_release(adi_ctx *ctx)
@@ -52,6 +61,7 @@ void cyl_release(adi_ctx *ctx)
     if (ctx->cyl->d_geom) cudaFree(ctx->cyl->d_geom);
     if (ctx->cyl->d_G) cudaFree(ctx->cyl->d_G);
     if (ctx->cyl->d_ghost) cudaFree(ctx->cyl->d_ghost);
+    if (ctx->cyl->d_zcode) cudaFree(ctx->cyl->d_zcode);
     delete ctx->cyl;
     ctx->cyl = nullptr;
 }
@@ -535,6 +545,32 @@ static int ensure_tables(adi_ctx *ctx, const adi_cyl_params &prm, cudaStream_t s
         ADI_CUDA(cudaMalloc(&T.d_G, Gmap.size() * sizeof(double)));
         ADI_CUDA(cudaMemcpyAsync(T.d_G, Gmap.data(), Gmap.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     }
+    {
+        // The z rows (build_coeff_z :255-298, theta = 1) are the rows of a Cartesian z sweep of a full line with
+        // g = fac and a Robin term on the exposed end cells: b = (1 + fac) + c, d = T + c*T_inf with c = fac*(h/k)*dz
+        // (neumann0: c = 0) -- adi_core.h make_row, CMODE 1 with dt = 1.  Dirichlet ends and two different ambient
+        // temperatures do not fit that form (k_cyl_z keeps them).
+        const double fac = 1.0 * alpha * prm.dt / (ctx->dz * ctx->dz);
+        const bool rb = prm.kind_bot == 2, rt = prm.kind_top == 2;
+        T.zt_ok = T.slab_nranks == 1 && prm.kind_bot != 1 && prm.kind_top != 1 && nz >= 2 &&
+                  !(rb && rt && prm.Tinf_bot != prm.Tinf_top);
+        memset(&T.zk, 0, sizeof(T.zk));
+        T.zk.g = fac; T.zk.dt = 1.0;
+        T.zk.Tinf = rb ? prm.Tinf_bot : prm.Tinf_top;
+        T.zk.h_lo = rb ? fac * (prm.h_bot / prm.k) * ctx->dz : 0.0;
+        T.zk.h_hi = rt ? fac * (prm.h_top / prm.k) * ctx->dz : 0.0;
+        std::vector<uint8_t> zc((size_t)nz + 16, 0);
+        for (int kz = 0; kz < nz; ++kz)
+            zc[kz] = (uint8_t)(CB_SELF | CB_XM | CB_XP | CB_YM | CB_YP | (kz > 0 ? CB_ZM : 0u) | (kz + 1 < nz ? CB_ZP : 0u));
+        if (T.zcode_cap < zc.size()) {
+            if (T.d_zcode) { ADI_CUDA(cudaStreamSynchronize(st)); ADI_CUDA(cudaFree(T.d_zcode)); }
+            T.d_zcode = nullptr;
+            ADI_CUDA(cudaMalloc(&T.d_zcode, zc.size()));
+            T.zcode_cap = zc.size();
+        }
+        ADI_CUDA(cudaMemcpyAsync(T.d_zcode, zc.data(), zc.size(), cudaMemcpyHostToDevice, st));
+        ADI_CUDA(cudaStreamSynchronize(st));
+    }
     ADI_CUDA(cudaStreamSynchronize(st));
     T.M = (int)ctx->opt_m;
     T.key = prm; T.nr = nr; T.nphi = nphi; T.nz = nz; T.valid = true;
@@ -768,8 +804,24 @@ static int cyl_run(adi_ctx *ctx, const double *d_Tin, double *d_Tout, const adi_
             ADI_CUDA(cudaGetLastError());
             a.ghost = T.d_ghost;
         }
-        rc = launch_z(ctx, a, zm != 1 && d_active != nullptr, st, zm);
-        if (rc) return rc;
+        int used = 0;
+        if (zm == 0 && !d_active && T.zt_ok && ctx->opt_cylzt && nz >= 64 && nr <= 0x7fff && (size_t)nr * nphi <= 0x7fffffffull) {
+            // whole lines, no mask: the Cartesian z kernel (bulk asynchronous copies, tabulated uniform runs from the
+            // constant bank) -- 0.48 -> 0.35 ms at 256 x 1024 x 512
+            SweepArgs s = {};
+            s.in = d_Tout; s.out = d_Tout; s.code = T.d_zcode;
+            s.nx = nr; s.ny = nphi; s.nz = nz;
+            s.k = T.zk;
+            s.line_batch = 1;                               // no tile lists (they belong to the Cartesian grid)
+            s.zpitch = pitch != nz ? (int)pitch : 0;
+            s.code_line = 1;
+            rc = launch_sweep_zt(ctx, s, false, false, 0, st, &used);
+            if (rc) return rc;
+        }
+        if (!used) {
+            rc = launch_z(ctx, a, zm != 1 && d_active != nullptr, st, zm);
+            if (rc) return rc;
+        }
         if (zm != 1) {
             rc = prof_mark(ctx, 4, st);
             if (rc) return rc;

@@ -27,7 +27,7 @@ static int launch_zt_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, bool ext
             grid = dim3((unsigned)nact);
         }
     }
-    int vec = ((a.nz & 1) == 0 && (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.code) & 15) == 0) ? 1 : 0;
+    int vec = ((a.nz & 1) == 0 && (a.zpitch & 1) == 0 && (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.code) & 15) == 0) ? 1 : 0;
     if (vec && (a.nz & 15) == 0 && a.in == a.out && ctx->opt_bulk) vec = 2;   // whole lines as bulk asynchronous copies
     const bool big = KT * P > 256;
 #define ADI_GOZ(M_, MAXT, MINB)                                                                                    \

@@ -111,6 +111,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
     uint8_t *sCode = reinterpret_cast<uint8_t *>(sEnd + 2 * KT + 2);
     const bool sparse = CMODE == 2;       // this kernel reads a dense coefficient field at exposed cells only
     const int nval = (int)min((size_t)KT, nlines - L0);                // lines of this tile that exist
+    // line stride of the field (pitched buffers of the cylindrical path) and of the code array (0: one code line
+    // shared by every z line -- the cylindrical z sweep, whose rows do not depend on the line)
+    const size_t zs = a.zpitch ? (size_t)a.zpitch : (size_t)nz;
+    const size_t cs = a.code_line ? 0 : (size_t)nz;
     // vec 2: whole lines travel as bulk asynchronous copies (one instruction per line and direction);
     // vec 1: 16-byte cp.async pieces / vector stores; vec 0: scalar loads and stores
     const bool bulk = vec == 2;
@@ -137,9 +141,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
             if (tid == 0) mbar_expect_tx(bar, (unsigned)nval * (unsigned)nz * 9u);
             __syncwarp();
             for (int l = tid; l < nval; l += 32) {
-                const size_t g = (L0 + l) * (size_t)nz;
-                bulk_g2s(sT + (size_t)l * pitch, a.in + g, (unsigned)nz * 8u, bar);
-                bulk_g2s(sCode + (size_t)l * cpitch, a.code + g, (unsigned)nz, bar);
+                bulk_g2s(sT + (size_t)l * pitch, a.in + (L0 + l) * zs, (unsigned)nz * 8u, bar);
+                bulk_g2s(sCode + (size_t)l * cpitch, a.code + (L0 + l) * cs, (unsigned)nz, bar);
             }
         }
     } else if (vec) {
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
         for (int l = 0; l < KT; ++l) {
             const size_t line = L0 + l;
             const bool lok = line < nlines;
-            const double *src = a.in + (lok ? line * (size_t)nz : 0);
+            const double *src = a.in + (lok ? line * zs : 0);
             for (int pr = tid; pr < ppl; pr += NTH) {
                 const int z = 2 * pr;
                 const bool ok = lok && z < nz;
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
             const size_t line = L0 + l;
             const bool lok = line < nlines;
             for (int z = tid; z < RL; z += NTH)
-                sT[(size_t)l * pitch + z] = (lok && z < nz) ? a.in[line * (size_t)nz + z] : 0.0;
+                sT[(size_t)l * pitch + z] = (lok && z < nz) ? a.in[line * zs + z] : 0.0;
         }
     }
     if (bulk) {
@@ -169,14 +172,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
             const int l = i / cpl, c16 = i - l * cpl;
             const size_t line = L0 + l;
             const bool ok = line < nlines && 16 * c16 < nz;
-            cp_async16(sCode + (size_t)l * cpitch + 16 * c16, a.code + (ok ? line * (size_t)nz + 16 * c16 : 0), ok ? 16 : 0);
+            cp_async16(sCode + (size_t)l * cpitch + 16 * c16, a.code + (ok ? line * cs + 16 * c16 : 0), ok ? 16 : 0);
         }
     } else {
         for (int l = 0; l < KT; ++l) {
             const size_t line = L0 + l;
             const bool lok = line < nlines;
             for (int z = tid; z < RL; z += NTH)
-                sCode[(size_t)l * cpitch + z] = (lok && z < nz) ? a.code[line * (size_t)nz + z] : (uint8_t)0;
+                sCode[(size_t)l * cpitch + z] = (lok && z < nz) ? a.code[line * cs + z] : (uint8_t)0;
         }
     }
     if (sparse) {
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
         __syncthreads();
         if (tid < 32) {
             for (int l = tid; l < nval; l += 32)
-                bulk_s2g(a.out + (L0 + l) * (size_t)nz, sT + (size_t)l * pitch, (unsigned)nz * 8u);
+                bulk_s2g(a.out + (L0 + l) * zs, sT + (size_t)l * pitch, (unsigned)nz * 8u);
             bulk_commit_wait_read();   // shared memory must outlive the reads of the copy engine
         }
         return;
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
                 if (z >= nz) break;
                 const double2 v = *reinterpret_cast<const double2 *>(sT + (size_t)l * pitch + z);
                 const unsigned cc = *reinterpret_cast<const unsigned short *>(sCode + (size_t)l * cpitch + z);
-                const size_t g = ln * (size_t)nz + z;
+                const size_t g = ln * zs + z;
                 const bool a0 = cc & 1u, a1 = (cc >> 8) & 1u;
                 if (a0 && a1) {
                     *reinterpret_cast<double2 *>(a.out + g) = v;
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
             const size_t ln = L0 + l;
             if (ln >= nlines) break;
             for (int z = tid; z < nz; z += NTH) {
-                const size_t g = ln * (size_t)nz + z;
+                const size_t g = ln * zs + z;
                 const bool act = sCode[(size_t)l * cpitch + z] & 1u;
                 if (act) a.out[g] = sT[(size_t)l * pitch + z];
                 else if (!inplace) a.out[g] = a.in[g];

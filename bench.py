@@ -1229,7 +1229,7 @@ def bench_cyl(args, local, sub=False):
     del A, B
     peak, peak_src = peaks()
     per = [ms4[i] / max(1, nst.value) for i in range(1, 4)]
-    names = ["k_cyl_strided<r>", "k_cyl_strided<phi>", "k_cyl_z"]
+    names = ["k_cyl_strided<r>", "k_cyl_strided<phi>", "k_sweep_zt (cylindrical rows)"]
     dom = int(np.argmax(per))
     achieved = 16.0 * cells / (per[dom] * 1e-3) / 1e9
     cpu = parity = None

@@ -218,3 +218,35 @@ def test_c3_slice_matches_reference_and_oracle(gc, golden_dir):
     # worst single r line / phi ring, not only the global norm
     num = np.sqrt(((out - ref) ** 2).sum(axis=0)); den = np.sqrt((ref ** 2).sum(axis=0))
     assert float((num / den).max()) <= 10 * TOL
+
+
+@pytest.mark.parametrize("zt", [1, 0], ids=["k_sweep_zt", "k_cyl_z"])
+@pytest.mark.parametrize("shape", [(6, 8, 64), (5, 12, 96), (4, 6, 130), (3, 5, 512), (7, 3, 2048)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("zk", [dict(kind_bot="neumann0", kind_top="robin", h_top=500.0, T_inf_top=20.0),
+                                dict(kind_bot="robin", kind_top="neumann0", h_bot=300.0, T_inf_bot=35.0),
+                                dict(kind_bot="robin", kind_top="robin", h_bot=80.0, h_top=500.0, T_inf_bot=20.0, T_inf_top=20.0),
+                                dict(kind_bot="robin", kind_top="robin", h_bot=80.0, h_top=500.0, T_inf_bot=15.0, T_inf_top=25.0),
+                                dict(kind_bot="neumann0", kind_top="neumann0"),
+                                dict(kind_bot="dirichlet", kind_top="robin", T_bot=400.0, h_top=0.0, T_inf_top=20.0)],
+                         ids=["n0-robin", "robin-n0", "robin-robin", "robin-robin-2Tinf", "n0-n0", "dirichlet-robin"])
+def test_z_sweep_on_the_cartesian_kernel(shape, zk, zt, gc):
+    """Unmasked z lines of 64..2048 cells run on the Cartesian z kernel (k_sweep_zt: the z rows of build_coeff_z are
+    those of a full line with a Robin term at its ends); Dirichlet ends and two different ambient temperatures keep
+    k_cyl_z.  cfl 1 and 30 (slowly decaying couplings), against the oracle; option cylzt=0 for comparison."""
+    from oracle import cyl
+    nr, nphi, nz = shape
+    R = 0.02
+    dr, dphi = R / 64, 2 * math.pi / nphi
+    mat = gc.Material(cases.C_RHO, cases.C_CP, cases.C_K)
+    gc.set_option("cylzt", zt)
+    try:
+        for cfl in (1.0, 30.0):
+            dt = cfl * dr * dr / mat.alpha
+            T0 = 20.0 + 980.0 * cases.splitmix_uniform(5100 + nz, shape)
+            out = gc.adi_step(T0, gc.GridCyl(nr, nphi, nz, dr, dphi, dr, R), mat, gc.Params(dt, 1.0, "be"),
+                              gc.RobinR(500.0, 20.0), gc.ZBC(**zk))
+            ref = cyl.adi_step(T0, cyl.GridCyl(nr, nphi, nz, dr, dphi, dr, R), cyl.Material(mat.rho, mat.cp, mat.k),
+                               cyl.Params(dt, 1.0, "be"), cyl.RobinR(500.0, 20.0), cyl.ZBC(**zk))
+            assert cases.rel_l2(out, ref) <= TOL
+    finally:
+        gc.set_option("cylzt", 1)

@@ -307,7 +307,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args, 1) | {"sample": sample},
+        # the arm's config is our arm's config at this N, verbatim; what was actually stepped is cpu_baseline.sample
+        "data": "synthetic", "config": workload_config(args, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                          "host_cpus": os.cpu_count(),
                          "what": ("adi3d_numba_coeff.adi_step_numba_coeff of the unmodified reference (baseline/_ref): serial "

@@ -275,6 +275,10 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
     else if (!strcmp(name, "xyu")) ctx->opt_xyu = value;      // 1 (default): all-uniform tiles of 1025..2048-cell x / y lines on k_sweep_xyu (two blocks per SM)
     else if (!strcmp(name, "cylsm")) ctx->opt_cylsm = value;  // cylindrical strided sweeps: 1 (default) tables staged in shared memory, blocks walk over 4 z tiles (n > 1: n tiles); 0 tables through L1
     else if (!strcmp(name, "cylzt")) ctx->opt_cylzt = value;  // 1 (default): unmasked cylindrical z sweep on the Cartesian z kernel (k_sweep_zt)
+    else if (!strcmp(name, "maskv")) {  // 1 (default): word forms of the per-mask-change kernels (adi_mask_core.h) where alignment allows
+        ctx->opt_maskv = value;
+        ctx->code_dirty = true;
+    }
     else if (!strcmp(name, "ukt")) ctx->opt_ukt = value;
     else if (!strcmp(name, "zm")) ctx->opt_zm = value;        // k_sweep_zt: chunk length (16 / 32) whatever the line length
     else if (!strcmp(name, "ejt")) ctx->opt_ejt = value;      // explicit stage: y rows per block (default 16)
@@ -326,6 +330,8 @@ long adi_get_option(adi_ctx *ctx, const char *name)
     if (!strcmp(name, "cylsm")) return ctx->opt_cylsm;
     if (!strcmp(name, "cylzt")) return ctx->opt_cylzt;
     if (!strcmp(name, "ukt")) return ctx->opt_ukt;
+    if (!strcmp(name, "maskv")) return ctx->opt_maskv;
+    if (!strcmp(name, "maskv_used")) return ctx->maskv_used;   // bit 0 / 1 / 2: the last code build / transposes / pack build took the word form
     if (!strcmp(name, "zm")) return ctx->opt_zm;
     if (!strcmp(name, "ejt")) return ctx->opt_ejt;
     if (!strcmp(name, "eth")) return ctx->opt_eth;

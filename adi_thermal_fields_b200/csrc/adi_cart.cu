@@ -51,9 +51,20 @@ int ensure_code(adi_ctx *ctx, cudaStream_t st)
     if (n) {
         const int threads = 256;
         const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, 148 * 64);
+        ctx->maskv_used &= ~3;
         for (int a = 0; a < ncodes; ++a) {
-            k_build_code<<<blocks, threads, 0, st>>>(ctx->d_mask, ctx->pack[a].dirm, ctx->code_buf[a],
-                                                     ctx->nx, ctx->ny, ctx->nz, ctx->d_mask_lo, ctx->d_mask_hi);
+            // word form: 16 cells per thread (adi_mask_core.h) when every z line starts on a 16-byte boundary
+            const bool wordform = ctx->opt_maskv && ctx->nz % 16 == 0 &&
+                                  (((uintptr_t)ctx->d_mask | (uintptr_t)ctx->pack[a].dirm | (uintptr_t)ctx->code_buf[a]) & 15) == 0;
+            if (wordform) {
+                const int vblocks = (int)std::min<size_t>((n / 16 + threads - 1) / threads, 148 * 32);
+                k_build_code_v<<<vblocks, threads, 0, st>>>(ctx->d_mask, ctx->pack[a].dirm, ctx->code_buf[a],
+                                                            ctx->nx, ctx->ny, ctx->nz, ctx->d_mask_lo, ctx->d_mask_hi);
+                ctx->maskv_used |= 1;
+            } else {
+                k_build_code<<<blocks, threads, 0, st>>>(ctx->d_mask, ctx->pack[a].dirm, ctx->code_buf[a],
+                                                         ctx->nx, ctx->ny, ctx->nz, ctx->d_mask_lo, ctx->d_mask_hi);
+            }
             ctx->launches++;
         }
         ADI_CUDA(cudaGetLastError());
@@ -72,9 +83,18 @@ int ensure_code(adi_ctx *ctx, cudaStream_t st)
             ctx->codeT_bytes[a] = bytes; ctx->npadT[a] = npad;
         }
         const size_t snx = (size_t)ctx->ny * ctx->nz;
-        dim3 tgrid((unsigned)((ctx->nz + 31) / 32), (unsigned)((len + 31) / 32), (unsigned)std::min(batch, 65535));
-        k_transpose_code<<<tgrid, dim3(32, 8), 0, st>>>(ctx->code[a], ctx->codeT[a], len, ctx->nz, npad, batch,
-                                                        a == 0 ? (size_t)ctx->nz : snx, a == 0 ? snx : (size_t)ctx->nz);
+        const size_t sb = a == 0 ? (size_t)ctx->nz : snx, sr = a == 0 ? snx : (size_t)ctx->nz;
+        // word form: 128 x 128 byte tiles (adi_mask_core.h) when rows are word aligned
+        if (ctx->opt_maskv && ctx->nz % 4 == 0 && (((uintptr_t)ctx->code[a] | (uintptr_t)ctx->codeT[a]) & 3) == 0) {
+            TrArgs t;
+            t.src = ctx->code[a]; t.dst = ctx->codeT[a]; t.n = len; t.nz = ctx->nz; t.npad = npad; t.sb = sb; t.sr = sr;
+            dim3 vgrid((unsigned)((ctx->nz + 127) / 128), (unsigned)((len + 127) / 128), (unsigned)std::min(batch, 65535));
+            k_transpose_code_v<<<vgrid, 256, 0, st>>>(t, batch);
+            ctx->maskv_used |= 2;
+        } else {
+            dim3 tgrid((unsigned)((ctx->nz + 31) / 32), (unsigned)((len + 31) / 32), (unsigned)std::min(batch, 65535));
+            k_transpose_code<<<tgrid, dim3(32, 8), 0, st>>>(ctx->code[a], ctx->codeT[a], len, ctx->nz, npad, batch, sb, sr);
+        }
         ctx->launches++;
         ADI_CUDA(cudaGetLastError());
     }
@@ -716,7 +736,17 @@ int adi_cart_build_packs(adi_ctx *ctx, double rho, double cp, const int h_kind[6
     if (!n) return ADI_OK;
     const int threads = 256;
     const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, 148 * 64);
-    k_build_packs<<<blocks, threads, 0, (cudaStream_t)stream>>>(a);
+    // word form: 4 cells per thread (adi_mask_core.h) when z lines are word aligned and the outputs take 16-byte stores
+    uintptr_t al = 0;
+    for (int ax = 0; ax < 3; ++ax) al |= (uintptr_t)a.coeff[ax] | (uintptr_t)a.qout[ax];
+    ctx->maskv_used &= ~4;
+    if (ctx->opt_maskv && a.nz % 4 == 0 && ((uintptr_t)a.mask & 3) == 0 && (al & 15) == 0) {
+        const int vblocks = (int)std::min<size_t>((n / 4 + threads - 1) / threads, 148 * 64);
+        k_build_packs_v<<<vblocks, threads, 0, (cudaStream_t)stream>>>(a);
+        ctx->maskv_used |= 4;
+    } else {
+        k_build_packs<<<blocks, threads, 0, (cudaStream_t)stream>>>(a);
+    }
     ctx->launches++;
     ADI_CUDA(cudaGetLastError());
     return ADI_OK;

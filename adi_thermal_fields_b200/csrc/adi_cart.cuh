@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include "adi_core.h"
+#include "adi_mask_core.h"
 
 namespace adi {
 
@@ -90,6 +91,17 @@ __global__ void k_build_code(const uint8_t *__restrict__ mask, const uint8_t *__
     }
 }
 
+// K0 in word form (adi_mask_core.h): 16 cells of a z line per thread, 16-byte loads and stores; runs of void
+// cells (most of the box while a part is being built) cost one load and one store.
+__global__ void __launch_bounds__(256) k_build_code_v(const uint8_t *__restrict__ mask, const uint8_t *__restrict__ dirm,
+                                                      uint8_t *__restrict__ code, int nx, int ny, int nz,
+                                                      const uint8_t *__restrict__ mlo, const uint8_t *__restrict__ mhi)
+{
+    const size_t n16 = (size_t)nx * ny * nz / 16;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n16; t += (size_t)gridDim.x * blockDim.x)
+        build_code16(mask, dirm, code, t * 16, nx, ny, nz, mlo, mhi);
+}
+
 // K0t: per-axis transposed copy of the code array for the x / y sweeps (adi_sweep_xy.cuh):
 // dst[(b*nz + c)*npad + r] = src[b*sb + r*sr + c],  r < n (line axis), c < nz, b < batch.
 // 32 x 32 byte tiles through shared memory; padding columns (r >= n) keep the zeros of the allocation.
@@ -111,6 +123,19 @@ __global__ void __launch_bounds__(256) k_transpose_code(const uint8_t *__restric
             const int c = c0 + ty + 8 * i, r = r0 + tx;
             if (c < nz && r < n) dst[((size_t)b * nz + c) * npad + r] = tile[tx][ty + 8 * i];
         }
+        __syncthreads();
+    }
+}
+
+// K0t in word form (adi_mask_core.h): 128 x 128 byte tiles, 128-byte rows both ways.
+__global__ void __launch_bounds__(256) k_transpose_code_v(const TrArgs a, int batch)
+{
+    __shared__ uint32_t S[128 * 32];
+    const int c0 = blockIdx.x * 128, r0 = blockIdx.y * 128;
+    for (int b = blockIdx.z; b < batch; b += gridDim.z) {
+        tr_load(a, S, threadIdx.x, c0, r0, b);
+        __syncthreads();
+        tr_store(a, S, threadIdx.x, c0, r0, b);
         __syncthreads();
     }
 }
@@ -1257,20 +1282,7 @@ __global__ void k_spike_apply(double *__restrict__ T, const double *__restrict__
 // ------------------------------------------------------------------------------------
 // K7: exposed_mask / precompute_coeff_packs_unified (adi3d_gpu_coeff.py:31-110).
 // ------------------------------------------------------------------------------------
-struct PackArgs {
-    const uint8_t *mask;
-    int nx, ny, nz;
-    const uint8_t *mlo, *mhi;  // mask planes of the adjacent z slabs (NULL: domain boundary)
-    double A, Ccell;  // dx*dx, rho*cp*dx^3 (adi3d_numba_coeff.py:69-71)
-    int h_kind[6];
-    double h_scalar[6];
-    const double *h_field[6];
-    int q_kind[6];
-    double q_scalar[6];
-    const double *q_field[6];
-    double *coeff[3];
-    double *qout[3];
-};
+// PackArgs: adi_mask_core.h
 
 __device__ __forceinline__ unsigned exposed_bits(const uint8_t *__restrict__ mask, size_t idx, int i,
                                                  int j, int k, int nx, int ny, int nz,
@@ -1322,6 +1334,14 @@ __global__ void k_build_packs(const PackArgs a)
             if (a.qout[ax]) a.qout[ax][idx] = q;
         }
     }
+}
+
+// K7 in word form (adi_mask_core.h): 4 cells of a z line per thread, 32 bytes per output field and thread.
+__global__ void __launch_bounds__(256) k_build_packs_v(const PackArgs a)
+{
+    const size_t n4 = (size_t)a.nx * a.ny * a.nz / 4;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (size_t)gridDim.x * blockDim.x)
+        build_packs4(a, t * 4);
 }
 
 __global__ void k_exposed_mask(const uint8_t *__restrict__ mask, uint8_t *__restrict__ out, int face,

@@ -607,3 +607,53 @@ long emu_text_field(const void *src, int dtype, int nx, int ny, int nz, int fmt,
 }
 
 }  // extern "C"
+
+// ---- word forms of the per-mask-change kernels (adi_mask_core.h), "thread" after "thread" ----------------------
+#include "adi_mask_core.h"
+
+extern "C" {
+
+// k_build_code_v: nz % 16 == 0
+void emu_build_code_v(const uint8_t *mask, const uint8_t *dirm, uint8_t *code, int nx, int ny, int nz,
+                      const uint8_t *mlo, const uint8_t *mhi)
+{
+    const size_t n16 = (size_t)nx * ny * nz / 16;
+    for (size_t t = 0; t < n16; ++t) build_code16(mask, dirm, code, t * 16, nx, ny, nz, mlo, mhi);
+}
+
+// k_transpose_code_v with its launch geometry: grid (ceil(nz/128), ceil(n/128), batch), 256 threads, two phases
+// around the barrier.  dst holds batch*nz*npad bytes (pre-filled by the caller, as cudaMemset does).
+void emu_transpose_code_v(const uint8_t *src, uint8_t *dst, int n, int nz, int npad, int batch, size_t sb, size_t sr)
+{
+    TrArgs a;
+    a.src = src; a.dst = dst; a.n = n; a.nz = nz; a.npad = npad; a.sb = sb; a.sr = sr;
+    std::vector<uint32_t> S(128 * 32);
+    for (int b = 0; b < batch; ++b)
+        for (int by = 0; by < (n + 127) / 128; ++by)
+            for (int bx = 0; bx < (nz + 127) / 128; ++bx) {
+                std::fill(S.begin(), S.end(), 0xdeadbeefu);
+                for (int tid = 0; tid < 256; ++tid) tr_load(a, S.data(), tid, bx * 128, by * 128, b);
+                for (int tid = 0; tid < 256; ++tid) tr_store(a, S.data(), tid, bx * 128, by * 128, b);
+            }
+}
+
+// k_build_packs_v: nz % 4 == 0.  kinds: 0 none, 1 scalar, 2 field (adi_cart_build_packs).
+void emu_build_packs_v(const uint8_t *mask, int nx, int ny, int nz, const uint8_t *mlo, const uint8_t *mhi, double dx,
+                       double rho, double cp, const int *h_kind, const double *h_scalar, const double *const *h_field,
+                       const int *q_kind, const double *q_scalar, const double *const *q_field, double *const *coeff,
+                       double *const *qout)
+{
+    PackArgs a;
+    a.mask = mask; a.nx = nx; a.ny = ny; a.nz = nz; a.mlo = mlo; a.mhi = mhi;
+    a.A = dx * dx;
+    a.Ccell = rho * cp * std::pow(dx, 3.0);
+    for (int f = 0; f < 6; ++f) {
+        a.h_kind[f] = h_kind[f]; a.h_scalar[f] = h_scalar[f]; a.h_field[f] = h_field[f];
+        a.q_kind[f] = q_kind[f]; a.q_scalar[f] = q_scalar[f]; a.q_field[f] = q_field[f];
+    }
+    for (int ax = 0; ax < 3; ++ax) { a.coeff[ax] = coeff[ax]; a.qout[ax] = qout[ax]; }
+    const size_t n4 = (size_t)nx * ny * nz / 4;
+    for (size_t t = 0; t < n4; ++t) build_packs4(a, t * 4);
+}
+
+}  // extern "C"

@@ -16,7 +16,7 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(ROOT, "tests", "_emu.so")
-        srcs = [os.path.join(CSRC, f) for f in ("host_emulation.cpp", "adi_core.h", "adi_tab_core.h", "adi_fmt_core.h", "adi_pow10_tab.h")]
+        srcs = [os.path.join(CSRC, f) for f in ("host_emulation.cpp", "adi_core.h", "adi_mask_core.h", "adi_tab_core.h", "adi_fmt_core.h", "adi_pow10_tab.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
                             "-o", so, srcs[0]], check=True)

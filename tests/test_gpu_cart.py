@@ -612,3 +612,46 @@ def test_long_lines_persistent_blocks(shape, mask_kind, opts, g, cp):
     finally:
         for k, v in restore.items():
             g.set_option(k, v)
+
+
+@pytest.mark.parametrize("shape", [(24, 27, 32), (19, 38, 64), (40, 132, 48), (130, 20, 144)])
+@pytest.mark.parametrize("mk,bk", [("full", "robin_dict3d"), ("cyl_holes", "combined"), ("thin", "dir_scalar_interior"),
+                                   ("random", "combined"), ("plate_track", "robin_mixed"), ("empty", "robin6")])
+def test_mask_kernels_word_forms(shape, mk, bk, g, cp):
+    """The per-mask-change kernels in word form (adi_mask_core.h: neighbour code by 16 cells, transposed codes by
+    128 x 128 byte tiles, pack builder by 4 cells; nz % 16 == 0 here so that all three run) against the oracle and,
+    bit for bit, against the one-cell-per-thread forms (option maskv=0)."""
+    from oracle import cart
+    nx, ny, nz = shape
+    seed = 4242 + nx
+    mask = cases.make_mask(mk, shape, seed)
+    bcs = cases.make_bcs(bk, shape, mask, seed, 20.0)
+    T0 = 20.0 + 1380.0 * cases.splitmix_uniform(seed + 1, shape)
+    T0[~mask] = np.nan
+    kappa = cases.K / (cases.RHO * cases.CP)
+    dt = 2.0 * cases.DX ** 2 / kappa
+    hg, hm = cart.Grid3D(nx, ny, nz, cases.DX, mask), cart.Material(cases.RHO, cases.CP, cases.K)
+    hp = cart.precompute_coeff_packs_unified(hg, hm, **bcs)
+    ref = cart.adi_step_numba_coeff(T0, hg, hm, cart.Params(dt, 0.5), hp, Tinf=20.0)
+    outs = {}
+    try:
+        for v in (1, 0):
+            g.set_option("maskv", v)
+            grid = g.Grid3D(nx, ny, nz, cases.DX, mask)
+            mat = g.Material(cases.RHO, cases.CP, cases.K)
+            packs = g.precompute_coeff_packs_unified(grid, mat, **bcs)
+            dense = packs[0]._coeff is not None
+            out = cp.asnumpy(g.adi_step_gpu_coeff(cp.asarray(T0), grid, mat, g.Params(dt, 0.5), packs, Tinf=20.0))
+            used = g.get_option("maskv_used")
+            assert (used & 3) == (3 if v else 0), used
+            if dense:
+                assert (used & 4) == (4 if v else 0), used
+            for a in range(3):
+                assert np.array_equal(cp.asnumpy(packs[a].coeff).view(np.uint64), hp[a].coeff.view(np.uint64))
+                assert np.array_equal(cp.asnumpy(packs[a].qflux).view(np.uint64), hp[a].qflux.view(np.uint64))
+            outs[v] = out
+    finally:
+        g.set_option("maskv", 1)
+    assert cases.rel_l2(outs[1], ref, mask) <= TOL
+    assert np.array_equal(outs[1][~mask], T0[~mask], equal_nan=True)
+    assert np.array_equal(outs[1].view(np.uint64), outs[0].view(np.uint64))

@@ -279,6 +279,8 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
         ctx->opt_maskv = value;
         ctx->code_dirty = true;
     }
+    else if (!strcmp(name, "pkb")) ctx->opt_pkb = value;      // word-form pack builder: blocks per SM (0: default 512)
+    else if (!strcmp(name, "pkm")) ctx->opt_pkm = value;      // word-form pack builder tuning aids: 1 plain instead of streaming stores, 4 four cells per thread
     else if (!strcmp(name, "ukt")) ctx->opt_ukt = value;
     else if (!strcmp(name, "zm")) ctx->opt_zm = value;        // k_sweep_zt: chunk length (16 / 32) whatever the line length
     else if (!strcmp(name, "ejt")) ctx->opt_ejt = value;      // explicit stage: y rows per block (default 16)
@@ -331,6 +333,8 @@ long adi_get_option(adi_ctx *ctx, const char *name)
     if (!strcmp(name, "cylzt")) return ctx->opt_cylzt;
     if (!strcmp(name, "ukt")) return ctx->opt_ukt;
     if (!strcmp(name, "maskv")) return ctx->opt_maskv;
+    if (!strcmp(name, "pkb")) return ctx->opt_pkb;
+    if (!strcmp(name, "pkm")) return ctx->opt_pkm;
     if (!strcmp(name, "maskv_used")) return ctx->maskv_used;   // bit 0 / 1 / 2: the last code build / transposes / pack build took the word form
     if (!strcmp(name, "zm")) return ctx->opt_zm;
     if (!strcmp(name, "ejt")) return ctx->opt_ejt;

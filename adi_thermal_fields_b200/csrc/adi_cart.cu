@@ -736,13 +736,21 @@ int adi_cart_build_packs(adi_ctx *ctx, double rho, double cp, const int h_kind[6
     if (!n) return ADI_OK;
     const int threads = 256;
     const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, 148 * 64);
-    // word form: 4 cells per thread (adi_mask_core.h) when z lines are word aligned and the outputs take 16-byte stores
+    // word form (adi_mask_core.h): 2 cells per thread when z lines are 2-byte aligned and the outputs take 16-byte stores.
+    // Measured at 1024^3, half-built part (profiles/r04f_packs_probe.txt): 4.6 ms = 5.6 TB/s of stores (memset of the
+    // three fields: 3.4 ms) against 7.0 ms for the cell form; 40 registers (6 blocks per SM), streaming stores, 512
+    // blocks per SM.  Option pkm: 1 = plain stores, 4 = 4 cells per thread (half-sector stores, 7.9 ms); pkb: blocks per SM.
     uintptr_t al = 0;
     for (int ax = 0; ax < 3; ++ax) al |= (uintptr_t)a.coeff[ax] | (uintptr_t)a.qout[ax];
     ctx->maskv_used &= ~4;
-    if (ctx->opt_maskv && a.nz % 4 == 0 && ((uintptr_t)a.mask & 3) == 0 && (al & 15) == 0) {
-        const int vblocks = (int)std::min<size_t>((n / 4 + threads - 1) / threads, 148 * 64);
-        k_build_packs_v<<<vblocks, threads, 0, (cudaStream_t)stream>>>(a);
+    const int nc = (ctx->opt_pkm & 4) ? 4 : 2;
+    if (ctx->opt_maskv && a.nz % nc == 0 && ((uintptr_t)a.mask & (nc - 1)) == 0 && (al & 15) == 0) {
+        const int per_sm = ctx->opt_pkb > 0 ? ctx->opt_pkb : 512;
+        const int vblocks = (int)std::min<size_t>((n / nc + threads - 1) / threads, (size_t)148 * per_sm);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (nc == 4) k_build_packs_v<4, true, 1><<<vblocks, threads, 0, st>>>(a);
+        else if (ctx->opt_pkm & 1) k_build_packs_v<2, false, 6><<<vblocks, threads, 0, st>>>(a);
+        else k_build_packs_v<2, true, 6><<<vblocks, threads, 0, st>>>(a);
         ctx->maskv_used |= 4;
     } else {
         k_build_packs<<<blocks, threads, 0, (cudaStream_t)stream>>>(a);

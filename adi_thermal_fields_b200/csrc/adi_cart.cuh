@@ -1336,12 +1336,20 @@ __global__ void k_build_packs(const PackArgs a)
     }
 }
 
-// K7 in word form (adi_mask_core.h): 4 cells of a z line per thread, 32 bytes per output field and thread.
-__global__ void __launch_bounds__(256) k_build_packs_v(const PackArgs a)
+// K7 in word form (adi_mask_core.h): NC cells of a z line per thread (NC = 2: 16 bytes per output field and thread).
+template <int NC, bool CS, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_build_packs_v(const PackArgs a)
 {
-    const size_t n4 = (size_t)a.nx * a.ny * a.nz / 4;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (size_t)gridDim.x * blockDim.x)
-        build_packs4(a, t * 4);
+    const size_t nw = (size_t)a.nx * a.ny * a.nz / NC, stride = (size_t)gridDim.x * blockDim.x;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t raw = t < nw ? ldcells<NC>(a.mask + t * NC) : 0u;
+    while (t < nw) {   // the next iteration's mask bytes are on their way while this one's fields are stored
+        const size_t tn = t + stride;
+        const uint32_t rawn = tn < nw ? ldcells<NC>(a.mask + tn * NC) : 0u;
+        build_packs_cells<NC, CS>(a, t * NC, raw);
+        t = tn;
+        raw = rawn;
+    }
 }
 
 __global__ void k_exposed_mask(const uint8_t *__restrict__ mask, uint8_t *__restrict__ out, int face,

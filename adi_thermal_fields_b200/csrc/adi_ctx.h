@@ -69,7 +69,7 @@ struct adi_ctx {
     long launches = 0;
     // options (adi_set_option)
     long opt_kt = 0, opt_lt = 0, opt_m = 0, opt_sync_check = 0, opt_profile = 0, opt_fuse = 0, opt_wide = 0, opt_sparse = 1,
-         opt_xy2 = 1, opt_uni = 1, opt_tw = 0, opt_remap = 0, opt_dbg = 0, opt_occ = 0, opt_zt = 1, opt_bulk = 1, opt_tiles = 1, opt_eorder = 0, opt_lb = 0, opt_hyb = 1, opt_xyp = 0, opt_seq = 0, opt_promo = 0, opt_ejt = 0, opt_eth = 0, opt_zm = 0, opt_xyu = 1, opt_ukt = 0, opt_cylsm = 1, opt_cylzt = 1, opt_maskv = 1;
+         opt_xy2 = 1, opt_uni = 1, opt_tw = 0, opt_remap = 0, opt_dbg = 0, opt_occ = 0, opt_zt = 1, opt_bulk = 1, opt_tiles = 1, opt_eorder = 0, opt_lb = 0, opt_hyb = 1, opt_xyp = 0, opt_seq = 0, opt_promo = 0, opt_ejt = 0, opt_eth = 0, opt_zm = 0, opt_xyu = 1, opt_ukt = 0, opt_cylsm = 1, opt_cylzt = 1, opt_maskv = 1, opt_pkb = 0, opt_pkm = 0;
     int sm_count = 0;
     int xyp_state = 0;   // tensor-map layout the driver accepted for k_sweep_xyp (0 / 1), -1: refused
     long xyp_used = 0;   // launches of k_sweep_xyp

@@ -103,15 +103,6 @@ ADI_HD void st16(uint8_t *p, const uint32_t w[4])
     memcpy(p, w, 16);
 #endif
 }
-ADI_HD void st4d(double *p, const double v[4])
-{
-#if defined(__CUDA_ARCH__)
-    reinterpret_cast<double2 *>(p)[0] = make_double2(v[0], v[1]);
-    reinterpret_cast<double2 *>(p)[1] = make_double2(v[2], v[3]);
-#else
-    for (int b = 0; b < 4; ++b) p[b] = v[b];
-#endif
-}
 ADI_HD double mul_rn(double a, double b)
 {
 #if defined(__CUDA_ARCH__)
@@ -211,9 +202,12 @@ ADI_HD void tr_store(const TrArgs &a, const uint32_t *S, int tid, int c0, int r0
     }
 }
 
-// ---- K7 in word form: precompute_coeff_packs_unified for the 4 cells idx .. idx+3 of one z line ---------------
-// (nz % 4 == 0, word-aligned mask, 16-byte aligned outputs).  Same operations per exposed face, in the same order,
-// as k_build_packs; cells without an exposed face (almost all of them) cost no field read.
+// ---- K7 in word form: precompute_coeff_packs_unified for the NC (2 or 4) cells idx .. idx+NC-1 of one z line ----
+// (nz % NC == 0, NC-byte aligned mask, 16-byte aligned outputs).  Same operations per exposed face, in the same
+// order, as k_build_packs; cells without an exposed face (almost all of them) cost no field read.  NC = 2 is the
+// form the library launches: a thread stores 16 bytes per field, so a warp's store covers whole 32-byte sectors
+// (with NC = 4 each of the two 16-byte stores of a thread fills half a sector: twice the L1 -> L2 sector traffic,
+// ncu profiles/r04d: 32 sectors per request, l1tex 68 % busy, 7.9 against 4.6 ms at 1024^3).
 struct PackArgs {
     const uint8_t *mask;
     int nx, ny, nz;
@@ -229,9 +223,40 @@ struct PackArgs {
     double *qout[3];
 };
 
-ADI_HD void build_packs4(const PackArgs &a, size_t idx)
+template <int NC>
+ADI_HD uint32_t ldcells(const uint8_t *p)   // NC mask bytes in the low bytes of a word
 {
-    const uint32_t s = nzbytes(ld4(a.mask + idx));
+    if (NC == 4) return ld4(p);
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(p));
+#else
+    uint16_t v;
+    memcpy(&v, p, 2);
+    return v;
+#endif
+}
+
+template <int NC, bool CS>
+ADI_HD void stcells(double *p, const double *v)
+{
+#if defined(__CUDA_ARCH__)
+    if (CS) {
+        __stcs(reinterpret_cast<double2 *>(p), make_double2(v[0], v[1]));
+        if (NC == 4) __stcs(reinterpret_cast<double2 *>(p) + 1, make_double2(v[2], v[3]));
+    } else {
+        reinterpret_cast<double2 *>(p)[0] = make_double2(v[0], v[1]);
+        if (NC == 4) reinterpret_cast<double2 *>(p)[1] = make_double2(v[2], v[3]);
+    }
+#else
+    for (int b = 0; b < NC; ++b) p[b] = v[b];
+#endif
+}
+
+// raw: the NC mask bytes of the cells (ldcells<NC>(a.mask + idx)), loaded by the caller one iteration ahead
+template <int NC = 2, bool CS = false>
+ADI_HD void build_packs_cells(const PackArgs &a, size_t idx, uint32_t raw)
+{
+    const uint32_t s = nzbytes(raw);
     uint32_t ex[6] = {0u, 0u, 0u, 0u, 0u, 0u};   // byte b of ex[f]: cell b active and exposed on face f (:38-55)
     if (s) {
         const int k = (int)(idx % (size_t)a.nz);
@@ -240,20 +265,22 @@ ADI_HD void build_packs4(const PackArgs &a, size_t idx)
         const int i = (int)(ij / (size_t)a.ny);
         const size_t snx = (size_t)a.ny * a.nz;
         const bool lo = k > 0 ? a.mask[idx - 1] != 0 : (a.mlo && a.mlo[ij]);
-        const bool hi = k + 4 < a.nz ? a.mask[idx + 4] != 0 : (a.mhi && a.mhi[ij]);
-        ex[0] = s & ~(i > 0 ? nzbytes(ld4(a.mask + idx - snx)) : 0u);
-        ex[1] = s & ~(i + 1 < a.nx ? nzbytes(ld4(a.mask + idx + snx)) : 0u);
-        ex[2] = s & ~(j > 0 ? nzbytes(ld4(a.mask + idx - a.nz)) : 0u);
-        ex[3] = s & ~(j + 1 < a.ny ? nzbytes(ld4(a.mask + idx + a.nz)) : 0u);
+        const bool hi = k + NC < a.nz ? a.mask[idx + NC] != 0 : (a.mhi && a.mhi[ij]);
+        ex[0] = s & ~(i > 0 ? nzbytes(ldcells<NC>(a.mask + idx - snx)) : 0u);
+        ex[1] = s & ~(i + 1 < a.nx ? nzbytes(ldcells<NC>(a.mask + idx + snx)) : 0u);
+        ex[2] = s & ~(j > 0 ? nzbytes(ldcells<NC>(a.mask + idx - a.nz)) : 0u);
+        ex[3] = s & ~(j + 1 < a.ny ? nzbytes(ldcells<NC>(a.mask + idx + a.nz)) : 0u);
         ex[4] = s & ~zminus4(s, lo ? 0xff000000u : 0u);
-        ex[5] = s & ~zplus4(s, hi ? 0xffu : 0u);
+        ex[5] = s & ~((s >> 8) | (hi ? (0xffu << (8 * (NC - 1))) : 0u));   // zplus4 with the next cell after byte NC-1
     }
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
-        double c[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
+        double c[NC], q[NC];
+#pragma unroll
+        for (int b = 0; b < NC; ++b) c[b] = q[b] = 0.0;
         if ((ex[2 * ax] | ex[2 * ax + 1]) != 0u) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
+            for (int b = 0; b < NC; ++b)
 #pragma unroll
                 for (int sd = 0; sd < 2; ++sd) {
                     const int f = 2 * ax + sd;
@@ -269,8 +296,8 @@ ADI_HD void build_packs4(const PackArgs &a, size_t idx)
                     }
                 }
         }
-        if (a.coeff[ax]) st4d(a.coeff[ax] + idx, c);
-        if (a.qout[ax]) st4d(a.qout[ax] + idx, q);
+        if (a.coeff[ax]) stcells<NC, CS>(a.coeff[ax] + idx, c);
+        if (a.qout[ax]) stcells<NC, CS>(a.qout[ax] + idx, q);
     }
 }
 

@@ -637,8 +637,8 @@ void emu_transpose_code_v(const uint8_t *src, uint8_t *dst, int n, int nz, int n
             }
 }
 
-// k_build_packs_v: nz % 4 == 0.  kinds: 0 none, 1 scalar, 2 field (adi_cart_build_packs).
-void emu_build_packs_v(const uint8_t *mask, int nx, int ny, int nz, const uint8_t *mlo, const uint8_t *mhi, double dx,
+// k_build_packs_v<nc>: nz % nc == 0, nc = 2 | 4.  kinds: 0 none, 1 scalar, 2 field (adi_cart_build_packs).
+void emu_build_packs_v(int nc, const uint8_t *mask, int nx, int ny, int nz, const uint8_t *mlo, const uint8_t *mhi, double dx,
                        double rho, double cp, const int *h_kind, const double *h_scalar, const double *const *h_field,
                        const int *q_kind, const double *q_scalar, const double *const *q_field, double *const *coeff,
                        double *const *qout)
@@ -652,8 +652,11 @@ void emu_build_packs_v(const uint8_t *mask, int nx, int ny, int nz, const uint8_
         a.q_kind[f] = q_kind[f]; a.q_scalar[f] = q_scalar[f]; a.q_field[f] = q_field[f];
     }
     for (int ax = 0; ax < 3; ++ax) { a.coeff[ax] = coeff[ax]; a.qout[ax] = qout[ax]; }
-    const size_t n4 = (size_t)nx * ny * nz / 4;
-    for (size_t t = 0; t < n4; ++t) build_packs4(a, t * 4);
+    const size_t nw = (size_t)nx * ny * nz / nc;
+    for (size_t t = 0; t < nw; ++t) {
+        if (nc == 4) build_packs_cells<4, false>(a, t * 4, ldcells<4>(mask + t * 4));
+        else build_packs_cells<2, false>(a, t * 2, ldcells<2>(mask + t * 2));
+    }
 }
 
 }  // extern "C"

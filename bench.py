@@ -1007,6 +1007,7 @@ def bench_c4(args, local, sub=False):
         return g.precompute_coeff_packs_unified(grid, mat, robin_h=h)
 
     kacc = [0.0, 0.0, 0.0, 0.0, 0]     # per-kernel times of the steady steps (engine events), their count
+    per_layer = []                     # (mask update + pack rebuild, first step) ms of every birth
 
     def run(layer_list, prof=None):
         """-> steps, ms spent on births (mask update + pack rebuild), ms of the FIRST step of every layer (it rebuilds the
@@ -1039,10 +1040,14 @@ def bench_c4(args, local, sub=False):
             tb += e0.elapsed_time(e1)
             t1 += e1.elapsed_time(e1b)
             ts += e1b.elapsed_time(e2)
+            per_layer.append((round(e0.elapsed_time(e1), 3), round(e1.elapsed_time(e1b), 3)))
         return nsteps, tb, t1, ts
 
-    nwarm = max(1, args.warmup // steps_per_layer)
+    # two births at least: the second one still allocates (the first generation of pack arrays is alive while the
+    # second is built); from the third on the caching allocator hands the blocks back and forth
+    nwarm = max(2, args.warmup // steps_per_layer)
     run(layers[:nwarm])
+    per_layer.clear()
     c4_steps = args.steps if not sub else min(args.steps, 16)
     nlay = max(1, c4_steps // steps_per_layer)
     mid = layers[len(layers) // 2: len(layers) // 2 + nlay]   # mid-build: half of the head is active
@@ -1094,6 +1099,7 @@ def bench_c4(args, local, sub=False):
                      "achieved": 75.0 * cells / (steady * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": 75.0 * cells / (steady * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                      "steady_ms_per_step": steady, "birth_ms": birth_ms, "kernel_ms": kernel_ms,
+                     "birth_ms_each": [{"mask_and_packs": a, "first_step": b} for a, b in per_layer],
                      "sweep_tiles": tiles,
                      "active_cell_steps_per_s": active_frac * cells / (steady * 1e-3),
                      "birth_note": "per birth: mask update + k_build_packs (6 dense h fields -> 3 coeff fields) + what the first "

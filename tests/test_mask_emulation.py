@@ -93,7 +93,7 @@ def test_transposed_code_word_form(shape, axis):
     assert np.array_equal(dst, want)
 
 
-def _packs_v(mask, dx, rho, cp, h, q, mlo=None, mhi=None, want_q=True):
+def _packs_v(mask, dx, rho, cp, h, q, mlo=None, mhi=None, want_q=True, nc=2):
     """h / q: six entries, each None, a scalar or a dense field."""
     nx, ny, nz = mask.shape
     kinds = lambda v: 0 if v is None else (1 if np.isscalar(v) else 2)
@@ -106,19 +106,20 @@ def _packs_v(mask, dx, rho, cp, h, q, mlo=None, mhi=None, want_q=True):
     coeff = [np.full(mask.shape, np.nan) for _ in range(3)]
     qout = [np.full(mask.shape, np.nan) for _ in range(3)] if want_q else [None] * 3
     L = emu.lib()
-    L.emu_build_packs_v.argtypes = [BP, C.c_int, C.c_int, C.c_int, BP, BP, C.c_double, C.c_double, C.c_double,
+    L.emu_build_packs_v.argtypes = [C.c_int, BP, C.c_int, C.c_int, C.c_int, BP, BP, C.c_double, C.c_double, C.c_double,
                                     C.POINTER(C.c_int), DP, C.POINTER(DP), C.POINTER(C.c_int), DP, C.POINTER(DP),
                                     C.POINTER(DP), C.POINTER(DP)]
     L.emu_build_packs_v.restype = None
-    L.emu_build_packs_v(_bp(mask), nx, ny, nz, _bp(mlo), _bp(mhi), dx, rho, cp, hk, hs, hf, qk, qs, qf,
+    L.emu_build_packs_v(nc, _bp(mask), nx, ny, nz, _bp(mlo), _bp(mhi), dx, rho, cp, hk, hs, hf, qk, qs, qf,
                         (DP * 3)(*[_dp(a) for a in coeff]), (DP * 3)(*[_dp(a) for a in qout]))
     return coeff, qout
 
 
-@pytest.mark.parametrize("shape", [(5, 6, 8), (4, 3, 12), (1, 1, 4), (6, 7, 32)])
+@pytest.mark.parametrize("shape,nc", [((5, 6, 8), 2), ((5, 6, 8), 4), ((4, 3, 12), 4), ((4, 3, 10), 2), ((1, 1, 4), 4),
+                                      ((1, 1, 2), 2), ((6, 7, 32), 2), ((6, 7, 32), 4)])
 @pytest.mark.parametrize("kind", ["full", "random", "layers", "void"])
 @pytest.mark.parametrize("bc", ["scalar", "fields", "mixed"])
-def test_pack_builder_word_form_bit_exact_vs_oracle(shape, kind, bc):
+def test_pack_builder_word_form_bit_exact_vs_oracle(shape, nc, kind, bc):
     rng = np.random.default_rng(11)
     mask = _mask(shape, kind, rng)
     dx, rho, cp = 1.3e-3, 7800.0, 490.0
@@ -132,7 +133,7 @@ def test_pack_builder_word_form_bit_exact_vs_oracle(shape, kind, bc):
     else:
         h = [fld(5, 500), 40.0, None, fld(1, 2), 300.0, fld(0, 1)]
         q = [None, fld(-1e4, 1e4), 5.0e3, None, None, fld(0, 10)]
-    coeff, qout = _packs_v(mask, dx, rho, cp, h, q)
+    coeff, qout = _packs_v(mask, dx, rho, cp, h, q, nc=nc)
     grid = cart.Grid3D(*shape, dx, mask.astype(bool))
     mat = cart.Material(rho, cp, 54.0)
     robin = {f: (0.0 if v is None else v) for f, v in zip(cart.FACES, h)}
@@ -157,7 +158,8 @@ def test_pack_builder_word_form_slab_halo_planes():
         sub = np.ascontiguousarray(mask[:, :, z0:z1])
         mlo = np.ascontiguousarray(mask[:, :, z0 - 1]) if z0 > 0 else None
         mhi = np.ascontiguousarray(mask[:, :, z1]) if z1 < shape[2] else None
-        coeff, _ = _packs_v(sub, dx, rho, cp, h, [None] * 6, mlo, mhi, want_q=False)
-        for ax in range(3):
-            assert np.array_equal(coeff[ax].view(np.uint64),
-                                  np.ascontiguousarray(packs[ax].coeff[:, :, z0:z1]).view(np.uint64))
+        for nc in (2, 4):
+            coeff, _ = _packs_v(sub, dx, rho, cp, h, [None] * 6, mlo, mhi, want_q=False, nc=nc)
+            for ax in range(3):
+                assert np.array_equal(coeff[ax].view(np.uint64),
+                                      np.ascontiguousarray(packs[ax].coeff[:, :, z0:z1]).view(np.uint64))

@@ -189,6 +189,8 @@ int adi_ctx_destroy(adi_ctx *ctx)
     if (ctx->d_ghost) cudaFree(ctx->d_ghost);
     if (ctx->d_maxk) cudaFree(ctx->d_maxk);
     if (ctx->d_viol) cudaFree(ctx->d_viol);
+    if (ctx->d_ztop) cudaFree(ctx->d_ztop);
+    if (ctx->h_ztop) cudaFreeHost(ctx->h_ztop);
     if (ctx->h_viol) cudaFreeHost(ctx->h_viol);
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 2; ++j)
@@ -279,6 +281,7 @@ int adi_set_option(adi_ctx *ctx, const char *name, long value)
         ctx->opt_maskv = value;
         ctx->code_dirty = true;
     }
+    else if (!strcmp(name, "ztrim")) ctx->opt_ztrim = value;  // 1 (default): the z sweep stops at the top of a part under construction
     else if (!strcmp(name, "pkb")) ctx->opt_pkb = value;      // word-form pack builder: blocks per SM (0: default 512)
     else if (!strcmp(name, "pkm")) ctx->opt_pkm = value;      // word-form pack builder tuning aids: 1 plain instead of streaming stores, 4 four cells per thread
     else if (!strcmp(name, "ukt")) ctx->opt_ukt = value;
@@ -333,6 +336,9 @@ long adi_get_option(adi_ctx *ctx, const char *name)
     if (!strcmp(name, "cylzt")) return ctx->opt_cylzt;
     if (!strcmp(name, "ukt")) return ctx->opt_ukt;
     if (!strcmp(name, "maskv")) return ctx->opt_maskv;
+    if (!strcmp(name, "ztrim")) return ctx->opt_ztrim;
+    if (!strcmp(name, "ztrim_used")) return ctx->ztrim_used;   // z sweeps launched on trimmed lines so far
+    if (!strcmp(name, "ztop")) return ctx->ztop;               // z + 1 of the highest active cell (-1: unknown / not read yet)
     if (!strcmp(name, "pkb")) return ctx->opt_pkb;
     if (!strcmp(name, "pkm")) return ctx->opt_pkm;
     if (!strcmp(name, "maskv_used")) return ctx->maskv_used;   // bit 0 / 1 / 2: the last code build / transposes / pack build took the word form

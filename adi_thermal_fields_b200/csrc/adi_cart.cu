@@ -52,14 +52,25 @@ int ensure_code(adi_ctx *ctx, cudaStream_t st)
         const int threads = 256;
         const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, 148 * 64);
         ctx->maskv_used &= ~3;
+        ctx->ztop = -1; ctx->ztop_pending = false;     // unknown unless the word form reports it
+        if (!ctx->d_ztop) {
+            ADI_CUDA(cudaMalloc(&ctx->d_ztop, sizeof(int)));
+            ADI_CUDA(cudaMallocHost(&ctx->h_ztop, sizeof(int)));
+        }
         for (int a = 0; a < ncodes; ++a) {
             // word form: 16 cells per thread (adi_mask_core.h) when every z line starts on a 16-byte boundary
             const bool wordform = ctx->opt_maskv && ctx->nz % 16 == 0 &&
                                   (((uintptr_t)ctx->d_mask | (uintptr_t)ctx->pack[a].dirm | (uintptr_t)ctx->code_buf[a]) & 15) == 0;
             if (wordform) {
                 const int vblocks = (int)std::min<size_t>((n / 16 + threads - 1) / threads, 148 * 32);
+                if (a == 0) ADI_CUDA(cudaMemsetAsync(ctx->d_ztop, 0, sizeof(int), st));
                 k_build_code_v<<<vblocks, threads, 0, st>>>(ctx->d_mask, ctx->pack[a].dirm, ctx->code_buf[a],
-                                                            ctx->nx, ctx->ny, ctx->nz, ctx->d_mask_lo, ctx->d_mask_hi);
+                                                            ctx->nx, ctx->ny, ctx->nz, ctx->d_mask_lo, ctx->d_mask_hi,
+                                                            a == 0 ? ctx->d_ztop : nullptr);
+                if (a == 0) {   // top of the part, read when the z sweep first needs it (launch_sweep_zt)
+                    ADI_CUDA(cudaMemcpyAsync(ctx->h_ztop, ctx->d_ztop, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    ctx->ztop_pending = true;
+                }
                 ctx->maskv_used |= 1;
             } else {
                 k_build_code<<<blocks, threads, 0, st>>>(ctx->d_mask, ctx->pack[a].dirm, ctx->code_buf[a],
@@ -350,7 +361,7 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
     a.k.invdx2 = 1.0 / (dx * dx);
     a.zlo = d_Tlo; a.zhi = d_Thi; a.iface_dyn = d_iface_dyn; a.iface_stat = d_iface_stat; a.ghost = d_ghost;
     a.codeT = nullptr; a.npad = 0; a.uni = 0; a.tw = 0; a.remap = 0; a.dbg = 0; a.halo_defer = 0;
-    a.tiles = nullptr; a.tiles_nx = 0; a.tsplit = 0; a.zpitch = 0; a.code_line = 0;
+    a.tiles = nullptr; a.tiles_nx = 0; a.tsplit = 0; a.zpitch = 0; a.code_line = 0; a.zfull = 0;
     a.line_batch = nlb != 0 ? 1 : 0;
     bool expl = a.k.beta != 0.0;
     bool x_in_place = false;

@@ -56,6 +56,9 @@ struct SweepArgs {
     int line_batch;                    // z sweep of a batch of lines (multi-GPU): the pointers are offset, no tile list
     int zpitch;                        // k_sweep_zt: elements between consecutive z lines of in / out (0: nz)
     int code_line;                     // k_sweep_zt: 1 = `code` holds ONE line of nz codes shared by all z lines
+    int zfull;                         // k_sweep_zt: elements between consecutive z lines of code / coeff / q / dirv (0: nz);
+                                       // set when the sweep solves only the first nz cells of longer lines (cells above
+                                       // the top of a part under construction are void: launch_sweep_zt)
     UniConst uc;
 };
 
@@ -95,11 +98,17 @@ __global__ void k_build_code(const uint8_t *__restrict__ mask, const uint8_t *__
 // cells (most of the box while a part is being built) cost one load and one store.
 __global__ void __launch_bounds__(256) k_build_code_v(const uint8_t *__restrict__ mask, const uint8_t *__restrict__ dirm,
                                                       uint8_t *__restrict__ code, int nx, int ny, int nz,
-                                                      const uint8_t *__restrict__ mlo, const uint8_t *__restrict__ mhi)
+                                                      const uint8_t *__restrict__ mlo, const uint8_t *__restrict__ mhi,
+                                                      int *__restrict__ ztop)
 {
     const size_t n16 = (size_t)nx * ny * nz / 16;
+    int top = 0;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n16; t += (size_t)gridDim.x * blockDim.x)
-        build_code16(mask, dirm, code, t * 16, nx, ny, nz, mlo, mhi);
+        top = max(top, build_code16(mask, dirm, code, t * 16, nx, ny, nz, mlo, mhi));
+    if (ztop) {   // *ztop = z + 1 of the highest active cell of the grid
+        top = __reduce_max_sync(0xffffffffu, top);
+        if ((threadIdx.x & 31) == 0 && top > 0) atomicMax(ztop, top);
+    }
 }
 
 // K0t: per-axis transposed copy of the code array for the x / y sweeps (adi_sweep_xy.cuh):

@@ -69,11 +69,17 @@ struct adi_ctx {
     long launches = 0;
     // options (adi_set_option)
     long opt_kt = 0, opt_lt = 0, opt_m = 0, opt_sync_check = 0, opt_profile = 0, opt_fuse = 0, opt_wide = 0, opt_sparse = 1,
-         opt_xy2 = 1, opt_uni = 1, opt_tw = 0, opt_remap = 0, opt_dbg = 0, opt_occ = 0, opt_zt = 1, opt_bulk = 1, opt_tiles = 1, opt_eorder = 0, opt_lb = 0, opt_hyb = 1, opt_xyp = 0, opt_seq = 0, opt_promo = 0, opt_ejt = 0, opt_eth = 0, opt_zm = 0, opt_xyu = 1, opt_ukt = 0, opt_cylsm = 1, opt_cylzt = 1, opt_maskv = 1, opt_pkb = 0, opt_pkm = 0;
+         opt_xy2 = 1, opt_uni = 1, opt_tw = 0, opt_remap = 0, opt_dbg = 0, opt_occ = 0, opt_zt = 1, opt_bulk = 1, opt_tiles = 1, opt_eorder = 0, opt_lb = 0, opt_hyb = 1, opt_xyp = 0, opt_seq = 0, opt_promo = 0, opt_ejt = 0, opt_eth = 0, opt_zm = 0, opt_xyu = 1, opt_ukt = 0, opt_cylsm = 1, opt_cylzt = 1, opt_maskv = 1, opt_pkb = 0, opt_pkm = 0, opt_ztrim = 1;
     int sm_count = 0;
     int xyp_state = 0;   // tensor-map layout the driver accepted for k_sweep_xyp (0 / 1), -1: refused
     long xyp_used = 0;   // launches of k_sweep_xyp
     long xyu_used = 0;   // launches of k_sweep_xyu
+    // top of the part (z + 1 of the highest active cell), reduced by k_build_code_v: the single-GPU z sweep solves only
+    // the cells below it (launch_sweep_zt).  -1: unknown (cell-form code build); pending: the copy to h_ztop is in flight
+    int *d_ztop = nullptr, *h_ztop = nullptr;
+    int ztop = -1;
+    bool ztop_pending = false;
+    long ztrim_used = 0;  // z sweeps launched on trimmed lines
     int maskv_used = 0;  // bit 0 / 1 / 2: the last code build / code transposes / pack build ran in word form (adi_mask_core.h)
     // per-kernel timing (adi_profile_*): 5 events per step, read lazily
     std::vector<cudaEvent_t> prof_ev;

@@ -120,12 +120,25 @@ ADI_HD double div_rn(double a, double b)
 #endif
 }
 
+// index + 1 of the highest non-zero byte of a word (0: none)
+ADI_HD int top_byte(uint32_t w)
+{
+#if defined(__CUDA_ARCH__)
+    return 4 - (__clz((int)w) >> 3);
+#else
+    return w ? 4 - (__builtin_clz(w) >> 3) : 0;
+#endif
+}
+
 // ---- K0 in word form: the neighbour codes of the 16 cells idx .. idx+15 of one z line ------------------------
 // (nz % 16 == 0, idx % 16 == 0, 16-byte aligned arrays).  A run without an active cell costs one load and one store.
-ADI_HD void build_code16(const uint8_t *mask, const uint8_t *dirm, uint8_t *code, size_t idx, int nx, int ny, int nz,
+// Returns z + 1 of the highest active cell of the run (0: none): the kernel reduces it to the top of the part, above
+// which the z sweep has nothing to solve (launch_sweep_zt).
+ADI_HD int build_code16(const uint8_t *mask, const uint8_t *dirm, uint8_t *code, size_t idx, int nx, int ny, int nz,
                          const uint8_t *mlo, const uint8_t *mhi)
 {
     uint32_t s[4], out[4] = {0u, 0u, 0u, 0u};
+    int top = 0;
     ld16(mask + idx, s);
     if ((s[0] | s[1] | s[2] | s[3]) != 0u) {
         const int k = (int)(idx % (size_t)nz);
@@ -152,9 +165,11 @@ ADI_HD void build_code16(const uint8_t *mask, const uint8_t *dirm, uint8_t *code
             out[q] = code4(s[q], nzbytes(xm[q]), nzbytes(xp[q]), nzbytes(ym[q]), nzbytes(yp[q]), zminus4(s[q], prev),
                            zplus4(s[q], next), nzbytes(d[q]));
             prev = s[q];
+            if (s[q]) top = k + 4 * q + top_byte(s[q]);
         }
     }
     st16(code + idx, out);
+    return top;
 }
 
 // ---- K0t in word form: dst[(b*nz + c)*npad + r] = src[b*sb + r*sr + c] by tiles of 128 (r) x 128 (c) bytes ---

@@ -49,10 +49,30 @@ static int launch_zt_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, bool ext
 // Shapes: nz <= 128: 16-cell chunks; longer lines: 32-cell chunks (the z-slab modes need nz % chunk == 0 and take
 // 16-cell chunks when nz is no multiple of 32); up to 32 chunks per line in 256-thread blocks (2 per SM), up to 64
 // in 512-thread blocks; KT lines per tile = threads / chunks, halved until the tile fits.
-int launch_sweep_zt(adi_ctx *ctx, const SweepArgs &a, bool dense, bool extra, int zmode, cudaStream_t st, int *used)
+int launch_sweep_zt(adi_ctx *ctx, const SweepArgs &a0, bool dense, bool extra, int zmode, cudaStream_t st, int *used)
 {
     *used = 0;
-    if (!ctx->opt_zt || a.nz > 2048) return ADI_OK;
+    if (!ctx->opt_zt || a0.nz > 2048) return ADI_OK;
+    // A part under construction (waam_from_stl_v7_mm.py:487-550: layers are born bottom-up along z): every cell above
+    // the top of the part is void -- an identity row coupled to nothing -- so the single-GPU, in-place sweep solves only
+    // the first ztop cells of each line (rounded up to whole 32-cell chunks, at least 256) and leaves the rest where the
+    // explicit stage put them.  The top comes from the code build (k_build_code_v); operand arrays keep their stride.
+    SweepArgs a = a0;
+    if (zmode == 0 && ctx->opt_ztrim && !a.line_batch && !a.code_line && a.zpitch == 0 && a.zfull == 0 && a.in == a.out &&
+        a.nz >= 512 && a.nz % 32 == 0 && a.nz == ctx->nz && a.code == ctx->code[2]) {
+        if (ctx->ztop_pending) {
+            ADI_CUDA(cudaStreamSynchronize(st));
+            ctx->ztop = *ctx->h_ztop;
+            ctx->ztop_pending = false;
+        }
+        if (ctx->ztop >= 0) {
+            const int ne = std::max(256, (ctx->ztop + 31) / 32 * 32);
+            if (ne < a.nz) {
+                a.zfull = a.nz; a.zpitch = a.nz; a.nz = ne;
+                ctx->ztrim_used++;
+            }
+        }
+    }
     if (dense && !a.sparse) return ADI_OK;     // a dense coefficient field that must be read everywhere: k_sweep_z stages it
     // 32-cell chunks from 64 cells up: on 2048 x 2048 x 128 (the slab of configs[4] at N = 8) 4 chunks x 16 lines take
     // 1.31 ms = 6.9 TB/s against 2.12 ms for k_sweep_z and 2.6 ms for 16-cell chunks (r02x)

@@ -614,11 +614,14 @@ long emu_text_field(const void *src, int dtype, int nx, int ny, int nz, int fmt,
 extern "C" {
 
 // k_build_code_v: nz % 16 == 0
-void emu_build_code_v(const uint8_t *mask, const uint8_t *dirm, uint8_t *code, int nx, int ny, int nz,
-                      const uint8_t *mlo, const uint8_t *mhi)
+// returns z + 1 of the highest active cell (0: none), as the kernel's reduction does
+int emu_build_code_v(const uint8_t *mask, const uint8_t *dirm, uint8_t *code, int nx, int ny, int nz,
+                     const uint8_t *mlo, const uint8_t *mhi)
 {
     const size_t n16 = (size_t)nx * ny * nz / 16;
-    for (size_t t = 0; t < n16; ++t) build_code16(mask, dirm, code, t * 16, nx, ny, nz, mlo, mhi);
+    int top = 0;
+    for (size_t t = 0; t < n16; ++t) top = std::max(top, build_code16(mask, dirm, code, t * 16, nx, ny, nz, mlo, mhi));
+    return top;
 }
 
 // k_transpose_code_v with its launch geometry: grid (ceil(nz/128), ceil(n/128), batch), 256 threads, two phases

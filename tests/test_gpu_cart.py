@@ -655,3 +655,54 @@ def test_mask_kernels_word_forms(shape, mk, bk, g, cp):
     assert cases.rel_l2(outs[1], ref, mask) <= TOL
     assert np.array_equal(outs[1][~mask], T0[~mask], equal_nan=True)
     assert np.array_equal(outs[1].view(np.uint64), outs[0].view(np.uint64))
+
+
+@pytest.mark.parametrize("top", [0, 1, 150, 289, 500])
+@pytest.mark.parametrize("bk", ["robin_dict3d", "robin6", "combined", "neumann_fields"])
+def test_z_sweep_stops_at_the_top_of_the_part(top, bk, g, cp):
+    """A part under construction (layers born bottom-up along z): the z sweep solves only the cells below the top of the
+    part (option ztrim; the top comes out of the code build) -- same answer as the oracle and as the untrimmed sweep,
+    void cells (NaN) untouched."""
+    from oracle import cart
+    shape = (20, 24, 512)
+    nx, ny, nz = shape
+    seed = 777 + top
+    mask = cases.make_mask("cyl_holes", shape, seed)
+    mask[:, :, top:] = False
+    if top > 40:
+        mask[3:9, 5:7, top - 40:top - 20] = False     # a cavity: interior exposed faces
+    bcs = cases.make_bcs(bk, shape, mask, seed, 20.0)
+    T0 = 20.0 + 1380.0 * cases.splitmix_uniform(seed + 1, shape)
+    T0[~mask] = np.nan
+    kappa = cases.K / (cases.RHO * cases.CP)
+    dt = 50.0 * cases.DX ** 2 / kappa
+    hg, hm = cart.Grid3D(nx, ny, nz, cases.DX, mask), cart.Material(cases.RHO, cases.CP, cases.K)
+    ref = cart.adi_step_numba_coeff(T0, hg, hm, cart.Params(dt, 0.5),
+                                    cart.precompute_coeff_packs_unified(hg, hm, **bcs), Tinf=20.0)
+    outs = {}
+    try:
+        for v in (1, 0):
+            g.set_option("ztrim", v)
+            grid = g.Grid3D(nx, ny, nz, cases.DX, mask)
+            mat = g.Material(cases.RHO, cases.CP, cases.K)
+            packs = g.precompute_coeff_packs_unified(grid, mat, **bcs)
+            used0 = g.get_option("ztrim_used")
+            out = g.adi_step_gpu_coeff(cp.asarray(T0), grid, mat, g.Params(dt, 0.5), packs, Tinf=20.0)
+            out = cp.asnumpy(g.adi_step_gpu_coeff(out, grid, mat, g.Params(dt, 0.5), packs, Tinf=20.0))
+            if v:
+                assert g.get_option("ztop") == top
+            trimmed = g.get_option("ztrim_used") - used0
+            # the trimmed length is ztop rounded up to 32-cell chunks, at least 256: 500 -> 512 = nz, nothing to trim
+            if not v or top > 480:
+                assert trimmed == 0, trimmed
+            elif top > 0 and bk in ("robin_dict3d", "robin6"):    # (operand sets that stay on k_sweep_z are not trimmed)
+                assert trimmed == 2, trimmed
+            outs[v] = out
+    finally:
+        g.set_option("ztrim", 1)
+    ref = cart.adi_step_numba_coeff(ref, hg, hm, cart.Params(dt, 0.5),
+                                    cart.precompute_coeff_packs_unified(hg, hm, **bcs), Tinf=20.0)
+    for v in (1, 0):
+        assert cases.rel_l2(outs[v], ref, mask) <= 2 * TOL
+        assert np.array_equal(outs[v][~mask], T0[~mask], equal_nan=True)
+    assert cases.rel_l2(outs[1], outs[0], mask) <= 1e-14

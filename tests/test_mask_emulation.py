@@ -66,10 +66,12 @@ def test_code_word_form_matches_the_cell_form(shape, kind, halo, with_dir):
     ref = _code_ref(mask, dirm, mlo, mhi)
     L = emu.lib()
     L.emu_build_code_v.argtypes = [BP, BP, BP, C.c_int, C.c_int, C.c_int, BP, BP]
-    L.emu_build_code_v.restype = None
+    L.emu_build_code_v.restype = C.c_int
     out = np.full(shape, 0xAA, dtype=np.uint8)
-    L.emu_build_code_v(_bp(mask), _bp(dirm), _bp(out), nx, ny, nz, _bp(mlo), _bp(mhi))
+    top = L.emu_build_code_v(_bp(mask), _bp(dirm), _bp(out), nx, ny, nz, _bp(mlo), _bp(mhi))
     assert np.array_equal(out, ref)
+    planes = np.nonzero(mask.any(axis=(0, 1)))[0]
+    assert top == (int(planes[-1]) + 1 if planes.size else 0)      # top of the part, for the trimmed z sweep
 
 
 @pytest.mark.parametrize("shape", [(5, 6, 16), (130, 3, 132), (33, 2, 4), (256, 2, 128), (100, 5, 260), (1, 1, 4)])

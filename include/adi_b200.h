@@ -164,7 +164,14 @@ int adi_cart_zsweep_apply(adi_ctx *ctx, double *d_T, const double *d_dyn_all, co
  *           examined (one pass, one small read-back); a field that is +0.0 on every active cell with both neighbours
  *           along its axis -- as everything precompute_coeff_packs_unified builds is -- is then read at exposed cells
  *           only.  Same bits as the dense reads; 0 switches the examination off
- *   "profile" 1: record per-kernel CUDA events (adi_profile_read)            "sync_check" 1: synchronise after every step */
+ *   "profile" 1: record per-kernel CUDA events (adi_profile_read)            "sync_check" 1: synchronise after every step
+ *   "maskv" 1 (default): the kernels that run once per mask change (neighbour code, its transposed copies, the pack
+ *           builder of adi_cart_build_packs) take their word-at-a-time forms where nz and the addresses allow
+ *           (nz % 16 / 4 / 2 == 0); 0: one cell per thread.  Same bits either way
+ *   "ztrim" 1 (default): a part under construction along z (waam_from_stl_v7_mm.py:487-550) -- the single-GPU z sweep
+ *           solves only the cells below the highest active plane (void cells above it are identity rows)
+ *   read-only: "maskv_used" (bit 0 / 1 / 2: code / transposes / packs last ran in word form), "ztop" (highest active
+ *           plane + 1, -1 unknown), "ztrim_used" (trimmed z sweeps so far) */
 int adi_set_option(adi_ctx *ctx, const char *name, long value);
 long adi_get_option(adi_ctx *ctx, const char *name);  /* value of an option; "sparse_active": bit a set when the
                                                           sweep along axis a reads its coefficient field at exposed

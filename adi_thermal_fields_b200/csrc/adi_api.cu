@@ -338,6 +338,9 @@ long adi_get_option(adi_ctx *ctx, const char *name)
     if (!strcmp(name, "maskv")) return ctx->opt_maskv;
     if (!strcmp(name, "ztrim")) return ctx->opt_ztrim;
     if (!strcmp(name, "ztrim_used")) return ctx->ztrim_used;   // z sweeps launched on trimmed lines so far
+    if (!strcmp(name, "xtrim_used")) return ctx->xtrim_used;   // x sweeps launched on the x extent of the part only
+    if (!strcmp(name, "xlo")) return ctx->xlo;
+    if (!strcmp(name, "xhi")) return ctx->xhi;
     if (!strcmp(name, "ztop")) return ctx->ztop;               // z + 1 of the highest active cell (-1: unknown / not read yet)
     if (!strcmp(name, "pkb")) return ctx->opt_pkb;
     if (!strcmp(name, "pkm")) return ctx->opt_pkm;

@@ -54,8 +54,8 @@ int ensure_code(adi_ctx *ctx, cudaStream_t st)
         ctx->maskv_used &= ~3;
         ctx->ztop = -1; ctx->ztop_pending = false;     // unknown unless the word form reports it
         if (!ctx->d_ztop) {
-            ADI_CUDA(cudaMalloc(&ctx->d_ztop, sizeof(int)));
-            ADI_CUDA(cudaMallocHost(&ctx->h_ztop, sizeof(int)));
+            ADI_CUDA(cudaMalloc(&ctx->d_ztop, 3 * sizeof(int)));
+            ADI_CUDA(cudaMallocHost(&ctx->h_ztop, 3 * sizeof(int)));
         }
         for (int a = 0; a < ncodes; ++a) {
             // word form: 16 cells per thread (adi_mask_core.h) when every z line starts on a 16-byte boundary
@@ -63,12 +63,12 @@ int ensure_code(adi_ctx *ctx, cudaStream_t st)
                                   (((uintptr_t)ctx->d_mask | (uintptr_t)ctx->pack[a].dirm | (uintptr_t)ctx->code_buf[a]) & 15) == 0;
             if (wordform) {
                 const int vblocks = (int)std::min<size_t>((n / 16 + threads - 1) / threads, 148 * 32);
-                if (a == 0) ADI_CUDA(cudaMemsetAsync(ctx->d_ztop, 0, sizeof(int), st));
+                if (a == 0) ADI_CUDA(cudaMemsetAsync(ctx->d_ztop, 0, 3 * sizeof(int), st));
                 k_build_code_v<<<vblocks, threads, 0, st>>>(ctx->d_mask, ctx->pack[a].dirm, ctx->code_buf[a],
                                                             ctx->nx, ctx->ny, ctx->nz, ctx->d_mask_lo, ctx->d_mask_hi,
                                                             a == 0 ? ctx->d_ztop : nullptr);
                 if (a == 0) {   // top of the part, read when the z sweep first needs it (launch_sweep_zt)
-                    ADI_CUDA(cudaMemcpyAsync(ctx->h_ztop, ctx->d_ztop, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    ADI_CUDA(cudaMemcpyAsync(ctx->h_ztop, ctx->d_ztop, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
                     ctx->ztop_pending = true;
                 }
                 ctx->maskv_used |= 1;
@@ -158,6 +158,21 @@ int ensure_sparse(adi_ctx *ctx, cudaStream_t st)
 }
 
 }  // namespace
+
+// The extent of the part as the last code build reduced it (k_build_code_v): ctx->ztop (z + 1 of the highest active
+// cell; -1 unknown), ctx->xlo / ctx->xhi (first x plane with an active cell / last + 1).  Waits for the small copy the
+// first time it is asked after a mask change.
+int adi::part_extent(adi_ctx *ctx, cudaStream_t st)
+{
+    if (ctx->ztop_pending) {
+        ADI_CUDA(cudaStreamSynchronize(st));
+        ctx->ztop = ctx->h_ztop[0];
+        ctx->xlo = ctx->h_ztop[0] > 0 ? ctx->nx - ctx->h_ztop[1] : 0;
+        ctx->xhi = ctx->h_ztop[0] > 0 ? ctx->h_ztop[2] : 0;
+        ctx->ztop_pending = false;
+    }
+    return ADI_OK;
+}
 
 // Active-tile list of a sweep axis for tiles of KT rows (see k_tile_flags): flags on the device, compaction on the
 // host (one small read-back per mask change), ascending order so that neighbouring blocks keep touching
@@ -361,7 +376,7 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
     a.k.invdx2 = 1.0 / (dx * dx);
     a.zlo = d_Tlo; a.zhi = d_Thi; a.iface_dyn = d_iface_dyn; a.iface_stat = d_iface_stat; a.ghost = d_ghost;
     a.codeT = nullptr; a.npad = 0; a.uni = 0; a.tw = 0; a.remap = 0; a.dbg = 0; a.halo_defer = 0;
-    a.tiles = nullptr; a.tiles_nx = 0; a.tsplit = 0; a.zpitch = 0; a.code_line = 0; a.zfull = 0;
+    a.tiles = nullptr; a.tiles_nx = 0; a.tsplit = 0; a.zpitch = 0; a.code_line = 0; a.zfull = 0; a.line0 = 0;
     a.line_batch = nlb != 0 ? 1 : 0;
     bool expl = a.k.beta != 0.0;
     bool x_in_place = false;
@@ -413,7 +428,31 @@ static int run_sweeps(adi_ctx *ctx, const double *d_Tin, double *d_Tout, double 
         a.k.h_hi = ctx->scalar_robin ? ctx->face_coeff[2 * axis + 1] : 0.0;
         const bool dense = p.coeff != nullptr;
         const bool extra = p.q != nullptr || p.dirm != nullptr;
-        if (axis == 0) rc = launch_sweep_x(ctx, a, dense, extra, expl, st);
+        if (axis == 0) {
+            // A part under construction occupies the x planes xlo .. xhi-1 only (reduced by the code build): the in-place
+            // x sweep runs on that sub-grid -- whole 32-cell chunks, at least 256 planes -- through offset pointers.
+            SweepArgs b = a;
+            int x0 = 0, x1 = a.nx;
+            if (ctx->opt_ztrim && a.in == a.out && a.nx >= 512 && a.nx % 32 == 0 && a.nx == ctx->nx) {
+                rc = part_extent(ctx, st);
+                if (rc) return rc;
+                if (ctx->ztop >= 0) {
+                    x0 = ctx->xlo / 32 * 32;
+                    x1 = std::min(a.nx, (std::max(ctx->xhi, x0 + 1) + 31) / 32 * 32);
+                    if (x1 - x0 < 256) { x0 = std::max(0, std::min(x0, a.nx - 256)); x1 = std::min(a.nx, x0 + 256); }
+                }
+            }
+            if (x1 - x0 < a.nx) {
+                const size_t off = (size_t)x0 * a.ny * a.nz;
+                b.in += off; b.out += off; b.code += off;
+                if (b.coeff) b.coeff += off;
+                if (b.q) b.q += off;
+                if (b.dirv) b.dirv += off;
+                b.nx = x1 - x0; b.line0 = x0;
+                ctx->xtrim_used++;
+            }
+            rc = launch_sweep_x(ctx, b, dense, extra, expl, st);
+        }
         else if (axis == 1) rc = launch_sweep_y(ctx, a, dense, extra, st);
         else if (nlb == 0) rc = launch_sweep_z(ctx, a, dense, extra, zmode == 5 ? 2 : zmode, st);
         else {

@@ -56,6 +56,9 @@ struct SweepArgs {
     int line_batch;                    // z sweep of a batch of lines (multi-GPU): the pointers are offset, no tile list
     int zpitch;                        // k_sweep_zt: elements between consecutive z lines of in / out (0: nz)
     int code_line;                     // k_sweep_zt: 1 = `code` holds ONE line of nz codes shared by all z lines
+    int line0;                         // x sweep over the planes line0 .. line0+nx-1 of the grid only (the x extent of a part
+                                       // under construction; the field / operand pointers are already offset): offset of
+                                       // the transposed code rows
     int zfull;                         // k_sweep_zt: elements between consecutive z lines of code / coeff / q / dirv (0: nz);
                                        // set when the sweep solves only the first nz cells of longer lines (cells above
                                        // the top of a part under construction are void: launch_sweep_zt)
@@ -102,12 +105,22 @@ __global__ void __launch_bounds__(256) k_build_code_v(const uint8_t *__restrict_
                                                       int *__restrict__ ztop)
 {
     const size_t n16 = (size_t)nx * ny * nz / 16;
-    int top = 0;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n16; t += (size_t)gridDim.x * blockDim.x)
-        top = max(top, build_code16(mask, dirm, code, t * 16, nx, ny, nz, mlo, mhi));
-    if (ztop) {   // *ztop = z + 1 of the highest active cell of the grid
+    int top = 0, xlo = 0x7fffffff, xhi = -1;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n16; t += (size_t)gridDim.x * blockDim.x) {
+        int xi = -1;
+        top = max(top, build_code16(mask, dirm, code, t * 16, nx, ny, nz, mlo, mhi, &xi));
+        if (xi >= 0) { xlo = min(xlo, xi); xhi = max(xhi, xi); }
+    }
+    if (ztop) {   // ztop[0] = z + 1 of the highest active cell of the grid; ztop[1] = nx - lowest, ztop[2] = highest + 1
+                  // x plane with an active cell (all three start at 0 and grow by atomicMax)
         top = __reduce_max_sync(0xffffffffu, top);
-        if ((threadIdx.x & 31) == 0 && top > 0) atomicMax(ztop, top);
+        xlo = __reduce_min_sync(0xffffffffu, xlo);
+        xhi = __reduce_max_sync(0xffffffffu, xhi);
+        if ((threadIdx.x & 31) == 0 && top > 0) {
+            atomicMax(ztop, top);
+            atomicMax(ztop + 1, nx - xlo);
+            atomicMax(ztop + 2, xhi + 1);
+        }
     }
 }
 

@@ -39,6 +39,8 @@ struct TileList {
 };
 // -> *list = device list (NULL when every tile is active or the option is off), *nactive = tiles to launch
 int ensure_tiles(adi_ctx *ctx, int axis, int KT, cudaStream_t st, const int **list, int *nactive, int *tiles_nx);
+// resolves ctx->ztop / xlo / xhi (the extent of the part, reduced by the code build) after a mask change
+int part_extent(adi_ctx *ctx, cudaStream_t st);
 // x / y axes: the same tiles as two lists, all-uniform tiles and the other active ones (either may be empty)
 int ensure_tiles_split(adi_ctx *ctx, int axis, int KT, cudaStream_t st, const int **uni, int *nuni, const int **gen, int *ngen,
                        int *tiles_nx);
@@ -77,9 +79,10 @@ struct adi_ctx {
     // top of the part (z + 1 of the highest active cell), reduced by k_build_code_v: the single-GPU z sweep solves only
     // the cells below it (launch_sweep_zt).  -1: unknown (cell-form code build); pending: the copy to h_ztop is in flight
     int *d_ztop = nullptr, *h_ztop = nullptr;
-    int ztop = -1;
+    int ztop = -1, xlo = 0, xhi = 0;   // xlo / xhi: first x plane with an active cell / last + 1 (valid when ztop >= 0)
     bool ztop_pending = false;
     long ztrim_used = 0;  // z sweeps launched on trimmed lines
+    long xtrim_used = 0;  // x sweeps launched on the x extent of the part only
     int maskv_used = 0;  // bit 0 / 1 / 2: the last code build / code transposes / pack build ran in word form (adi_mask_core.h)
     // per-kernel timing (adi_profile_*): 5 events per step, read lazily
     std::vector<cudaEvent_t> prof_ev;

@@ -133,9 +133,10 @@ ADI_HD int top_byte(uint32_t w)
 // ---- K0 in word form: the neighbour codes of the 16 cells idx .. idx+15 of one z line ------------------------
 // (nz % 16 == 0, idx % 16 == 0, 16-byte aligned arrays).  A run without an active cell costs one load and one store.
 // Returns z + 1 of the highest active cell of the run (0: none): the kernel reduces it to the top of the part, above
-// which the z sweep has nothing to solve (launch_sweep_zt).
+// which the z sweep has nothing to solve (launch_sweep_zt); likewise the x planes that hold an active cell bound the
+// x sweep (adi_cart_step).
 ADI_HD int build_code16(const uint8_t *mask, const uint8_t *dirm, uint8_t *code, size_t idx, int nx, int ny, int nz,
-                         const uint8_t *mlo, const uint8_t *mhi)
+                         const uint8_t *mlo, const uint8_t *mhi, int *xplane = nullptr)
 {
     uint32_t s[4], out[4] = {0u, 0u, 0u, 0u};
     int top = 0;
@@ -145,6 +146,7 @@ ADI_HD int build_code16(const uint8_t *mask, const uint8_t *dirm, uint8_t *code,
         const size_t ij = idx / (size_t)nz;
         const int j = (int)(ij % (size_t)ny);
         const int i = (int)(ij / (size_t)ny);
+        if (xplane) *xplane = i;     // the run's x index, for the x extent of the part (written only when a cell is active)
         const size_t snx = (size_t)ny * nz;
         uint32_t xm[4] = {0u, 0u, 0u, 0u}, xp[4] = {0u, 0u, 0u, 0u}, ym[4] = {0u, 0u, 0u, 0u}, yp[4] = {0u, 0u, 0u, 0u},
                  d[4] = {0u, 0u, 0u, 0u};

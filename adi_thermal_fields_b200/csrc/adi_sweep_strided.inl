@@ -38,7 +38,7 @@ static int launch_strided_axis(adi_ctx *ctx, const SweepArgs &a, bool dense, boo
         }
         const int NTH = KT * P;
         SweepArgs b = a;
-        b.codeT = ctx->codeT[AXIS];
+        b.codeT = ctx->codeT[AXIS] + a.line0;
         b.npad = ctx->npadT[AXIS];
         b.tw = (ctx->opt_tw && NTH >= 32) ? 1 : 0;
         b.remap = ctx->opt_remap ? 1 : 0;

@@ -60,11 +60,8 @@ int launch_sweep_zt(adi_ctx *ctx, const SweepArgs &a0, bool dense, bool extra, i
     SweepArgs a = a0;
     if (zmode == 0 && ctx->opt_ztrim && !a.line_batch && !a.code_line && a.zpitch == 0 && a.zfull == 0 && a.in == a.out &&
         a.nz >= 512 && a.nz % 32 == 0 && a.nz == ctx->nz && a.code == ctx->code[2]) {
-        if (ctx->ztop_pending) {
-            ADI_CUDA(cudaStreamSynchronize(st));
-            ctx->ztop = *ctx->h_ztop;
-            ctx->ztop_pending = false;
-        }
+        int rc = part_extent(ctx, st);
+        if (rc) return rc;
         if (ctx->ztop >= 0) {
             const int ne = std::max(256, (ctx->ztop + 31) / 32 * 32);
             if (ne < a.nz) {

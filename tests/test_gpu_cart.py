@@ -706,3 +706,53 @@ def test_z_sweep_stops_at_the_top_of_the_part(top, bk, g, cp):
         assert cases.rel_l2(outs[v], ref, mask) <= 2 * TOL
         assert np.array_equal(outs[v][~mask], T0[~mask], equal_nan=True)
     assert cases.rel_l2(outs[1], outs[0], mask) <= 1e-14
+
+
+@pytest.mark.parametrize("xr", [(100, 300), (40, 500), (0, 10), (505, 512), (0, 512)])
+@pytest.mark.parametrize("shape,bk", [((512, 20, 64), "robin_dict3d"), ((512, 20, 64), "combined"), ((512, 20, 64), "robin6"),
+                                      ((512, 6, 512), "robin_dict3d")])
+def test_x_sweep_runs_on_the_x_extent_of_the_part(xr, shape, bk, g, cp):
+    """The in-place x sweep covers only the x planes that hold an active cell (whole 32-cell chunks, at least 256
+    planes; the extent comes out of the code build) -- same answer as the oracle and as the full sweep."""
+    from oracle import cart
+    nx, ny, nz = shape
+    seed = 900 + xr[0]
+    mask = cases.make_mask("random", shape, seed)
+    mask[:xr[0]] = False
+    mask[xr[1]:] = False
+    if nz == 512:
+        mask[:, :, 300:] = False                      # z and x trimmed together
+    bcs = cases.make_bcs(bk, shape, mask, seed, 20.0)
+    T0 = 20.0 + 1380.0 * cases.splitmix_uniform(seed + 1, shape)
+    T0[~mask] = np.nan
+    kappa = cases.K / (cases.RHO * cases.CP)
+    dt = 50.0 * cases.DX ** 2 / kappa
+    hg, hm = cart.Grid3D(nx, ny, nz, cases.DX, mask), cart.Material(cases.RHO, cases.CP, cases.K)
+    hp = cart.precompute_coeff_packs_unified(hg, hm, **bcs)
+    ref = cart.adi_step_numba_coeff(T0, hg, hm, cart.Params(dt, 0.5), hp, Tinf=20.0)
+    ref = cart.adi_step_numba_coeff(ref, hg, hm, cart.Params(dt, 0.5), hp, Tinf=20.0)
+    planes = np.nonzero(mask.any(axis=(1, 2)))[0]
+    outs = {}
+    try:
+        for v in (1, 0):
+            g.set_option("ztrim", v)
+            grid = g.Grid3D(nx, ny, nz, cases.DX, mask)
+            mat = g.Material(cases.RHO, cases.CP, cases.K)
+            packs = g.precompute_coeff_packs_unified(grid, mat, **bcs)
+            used0 = g.get_option("xtrim_used")
+            out = g.adi_step_gpu_coeff(cp.asarray(T0), grid, mat, g.Params(dt, 0.5), packs, Tinf=20.0)
+            outs[v] = cp.asnumpy(g.adi_step_gpu_coeff(out, grid, mat, g.Params(dt, 0.5), packs, Tinf=20.0))
+            trimmed = g.get_option("xtrim_used") - used0
+            if v and planes.size:
+                assert (g.get_option("xlo"), g.get_option("xhi")) == (int(planes[0]), int(planes[-1]) + 1)
+                lo = planes[0] // 32 * 32
+                hi = min(nx, (planes[-1] + 32) // 32 * 32)
+                assert trimmed == (2 if max(hi - lo, 256) < nx else 0), trimmed
+            if not v:
+                assert trimmed == 0
+    finally:
+        g.set_option("ztrim", 1)
+    for v in (1, 0):
+        assert cases.rel_l2(outs[v], ref, mask) <= 2 * TOL
+        assert np.array_equal(outs[v][~mask], T0[~mask], equal_nan=True)
+    assert cases.rel_l2(outs[1], outs[0], mask) <= 1e-14

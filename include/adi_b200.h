@@ -169,9 +169,11 @@ int adi_cart_zsweep_apply(adi_ctx *ctx, double *d_T, const double *d_dyn_all, co
  *           builder of adi_cart_build_packs) take their word-at-a-time forms where nz and the addresses allow
  *           (nz % 16 / 4 / 2 == 0); 0: one cell per thread.  Same bits either way
  *   "ztrim" 1 (default): a part under construction along z (waam_from_stl_v7_mm.py:487-550) -- the single-GPU z sweep
- *           solves only the cells below the highest active plane (void cells above it are identity rows)
+ *           solves only the cells below the highest active plane (void cells above it are identity rows), the x sweep
+ *           only the x planes that hold an active cell
  *   read-only: "maskv_used" (bit 0 / 1 / 2: code / transposes / packs last ran in word form), "ztop" (highest active
- *           plane + 1, -1 unknown), "ztrim_used" (trimmed z sweeps so far) */
+ *           plane + 1, -1 unknown), "xlo" / "xhi" (first x plane with an active cell / last + 1), "ztrim_used" /
+ *           "xtrim_used" (trimmed z / x sweeps so far) */
 int adi_set_option(adi_ctx *ctx, const char *name, long value);
 long adi_get_option(adi_ctx *ctx, const char *name);  /* value of an option; "sparse_active": bit a set when the
                                                           sweep along axis a reads its coefficient field at exposed

@@ -56,13 +56,13 @@ struct SweepArgs {
     int line_batch;                    // z sweep of a batch of lines (multi-GPU): the pointers are offset, no tile list
     int zpitch;                        // k_sweep_zt: elements between consecutive z lines of in / out (0: nz)
     int code_line;                     // k_sweep_zt: 1 = `code` holds ONE line of nz codes shared by all z lines
+    UniConst uc;
     int line0;                         // x sweep over the planes line0 .. line0+nx-1 of the grid only (the x extent of a part
                                        // under construction; the field / operand pointers are already offset): offset of
                                        // the transposed code rows
     int zfull;                         // k_sweep_zt: elements between consecutive z lines of code / coeff / q / dirv (0: nz);
                                        // set when the sweep solves only the first nz cells of longer lines (cells above
                                        // the top of a part under construction are void: launch_sweep_zt)
-    UniConst uc;
 };
 
 #ifdef ADI_CART_MISC_KERNELS  // defined by adi_cart.cu, the one unit that launches K0/K7

@@ -30,17 +30,23 @@ static int launch_zt_mode(adi_ctx *ctx, const SweepArgs &a, bool dense, bool ext
     int vec = ((a.nz & 1) == 0 && (a.zpitch & 1) == 0 && (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.code) & 15) == 0) ? 1 : 0;
     if (vec && (a.nz & 15) == 0 && a.in == a.out && ctx->opt_bulk) vec = 2;   // whole lines as bulk asynchronous copies
     const bool big = KT * P > 256;
-#define ADI_GOZ(M_, MAXT, MINB)                                                                                    \
-    {                                                                                                              \
-        if (dense) {                                                                                               \
-            if (extra) return launch(k_sweep_zt<M_, 2, true, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, b, vec);  \
-            return launch(k_sweep_zt<M_, 2, false, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, b, vec);            \
-        }                                                                                                          \
-        if (extra) return launch(k_sweep_zt<M_, 1, true, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, b, vec);      \
-        return launch(k_sweep_zt<M_, 1, false, MAXT, MINB, ZMODE>, grid, block, smem, st, ctx, b, vec);                \
+#define ADI_GOZ(M_, MAXT, MINB, ZF_)                                                                                   \
+    {                                                                                                                  \
+        if (dense) {                                                                                                   \
+            if (extra) return launch(k_sweep_zt<M_, 2, true, MAXT, MINB, ZMODE, ZF_>, grid, block, smem, st, ctx, b, vec);  \
+            return launch(k_sweep_zt<M_, 2, false, MAXT, MINB, ZMODE, ZF_>, grid, block, smem, st, ctx, b, vec);            \
+        }                                                                                                              \
+        if (extra) return launch(k_sweep_zt<M_, 1, true, MAXT, MINB, ZMODE, ZF_>, grid, block, smem, st, ctx, b, vec);      \
+        return launch(k_sweep_zt<M_, 1, false, MAXT, MINB, ZMODE, ZF_>, grid, block, smem, st, ctx, b, vec);                \
     }
-    if (M == 16) { if (big) ADI_GOZ(16, 512, 1) else ADI_GOZ(16, 256, 2) }
-    else { if (big) ADI_GOZ(32, 512, 1) else ADI_GOZ(32, 256, 2) }
+    if constexpr (ZMODE == 0) {
+        if (a.zfull) {   // trimmed lines (always 32-cell chunks: nz >= 256)
+            if (M != 32) { set_error("adi_cart_step: trimmed z sweep needs 32-cell chunks"); return ADI_EINVAL; }
+            if (big) ADI_GOZ(32, 512, 1, true) else ADI_GOZ(32, 256, 2, true)
+        }
+    }
+    if (M == 16) { if (big) ADI_GOZ(16, 512, 1, false) else ADI_GOZ(16, 256, 2, false) }
+    else { if (big) ADI_GOZ(32, 512, 1, false) else ADI_GOZ(32, 256, 2, false) }
 #undef ADI_GOZ
     return ADI_OK;
 }

@@ -89,7 +89,9 @@ struct ZtOps {
 };
 
 // smem: sT[KT][RL+2] doubles | xch[(ZMODE 1 ? 10 : 6) * NTH] | sEnd[KT][2] | mbarrier (16 B) | sCode[KT][RL+16] bytes
-template <int M, int CMODE, bool EXTRA, int MAXT, int MINB, int ZMODE>
+// ZF: the sweep solves only the first nz cells of lines whose operand arrays are a.zfull apart (launch_sweep_zt); its
+// own instantiation, so that the common kernel keeps one stride
+template <int M, int CMODE, bool EXTRA, int MAXT, int MINB, int ZMODE, bool ZF = false>
 __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, const int vec)
 {
     static_assert(M % 16 == 0, "codes are read sixteen at a time");
@@ -114,8 +116,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
     // line stride of the field (pitched buffers of the cylindrical path) and of the code array (0: one code line
     // shared by every z line -- the cylindrical z sweep, whose rows do not depend on the line)
     const size_t zs = a.zpitch ? (size_t)a.zpitch : (size_t)nz;
-    const size_t zf = a.zfull ? (size_t)a.zfull : (size_t)nz;   // line stride of the operand arrays (trimmed sweeps: the full nz)
-    const size_t cs = a.code_line ? 0 : zf;
+    // line stride of the operand arrays (trimmed sweeps: the full nz).  Spelled out at every use: one hoisted 64-bit
+    // value cost the common kernel 52 bytes of spill stores (ptxas) and 5 % at 512^3.
+#define ADI_ZT_OPSTRIDE (ZF ? (size_t)a.zfull : (size_t)nz)
+    const size_t cs = a.code_line ? 0 : ADI_ZT_OPSTRIDE;
     // vec 2: whole lines travel as bulk asynchronous copies (one instruction per line and direction);
     // vec 1: 16-byte cp.async pieces / vector stores; vec 0: scalar loads and stores
     const bool bulk = vec == 2;
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
         // the two ends of every line (always exposed when active) are requested with the tile
         for (int i = tid; i < 2 * KT; i += NTH) {
             const size_t line = min(L0 + (size_t)(i >> 1), nlines - 1);
-            cp_async8(smem_u32(sEnd + i), a.coeff + line * zf + ((i & 1) ? nz - 1 : 0));
+            cp_async8(smem_u32(sEnd + i), a.coeff + line * ADI_ZT_OPSTRIDE + ((i & 1) ? nz - 1 : 0));
         }
     }
     cp_async_wait_all();
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
         if (!__syncthreads_or(any)) return;
     }
     const size_t line = L0 + kk;
-    const size_t gline = min(line, nlines - 1) * zf;
+    const size_t gline = min(line, nlines - 1) * ADI_ZT_OPSTRIDE;
     const int nv = line < nlines ? min(max(nz - p * M, 0), M) : 0;
 
     // coefficient of ACTIVE cell e of this chunk (exposed cells only carry one)
@@ -408,5 +412,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sweep_zt(const SweepArgs a, cons
         }
     }
 }
+#undef ADI_ZT_OPSTRIDE
 
 }  // namespace adi

@@ -112,11 +112,17 @@ class AxisCoeffPack:
     def _has_dirichlet(self):
         if self._dir_mask is None:
             return False
-        t = self._dir_mask._t
+        # the three packs of one precompute share ONE dir_mask array (adi3d_gpu_coeff.py:108-110): the answer is kept
+        # on that array, so a pack rebuild costs one reduction + read-back instead of three
+        m = self._dir_mask
+        t = m._t
         key = (t.data_ptr(), t._version)
-        if self._dir_any is None or self._dir_any[0] != key:
-            self._dir_any = (key, bool(t.any().item()))
-        return self._dir_any[1]
+        cached = getattr(m, "_any_true", None)
+        if cached is None or cached[0] != key:
+            cached = (key, bool(t.any().item()))
+            m._any_true = cached
+        self._dir_any = cached
+        return cached[1]
 
 
 class _Engine:
